@@ -1,0 +1,166 @@
+/*
+ * macaw_b200.h — C ABI of libmacaw_b200.so, the sm_100a kernel library behind the MM_LLMs forward hot path.
+ *
+ * The reference (lyuchenyang/Macaw-LLM) has no FFI layer of its own: its hot path is Python calling
+ * torch / transformers modules.  Each entry point below therefore cites the reference
+ * call site(s) whose arithmetic it replaces; the Python host code in macaw-llm_b200/ binds them with
+ * ctypes (INTEGRATION.md shows the stub a maintainer of the reference would add).
+ *
+ * Conventions
+ *   - every function returns 0 on success, non-zero on error; mm_last_error() returns a message for the
+ *     calling thread.  No exceptions cross this boundary and nothing here calls cudaMalloc.
+ *   - all pointers are DEVICE pointers owned by the caller (torch's caching allocator in practice).
+ *   - `stream` is a cudaStream_t passed as void*; all calls are asynchronous and never synchronise.
+ *   - "bf16" means 16-bit bfloat16 storage, row-major unless a leading dimension says otherwise; all
+ *     accumulation is fp32.
+ */
+#ifndef MACAW_B200_H_
+#define MACAW_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ------------------------------------------------------------------------------------------------ meta */
+const char* mm_last_error(void);
+int32_t mm_abi_version(void);
+/* Number of kernel launches issued through this library by the calling process since the last reset. */
+int64_t mm_launch_count(void);
+void mm_launch_count_reset(void);
+
+/* ------------------------------------------------------------------------------------------------ GEMM
+ * C[b] = epilogue( alpha * A[b] (M x K, K contiguous) * B[b]^T ) for b in [0, batch).
+ * Replaces every nn.Linear / Conv-as-matmul / bmm on the path:
+ *   LLaMA q/k/v/o/gate/up/down/lm_head   modeling.py:134-140, 159-162, 179-181, 226, 597
+ *   alignment MHA in/out projections      modeling.py:986-987, 1007-1008, 1025-1026 -> torch F.multi_head_attention_forward
+ *   Conv1d down-samplers, Linear C->E     modeling.py:982-984, 999-1001, 1022-1024
+ *   CLIP / Whisper encoder linears, convs  modeling.py:1073, 1082, 1092 -> transformers modeling_clip / modeling_whisper
+ * Implementation: persistent, warp-specialised TMA -> tcgen05.mma (TMEM accumulators) kernel.
+ */
+enum {
+  MM_ACT_NONE = 0,
+  MM_ACT_GELU = 1,        /* exact erf GELU (Whisper) */
+  MM_ACT_QUICK_GELU = 2,  /* x * sigmoid(1.702 x) (CLIP) */
+  MM_ACT_SILU = 3
+};
+enum {
+  MM_EPI_STD = 0,    /* bias / activation / residual */
+  MM_EPI_SWIGLU = 1, /* B rows interleaved [32 gate | 32 up]; C[:, j] = silu(gate_j) * up_j, N_out = N/2 */
+  MM_EPI_ROPE = 2    /* rotate-half RoPE (head_dim 128) on columns < rope_cols, pos = row % rope_T */
+};
+
+typedef struct mm_gemm_args {
+  /* problem: batch (inner) x batch2 (outer, 0 or 1 = none) independent products */
+  int32_t M, N, K, batch, batch2;
+  /* A: bf16 [batch][M][K], row stride lda (elements), batch stride a_bs (elements; rows may overlap) */
+  const void* A;
+  int64_t lda, a_bs, a_bs2;
+  /* B: bf16.  b_mn_major == 0: [batch][N][K] (K contiguous, i.e. an nn.Linear weight), row stride ldb.
+   *           b_mn_major == 1: [batch][K][N] (N contiguous), row stride ldb.  b_bs == 0 shares B across batch. */
+  const void* B;
+  int64_t ldb, b_bs, b_bs2;
+  int32_t b_mn_major;
+  /* C: bf16 (c_fp32 == 0) or fp32 (c_fp32 == 1) [batch][M][N_out], row stride ldc */
+  void* C;
+  int64_t ldc, c_bs, c_bs2;
+  int32_t c_fp32;
+  /* epilogue */
+  int32_t epi;            /* MM_EPI_* */
+  int32_t act;            /* MM_ACT_* (MM_EPI_STD only) */
+  float alpha;
+  const void* bias;       /* bf16 [N] or NULL; bias_bs = per-batch stride in elements */
+  int64_t bias_bs;
+  const float* row_scale; /* fp32 [batch2*batch*M] or NULL: multiplies row m of the product before bias */
+  const void* residual;   /* bf16, added after activation; row index = m % res_row_mod if res_row_mod > 0 */
+  int64_t ldr, r_bs, r_bs2;
+  int32_t res_row_mod;
+  const float* rope_cos;  /* fp32 [rope_T][64] */
+  const float* rope_sin;
+  int32_t rope_T, rope_cols;
+} mm_gemm_args;
+
+int32_t mm_gemm_fwd(const mm_gemm_args* args, void* stream);
+
+/* Sum fp32 partials [splits][M][N] (+ bf16 bias[N]) -> bf16 [M][N] (row stride ldo).  Split-K tail of the
+ * Conv1d down-samplers (modeling.py:982, 999, 1022). */
+int32_t mm_splitk_reduce(const float* partial, int32_t splits, int32_t M, int32_t N, const void* bias, void* out,
+                         int64_t ldo, void* stream);
+
+/* ------------------------------------------------------------------------------------------------ attention
+ * out[b,t,h,:] = softmax(scale * q k^T + mask) v, flash-style (no T x T tensor in HBM).
+ * Replaces: LlamaAttention.forward modeling.py:197-215 (causal + key padding), CLIP / Whisper encoder
+ * self-attention (transformers modeling_clip.py / modeling_whisper.py eager attention), and
+ * video_long_self_attention modeling.py:1078 (two synthetic keys are materialised by the caller).
+ * q/k/v/out: bf16 with element strides (batch, token, head); head_dim contiguous, head_dim in {64, 96, 128}.
+ * key_mask: int32 [B][Tk] (1 = attend, 0 = masked) or NULL.  causal: key j visible to query i iff j <= i + (Tk - Tq).
+ */
+typedef struct mm_attn_args {
+  const void *q, *k, *v;
+  void* out;
+  int32_t B, H, Tq, Tk, head_dim;
+  int64_t q_bs, q_ts, q_hs;
+  int64_t k_bs, k_ts, k_hs;
+  int64_t v_bs, v_ts, v_hs;
+  int64_t o_bs, o_ts, o_hs;
+  const int32_t* key_mask;
+  int32_t causal;
+  float scale;
+} mm_attn_args;
+int32_t mm_attn_fwd(const mm_attn_args* args, void* stream);
+
+/* ------------------------------------------------------------------------------------------------ norms
+ * LlamaRMSNorm modeling.py:311-319 (fp32 variance);  y = x * rsqrt(mean(x^2) + eps) * w.  x, y bf16 [rows][cols]. */
+int32_t mm_rmsnorm_fwd(const void* x, const void* w, void* y, int32_t rows, int32_t cols, float eps, void* stream);
+/* nn.LayerNorm of the CLIP / Whisper encoders (transformers modeling_clip.py:CLIPEncoderLayer, modeling_whisper.py). */
+int32_t mm_layernorm_fwd(const void* x, int64_t ldx, const void* w, const void* b, void* y, int64_t ldy, int32_t rows,
+                         int32_t cols, float eps, void* stream);
+
+/* ------------------------------------------------------------------------------------------------ gathers / layout
+ * embed_tokens lookup modeling.py:971-972, 979-980, 996-997, 1019-1020: out[i,:] = table[ids[i],:] (ids int64). */
+int32_t mm_embed_gather(const void* table, int32_t vocab, int32_t dim, const int64_t* ids, int64_t n_ids, void* out,
+                        int64_t ldo, void* stream);
+/* Splice modeling.py:989-993, 1010-1016, 1028-1034 done in one pass.
+ * dst (B, T, E) bf16 with T = 1 + n_prefix + (L-1):  dst[b,0] = text[b,0]; dst[b,1+j] = prefix[b,j]; dst[b,1+n_prefix+j] = text[b,1+j].
+ * Also builds the int64 mask/label prefix of modeling.py:1036-1046 (bit-exact): mask_out = [1]*n_prefix ++ mask_in,
+ * labels_out = [-100]*n_prefix ++ labels_in.  mask_in/labels_in may be NULL (then the outputs are not written). */
+int32_t mm_splice_prefix(const void* text, const void* prefix, void* dst, int32_t B, int32_t L, int32_t n_prefix,
+                         int32_t E, const int64_t* mask_in, int64_t* mask_out, const int64_t* labels_in,
+                         int64_t* labels_out, void* stream);
+/* CLIP patch embedding im2col (transformers modeling_clip.py:CLIPVisionEmbeddings): images (B,3,H,W) bf16 ->
+ * rows (B*gh*gw, ldo) with column order (c, py, px); columns >= 3*p*p are zero. */
+int32_t mm_patchify(const void* images, int32_t B, int32_t C, int32_t H, int32_t W, int32_t patch, void* out,
+                    int64_t ldo, void* stream);
+/* (B, C, T) -> (B, T + 2*pad, C) with zero pad rows (Whisper conv stem input, modeling_whisper.py:WhisperEncoder.forward). */
+int32_t mm_transpose_pad(const void* x, int32_t B, int32_t C, int32_t T, int32_t pad, void* out, void* stream);
+/* y[r,:] = x[r,:] + add[r % add_rows,:]  (bf16; CLIP class/position embeddings, video sinusoid PE modeling.py:1108-1118) */
+int32_t mm_add_rows(const void* x, int64_t ldx, const void* add, int64_t lda, int32_t add_rows, void* y, int64_t ldy,
+                    int32_t rows, int32_t cols, void* stream);
+/* generic strided 2-D copy of bf16 rows (concats, CLS drop) */
+int32_t mm_copy_rows(const void* x, int64_t ldx, void* y, int64_t ldy, int32_t rows, int32_t cols, void* stream);
+
+/* ------------------------------------------------------------------------------------------------ alignment softmax
+ * Row softmax of the absorbed-form alignment scores (torch F.multi_head_attention_forward: softmax over S = V + 2 keys,
+ * functional.py:6531-6537, 6585-6602, 6630-6650).  scores fp32 [R][V] hold q~ . table[v]; the kernel adds row_bias[r]
+ * (q_h . b_k[h]; read at row_bias[r * stat_stride], same stride for extra_score) to every real key, includes the bias_k key (score extra_score[r]) and the zero key (score 0) in the
+ * normaliser, and writes P bf16 [R][V] (row stride ldp), p_sum_real[r] = sum_v P[r,v] and p_extra[r] = P of the bias_k key. */
+int32_t mm_align_softmax(const float* scores, int64_t lds, const float* row_bias, const float* extra_score,
+                         int64_t stat_stride, void* P, int64_t ldp, float* p_sum_real, float* p_extra, int32_t R,
+                         int32_t V, void* stream);
+/* Value-side bias terms of the absorbed form (functional.py:6531-6537: bias_v is appended un-projected; b_v rides on
+ * every real key):  ctx[n, h*hd + d] += p_sum_real[h*Nq + n] * b_v[h*hd + d] + p_extra[h*Nq + n] * bias_v[h*hd + d]. */
+int32_t mm_align_ctx_fixup(void* ctx, int64_t ldc, const float* p_sum_real, const float* p_extra, const void* b_v,
+                           const void* bias_v, int32_t Nq, int32_t E, int32_t head_dim, void* stream);
+
+/* ------------------------------------------------------------------------------------------------ loss
+ * Shifted cross entropy of LlamaForCausalLM.forward modeling.py:600-610: logits bf16 (B, T, V), labels int64 (B, T);
+ * position t predicts labels[t+1]; ignore_index -100; writes loss_sum[0] (fp32) and n_valid[0] (int32);
+ * both must be zeroed by the caller. */
+int32_t mm_ce_loss(const void* logits, const int64_t* labels, int32_t B, int32_t T, int32_t V, float* loss_sum,
+                   int32_t* n_valid, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MACAW_B200_H_ */

@@ -1,0 +1,97 @@
+"""ctypes loader for libmacaw_b200.so (the C ABI declared in include/macaw_b200.h).
+
+There is deliberately no fallback: if the library is missing it is built with nvcc, and if that fails the import
+raises — the product path never silently routes through torch or the CPU oracle.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libmacaw_b200.so")
+
+c_i32, c_i64, c_f32, c_vp = C.c_int32, C.c_int64, C.c_float, C.c_void_p
+
+
+class GemmArgs(C.Structure):
+    """Mirror of `mm_gemm_args` (include/macaw_b200.h)."""
+
+    _fields_ = [
+        ("M", c_i32), ("N", c_i32), ("K", c_i32), ("batch", c_i32), ("batch2", c_i32),
+        ("A", c_vp), ("lda", c_i64), ("a_bs", c_i64), ("a_bs2", c_i64),
+        ("B", c_vp), ("ldb", c_i64), ("b_bs", c_i64), ("b_bs2", c_i64), ("b_mn_major", c_i32),
+        ("C", c_vp), ("ldc", c_i64), ("c_bs", c_i64), ("c_bs2", c_i64), ("c_fp32", c_i32),
+        ("epi", c_i32), ("act", c_i32), ("alpha", c_f32),
+        ("bias", c_vp), ("bias_bs", c_i64),
+        ("row_scale", c_vp),
+        ("residual", c_vp), ("ldr", c_i64), ("r_bs", c_i64), ("r_bs2", c_i64), ("res_row_mod", c_i32),
+        ("rope_cos", c_vp), ("rope_sin", c_vp), ("rope_T", c_i32), ("rope_cols", c_i32),
+    ]
+
+
+class AttnArgs(C.Structure):
+    """Mirror of `mm_attn_args` (include/macaw_b200.h)."""
+
+    _fields_ = [
+        ("q", c_vp), ("k", c_vp), ("v", c_vp), ("out", c_vp),
+        ("B", c_i32), ("H", c_i32), ("Tq", c_i32), ("Tk", c_i32), ("head_dim", c_i32),
+        ("q_bs", c_i64), ("q_ts", c_i64), ("q_hs", c_i64),
+        ("k_bs", c_i64), ("k_ts", c_i64), ("k_hs", c_i64),
+        ("v_bs", c_i64), ("v_ts", c_i64), ("v_hs", c_i64),
+        ("o_bs", c_i64), ("o_ts", c_i64), ("o_hs", c_i64),
+        ("key_mask", c_vp), ("causal", c_i32), ("scale", c_f32),
+    ]
+
+
+# name -> (restype, argtypes).  Every symbol declared in include/macaw_b200.h must appear here
+# (tests/test_abi.py cross-checks the header against this table and against the built library).
+SIGNATURES = {
+    "mm_last_error": (C.c_char_p, []),
+    "mm_abi_version": (c_i32, []),
+    "mm_launch_count": (c_i64, []),
+    "mm_launch_count_reset": (None, []),
+    "mm_gemm_fwd": (c_i32, [C.POINTER(GemmArgs), c_vp]),
+    "mm_splitk_reduce": (c_i32, [c_vp, c_i32, c_i32, c_i32, c_vp, c_vp, c_i64, c_vp]),
+    "mm_attn_fwd": (c_i32, [C.POINTER(AttnArgs), c_vp]),
+    "mm_rmsnorm_fwd": (c_i32, [c_vp, c_vp, c_vp, c_i32, c_i32, c_f32, c_vp]),
+    "mm_layernorm_fwd": (c_i32, [c_vp, c_i64, c_vp, c_vp, c_vp, c_i64, c_i32, c_i32, c_f32, c_vp]),
+    "mm_embed_gather": (c_i32, [c_vp, c_i32, c_i32, c_vp, c_i64, c_vp, c_i64, c_vp]),
+    "mm_splice_prefix": (c_i32, [c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "mm_patchify": (c_i32, [c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp, c_i64, c_vp]),
+    "mm_transpose_pad": (c_i32, [c_vp, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp]),
+    "mm_add_rows": (c_i32, [c_vp, c_i64, c_vp, c_i64, c_i32, c_vp, c_i64, c_i32, c_i32, c_vp]),
+    "mm_copy_rows": (c_i32, [c_vp, c_i64, c_vp, c_i64, c_i32, c_i32, c_vp]),
+    "mm_align_softmax": (c_i32, [c_vp, c_i64, c_vp, c_vp, c_i64, c_vp, c_i64, c_vp, c_vp, c_i32, c_i32, c_vp]),
+    "mm_align_ctx_fixup": (c_i32, [c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_vp]),
+    "mm_ce_loss": (c_i32, [c_vp, c_vp, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp]),
+}
+
+_lib = None
+
+
+def load(build_if_missing: bool = True) -> C.CDLL:
+    """Load (building first if necessary) the kernel library and bind every signature."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        if not build_if_missing:
+            raise RuntimeError(f"{LIB_PATH} is missing; run `python macaw-llm_b200/build.py`")
+        import importlib.util
+
+        spec = importlib.util.spec_from_file_location("_macaw_b200_build", os.path.join(HERE, "build.py"))
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        mod.build()
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError here == ABI drift; fail loudly
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def last_error() -> str:
+    return load().mm_last_error().decode("utf-8", "replace")

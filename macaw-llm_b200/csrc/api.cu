@@ -1,0 +1,26 @@
+// C-ABI meta entry points: error string, ABI version, launch counter.
+#include "common.cuh"
+#include "../../include/macaw_b200.h"
+#include <atomic>
+
+namespace mm {
+
+static thread_local char g_err[512] = "";
+static std::atomic<long long> g_launches{0};
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+}  // namespace mm
+
+extern "C" {
+const char* mm_last_error(void) { return mm::g_err; }
+int32_t mm_abi_version(void) { return 1; }
+int64_t mm_launch_count(void) { return mm::g_launches.load(); }
+void mm_launch_count_reset(void) { mm::g_launches.store(0); }
+}

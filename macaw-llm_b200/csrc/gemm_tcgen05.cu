@@ -1,0 +1,595 @@
+// Persistent, warp-specialised bf16 GEMM for sm_100a:  C = epilogue(alpha * A * B^T)
+//
+//   warp 0      : TMA producer  (cp.async.bulk.tensor -> 128B-swizzled smem ring, mbarrier complete_tx)
+//   warp 1      : TMEM allocator + single-thread tcgen05.mma issuer (accumulators live in TMEM, 2 buffers)
+//   warps 2..5  : epilogue (tcgen05.ld -> registers -> bias/activation/residual/RoPE/SwiGLU -> global)
+//
+// Tile = 128 (M) x BN (N) x 64 (K) per stage; UMMA shape 128 x BN x 16.  Two TMEM accumulator buffers let the
+// epilogue of tile i overlap the main loop of tile i+1.  One CTA per SM, static round-robin tile schedule with
+// grouped rasterisation for L2 reuse.
+//
+// Reference call sites replaced: see include/macaw_b200.h (mm_gemm_fwd).
+#include "common.cuh"
+#include "ptx.cuh"
+#include "../../include/macaw_b200.h"
+
+namespace mm {
+
+struct GemmKParams {
+  int M, N, K, batch, batch2;
+  int m_tiles, n_tiles, num_k;
+  int b_shared, b2_shared;
+  void* C;
+  long long ldc, c_bs, c_bs2;
+  int c_fp32;
+  int act;
+  float alpha;
+  const bf16* bias;
+  long long bias_bs;
+  const float* row_scale;
+  const bf16* residual;
+  long long ldr, r_bs, r_bs2;
+  int res_row_mod;
+  const float* rope_cos;
+  const float* rope_sin;
+  int rope_T, rope_cols;
+  int vec_ok;
+};
+
+constexpr int kBlockM = 128;
+constexpr int kBlockK = 64;
+constexpr int kGroupM = 16;
+constexpr uint32_t kABytes = kBlockM * kBlockK * 2;  // 16 KiB per stage
+
+__host__ __device__ constexpr int gemm_stages(int BN) {
+  // keep the ring within ~200 KiB
+  return BN >= 256 ? 4 : (BN >= 128 ? 6 : 8);
+}
+__host__ __device__ constexpr uint32_t gemm_tmem_cols(int BN) {
+  return 2 * BN <= 32 ? 32 : (2 * BN <= 64 ? 64 : (2 * BN <= 128 ? 128 : (2 * BN <= 256 ? 256 : 512)));
+}
+__host__ __device__ constexpr size_t gemm_smem_bytes(int BN) {
+  return 1024 /*align slack*/ + (size_t)gemm_stages(BN) * (kABytes + BN * kBlockK * 2) + 256 /*barriers*/;
+}
+
+struct TileCoord {
+  int b, b_lo, b_hi, m_blk, n_blk;  // b = b_hi * batch + b_lo
+};
+__device__ __forceinline__ TileCoord tile_coord(int idx, const GemmKParams& p) {
+  const int per_batch = p.m_tiles * p.n_tiles;
+  TileCoord t;
+  t.b = idx / per_batch;
+  t.b_hi = t.b / p.batch;
+  t.b_lo = t.b - t.b_hi * p.batch;
+  int r = idx - t.b * per_batch;
+  const int in_group = kGroupM * p.n_tiles;
+  const int g = r / in_group;
+  const int first_m = g * kGroupM;
+  const int gsz = min(p.m_tiles - first_m, kGroupM);
+  const int rr = r - g * in_group;
+  t.m_blk = first_m + rr % gsz;
+  t.n_blk = rr / gsz;
+  return t;
+}
+
+__device__ __forceinline__ float apply_act(float x, int act) {
+  switch (act) {
+    case MM_ACT_GELU:
+      return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f));
+    case MM_ACT_QUICK_GELU:
+      return x / (1.0f + __expf(-1.702f * x));
+    case MM_ACT_SILU:
+      return x / (1.0f + __expf(-x));
+    default:
+      return x;
+  }
+}
+
+// Store 32 consecutive outputs of one row (columns col0..col0+31), masked by N.
+__device__ __forceinline__ void store_row32(const GemmKParams& p, void* crow, int col0, int ncols_total,
+                                            const float (&v)[32]) {
+  if (p.c_fp32) {
+    float* c = reinterpret_cast<float*>(crow) + col0;
+    if (p.vec_ok && col0 + 32 <= ncols_total) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        reinterpret_cast<float4*>(c)[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 32; ++i)
+        if (col0 + i < ncols_total) c[i] = v[i];
+    }
+  } else {
+    bf16* c = reinterpret_cast<bf16*>(crow) + col0;
+    if (p.vec_ok && col0 + 32 <= ncols_total) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        uint4 u;
+        u.x = pack_bf16x2(v[8 * i + 0], v[8 * i + 1]);
+        u.y = pack_bf16x2(v[8 * i + 2], v[8 * i + 3]);
+        u.z = pack_bf16x2(v[8 * i + 4], v[8 * i + 5]);
+        u.w = pack_bf16x2(v[8 * i + 6], v[8 * i + 7]);
+        reinterpret_cast<uint4*>(c)[i] = u;
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 32; ++i)
+        if (col0 + i < ncols_total) c[i] = __float2bfloat16(v[i]);
+    }
+  }
+}
+
+template <int BN, int EPI, bool B_MN>
+__global__ void __launch_bounds__(192, 1)
+gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                 const GemmKParams p) {
+  constexpr int STAGES = gemm_stages(BN);
+  constexpr uint32_t B_BYTES = BN * kBlockK * 2;
+  constexpr uint32_t TMEM_COLS = gemm_tmem_cols(BN);
+  constexpr uint32_t IDESC = make_idesc_bf16(kBlockM, BN, false, B_MN);
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + STAGES * kABytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(sB + STAGES * B_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tfull_bar = empty_bar + STAGES;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int total_tiles = p.batch * p.batch2 * p.m_tiles * p.n_tiles;
+
+  if (warp == 0 && elect_one()) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1) {
+    if (elect_one()) {
+      for (int s = 0; s < STAGES; ++s) {
+        mbar_init(&full_bar[s], 1);
+        mbar_init(&empty_bar[s], 1);
+      }
+      for (int s = 0; s < 2; ++s) {
+        mbar_init(&tfull_bar[s], 1);
+        mbar_init(&tempty_bar[s], 4);
+      }
+      fence_mbar_init();
+    }
+    __syncwarp();
+    tmem_alloc(tmem_slot, TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const TileCoord t = tile_coord(tile, p);
+        const int bb = p.b_shared ? 0 : t.b_lo;
+        const int bh = p.b2_shared ? 0 : t.b_hi;
+        for (int kb = 0; kb < p.num_k; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          mbar_arrive_expect_tx(&full_bar[stage], kABytes + B_BYTES);
+          tma_load_4d(&tmA, &full_bar[stage], sA + stage * kABytes, kb * kBlockK, t.m_blk * kBlockM, t.b_lo, t.b_hi);
+          if constexpr (!B_MN) {
+            tma_load_4d(&tmB, &full_bar[stage], sB + stage * B_BYTES, kb * kBlockK, t.n_blk * BN, bb, bh);
+          } else {
+#pragma unroll
+            for (int j = 0; j < BN / 64; ++j)
+              tma_load_4d(&tmB, &full_bar[stage], sB + stage * B_BYTES + j * 8192, t.n_blk * BN + j * 64,
+                          kb * kBlockK, bb, bh);
+          }
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = 0; kb < p.num_k; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(sA + stage * kABytes);
+          const uint32_t b_addr = smem_u32(sB + stage * B_BYTES);
+          // K-major operand: 8-row groups are 1024 B apart (SBO); LBO unused with 128B swizzle.
+          const uint64_t a_desc = make_sdesc_sw128(a_addr, 16, 1024);
+          // MN-major operand: 64-column blocks are 8192 B apart (LBO); 8-k groups 1024 B apart (SBO).
+          const uint64_t b_desc = B_MN ? make_sdesc_sw128(b_addr, 8192, 1024) : make_sdesc_sw128(b_addr, 16, 1024);
+#pragma unroll
+          for (int kk = 0; kk < kBlockK / 16; ++kk) {
+            const uint64_t a_k = a_desc + static_cast<uint64_t>(kk * 2);                  // +32 B along K
+            const uint64_t b_k = b_desc + static_cast<uint64_t>(B_MN ? kk * 128 : kk * 2);  // +2048 B | +32 B
+            umma_bf16(d_tmem, a_k, b_k, IDESC, (kb | kk) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs retire
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit(&tfull_bar[acc]);  // accumulator complete
+        if (++acc == 2) {
+          acc = 0;
+          acc_phase ^= 1;
+        }
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue warps
+    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    const int n_out_total = (EPI == MM_EPI_SWIGLU) ? p.N / 2 : p.N;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const TileCoord t = tile_coord(tile, p);
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after();
+      const int row = t.m_blk * kBlockM + q * 32 + lane;
+      const bool row_ok = row < p.M;
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN;
+      char* crow = reinterpret_cast<char*>(p.C) +
+                   (static_cast<long long>(t.b_lo) * p.c_bs + static_cast<long long>(t.b_hi) * p.c_bs2 +
+                    static_cast<long long>(row) * p.ldc) * (p.c_fp32 ? 4 : 2);
+      float rs = 1.0f;
+      if (p.row_scale != nullptr && row_ok) rs = p.row_scale[static_cast<long long>(t.b) * p.M + row];
+      rs *= p.alpha;
+
+      if constexpr (EPI == MM_EPI_STD) {
+        const bf16* bias = p.bias ? p.bias + static_cast<long long>(t.b_lo) * p.bias_bs : nullptr;
+        const bf16* rrow = nullptr;
+        if (p.residual != nullptr && row_ok) {
+          const int rr = p.res_row_mod > 0 ? row % p.res_row_mod : row;
+          rrow = p.residual + static_cast<long long>(t.b_lo) * p.r_bs + static_cast<long long>(t.b_hi) * p.r_bs2 +
+                 static_cast<long long>(rr) * p.ldr;
+        }
+#pragma unroll 1
+        for (int c = 0; c < BN / 32; ++c) {
+          uint32_t r[32];
+          tmem_ld32(taddr + c * 32, r);
+          tmem_ld_wait();
+          const int col0 = t.n_blk * BN + c * 32;
+          if (col0 >= p.N) continue;  // warp-uniform
+          float v[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]) * rs;
+          const bool full = p.vec_ok && (col0 + 32 <= p.N);
+          if (bias != nullptr) {
+            if (full) {
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const uint4 u = __ldg(reinterpret_cast<const uint4*>(bias + col0) + i);
+                v[8 * i + 0] += bf16lo(u.x); v[8 * i + 1] += bf16hi(u.x);
+                v[8 * i + 2] += bf16lo(u.y); v[8 * i + 3] += bf16hi(u.y);
+                v[8 * i + 4] += bf16lo(u.z); v[8 * i + 5] += bf16hi(u.z);
+                v[8 * i + 6] += bf16lo(u.w); v[8 * i + 7] += bf16hi(u.w);
+              }
+            } else {
+#pragma unroll
+              for (int i = 0; i < 32; ++i)
+                if (col0 + i < p.N) v[i] += __bfloat162float(bias[col0 + i]);
+            }
+          }
+          if (p.act != MM_ACT_NONE) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = apply_act(v[i], p.act);
+          }
+          if (rrow != nullptr) {
+            if (full) {
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const uint4 u = *(reinterpret_cast<const uint4*>(rrow + col0) + i);
+                v[8 * i + 0] += bf16lo(u.x); v[8 * i + 1] += bf16hi(u.x);
+                v[8 * i + 2] += bf16lo(u.y); v[8 * i + 3] += bf16hi(u.y);
+                v[8 * i + 4] += bf16lo(u.z); v[8 * i + 5] += bf16hi(u.z);
+                v[8 * i + 6] += bf16lo(u.w); v[8 * i + 7] += bf16hi(u.w);
+              }
+            } else {
+#pragma unroll
+              for (int i = 0; i < 32; ++i)
+                if (col0 + i < p.N) v[i] += __bfloat162float(rrow[col0 + i]);
+            }
+          }
+          if (row_ok) store_row32(p, crow, col0, n_out_total, v);
+        }
+      } else if constexpr (EPI == MM_EPI_SWIGLU) {
+#pragma unroll 1
+        for (int c = 0; c < BN / 64; ++c) {
+          uint32_t g[32], u[32];
+          tmem_ld32(taddr + c * 64, g);
+          tmem_ld32(taddr + c * 64 + 32, u);
+          tmem_ld_wait();
+          const int col_in = t.n_blk * BN + c * 64;
+          if (col_in >= p.N) continue;
+          float v[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const float gg = __uint_as_float(g[i]) * rs;
+            const float uu = __uint_as_float(u[i]) * rs;
+            v[i] = gg / (1.0f + __expf(-gg)) * uu;
+          }
+          if (row_ok) store_row32(p, crow, col_in / 2, n_out_total, v);
+        }
+      } else {  // MM_EPI_ROPE, head_dim 128: pairs (i, i + 64) within each head
+        const int pos = row_ok ? (row % p.rope_T) : 0;
+        const float* cs = p.rope_cos + static_cast<long long>(pos) * 64;
+        const float* sn = p.rope_sin + static_cast<long long>(pos) * 64;
+#pragma unroll 1
+        for (int h = 0; h < BN / 128; ++h) {
+#pragma unroll 1
+          for (int hc = 0; hc < 2; ++hc) {
+            uint32_t x1[32], x2[32];
+            tmem_ld32(taddr + h * 128 + hc * 32, x1);
+            tmem_ld32(taddr + h * 128 + 64 + hc * 32, x2);
+            tmem_ld_wait();
+            const int col1 = t.n_blk * BN + h * 128 + hc * 32;
+            if (col1 >= p.N) continue;
+            float o1[32], o2[32];
+            if (col1 < p.rope_cols) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const float4 c4 = __ldg(reinterpret_cast<const float4*>(cs + hc * 32) + i);
+                const float4 s4 = __ldg(reinterpret_cast<const float4*>(sn + hc * 32) + i);
+                const float cc[4] = {c4.x, c4.y, c4.z, c4.w};
+                const float ss[4] = {s4.x, s4.y, s4.z, s4.w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  const float a = __uint_as_float(x1[4 * i + j]) * rs;
+                  const float b = __uint_as_float(x2[4 * i + j]) * rs;
+                  o1[4 * i + j] = a * cc[j] - b * ss[j];
+                  o2[4 * i + j] = b * cc[j] + a * ss[j];
+                }
+              }
+            } else {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) {
+                o1[i] = __uint_as_float(x1[i]) * rs;
+                o2[i] = __uint_as_float(x2[i]) * rs;
+              }
+            }
+            if (row_ok) {
+              store_row32(p, crow, col1, n_out_total, o1);
+              store_row32(p, crow, col1 + 64, n_out_total, o2);
+            }
+          }
+        }
+      }
+      // release this accumulator buffer back to the MMA warp
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      if (++acc == 2) {
+        acc = 0;
+        acc_phase ^= 1;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn == nullptr) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// bf16 4-D map {inner, rows, batch, batch2}; strides in elements; 128B swizzle; box {64, box_rows, 1, 1}.
+static int make_map(CUtensorMap* m, const void* ptr, uint64_t inner, uint64_t rows, uint64_t batch, uint64_t batch2,
+                    int64_t ld, int64_t bs, int64_t bs2, uint32_t box_rows) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (fn == nullptr) {
+    set_error("cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)");
+    return 1;
+  }
+  cuuint64_t dims[4] = {inner, rows, batch, batch2};
+  if (bs <= 0) bs = static_cast<int64_t>(rows) * ld;
+  if (bs2 <= 0) bs2 = static_cast<int64_t>(batch) * bs;
+  cuuint64_t strides[3] = {static_cast<cuuint64_t>(ld) * 2, static_cast<cuuint64_t>(bs) * 2,
+                           static_cast<cuuint64_t>(bs2) * 2};
+  cuuint32_t box[4] = {64, box_rows, 1, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed (%d): ptr=%p dims={%llu,%llu,%llu,%llu} ld=%lld bs=%lld bs2=%lld box_rows=%u",
+              static_cast<int>(r), ptr, (unsigned long long)inner, (unsigned long long)rows,
+              (unsigned long long)batch, (unsigned long long)batch2, (long long)ld, (long long)bs, (long long)bs2,
+              box_rows);
+    return 1;
+  }
+  return 0;
+}
+
+static int num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+template <int BN, int EPI, bool B_MN>
+static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmKParams& p, cudaStream_t st) {
+  static bool attr_set = false;
+  constexpr size_t smem = gemm_smem_bytes(BN);
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_bf16_kernel<BN, EPI, B_MN>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    if (e != cudaSuccess) {
+      set_error("cudaFuncSetAttribute(smem=%zu) failed: %s", smem, cudaGetErrorString(e));
+      return 2;
+    }
+    attr_set = true;
+  }
+  const int total = p.batch * p.batch2 * p.m_tiles * p.n_tiles;
+  const int grid = total < num_sms() ? total : num_sms();
+  gemm_bf16_kernel<BN, EPI, B_MN><<<grid, 192, smem, st>>>(ta, tb, p);
+  return check_launch("mm_gemm_fwd");
+}
+
+}  // namespace mm
+
+using namespace mm;
+
+extern "C" int32_t mm_gemm_fwd(const mm_gemm_args* a, void* stream) {
+  MM_REQUIRE(a != nullptr, "mm_gemm_fwd: null args");
+  MM_REQUIRE(a->M > 0 && a->N > 0 && a->K > 0 && a->batch > 0 && a->batch2 >= 0,
+             "mm_gemm_fwd: bad shape M=%d N=%d K=%d batch=%d batch2=%d", a->M, a->N, a->K, a->batch, a->batch2);
+  const int batch2 = a->batch2 > 0 ? a->batch2 : 1;
+  MM_REQUIRE(a->A && a->B && a->C, "mm_gemm_fwd: null operand");
+  MM_REQUIRE((reinterpret_cast<uintptr_t>(a->A) & 15) == 0 && (reinterpret_cast<uintptr_t>(a->B) & 15) == 0,
+             "mm_gemm_fwd: A/B must be 16-byte aligned");
+  MM_REQUIRE(a->lda % 8 == 0 && a->ldb % 8 == 0, "mm_gemm_fwd: lda/ldb must be multiples of 8 elements (lda=%lld ldb=%lld)",
+             (long long)a->lda, (long long)a->ldb);
+  MM_REQUIRE(a->batch == 1 || (a->a_bs % 8 == 0 && a->b_bs % 8 == 0), "mm_gemm_fwd: batch strides must be multiples of 8");
+  MM_REQUIRE(batch2 == 1 || (a->a_bs2 % 8 == 0 && a->b_bs2 % 8 == 0), "mm_gemm_fwd: batch2 strides must be multiples of 8");
+  MM_REQUIRE(a->epi >= MM_EPI_STD && a->epi <= MM_EPI_ROPE, "mm_gemm_fwd: bad epilogue %d", a->epi);
+
+  GemmKParams p;
+  p.M = a->M; p.N = a->N; p.K = a->K; p.batch = a->batch; p.batch2 = batch2;
+  p.num_k = (a->K + kBlockK - 1) / kBlockK;
+  p.m_tiles = (a->M + kBlockM - 1) / kBlockM;
+  p.b_shared = (a->batch > 1 && a->b_bs == 0) ? 1 : 0;
+  p.b2_shared = (batch2 > 1 && a->b_bs2 == 0) ? 1 : 0;
+  p.C = a->C; p.ldc = a->ldc; p.c_bs = a->c_bs; p.c_bs2 = a->c_bs2; p.c_fp32 = a->c_fp32;
+  p.act = a->act; p.alpha = a->alpha;
+  p.bias = reinterpret_cast<const bf16*>(a->bias); p.bias_bs = a->bias_bs;
+  p.row_scale = a->row_scale;
+  p.residual = reinterpret_cast<const bf16*>(a->residual); p.ldr = a->ldr; p.r_bs = a->r_bs; p.r_bs2 = a->r_bs2;
+  p.res_row_mod = a->res_row_mod;
+  p.rope_cos = a->rope_cos; p.rope_sin = a->rope_sin; p.rope_T = a->rope_T; p.rope_cols = a->rope_cols;
+
+  const int esz = a->c_fp32 ? 4 : 2;
+  bool vec = (reinterpret_cast<uintptr_t>(a->C) % 16 == 0) && ((a->ldc * esz) % 16 == 0) &&
+             ((a->c_bs * esz) % 16 == 0) && ((a->c_bs2 * esz) % 16 == 0);
+  if (a->bias) vec = vec && (reinterpret_cast<uintptr_t>(a->bias) % 16 == 0) && (a->bias_bs % 8 == 0);
+  if (a->residual)
+    vec = vec && (reinterpret_cast<uintptr_t>(a->residual) % 16 == 0) && (a->ldr % 8 == 0) && (a->r_bs % 8 == 0) &&
+          (a->r_bs2 % 8 == 0);
+  p.vec_ok = vec ? 1 : 0;
+
+  // ---- tile width: widest BN that still yields enough tiles to occupy the SMs
+  const int sms = num_sms();
+  int BN = 256;
+  if (a->epi == MM_EPI_ROPE) {
+    MM_REQUIRE(a->N % 128 == 0 && a->rope_cos && a->rope_sin && a->rope_T > 0 && vec && a->rope_cols % 128 == 0,
+               "mm_gemm_fwd: RoPE epilogue needs N %% 128 == 0, cos/sin tables and vector-aligned C");
+    const long long t256 = (long long)a->batch * batch2 * p.m_tiles * ((a->N + 255) / 256);
+    BN = (a->N % 256 == 0 && t256 >= sms) ? 256 : 128;
+  } else if (a->epi == MM_EPI_SWIGLU) {
+    MM_REQUIRE(a->N % 64 == 0, "mm_gemm_fwd: SwiGLU epilogue needs N %% 64 == 0");
+    const long long t256 = (long long)a->batch * batch2 * p.m_tiles * ((a->N + 255) / 256);
+    BN = (t256 >= sms) ? 256 : 128;
+  } else {
+    const int cands[4] = {256, 128, 64, 32};
+    BN = 32;
+    for (int i = 0; i < 4; ++i) {
+      const int bn = cands[i];
+      if (a->b_mn_major && bn < 64) continue;
+      if (bn > 32 && a->N <= bn / 2) continue;  // do not waste more than half a tile on padding
+      const long long tiles = (long long)a->batch * batch2 * p.m_tiles * ((a->N + bn - 1) / bn);
+      BN = bn;
+      if (tiles >= sms) break;
+    }
+    if (a->b_mn_major && BN < 64) BN = 64;
+  }
+  p.n_tiles = (a->N + BN - 1) / BN;
+
+  CUtensorMap ta, tb;
+  if (make_map(&ta, a->A, a->K, a->M, a->batch, batch2, a->lda, a->a_bs, a->a_bs2, kBlockM)) return 1;
+  const uint64_t b_batch = p.b_shared ? 1 : a->batch;
+  const uint64_t b_batch2 = p.b2_shared ? 1 : batch2;
+  if (!a->b_mn_major) {
+    if (make_map(&tb, a->B, a->K, a->N, b_batch, b_batch2, a->ldb, a->b_bs, a->b_bs2, BN)) return 1;
+  } else {
+    MM_REQUIRE(a->epi == MM_EPI_STD, "mm_gemm_fwd: MN-major B only with the standard epilogue");
+    if (make_map(&tb, a->B, a->N, a->K, b_batch, b_batch2, a->ldb, a->b_bs, a->b_bs2, 64)) return 1;
+  }
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+
+#define MM_LAUNCH(BN_, EPI_, MN_) return launch_gemm<BN_, EPI_, MN_>(ta, tb, p, st)
+  if (a->epi == MM_EPI_ROPE) {
+    if (BN == 256) MM_LAUNCH(256, MM_EPI_ROPE, false);
+    MM_LAUNCH(128, MM_EPI_ROPE, false);
+  }
+  if (a->epi == MM_EPI_SWIGLU) {
+    if (BN == 256) MM_LAUNCH(256, MM_EPI_SWIGLU, false);
+    MM_LAUNCH(128, MM_EPI_SWIGLU, false);
+  }
+  if (a->b_mn_major) {
+    if (BN == 256) MM_LAUNCH(256, MM_EPI_STD, true);
+    if (BN == 128) MM_LAUNCH(128, MM_EPI_STD, true);
+    MM_LAUNCH(64, MM_EPI_STD, true);
+  }
+  if (BN == 256) MM_LAUNCH(256, MM_EPI_STD, false);
+  if (BN == 128) MM_LAUNCH(128, MM_EPI_STD, false);
+  if (BN == 64) MM_LAUNCH(64, MM_EPI_STD, false);
+  MM_LAUNCH(32, MM_EPI_STD, false);
+#undef MM_LAUNCH
+}
+
+// ------------------------------------------------------------------------------------------------ split-K reduce
+namespace mm {
+__global__ void splitk_reduce_kernel(const float* __restrict__ part, int splits, int M, int N,
+                                     const bf16* __restrict__ bias, bf16* __restrict__ out, long long ldo) {
+  const long long total = static_cast<long long>(M) * N;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int m = static_cast<int>(i / N), n = static_cast<int>(i % N);
+    float acc = bias ? __bfloat162float(bias[n]) : 0.0f;
+    for (int s = 0; s < splits; ++s) acc += part[static_cast<long long>(s) * total + i];
+    out[static_cast<long long>(m) * ldo + n] = __float2bfloat16(acc);
+  }
+}
+}  // namespace mm
+
+extern "C" int32_t mm_splitk_reduce(const float* partial, int32_t splits, int32_t M, int32_t N, const void* bias,
+                                    void* out, int64_t ldo, void* stream) {
+  MM_REQUIRE(partial && out && splits > 0 && M > 0 && N > 0, "mm_splitk_reduce: bad arguments");
+  const long long total = static_cast<long long>(M) * N;
+  int blocks = static_cast<int>((total + 255) / 256);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  splitk_reduce_kernel<<<blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      partial, splits, M, N, reinterpret_cast<const bf16*>(bias), reinterpret_cast<bf16*>(out), ldo);
+  return check_launch("mm_splitk_reduce");
+}

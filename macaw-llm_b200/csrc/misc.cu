@@ -1,0 +1,473 @@
+// HBM-bound kernels of the MM_LLMs forward: norms, gathers, layout changes, the alignment row-softmax, CE loss.
+// All are one-pass-over-HBM designs with 128-bit accesses where the layout allows; reductions are fp32 with
+// warp-shuffle + one shared-memory stage.  Reference call sites: see include/macaw_b200.h.
+#include "common.cuh"
+#include "ptx.cuh"
+#include "../../include/macaw_b200.h"
+
+namespace mm {
+
+constexpr int kSMs = 148;
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+// Block-wide sum / max broadcast to every thread (blockDim.x multiple of 32, <= 1024).
+__device__ __forceinline__ float block_sum(float v, float* sh) {
+  v = warp_sum(v);
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31, nw = blockDim.x >> 5;
+  __syncthreads();
+  if (l == 0) sh[w] = v;
+  __syncthreads();
+  float r = (l < nw) ? sh[l] : 0.f;
+  r = warp_sum(r);
+  return r;
+}
+__device__ __forceinline__ float block_max(float v, float* sh) {
+  v = warp_max(v);
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31, nw = blockDim.x >> 5;
+  __syncthreads();
+  if (l == 0) sh[w] = v;
+  __syncthreads();
+  float r = (l < nw) ? sh[l] : -INFINITY;
+  r = warp_max(r);
+  return r;
+}
+
+__device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
+  f[0] = bf16lo(u.x); f[1] = bf16hi(u.x); f[2] = bf16lo(u.y); f[3] = bf16hi(u.y);
+  f[4] = bf16lo(u.z); f[5] = bf16hi(u.z); f[6] = bf16lo(u.w); f[7] = bf16hi(u.w);
+}
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+  uint4 u;
+  u.x = pack_bf16x2(f[0], f[1]); u.y = pack_bf16x2(f[2], f[3]);
+  u.z = pack_bf16x2(f[4], f[5]); u.w = pack_bf16x2(f[6], f[7]);
+  return u;
+}
+
+// ------------------------------------------------------------------------------------------------ RMSNorm
+// one CTA per row; cols % 8 == 0
+__global__ void __launch_bounds__(256) rmsnorm_kernel(const bf16* __restrict__ x, const bf16* __restrict__ w,
+                                                      bf16* __restrict__ y, int cols, float eps) {
+  __shared__ float sh[32];
+  const long long row = blockIdx.x;
+  const uint4* xr = reinterpret_cast<const uint4*>(x + row * cols);
+  const uint4* wr = reinterpret_cast<const uint4*>(w);
+  uint4* yr = reinterpret_cast<uint4*>(y + row * cols);
+  const int nch = cols >> 3;
+  float ss = 0.f;
+  for (int c = threadIdx.x; c < nch; c += blockDim.x) {
+    float f[8];
+    unpack8(xr[c], f);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) ss += f[i] * f[i];
+  }
+  ss = block_sum(ss, sh);
+  const float rstd = rsqrtf(ss / static_cast<float>(cols) + eps);
+  for (int c = threadIdx.x; c < nch; c += blockDim.x) {
+    float f[8], g[8];
+    unpack8(xr[c], f);
+    unpack8(__ldg(wr + c), g);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) f[i] = f[i] * rstd * g[i];
+    yr[c] = pack8(f);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ LayerNorm
+__global__ void __launch_bounds__(256) layernorm_kernel(const bf16* __restrict__ x, long long ldx,
+                                                        const bf16* __restrict__ w, const bf16* __restrict__ b,
+                                                        bf16* __restrict__ y, long long ldy, int cols, float eps) {
+  __shared__ float sh[32];
+  const long long row = blockIdx.x;
+  const uint4* xr = reinterpret_cast<const uint4*>(x + row * ldx);
+  uint4* yr = reinterpret_cast<uint4*>(y + row * ldy);
+  const int nch = cols >> 3;
+  float s = 0.f;
+  for (int c = threadIdx.x; c < nch; c += blockDim.x) {
+    float f[8];
+    unpack8(xr[c], f);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += f[i];
+  }
+  const float mean = block_sum(s, sh) / static_cast<float>(cols);
+  float vs = 0.f;
+  for (int c = threadIdx.x; c < nch; c += blockDim.x) {
+    float f[8];
+    unpack8(xr[c], f);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float d = f[i] - mean;
+      vs += d * d;
+    }
+  }
+  const float rstd = rsqrtf(block_sum(vs, sh) / static_cast<float>(cols) + eps);
+  for (int c = threadIdx.x; c < nch; c += blockDim.x) {
+    float f[8], g[8], h[8];
+    unpack8(xr[c], f);
+    unpack8(__ldg(reinterpret_cast<const uint4*>(w) + c), g);
+    unpack8(__ldg(reinterpret_cast<const uint4*>(b) + c), h);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) f[i] = (f[i] - mean) * rstd * g[i] + h[i];
+    yr[c] = pack8(f);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ gathers / copies
+__global__ void __launch_bounds__(128) embed_gather_kernel(const bf16* __restrict__ table, int vocab, int dim,
+                                                           const long long* __restrict__ ids, bf16* __restrict__ out,
+                                                           long long ldo) {
+  const long long i = blockIdx.x;
+  long long id = ids[i];
+  if (id < 0) id = 0;
+  if (id >= vocab) id = vocab - 1;
+  const uint4* src = reinterpret_cast<const uint4*>(table + id * dim);
+  uint4* dst = reinterpret_cast<uint4*>(out + i * ldo);
+  for (int c = threadIdx.x; c < (dim >> 3); c += blockDim.x) dst[c] = __ldg(src + c);
+}
+
+__global__ void __launch_bounds__(128) splice_kernel(const bf16* __restrict__ text, const bf16* __restrict__ prefix,
+                                                     bf16* __restrict__ dst, int L, int n_prefix, int E,
+                                                     const long long* __restrict__ mask_in,
+                                                     long long* __restrict__ mask_out,
+                                                     const long long* __restrict__ labels_in,
+                                                     long long* __restrict__ labels_out) {
+  const int T = n_prefix + L;
+  const int b = blockIdx.x / T, t = blockIdx.x % T;
+  const bf16* src;
+  if (t == 0)
+    src = text + static_cast<long long>(b) * L * E;
+  else if (t <= n_prefix)
+    src = prefix + (static_cast<long long>(b) * n_prefix + (t - 1)) * E;
+  else
+    src = text + (static_cast<long long>(b) * L + (t - n_prefix)) * E;
+  uint4* d = reinterpret_cast<uint4*>(dst + (static_cast<long long>(b) * T + t) * E);
+  const uint4* s = reinterpret_cast<const uint4*>(src);
+  for (int c = threadIdx.x; c < (E >> 3); c += blockDim.x) d[c] = s[c];
+  if (threadIdx.x == 0) {
+    // modeling.py:1036-1046: the mask / label prefix is PREPENDED (not spliced after BOS)
+    if (mask_in != nullptr)
+      mask_out[static_cast<long long>(b) * T + t] = (t < n_prefix) ? 1ll : mask_in[static_cast<long long>(b) * L + (t - n_prefix)];
+    if (labels_in != nullptr)
+      labels_out[static_cast<long long>(b) * T + t] =
+          (t < n_prefix) ? -100ll : labels_in[static_cast<long long>(b) * L + (t - n_prefix)];
+  }
+}
+
+__global__ void patchify_kernel(const bf16* __restrict__ img, int C, int H, int W, int patch, bf16* __restrict__ out,
+                                long long ldo, long long total) {
+  const int gw = W / patch, gh = H / patch;
+  const int kreal = C * patch * patch;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long row = i / ldo;
+    const int col = static_cast<int>(i % ldo);
+    bf16 v = __float2bfloat16(0.f);
+    if (col < kreal) {
+      const int c = col / (patch * patch), rem = col % (patch * patch), py = rem / patch, px = rem % patch;
+      const int b = static_cast<int>(row / (gh * gw)), g = static_cast<int>(row % (gh * gw));
+      const int gy = g / gw, gx = g % gw;
+      v = img[((static_cast<long long>(b) * C + c) * H + gy * patch + py) * W + gx * patch + px];
+    }
+    out[i] = v;
+  }
+}
+
+// (B, C, T) -> (B, T + 2 pad, C); 32 x 32 tiles through shared memory
+__global__ void transpose_pad_kernel(const bf16* __restrict__ x, int C, int T, int pad, bf16* __restrict__ out) {
+  __shared__ bf16 tile[32][33];
+  const int b = blockIdx.z;
+  const int t0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  const bf16* xb = x + static_cast<long long>(b) * C * T;
+  bf16* ob = out + static_cast<long long>(b) * (T + 2 * pad) * C;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int c = c0 + i, t = t0 + threadIdx.x;
+    tile[i][threadIdx.x] = (c < C && t < T) ? xb[static_cast<long long>(c) * T + t] : __float2bfloat16(0.f);
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int t = t0 + i, c = c0 + threadIdx.x;
+    if (t < T && c < C) ob[static_cast<long long>(t + pad) * C + c] = tile[threadIdx.x][i];
+  }
+  // zero the pad rows once (block (0, y, b) handles its 32 channels)
+  if (blockIdx.x == 0) {
+    for (int r = threadIdx.y; r < pad; r += blockDim.y) {
+      const int c = c0 + threadIdx.x;
+      if (c < C) {
+        ob[static_cast<long long>(r) * C + c] = __float2bfloat16(0.f);
+        ob[static_cast<long long>(T + pad + r) * C + c] = __float2bfloat16(0.f);
+      }
+    }
+  }
+}
+
+__global__ void add_rows_kernel(const bf16* __restrict__ x, long long ldx, const bf16* __restrict__ add, long long lda,
+                                int add_rows, bf16* __restrict__ y, long long ldy, int rows, int cols) {
+  const int nch = cols >> 3;
+  const long long total = static_cast<long long>(rows) * nch;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long r = i / nch;
+    const int c = static_cast<int>(i % nch);
+    float f[8], g[8];
+    unpack8(*reinterpret_cast<const uint4*>(x + r * ldx + c * 8), f);
+    if (add != nullptr) {
+      unpack8(__ldg(reinterpret_cast<const uint4*>(add + (r % add_rows) * lda + c * 8)), g);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) f[k] += g[k];
+    }
+    *reinterpret_cast<uint4*>(y + r * ldy + c * 8) = pack8(f);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ alignment softmax
+// one CTA per score row.  See mm_align_softmax in the header for the exact semantics.
+__global__ void __launch_bounds__(512) align_softmax_kernel(const float* __restrict__ scores, long long lds,
+                                                            const float* __restrict__ row_bias,
+                                                            const float* __restrict__ extra_score, long long sstride,
+                                                            bf16* __restrict__ P, long long ldp,
+                                                            float* __restrict__ p_sum_real, float* __restrict__ p_extra,
+                                                            int V) {
+  __shared__ float sh[32];
+  const long long r = blockIdx.x;
+  const float* s = scores + r * lds;
+  const float rb = row_bias ? row_bias[r * sstride] : 0.f;
+  const float ex = extra_score[r * sstride];
+  const bool vec = (lds % 4 == 0) && ((reinterpret_cast<uintptr_t>(scores) & 15) == 0);
+  // pass 1: running max / sum of exp (online, per thread), in the log2 domain
+  constexpr float L2E = 1.4426950408889634f;
+  float m = -INFINITY, l = 0.f;
+  if (vec) {
+    const int n4 = V >> 2;
+    for (int c = threadIdx.x; c < n4; c += blockDim.x) {
+      const float4 v4 = *reinterpret_cast<const float4*>(s + 4 * c);
+      const float mx = fmaxf(fmaxf(v4.x, v4.y), fmaxf(v4.z, v4.w));
+      if (mx > m) {
+        l *= exp2f((m - mx) * L2E);
+        m = mx;
+      }
+      l += exp2f((v4.x - m) * L2E) + exp2f((v4.y - m) * L2E) + exp2f((v4.z - m) * L2E) + exp2f((v4.w - m) * L2E);
+    }
+    for (int c = (n4 << 2) + threadIdx.x; c < V; c += blockDim.x) {
+      const float v = s[c];
+      if (v > m) {
+        l *= exp2f((m - v) * L2E);
+        m = v;
+      }
+      l += exp2f((v - m) * L2E);
+    }
+  } else {
+    for (int c = threadIdx.x; c < V; c += blockDim.x) {
+      const float v = s[c];
+      if (v > m) {
+        l *= exp2f((m - v) * L2E);
+        m = v;
+      }
+      l += exp2f((v - m) * L2E);
+    }
+  }
+  const float m_real = block_max(m, sh);  // max over real keys (before row bias)
+  l = (m == -INFINITY) ? 0.f : l * exp2f((m - m_real) * L2E);
+  const float l_real = block_sum(l, sh);  // sum_v exp(s_v - m_real)
+  // fold in the two synthetic keys: bias_k key (score ex) and the zero key (score 0)
+  const float m_all = fmaxf(fmaxf(m_real + rb, ex), 0.f);
+  const float e_real = exp2f((m_real + rb - m_all) * L2E);  // rescale of the real-key sum
+  const float e_ex = exp2f((ex - m_all) * L2E);
+  const float e_zero = exp2f((0.f - m_all) * L2E);
+  const float denom = l_real * e_real + e_ex + e_zero;
+  const float inv = 1.0f / denom;
+  if (threadIdx.x == 0) {
+    p_sum_real[r] = l_real * e_real * inv;
+    p_extra[r] = e_ex * inv;
+  }
+  // pass 2: P = exp(s + rb - m_all) / denom
+  bf16* pr = P + r * ldp;
+  const float off = rb - m_all;
+  if (vec && (ldp % 4 == 0)) {
+    const int n4 = V >> 2;
+    for (int c = threadIdx.x; c < n4; c += blockDim.x) {
+      const float4 v4 = *reinterpret_cast<const float4*>(s + 4 * c);
+      uint2 u;
+      u.x = pack_bf16x2(exp2f((v4.x + off) * L2E) * inv, exp2f((v4.y + off) * L2E) * inv);
+      u.y = pack_bf16x2(exp2f((v4.z + off) * L2E) * inv, exp2f((v4.w + off) * L2E) * inv);
+      *reinterpret_cast<uint2*>(pr + 4 * c) = u;
+    }
+    for (int c = (n4 << 2) + threadIdx.x; c < V; c += blockDim.x)
+      pr[c] = __float2bfloat16(exp2f((s[c] + off) * L2E) * inv);
+  } else {
+    for (int c = threadIdx.x; c < V; c += blockDim.x) pr[c] = __float2bfloat16(exp2f((s[c] + off) * L2E) * inv);
+  }
+  // zero the alignment padding of the row so that the K tail of the P.table GEMM reads zeros
+  for (int c = V + threadIdx.x; c < ldp; c += blockDim.x) pr[c] = __float2bfloat16(0.f);
+}
+
+// ctx[n, h*hd + d] += psum[h*Nq + n] * b_v[h*hd + d] + pextra[h*Nq + n] * bias_v[h*hd + d]
+__global__ void align_ctx_fixup_kernel(bf16* __restrict__ ctx, long long ldc, const float* __restrict__ psum,
+                                       const float* __restrict__ pextra, const bf16* __restrict__ b_v,
+                                       const bf16* __restrict__ bias_v, int Nq, int E, int hd) {
+  const long long total = static_cast<long long>(Nq) * E;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int n = static_cast<int>(i / E), e = static_cast<int>(i % E), h = e / hd;
+    const long long r = static_cast<long long>(h) * Nq + n;
+    const float v = __bfloat162float(ctx[n * ldc + e]) + psum[r] * __bfloat162float(b_v[e]) +
+                    pextra[r] * __bfloat162float(bias_v[e]);
+    ctx[n * ldc + e] = __float2bfloat16(v);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ CE loss
+__global__ void __launch_bounds__(512) ce_loss_kernel(const bf16* __restrict__ logits, const long long* __restrict__ labels,
+                                                      int T, int V, float* __restrict__ loss_sum,
+                                                      int* __restrict__ n_valid) {
+  __shared__ float sh[32];
+  const int b = blockIdx.x / (T - 1), t = blockIdx.x % (T - 1);
+  const long long tgt = labels[static_cast<long long>(b) * T + t + 1];
+  if (tgt < 0 || tgt >= V) return;  // ignore_index (-100): whole CTA exits together
+  const bf16* row = logits + (static_cast<long long>(b) * T + t) * V;
+  float m = -INFINITY, l = 0.f;
+  for (int c = threadIdx.x; c < V; c += blockDim.x) {
+    const float v = __bfloat162float(row[c]);
+    if (v > m) {
+      l *= __expf(m - v);
+      m = v;
+    }
+    l += __expf(v - m);
+  }
+  const float mm_ = block_max(m, sh);
+  l = (m == -INFINITY) ? 0.f : l * __expf(m - mm_);
+  const float ll = block_sum(l, sh);
+  if (threadIdx.x == 0) {
+    const float lse = mm_ + logf(ll);
+    atomicAdd(loss_sum, lse - __bfloat162float(row[tgt]));
+    atomicAdd(n_valid, 1);
+  }
+}
+
+static inline int grid_for(long long total, int block) {
+  long long g = (total + block - 1) / block;
+  const long long cap = static_cast<long long>(kSMs) * 16;
+  return static_cast<int>(g < cap ? (g > 0 ? g : 1) : cap);
+}
+
+}  // namespace mm
+
+using namespace mm;
+#define ST(s) reinterpret_cast<cudaStream_t>(s)
+#define AL16(p) ((reinterpret_cast<uintptr_t>(p) & 15) == 0)
+
+extern "C" int32_t mm_rmsnorm_fwd(const void* x, const void* w, void* y, int32_t rows, int32_t cols, float eps,
+                                  void* stream) {
+  MM_REQUIRE(x && w && y && rows > 0 && cols > 0 && cols % 8 == 0, "mm_rmsnorm_fwd: bad arguments (cols %% 8 != 0?)");
+  MM_REQUIRE(AL16(x) && AL16(w) && AL16(y), "mm_rmsnorm_fwd: pointers must be 16-byte aligned");
+  rmsnorm_kernel<<<rows, 256, 0, ST(stream)>>>((const bf16*)x, (const bf16*)w, (bf16*)y, cols, eps);
+  return check_launch("mm_rmsnorm_fwd");
+}
+
+extern "C" int32_t mm_layernorm_fwd(const void* x, int64_t ldx, const void* w, const void* b, void* y, int64_t ldy,
+                                    int32_t rows, int32_t cols, float eps, void* stream) {
+  MM_REQUIRE(x && w && b && y && rows > 0 && cols > 0 && cols % 8 == 0 && ldx % 8 == 0 && ldy % 8 == 0,
+             "mm_layernorm_fwd: bad arguments");
+  MM_REQUIRE(AL16(x) && AL16(w) && AL16(b) && AL16(y), "mm_layernorm_fwd: pointers must be 16-byte aligned");
+  layernorm_kernel<<<rows, 128, 0, ST(stream)>>>((const bf16*)x, ldx, (const bf16*)w, (const bf16*)b, (bf16*)y, ldy,
+                                                 cols, eps);
+  return check_launch("mm_layernorm_fwd");
+}
+
+extern "C" int32_t mm_embed_gather(const void* table, int32_t vocab, int32_t dim, const int64_t* ids, int64_t n_ids,
+                                   void* out, int64_t ldo, void* stream) {
+  MM_REQUIRE(table && ids && out && vocab > 0 && dim > 0 && dim % 8 == 0 && ldo % 8 == 0 && n_ids > 0,
+             "mm_embed_gather: bad arguments");
+  MM_REQUIRE(AL16(table) && AL16(out), "mm_embed_gather: pointers must be 16-byte aligned");
+  embed_gather_kernel<<<static_cast<unsigned>(n_ids), 128, 0, ST(stream)>>>((const bf16*)table, vocab, dim,
+                                                                            (const long long*)ids, (bf16*)out, ldo);
+  return check_launch("mm_embed_gather");
+}
+
+extern "C" int32_t mm_splice_prefix(const void* text, const void* prefix, void* dst, int32_t B, int32_t L,
+                                    int32_t n_prefix, int32_t E, const int64_t* mask_in, int64_t* mask_out,
+                                    const int64_t* labels_in, int64_t* labels_out, void* stream) {
+  MM_REQUIRE(text && dst && B > 0 && L > 0 && n_prefix >= 0 && E > 0 && E % 8 == 0, "mm_splice_prefix: bad arguments");
+  MM_REQUIRE(n_prefix == 0 || prefix != nullptr, "mm_splice_prefix: null prefix");
+  MM_REQUIRE((mask_in == nullptr) == (mask_out == nullptr) && (labels_in == nullptr) == (labels_out == nullptr),
+             "mm_splice_prefix: mask/label in/out must be given together");
+  MM_REQUIRE(AL16(text) && AL16(dst) && (prefix == nullptr || AL16(prefix)), "mm_splice_prefix: alignment");
+  splice_kernel<<<B * (n_prefix + L), 128, 0, ST(stream)>>>((const bf16*)text, (const bf16*)prefix, (bf16*)dst, L,
+                                                            n_prefix, E, (const long long*)mask_in,
+                                                            (long long*)mask_out, (const long long*)labels_in,
+                                                            (long long*)labels_out);
+  return check_launch("mm_splice_prefix");
+}
+
+extern "C" int32_t mm_patchify(const void* images, int32_t B, int32_t C, int32_t H, int32_t W, int32_t patch, void* out,
+                               int64_t ldo, void* stream) {
+  MM_REQUIRE(images && out && B > 0 && C > 0 && patch > 0 && H % patch == 0 && W % patch == 0 &&
+                 ldo >= (int64_t)C * patch * patch,
+             "mm_patchify: bad arguments");
+  const long long total = static_cast<long long>(B) * (H / patch) * (W / patch) * ldo;
+  patchify_kernel<<<grid_for(total, 256), 256, 0, ST(stream)>>>((const bf16*)images, C, H, W, patch, (bf16*)out, ldo,
+                                                                total);
+  return check_launch("mm_patchify");
+}
+
+extern "C" int32_t mm_transpose_pad(const void* x, int32_t B, int32_t C, int32_t T, int32_t pad, void* out,
+                                    void* stream) {
+  MM_REQUIRE(x && out && B > 0 && C > 0 && T > 0 && pad >= 0, "mm_transpose_pad: bad arguments");
+  dim3 grid((T + 31) / 32, (C + 31) / 32, B), block(32, 8);
+  transpose_pad_kernel<<<grid, block, 0, ST(stream)>>>((const bf16*)x, C, T, pad, (bf16*)out);
+  return check_launch("mm_transpose_pad");
+}
+
+extern "C" int32_t mm_add_rows(const void* x, int64_t ldx, const void* add, int64_t lda, int32_t add_rows, void* y,
+                               int64_t ldy, int32_t rows, int32_t cols, void* stream) {
+  MM_REQUIRE(x && y && rows > 0 && cols > 0 && cols % 8 == 0 && ldx % 8 == 0 && ldy % 8 == 0,
+             "mm_add_rows: bad arguments");
+  MM_REQUIRE(add == nullptr || (add_rows > 0 && lda % 8 == 0 && AL16(add)), "mm_add_rows: bad addend");
+  MM_REQUIRE(AL16(x) && AL16(y), "mm_add_rows: alignment");
+  const long long total = static_cast<long long>(rows) * (cols / 8);
+  add_rows_kernel<<<grid_for(total, 256), 256, 0, ST(stream)>>>((const bf16*)x, ldx, (const bf16*)add, lda, add_rows,
+                                                                (bf16*)y, ldy, rows, cols);
+  return check_launch("mm_add_rows");
+}
+
+extern "C" int32_t mm_copy_rows(const void* x, int64_t ldx, void* y, int64_t ldy, int32_t rows, int32_t cols,
+                                void* stream) {
+  return mm_add_rows(x, ldx, nullptr, 0, 1, y, ldy, rows, cols, stream);
+}
+
+extern "C" int32_t mm_align_softmax(const float* scores, int64_t lds, const float* row_bias, const float* extra_score,
+                                    int64_t stat_stride, void* P, int64_t ldp, float* p_sum_real, float* p_extra,
+                                    int32_t R, int32_t V, void* stream) {
+  MM_REQUIRE(scores && extra_score && P && p_sum_real && p_extra && R > 0 && V > 0 && lds >= V && ldp >= V,
+             "mm_align_softmax: bad arguments");
+  align_softmax_kernel<<<R, 512, 0, ST(stream)>>>(scores, lds, row_bias, extra_score, stat_stride, (bf16*)P, ldp,
+                                                  p_sum_real, p_extra, V);
+  return check_launch("mm_align_softmax");
+}
+
+extern "C" int32_t mm_align_ctx_fixup(void* ctx, int64_t ldc, const float* p_sum_real, const float* p_extra,
+                                      const void* b_v, const void* bias_v, int32_t Nq, int32_t E, int32_t head_dim,
+                                      void* stream) {
+  MM_REQUIRE(ctx && p_sum_real && p_extra && b_v && bias_v && Nq > 0 && E > 0 && head_dim > 0 && E % head_dim == 0,
+             "mm_align_ctx_fixup: bad arguments");
+  const long long total = static_cast<long long>(Nq) * E;
+  align_ctx_fixup_kernel<<<grid_for(total, 256), 256, 0, ST(stream)>>>((bf16*)ctx, ldc, p_sum_real, p_extra,
+                                                                       (const bf16*)b_v, (const bf16*)bias_v, Nq, E,
+                                                                       head_dim);
+  return check_launch("mm_align_ctx_fixup");
+}
+
+extern "C" int32_t mm_ce_loss(const void* logits, const int64_t* labels, int32_t B, int32_t T, int32_t V,
+                              float* loss_sum, int32_t* n_valid, void* stream) {
+  MM_REQUIRE(logits && labels && loss_sum && n_valid && B > 0 && T > 1 && V > 0, "mm_ce_loss: bad arguments");
+  ce_loss_kernel<<<B * (T - 1), 512, 0, ST(stream)>>>((const bf16*)logits, (const long long*)labels, T, V, loss_sum,
+                                                      n_valid);
+  return check_launch("mm_ce_loss");
+}

@@ -1,0 +1,252 @@
+"""torch-tensor front end of the C ABI (include/macaw_b200.h).
+
+torch is used only for device memory and streams; every function here launches kernels from libmacaw_b200.so on
+torch's current CUDA stream and raises if an operand is not a CUDA tensor (there is no CPU or eager fallback).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import torch
+
+from . import _lib
+from ._lib import AttnArgs, GemmArgs
+
+ACT_NONE, ACT_GELU, ACT_QUICK_GELU, ACT_SILU = 0, 1, 2, 3
+EPI_STD, EPI_SWIGLU, EPI_ROPE = 0, 1, 2
+
+_BF16 = torch.bfloat16
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _check(rc: int, what: str) -> None:
+    if rc != 0:
+        raise RuntimeError(f"{what} failed (rc={rc}): {_lib.last_error()}")
+
+
+def _cuda(t: torch.Tensor, dtype=None, name: str = "tensor") -> torch.Tensor:
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise RuntimeError(f"macaw_b200: {name} must be a CUDA tensor (no CPU fallback exists)")
+    if dtype is not None and t.dtype != dtype:
+        raise TypeError(f"macaw_b200: {name} must be {dtype}, got {t.dtype}")
+    return t
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def launch_count() -> int:
+    return int(_lib.load().mm_launch_count())
+
+
+def launch_count_reset() -> None:
+    _lib.load().mm_launch_count_reset()
+
+
+# ---------------------------------------------------------------------------------------------------- GEMM
+def gemm_raw(*, M, N, K, A, lda, B, ldb, Cout, ldc, batch=1, a_bs=0, b_bs=0, c_bs=0, batch2=1, a_bs2=0, b_bs2=0,
+             c_bs2=0, b_mn_major=False, c_fp32=False, epi=EPI_STD, act=ACT_NONE, alpha=1.0, bias=None, bias_bs=0,
+             row_scale=None, residual=None, ldr=0, r_bs=0, r_bs2=0, res_row_mod=0, rope_cos=None, rope_sin=None,
+             rope_T=0, rope_cols=0) -> None:
+    """Direct binding of mm_gemm_fwd; pointers are ints (data_ptr() + byte offsets)."""
+    a = GemmArgs(M, N, K, batch, batch2, A, lda, a_bs, a_bs2, B, ldb, b_bs, b_bs2, int(b_mn_major), Cout, ldc, c_bs,
+                 c_bs2, int(c_fp32), epi, act, float(alpha), bias, bias_bs, row_scale, residual, ldr, r_bs, r_bs2,
+                 res_row_mod, rope_cos, rope_sin, rope_T, rope_cols)
+    _check(_lib.load().mm_gemm_fwd(C.byref(a), _stream()), "mm_gemm_fwd")
+
+
+def linear(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, *, act: int = ACT_NONE,
+           residual: Optional[torch.Tensor] = None, res_row_mod: int = 0, out: Optional[torch.Tensor] = None,
+           out_fp32: bool = False, alpha: float = 1.0, row_scale: Optional[torch.Tensor] = None, epi: int = EPI_STD,
+           rope=None) -> torch.Tensor:
+    """out = epilogue(alpha * x @ w.T): x (M, K) bf16 with unit inner stride, w (N, K) bf16 (an nn.Linear weight)."""
+    _cuda(x, _BF16, "x"); _cuda(w, _BF16, "w")
+    assert x.dim() == 2 and w.dim() == 2 and x.shape[1] == w.shape[1], (x.shape, w.shape)
+    assert x.stride(1) == 1 and w.stride(1) == 1
+    M, K = x.shape
+    N = w.shape[0]
+    n_out = N // 2 if epi == EPI_SWIGLU else N
+    if out is None:
+        out = torch.empty((M, n_out), device=x.device, dtype=torch.float32 if out_fp32 else _BF16)
+    assert out.shape[0] == M and out.shape[1] == n_out and out.stride(1) == 1
+    kw = {}
+    if residual is not None:
+        _cuda(residual, _BF16, "residual")
+        assert residual.stride(-1) == 1
+        kw.update(residual=residual.data_ptr(), ldr=residual.stride(0), res_row_mod=res_row_mod)
+    if rope is not None:
+        cos, sin, T, cols = rope
+        kw.update(rope_cos=cos.data_ptr(), rope_sin=sin.data_ptr(), rope_T=T, rope_cols=cols)
+    gemm_raw(M=M, N=N, K=K, A=x.data_ptr(), lda=x.stride(0), B=w.data_ptr(), ldb=w.stride(0), Cout=out.data_ptr(),
+             ldc=out.stride(0), c_fp32=out.dtype == torch.float32, epi=epi, act=act, alpha=alpha, bias=_ptr(bias),
+             row_scale=_ptr(row_scale), **kw)
+    return out
+
+
+def splitk_reduce(partial: torch.Tensor, bias: Optional[torch.Tensor], out: torch.Tensor) -> torch.Tensor:
+    _cuda(partial, torch.float32, "partial"); _cuda(out, _BF16, "out")
+    S, M, N = partial.shape
+    _check(_lib.load().mm_splitk_reduce(partial.data_ptr(), S, M, N, _ptr(bias), out.data_ptr(), out.stride(0),
+                                        _stream()), "mm_splitk_reduce")
+    return out
+
+
+# ---------------------------------------------------------------------------------------------------- attention
+def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, *, scale: float, causal: bool = False,
+              key_mask: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """q (B, Tq, H, hd), k/v (B, Tk, H, hd) bf16 views (hd contiguous, arbitrary other strides) -> (B, Tq, H, hd)."""
+    for n, t in (("q", q), ("k", k), ("v", v)):
+        _cuda(t, _BF16, n)
+        assert t.dim() == 4 and t.stride(3) == 1
+    B, Tq, H, hd = q.shape
+    Tk = k.shape[1]
+    if out is None:
+        out = torch.empty((B, Tq, H, hd), device=q.device, dtype=_BF16)
+    if key_mask is not None:
+        _cuda(key_mask, torch.int32, "key_mask")
+        assert key_mask.shape == (B, Tk) and key_mask.is_contiguous()
+    a = AttnArgs(q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), B, H, Tq, Tk, hd,
+                 q.stride(0), q.stride(1), q.stride(2), k.stride(0), k.stride(1), k.stride(2),
+                 v.stride(0), v.stride(1), v.stride(2), out.stride(0), out.stride(1), out.stride(2),
+                 _ptr(key_mask), int(causal), float(scale))
+    _check(_lib.load().mm_attn_fwd(C.byref(a), _stream()), "mm_attn_fwd")
+    return out
+
+
+# ---------------------------------------------------------------------------------------------------- norms
+def rmsnorm(x: torch.Tensor, w: torch.Tensor, eps: float, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    _cuda(x, _BF16, "x"); _cuda(w, _BF16, "w")
+    assert x.is_contiguous()
+    cols = x.shape[-1]
+    rows = x.numel() // cols
+    if out is None:
+        out = torch.empty_like(x)
+    _check(_lib.load().mm_rmsnorm_fwd(x.data_ptr(), w.data_ptr(), out.data_ptr(), rows, cols, float(eps), _stream()),
+           "mm_rmsnorm_fwd")
+    return out
+
+
+def layernorm(x: torch.Tensor, w: torch.Tensor, b: torch.Tensor, eps: float,
+              out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """x (rows, cols) bf16 with unit inner stride (row stride free)."""
+    _cuda(x, _BF16, "x"); _cuda(w, _BF16, "w"); _cuda(b, _BF16, "b")
+    assert x.dim() == 2 and x.stride(1) == 1
+    rows, cols = x.shape
+    if out is None:
+        out = torch.empty((rows, cols), device=x.device, dtype=_BF16)
+    _check(_lib.load().mm_layernorm_fwd(x.data_ptr(), x.stride(0), w.data_ptr(), b.data_ptr(), out.data_ptr(),
+                                        out.stride(0), rows, cols, float(eps), _stream()), "mm_layernorm_fwd")
+    return out
+
+
+# ---------------------------------------------------------------------------------------------------- gathers / layout
+def embed_gather(table: torch.Tensor, ids: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """out[i] = table[ids[i]]; ids any integer dtype (converted to int64 on device), out (n, dim) row stride free."""
+    _cuda(table, _BF16, "table"); _cuda(ids, None, "ids")
+    ids64 = ids.reshape(-1).to(torch.int64)
+    n, dim = ids64.numel(), table.shape[1]
+    if out is None:
+        out = torch.empty((n, dim), device=table.device, dtype=_BF16)
+    assert out.stride(-1) == 1
+    _check(_lib.load().mm_embed_gather(table.data_ptr(), table.shape[0], dim, ids64.data_ptr(), n, out.data_ptr(),
+                                       out.stride(0), _stream()), "mm_embed_gather")
+    return out
+
+
+def splice_prefix(text: torch.Tensor, prefix: Optional[torch.Tensor], mask_in: Optional[torch.Tensor],
+                  labels_in: Optional[torch.Tensor]):
+    """text (B, L, E), prefix (B, P, E) -> embeds (B, P + L, E), mask (B, P + L) | None, labels (B, P + L) | None."""
+    _cuda(text, _BF16, "text")
+    B, L, E = text.shape
+    P = 0 if prefix is None else prefix.shape[1]
+    assert text.is_contiguous() and (prefix is None or prefix.is_contiguous())
+    dst = torch.empty((B, P + L, E), device=text.device, dtype=_BF16)
+    mask_out = labels_out = None
+    if mask_in is not None:
+        mask_in = _cuda(mask_in, None, "attention_mask").to(torch.int64).contiguous()
+        mask_out = torch.empty((B, P + L), device=text.device, dtype=torch.int64)
+    if labels_in is not None:
+        labels_in = _cuda(labels_in, None, "labels").to(torch.int64).contiguous()
+        labels_out = torch.empty((B, P + L), device=text.device, dtype=torch.int64)
+    _check(_lib.load().mm_splice_prefix(text.data_ptr(), _ptr(prefix), dst.data_ptr(), B, L, P, E, _ptr(mask_in),
+                                        _ptr(mask_out), _ptr(labels_in), _ptr(labels_out), _stream()),
+           "mm_splice_prefix")
+    return dst, mask_out, labels_out
+
+
+def patchify(images: torch.Tensor, patch: int, ldo: int) -> torch.Tensor:
+    _cuda(images, _BF16, "images")
+    assert images.is_contiguous()
+    B, Cc, H, W = images.shape
+    out = torch.empty((B * (H // patch) * (W // patch), ldo), device=images.device, dtype=_BF16)
+    _check(_lib.load().mm_patchify(images.data_ptr(), B, Cc, H, W, patch, out.data_ptr(), ldo, _stream()),
+           "mm_patchify")
+    return out
+
+
+def transpose_pad(x: torch.Tensor, pad: int) -> torch.Tensor:
+    """(B, C, T) -> (B, T + 2 pad, C) with zero pad rows."""
+    _cuda(x, _BF16, "x")
+    assert x.is_contiguous()
+    B, Cc, T = x.shape
+    out = torch.empty((B, T + 2 * pad, Cc), device=x.device, dtype=_BF16)
+    _check(_lib.load().mm_transpose_pad(x.data_ptr(), B, Cc, T, pad, out.data_ptr(), _stream()), "mm_transpose_pad")
+    return out
+
+
+def add_rows(x: torch.Tensor, add: Optional[torch.Tensor], out: torch.Tensor) -> torch.Tensor:
+    """out[r] = x[r] + add[r % add.shape[0]] over 2-D bf16 views with unit inner stride."""
+    _cuda(x, _BF16, "x"); _cuda(out, _BF16, "out")
+    rows, cols = x.shape
+    assert x.stride(1) == 1 and out.stride(1) == 1 and out.shape == x.shape
+    if add is None:
+        _check(_lib.load().mm_copy_rows(x.data_ptr(), x.stride(0), out.data_ptr(), out.stride(0), rows, cols,
+                                        _stream()), "mm_copy_rows")
+    else:
+        _cuda(add, _BF16, "add")
+        assert add.stride(1) == 1 and add.shape[1] == cols
+        _check(_lib.load().mm_add_rows(x.data_ptr(), x.stride(0), add.data_ptr(), add.stride(0), add.shape[0],
+                                       out.data_ptr(), out.stride(0), rows, cols, _stream()), "mm_add_rows")
+    return out
+
+
+# ---------------------------------------------------------------------------------------------------- alignment
+def align_softmax(scores: torch.Tensor, stats: torch.Tensor, P: torch.Tensor, V: int):
+    """scores fp32 (R, >=V); stats fp32 (R, 2) = [row_bias, extra_score]; P bf16 (R, ldp) -> (p_sum_real, p_extra)."""
+    _cuda(scores, torch.float32, "scores"); _cuda(stats, torch.float32, "stats"); _cuda(P, _BF16, "P")
+    R = scores.shape[0]
+    assert stats.shape == (R, 2) and stats.is_contiguous() and P.shape[0] == R
+    psum = torch.empty((R,), device=scores.device, dtype=torch.float32)
+    pext = torch.empty((R,), device=scores.device, dtype=torch.float32)
+    _check(_lib.load().mm_align_softmax(scores.data_ptr(), scores.stride(0), stats.data_ptr(), stats.data_ptr() + 4, 2,
+                                        P.data_ptr(), P.stride(0), psum.data_ptr(), pext.data_ptr(), R, V, _stream()),
+           "mm_align_softmax")
+    return psum, pext
+
+
+def align_ctx_fixup(ctx: torch.Tensor, psum: torch.Tensor, pext: torch.Tensor, b_v: torch.Tensor,
+                    bias_v: torch.Tensor, head_dim: int) -> torch.Tensor:
+    _cuda(ctx, _BF16, "ctx")
+    Nq, E = ctx.shape
+    _check(_lib.load().mm_align_ctx_fixup(ctx.data_ptr(), ctx.stride(0), psum.data_ptr(), pext.data_ptr(),
+                                          b_v.data_ptr(), bias_v.data_ptr(), Nq, E, head_dim, _stream()),
+           "mm_align_ctx_fixup")
+    return ctx
+
+
+# ---------------------------------------------------------------------------------------------------- loss
+def ce_loss(logits: torch.Tensor, labels: torch.Tensor) -> torch.Tensor:
+    """Shifted CE (mean over labels != -100) of bf16 logits (B, T, V) against int64 labels (B, T); returns fp32 scalar."""
+    _cuda(logits, _BF16, "logits"); _cuda(labels, torch.int64, "labels")
+    assert logits.is_contiguous() and labels.is_contiguous()
+    B, T, V = logits.shape
+    acc = torch.zeros((2,), device=logits.device, dtype=torch.float32)
+    cnt = acc[1:].view(torch.int32)
+    _check(_lib.load().mm_ce_loss(logits.data_ptr(), labels.data_ptr(), B, T, V, acc.data_ptr(), cnt.data_ptr(),
+                                  _stream()), "mm_ce_loss")
+    return acc[0] / cnt[0].to(torch.float32)

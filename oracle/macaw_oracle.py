@@ -1,0 +1,302 @@
+"""CPU oracle for the MM_LLMs forward hot path — TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / `--impl reference` leg may import this module; the
+product path (macaw-llm_b200/) never does and fails loudly when its CUDA library is missing.
+
+What it is: a plain-torch fp32 restatement, on CPU, of the arithmetic the reference executes for
+`MM_LLMs.forward` (/root/reference/modeling.py), written as pure functions over a `state_dict` so that it does not
+depend on the transformers version for its *arithmetic* (CLIP / Whisper encoder math is restated here too).
+Each function cites the reference lines (or the third-party lines the reference delegates to) it follows.
+
+Pin: the reference ships no tests or golden vectors.  The pin is therefore the reference ITSELF,
+imported in-process in the build container by tests/golden/make_golden.py (which cannot travel to the GPU box):
+that script runs the unmodified /root/reference/modeling.py on seeded tiny configurations, checks this oracle
+against it (fp64, <= 1e-9) and commits inputs/outputs as fixtures under tests/golden/.  tests/test_oracle.py re-checks
+the oracle against those fixtures everywhere, and against the live reference when /root/reference exists.
+
+Third-party arithmetic the reference delegates to (absent from /root/reference):
+  torch == 2.0.0 (requirements.txt:1)           nn.MultiheadAttention, Conv1d, Linear, Embedding, CrossEntropyLoss
+  transformers == 4.29.0 (requirements.txt:24)  CLIPModel.vision_model / visual_projection, WhisperModel.encoder
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, Optional
+
+import torch
+import torch.nn.functional as F
+
+Tensor = torch.Tensor
+
+
+# ------------------------------------------------------------------------------------------------ hyper-parameters
+def hp_from_config(cfg) -> dict:
+    """Flatten an MM_LLMs_Config-like object (modeling.py:807-829) into plain numbers."""
+    ic, ac, lc = cfg.image_config, cfg.audio_config, cfg.llm_config
+    vc = ic.vision_config
+    return dict(
+        n_frames=cfg.n_frames, attention_heads=cfg.attention_heads,
+        image_conv=(cfg.image_conv_kernel, cfg.image_conv_stride),
+        video_conv=(cfg.video_conv_kernel, cfg.video_conv_stride),
+        audio_conv=(cfg.audio_conv_kernel, cfg.audio_conv_stride),
+        clip=dict(hidden=vc.hidden_size, layers=vc.num_hidden_layers, heads=vc.num_attention_heads,
+                  patch=vc.patch_size, image_size=vc.image_size, eps=vc.layer_norm_eps, act=vc.hidden_act,
+                  proj=ic.projection_dim),
+        whisper=dict(d_model=ac.d_model, layers=ac.encoder_layers, heads=ac.encoder_attention_heads,
+                     act=ac.activation_function, max_pos=ac.max_source_positions),
+        llama=dict(hidden=lc.hidden_size, layers=lc.num_hidden_layers, heads=lc.num_attention_heads,
+                   eps=lc.rms_norm_eps, vocab=lc.vocab_size),
+    )
+
+
+def _act(name: str):
+    if name == "quick_gelu":
+        return lambda x: x * torch.sigmoid(1.702 * x)
+    if name == "gelu":
+        return F.gelu
+    if name in ("silu", "swish"):
+        return F.silu
+    raise ValueError(f"oracle: unsupported activation {name}")
+
+
+class _SD:
+    """state_dict view that upcasts on access (so bf16 checkpoints can be consumed layer by layer)."""
+
+    def __init__(self, sd: Dict[str, Tensor], dtype=torch.float32, prefix: str = ""):
+        self.sd, self.dtype, self.prefix = sd, dtype, prefix
+
+    def __call__(self, name: str) -> Tensor:
+        return self.sd[self.prefix + name].detach().to("cpu").to(self.dtype)
+
+    def has(self, name: str) -> bool:
+        return (self.prefix + name) in self.sd
+
+    def sub(self, prefix: str) -> "_SD":
+        return _SD(self.sd, self.dtype, self.prefix + prefix)
+
+
+# ------------------------------------------------------------------------------------------------ torch MHA restatement
+def mha_forward(query: Tensor, key: Tensor, value: Tensor, w: _SD, num_heads: int) -> Tensor:
+    """nn.MultiheadAttention(E, H, add_bias_kv=True, add_zero_attn=True), eval mode, seq-first layout.
+
+    Follows torch/nn/functional.py multi_head_attention_forward:
+      in-projection (functional.py:5798-5868), bias_k/bias_v appended AFTER projection (:6531-6537), head split,
+      one zero key/value per head appended (:6585-6602), q scaled by 1/sqrt(hd) (:6632), softmax, PV, out_proj
+      (:6647-6653).  Call sites: modeling.py:986-987, 1007-1008, 1025-1026, 1078.
+    query (Lq, B, E), key/value (S, B, E) -> (Lq, B, E).
+    """
+    Lq, B, E = query.shape
+    S = key.shape[0]
+    hd = E // num_heads
+    W, bias = w("in_proj_weight"), w("in_proj_bias")
+    q = F.linear(query, W[:E], bias[:E])
+    k = F.linear(key, W[E:2 * E], bias[E:2 * E])
+    v = F.linear(value, W[2 * E:], bias[2 * E:])
+    k = torch.cat([k, w("bias_k").expand(1, B, E)], dim=0)
+    v = torch.cat([v, w("bias_v").expand(1, B, E)], dim=0)
+    q = q.reshape(Lq, B * num_heads, hd).transpose(0, 1)
+    k = k.reshape(S + 1, B * num_heads, hd).transpose(0, 1)
+    v = v.reshape(S + 1, B * num_heads, hd).transpose(0, 1)
+    zeros = torch.zeros(B * num_heads, 1, hd, dtype=k.dtype)
+    k = torch.cat([k, zeros], dim=1)
+    v = torch.cat([v, zeros], dim=1)
+    q = q * (1.0 / math.sqrt(hd))
+    p = torch.softmax(torch.bmm(q, k.transpose(1, 2)), dim=-1)
+    ctx = torch.bmm(p, v).transpose(0, 1).reshape(Lq, B, E)
+    return F.linear(ctx, w("out_proj.weight"), w("out_proj.bias"))
+
+
+def align_block(feats: Tensor, table: Tensor, conv: _SD, lin: _SD, mha: _SD, stride: int, num_heads: int) -> Tensor:
+    """One modality of modeling.py:982-987 / 999-1008 / 1022-1026: Conv1d over tokens -> Linear C->E -> MHA(Q=feats,
+    K=V=the whole embedding table).  The reference repeats the table per batch element (modeling.py:974-975); K/V
+    are batch-invariant, so this restatement projects them once and broadcasts — numerically the same function.
+    feats (B, N, C), table (V, E) -> (B, Lq, E)."""
+    y = F.conv1d(feats.transpose(1, 2), conv("weight"), conv("bias"), stride=stride).transpose(1, 2)
+    z = F.linear(y, lin("weight"), lin("bias"))
+    B = z.shape[0]
+    kv = table.unsqueeze(1).expand(-1, B, -1)
+    return mha_forward(z.transpose(0, 1), kv, kv, mha, num_heads).transpose(0, 1)
+
+
+# ------------------------------------------------------------------------------------------------ CLIP vision tower
+def clip_tokens(images: Tensor, w: _SD, hp: dict) -> Tensor:
+    """`visual_projection(vision_model(images)[0])[:, 1:, :]` (modeling.py:1092): the UN-pooled last hidden state (no
+    post_layernorm), projected per token, CLS dropped.  Restates transformers modeling_clip.py CLIPVisionEmbeddings
+    (:138-219), CLIPAttention / CLIPMLP / CLIPEncoderLayer (:261-386), CLIPVisionTransformer.forward (:667-691)."""
+    c = hp["clip"]
+    vm = w.sub("vision_model.")
+    B = images.shape[0]
+    x = F.conv2d(images, vm("embeddings.patch_embedding.weight"), stride=c["patch"]).flatten(2).transpose(1, 2)
+    cls = vm("embeddings.class_embedding").expand(B, 1, -1)
+    x = torch.cat([cls, x], dim=1) + vm("embeddings.position_embedding.weight")[None]
+    D, H = c["hidden"], c["heads"]
+    hd = D // H
+    x = F.layer_norm(x, (D,), vm("pre_layrnorm.weight"), vm("pre_layrnorm.bias"), c["eps"])
+    act = _act(c["act"])
+    for i in range(c["layers"]):
+        l = vm.sub(f"encoder.layers.{i}.")
+        h = F.layer_norm(x, (D,), l("layer_norm1.weight"), l("layer_norm1.bias"), c["eps"])
+        q = F.linear(h, l("self_attn.q_proj.weight"), l("self_attn.q_proj.bias")).view(B, -1, H, hd).transpose(1, 2)
+        k = F.linear(h, l("self_attn.k_proj.weight"), l("self_attn.k_proj.bias")).view(B, -1, H, hd).transpose(1, 2)
+        v = F.linear(h, l("self_attn.v_proj.weight"), l("self_attn.v_proj.bias")).view(B, -1, H, hd).transpose(1, 2)
+        p = torch.softmax((q @ k.transpose(-1, -2)) * hd ** -0.5, dim=-1)
+        a = (p @ v).transpose(1, 2).reshape(B, -1, D)
+        x = x + F.linear(a, l("self_attn.out_proj.weight"), l("self_attn.out_proj.bias"))
+        h = F.layer_norm(x, (D,), l("layer_norm2.weight"), l("layer_norm2.bias"), c["eps"])
+        h = F.linear(act(F.linear(h, l("mlp.fc1.weight"), l("mlp.fc1.bias"))), l("mlp.fc2.weight"), l("mlp.fc2.bias"))
+        x = x + h
+    return F.linear(x, w("visual_projection.weight"))[:, 1:, :]
+
+
+# ------------------------------------------------------------------------------------------------ Whisper encoder
+def whisper_encode(mel: Tensor, w: _SD, hp: dict) -> Tensor:
+    """`audio_encoder.encoder(mel)[0]` (modeling.py:1081-1083).  Restates transformers modeling_whisper.py
+    WhisperEncoder.forward (:593-647), WhisperAttention (:241-357; q scaled, k_proj bias-free), WhisperEncoderLayer
+    (:360-415).  mel (B, 80, 3000) -> (B, 1500, d_model)."""
+    c = hp["whisper"]
+    D, H = c["d_model"], c["heads"]
+    hd = D // H
+    act = _act(c["act"])
+    x = F.gelu(F.conv1d(mel, w("conv1.weight"), w("conv1.bias"), padding=1))
+    x = F.gelu(F.conv1d(x, w("conv2.weight"), w("conv2.bias"), stride=2, padding=1))
+    x = x.permute(0, 2, 1) + w("embed_positions.weight")[None]
+    B = x.shape[0]
+    for i in range(c["layers"]):
+        l = w.sub(f"layers.{i}.")
+        h = F.layer_norm(x, (D,), l("self_attn_layer_norm.weight"), l("self_attn_layer_norm.bias"), 1e-5)
+        q = (F.linear(h, l("self_attn.q_proj.weight"), l("self_attn.q_proj.bias")) * hd ** -0.5)
+        q = q.view(B, -1, H, hd).transpose(1, 2)
+        k = F.linear(h, l("self_attn.k_proj.weight")).view(B, -1, H, hd).transpose(1, 2)
+        v = F.linear(h, l("self_attn.v_proj.weight"), l("self_attn.v_proj.bias")).view(B, -1, H, hd).transpose(1, 2)
+        p = torch.softmax(q @ k.transpose(-1, -2), dim=-1)
+        a = (p @ v).transpose(1, 2).reshape(B, -1, D)
+        x = x + F.linear(a, l("self_attn.out_proj.weight"), l("self_attn.out_proj.bias"))
+        h = F.layer_norm(x, (D,), l("final_layer_norm.weight"), l("final_layer_norm.bias"), 1e-5)
+        x = x + F.linear(act(F.linear(h, l("fc1.weight"), l("fc1.bias"))), l("fc2.weight"), l("fc2.bias"))
+    return F.layer_norm(x, (D,), w("layer_norm.weight"), w("layer_norm.bias"), 1e-5)
+
+
+# ------------------------------------------------------------------------------------------------ video-long
+def video_positional_encoding(L: int, h: int, dtype=torch.float32) -> Tensor:
+    """create_positional_encoding (modeling.py:1095-1106), vectorised.  The reference computes, in fp32,
+    div = exp(-(ln(10000)/h) * (2*i)) for even i (note 2*i with i already even — a non-standard frequency ladder),
+    pe[pos, i] = sin(pos * div), pe[pos, i+1] = cos(pos * div).  Computed in fp32 exactly as written, then cast."""
+    i = torch.arange(0, h, 2, dtype=torch.float32)
+    div = torch.exp(-(math.log(10000.0) / h * (2 * i)))  # python double scalar * fp32 tensor -> fp32, as torch.tensor(.) does
+    pos = torch.arange(L, dtype=torch.float32)[:, None]
+    pe = torch.zeros(L, h, dtype=torch.float32)
+    pe[:, 0::2] = torch.sin(pos * div)
+    pe[:, 1::2] = torch.cos(pos * div)
+    return pe.to(dtype)
+
+
+def encode_video_long(videos: Tensor, sd: _SD, hp: dict) -> Tensor:
+    """modeling.py:1070-1079: CLIP per frame -> (B, F*256, D) -> + sinusoid PE -> video_long_self_attention(x, x, x)."""
+    F_ = hp["n_frames"]
+    frames = videos.reshape(-1, *videos.shape[-3:])
+    tok = clip_tokens(frames, sd.sub("video_encoder."), hp)
+    B = frames.shape[0] // F_
+    x = tok.reshape(B, F_ * tok.shape[1], -1)
+    x = x + video_positional_encoding(x.shape[1], x.shape[2], x.dtype)[None]
+    xs = x.transpose(0, 1)
+    return mha_forward(xs, xs, xs, sd.sub("video_long_self_attention."), hp["attention_heads"]).transpose(0, 1)
+
+
+# ------------------------------------------------------------------------------------------------ LLaMA
+def llama_forward(embeds: Tensor, attention_mask: Optional[Tensor], sd: _SD, hp: dict) -> Tensor:
+    """Vendored LlamaModel + lm_head (modeling.py:397-522, 597): position_ids = arange(T) regardless of padding
+    (:434-439); additive causal + padding mask clamped at finfo.min (:373-394, 210-211); rotate-half RoPE base 1e4
+    (:76-123); fp32 softmax (:214); RMSNorm with fp32 variance (:311-319); SwiGLU MLP (:139-140).
+    embeds (B, T, E), attention_mask (B, T) of {0,1} or None -> logits (B, T, V)."""
+    c = hp["llama"]
+    E, H = c["hidden"], c["heads"]
+    hd = E // H
+    B, T, _ = embeds.shape
+    dt = embeds.dtype
+    fmin = torch.finfo(dt).min
+    causal = torch.full((T, T), fmin, dtype=dt)
+    causal = torch.triu(causal, diagonal=1)
+    mask = causal[None, None].expand(B, 1, T, T)
+    if attention_mask is not None:
+        inv = 1.0 - attention_mask[:, None, None, :].to(dt).expand(B, 1, T, T)
+        mask = inv.masked_fill(inv.bool(), fmin) + mask
+    inv_freq = 1.0 / (10000 ** (torch.arange(0, hd, 2).float() / hd))
+    freqs = torch.arange(T).float()[:, None] * inv_freq[None]
+    emb = torch.cat([freqs, freqs], dim=-1)
+    cos, sin = emb.cos().to(dt)[None, None], emb.sin().to(dt)[None, None]
+
+    def rms(x, wt):
+        var = x.float().pow(2).mean(-1, keepdim=True)
+        return wt * (x * torch.rsqrt(var + c["eps"])).to(dt)
+
+    def rot(x):
+        return torch.cat([-x[..., hd // 2:], x[..., : hd // 2]], dim=-1)
+
+    x = embeds
+    m = sd.sub("llm.model.")
+    for i in range(c["layers"]):
+        l = m.sub(f"layers.{i}.")
+        h = rms(x, l("input_layernorm.weight"))
+        q = F.linear(h, l("self_attn.q_proj.weight")).view(B, T, H, hd).transpose(1, 2)
+        k = F.linear(h, l("self_attn.k_proj.weight")).view(B, T, H, hd).transpose(1, 2)
+        v = F.linear(h, l("self_attn.v_proj.weight")).view(B, T, H, hd).transpose(1, 2)
+        q, k = q * cos + rot(q) * sin, k * cos + rot(k) * sin
+        s = q @ k.transpose(2, 3) / math.sqrt(hd) + mask
+        s = torch.max(s, torch.tensor(fmin, dtype=dt))
+        p = torch.softmax(s, dim=-1, dtype=torch.float32).to(dt)
+        a = (p @ v).transpose(1, 2).reshape(B, T, E)
+        x = x + F.linear(a, l("self_attn.o_proj.weight"))
+        h = rms(x, l("post_attention_layernorm.weight"))
+        h = F.linear(F.silu(F.linear(h, l("mlp.gate_proj.weight"))) * F.linear(h, l("mlp.up_proj.weight")),
+                     l("mlp.down_proj.weight"))
+        x = x + h
+    x = rms(x, m("norm.weight"))
+    return F.linear(x, sd("llm.lm_head.weight"))
+
+
+def shifted_ce(logits: Tensor, labels: Tensor) -> Tensor:
+    """modeling.py:600-610: logits[:, :-1] vs labels[:, 1:], mean over labels != -100."""
+    V = logits.shape[-1]
+    return F.cross_entropy(logits[:, :-1].reshape(-1, V).float(), labels[:, 1:].reshape(-1), ignore_index=-100)
+
+
+# ------------------------------------------------------------------------------------------------ whole forward
+def prepare_inputs(inputs: dict, sd_raw: Dict[str, Tensor], hp: dict, dtype=torch.float32):
+    """MM_LLMs.prepare_inputs_for_generation (modeling.py:965-1048) -> (embeds, attention_mask | None, labels | None)."""
+    sd = _SD(sd_raw, dtype)
+    table = sd("llm.model.embed_tokens.weight")
+    H2 = hp["attention_heads"] * 2
+    cast = lambda t: None if t is None else t.to("cpu").to(dtype)
+    image_feats = clip_tokens(cast(inputs["images"]), sd.sub("image_encoder."), hp) if inputs.get("images") is not None else None
+    audio_feats = whisper_encode(cast(inputs["audios"]), sd.sub("audio_encoder.encoder."), hp) if inputs.get("audios") is not None else None
+    video_feats = encode_video_long(cast(inputs["videos"]), sd, hp) if inputs.get("videos") is not None else None
+    ids = inputs["input_ids"].to("cpu").long()
+    text = table[ids]
+    n_ignore = 0
+    # order matters: video, then audio, then image — each block is spliced right after BOS (modeling.py:978-1034)
+    for name, feats in (("video", video_feats), ("audio", audio_feats), ("image", image_feats)):
+        if feats is None:
+            continue
+        starts = table[inputs[f"{name}_starts"].to("cpu").long()].unsqueeze(1)
+        ends = table[inputs[f"{name}_ends"].to("cpu").long()].unsqueeze(1)
+        out = align_block(feats, table, sd.sub(f"project_{name}."), sd.sub(f"transform_{name}_to_hidden."),
+                          sd.sub(f"{name}_align_attention."), hp[f"{name}_conv"][1], H2)
+        block = torch.cat([starts, out, ends], dim=1)
+        text = torch.cat([text[:, :1], block, text[:, 1:]], dim=1)
+        n_ignore += block.shape[1]
+    B = text.shape[0]
+    mask = labels = None
+    if "attention_mask" in inputs:
+        mask = torch.cat([torch.ones(B, n_ignore, dtype=torch.int64), inputs["attention_mask"].to("cpu").long()], dim=1)
+    if inputs.get("labels") is not None:
+        labels = torch.cat([torch.full((B, n_ignore), -100, dtype=torch.int64), inputs["labels"].to("cpu").long()], dim=1)
+    return text, mask, labels
+
+
+def forward(inputs: dict, sd_raw: Dict[str, Tensor], hp: dict, dtype=torch.float32):
+    """MM_LLMs.forward (modeling.py:941-963) without the generate branch -> dict(loss | None, logits, embeds, mask, labels)."""
+    with torch.no_grad():
+        embeds, mask, labels = prepare_inputs(inputs, sd_raw, hp, dtype)
+        logits = llama_forward(embeds, mask, _SD(sd_raw, dtype), hp)
+        loss = shifted_ce(logits, labels) if labels is not None else None
+    return dict(loss=loss, logits=logits, embeds=embeds, attention_mask=mask, labels=labels)

@@ -1,0 +1,293 @@
+"""Per-kernel numerics on the B200: every C-ABI kernel against a plain torch fp32 restatement of the same op
+(bf16-rounded inputs, fp32 math).  Tolerances are norm-wise relative errors; bf16 output rounding alone is ~2e-3
+element-wise / ~1.5e-3 norm-wise, so GEMM-class outputs are held to 4e-3 and fp32 outputs to 1e-4."""
+import math
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda"
+
+
+def _ops():
+    from macaw_llm_b200 import ops
+
+    return ops
+
+
+def rel_err(a: torch.Tensor, b: torch.Tensor) -> float:
+    a, b = a.float(), b.float()
+    return float((a - b).norm() / (b.norm() + 1e-20))
+
+
+def rnd(*shape, scale=1.0, seed=0):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    return (torch.randn(*shape, generator=g) * scale).to(DEV).to(torch.bfloat16)
+
+
+# ------------------------------------------------------------------------------------------------ GEMM
+@pytest.mark.parametrize(
+    "M,N,K",
+    [
+        (128, 256, 64),      # one tile, one k-block
+        (128, 256, 256),     # one tile, pipeline wraps
+        (256, 512, 4096),    # several tiles
+        (264, 4096, 4096),   # LLaMA B=1 shape (M tail)
+        (6, 4096, 768),      # alignment Linear C->E (tiny M)
+        (300, 1000, 1096),   # ragged everything (N % 32 != 0, K % 64 != 0)
+        (2112, 11008, 4096), # LLaMA MLP up, many tiles -> multi-wave persistent loop
+        (1500, 512, 2048),   # Whisper fc2
+    ],
+)
+def test_gemm_plain(M, N, K):
+    ops = _ops()
+    x, w = rnd(M, K, seed=1), rnd(N, K, scale=K ** -0.5, seed=2)
+    out = ops.linear(x, w)
+    ref = x.float() @ w.float().t()
+    assert rel_err(out, ref) < 4e-3
+    out32 = ops.linear(x, w, out_fp32=True)
+    assert rel_err(out32, ref) < 1e-4
+
+
+@pytest.mark.parametrize("act", [0, 1, 2, 3])
+def test_gemm_bias_act_residual(act):
+    ops = _ops()
+    M, N, K = 514, 1024, 1024
+    x, w, b = rnd(M, K, seed=3), rnd(N, K, scale=K ** -0.5, seed=4), rnd(N, seed=5)
+    res = rnd(M, N, seed=6)
+    out = ops.linear(x, w, b, act=act, residual=res)
+    y = x.float() @ w.float().t() + b.float()
+    if act == 1:
+        y = torch.nn.functional.gelu(y)
+    elif act == 2:
+        y = y * torch.sigmoid(1.702 * y)
+    elif act == 3:
+        y = torch.nn.functional.silu(y)
+    ref = y + res.float()
+    assert rel_err(out, ref) < 4e-3
+
+
+def test_gemm_residual_row_mod_and_inplace():
+    ops = _ops()
+    M, N, K = 771, 1024, 640  # 3 x 257 rows, CLIP-like
+    x, w = rnd(M, K, seed=7), rnd(N, K, scale=K ** -0.5, seed=8)
+    pos = rnd(257, N, seed=9)
+    out = ops.linear(x, w, residual=pos, res_row_mod=257)
+    ref = x.float() @ w.float().t() + pos.float().repeat(3, 1)
+    assert rel_err(out, ref) < 4e-3
+    # in-place residual add (out aliases residual) as used for the transformer residual stream
+    h = rnd(M, N, seed=10)
+    ref2 = x.float() @ w.float().t() + h.float()
+    ops.linear(x, w, residual=h, out=h)
+    assert rel_err(h, ref2) < 4e-3
+
+
+def test_gemm_row_scale_alpha():
+    ops = _ops()
+    M, N, K = 200, 512, 512
+    x, w = rnd(M, K, seed=11), rnd(N, K, scale=K ** -0.5, seed=12)
+    rs = torch.rand(M, device=DEV) + 0.5
+    out = ops.linear(x, w, row_scale=rs, alpha=0.25, out_fp32=True)
+    ref = (x.float() @ w.float().t()) * rs[:, None] * 0.25
+    assert rel_err(out, ref) < 1e-4
+
+
+def test_gemm_swiglu():
+    ops = _ops()
+    M, K, I = 300, 1024, 2752
+    x = rnd(M, K, seed=13)
+    wg, wu = rnd(I, K, scale=K ** -0.5, seed=14), rnd(I, K, scale=K ** -0.5, seed=15)
+    # interleave rows in blocks of 32: [g0..g31, u0..u31, g32.., ...]
+    wgu = torch.stack([wg.view(I // 32, 32, K), wu.view(I // 32, 32, K)], dim=1).reshape(2 * I, K).contiguous()
+    out = ops.linear(x, wgu, epi=ops.EPI_SWIGLU)
+    ref = torch.nn.functional.silu(x.float() @ wg.float().t()) * (x.float() @ wu.float().t())
+    assert out.shape == (M, I)
+    assert rel_err(out, ref) < 4e-3
+
+
+def test_gemm_rope():
+    ops = _ops()
+    B, T, E, H = 2, 100, 512, 4  # head_dim 128
+    x = rnd(B * T, E, seed=16)
+    w = rnd(3 * E, E, scale=E ** -0.5, seed=17)
+    inv = 1.0 / (10000 ** (torch.arange(0, 128, 2, device=DEV).float() / 128))
+    ang = torch.arange(T, device=DEV).float()[:, None] * inv[None, :]
+    cos, sin = ang.cos().contiguous(), ang.sin().contiguous()
+    out = ops.linear(x, w, epi=ops.EPI_ROPE, rope=(cos, sin, T, 2 * E))
+    y = (x.float() @ w.float().t()).view(B, T, 3, H, 128)
+    c = torch.cat([cos, cos], -1)[None, :, None, None, :]
+    s = torch.cat([sin, sin], -1)[None, :, None, None, :]
+    rot = torch.cat([-y[..., 64:], y[..., :64]], -1)
+    yr = y * c + rot * s
+    ref = torch.cat([yr[:, :, :2], y[:, :, 2:]], dim=2).reshape(B * T, 3 * E)
+    assert rel_err(out, ref) < 4e-3
+
+
+def test_gemm_batched_strided_and_mn_major():
+    ops = _ops()
+    # per-head absorbed query: q (Nq, 16*256) x W_k[h] (256, E) -> (H, Nq, E); B operand is MN-major (N contiguous)
+    Nq, H, hd, E = 24, 4, 256, 1024
+    q = rnd(Nq, H * hd, seed=18)
+    wk = rnd(H * hd, E, scale=hd ** -0.5, seed=19)
+    out = torch.empty(H, Nq, E, device=DEV, dtype=torch.bfloat16)
+    ops.gemm_raw(M=Nq, N=E, K=hd, batch=H, A=q.data_ptr(), lda=q.stride(0), a_bs=hd, B=wk.data_ptr(), ldb=E,
+                 b_bs=hd * E, b_mn_major=True, Cout=out.data_ptr(), ldc=E, c_bs=Nq * E, alpha=0.5)
+    ref = 0.5 * torch.einsum("nhd,hde->hne", q.float().view(Nq, H, hd), wk.float().view(H, hd, E))
+    assert rel_err(out, ref) < 4e-3
+
+
+def test_gemm_mn_major_long_k():
+    ops = _ops()
+    # P (R, V) x table (V, E): K = V is the table's row index -> MN-major B, ragged K
+    R, V, E = 200, 3001, 512
+    P = rnd(R, 3008, seed=20).abs()
+    P[:, V:] = 0
+    tab = rnd(V, E, seed=21)
+    out = torch.empty(R, E, device=DEV, dtype=torch.float32)
+    ops.gemm_raw(M=R, N=E, K=V, A=P.data_ptr(), lda=P.stride(0), B=tab.data_ptr(), ldb=E, b_mn_major=True,
+                 Cout=out.data_ptr(), ldc=E, c_fp32=True)
+    ref = P[:, :V].float() @ tab.float()
+    assert rel_err(out, ref) < 1e-4
+
+
+def test_gemm_overlapping_rows_conv_view_and_splitk():
+    ops = _ops()
+    # Conv1d(C, C, k, stride s) over the token axis as a GEMM on overlapping row views, split over K
+    B, Ntok, Cc, k, s = 3, 256, 64, 48, 36
+    Lq = (Ntok - k) // s + 1
+    x = rnd(B, Ntok, Cc, seed=22)
+    w = rnd(Cc, Cc, k, scale=(Cc * k) ** -0.5, seed=23)       # torch Conv1d weight (out, in, k)
+    bias = rnd(Cc, seed=24)
+    wp = w.permute(0, 2, 1).reshape(Cc, k * Cc).contiguous()    # (out, k*in): matches the contiguous token window
+    S = 4
+    Kc = k * Cc // S
+    part = torch.empty(S, B * Lq, Cc, device=DEV, dtype=torch.float32)
+    # inner batch = K split, outer batch (batch2) = sample; one launch
+    ops.gemm_raw(M=Lq, N=Cc, K=Kc, batch=S, batch2=B, A=x.data_ptr(), lda=s * Cc, a_bs=Kc, a_bs2=Ntok * Cc,
+                 B=wp.data_ptr(), ldb=k * Cc, b_bs=Kc, b_bs2=0, Cout=part.data_ptr(), ldc=Cc, c_bs=B * Lq * Cc,
+                 c_bs2=Lq * Cc, c_fp32=True)
+    out = torch.empty(B * Lq, Cc, device=DEV, dtype=torch.bfloat16)
+    ops.splitk_reduce(part, bias, out)
+    ref = torch.nn.functional.conv1d(x.float().transpose(1, 2), w.float(), bias.float(), stride=s).transpose(1, 2)
+    assert rel_err(out, ref.reshape(B * Lq, Cc)) < 4e-3
+
+
+# ------------------------------------------------------------------------------------------------ attention
+def _attn_ref(q, k, v, scale, causal, key_mask):
+    qf, kf, vf = (t.float().permute(0, 2, 1, 3) for t in (q, k, v))  # B H T d
+    s = (qf @ kf.transpose(-1, -2)) * scale
+    Tq, Tk = s.shape[-2:]
+    if causal:
+        i = torch.arange(Tq, device=s.device)[:, None]
+        j = torch.arange(Tk, device=s.device)[None, :]
+        s = s.masked_fill(j > i + (Tk - Tq), float("-inf"))
+    if key_mask is not None:
+        s = s.masked_fill(key_mask[:, None, None, :] == 0, float("-inf"))
+    p = torch.softmax(s, dim=-1)
+    p = torch.nan_to_num(p, nan=0.0)
+    return (p @ vf).permute(0, 2, 1, 3)
+
+
+@pytest.mark.parametrize(
+    "B,H,Tq,Tk,hd,causal,masked",
+    [
+        (2, 4, 257, 257, 64, False, False),    # CLIP
+        (1, 8, 1500, 1500, 64, False, False),  # Whisper
+        (1, 8, 200, 202, 96, False, False),    # video-long (two synthetic keys appended)
+        (2, 4, 264, 264, 128, True, False),    # LLaMA causal
+        (2, 4, 130, 130, 128, True, True),     # LLaMA causal + right padding
+        (1, 2, 64, 64, 128, True, False),
+        (1, 2, 1, 70, 64, False, False),
+    ],
+)
+def test_attention(B, H, Tq, Tk, hd, causal, masked):
+    ops = _ops()
+    # q/k/v as strided views of one fused (B, T, 3, H, hd) projection output, as the engine uses them
+    qkv_q = rnd(B, Tq, 3, H, hd, seed=30)
+    qkv_k = qkv_q if Tq == Tk else rnd(B, Tk, 3, H, hd, seed=31)
+    q, k, v = qkv_q[:, :, 0], qkv_k[:, :, 1], qkv_k[:, :, 2]
+    km = None
+    if masked:
+        km = torch.ones(B, Tk, dtype=torch.int32, device=DEV)
+        km[0, Tk - 17:] = 0
+    scale = hd ** -0.5
+    out = ops.attention(q, k, v, scale=scale, causal=causal, key_mask=km)
+    ref = _attn_ref(q, k, v, scale, causal, km)
+    if masked:  # rows whose own key is padding are unspecified; compare valid query rows only
+        valid = km.bool()[:, -Tq:]
+        out, ref = out[valid], ref[valid]
+    assert rel_err(out, ref) < 5e-3
+
+
+# ------------------------------------------------------------------------------------------------ norms & misc
+def test_rmsnorm_layernorm():
+    ops = _ops()
+    x, w, b = rnd(300, 4096, seed=40), rnd(4096, seed=41), rnd(4096, seed=42)
+    y = ops.rmsnorm(x, w, 1e-6)
+    xf = x.float()
+    ref = xf * torch.rsqrt(xf.pow(2).mean(-1, keepdim=True) + 1e-6) * w.float()
+    assert rel_err(y, ref) < 3e-3
+    x2 = rnd(514, 1024, seed=43)
+    y2 = ops.layernorm(x2, w[:1024].contiguous(), b[:1024].contiguous(), 1e-5)
+    ref2 = torch.nn.functional.layer_norm(x2.float(), (1024,), w[:1024].float(), b[:1024].float(), 1e-5)
+    assert rel_err(y2, ref2) < 3e-3
+
+
+def test_embed_gather_and_splice_bit_exact():
+    ops = _ops()
+    V, E, B, L, P = 1000, 256, 3, 17, 8
+    table = rnd(V, E, seed=44)
+    ids = torch.randint(0, V, (B, L), device=DEV)
+    text = ops.embed_gather(table, ids).view(B, L, E)
+    assert torch.equal(text, table[ids])
+    prefix = rnd(B, P, E, seed=45)
+    mask = torch.randint(0, 2, (B, L), device=DEV)
+    labels = torch.randint(-100, V, (B, L), device=DEV)
+    emb, m, l = ops.splice_prefix(text, prefix, mask, labels)
+    ref = torch.cat([text[:, :1], prefix, text[:, 1:]], dim=1)
+    assert torch.equal(emb, ref)
+    assert torch.equal(m, torch.cat([torch.ones(B, P, dtype=torch.int64, device=DEV), mask], 1))
+    assert torch.equal(l, torch.cat([torch.full((B, P), -100, dtype=torch.int64, device=DEV), labels], 1))
+    emb2, m2, l2 = ops.splice_prefix(text, None, None, None)
+    assert torch.equal(emb2, text) and m2 is None and l2 is None
+
+
+def test_patchify_transpose_addrows():
+    ops = _ops()
+    img = rnd(2, 3, 28, 42, seed=46)
+    out = ops.patchify(img, 14, 640)
+    ref = torch.nn.functional.unfold(img.float(), kernel_size=14, stride=14).transpose(1, 2).reshape(-1, 588)
+    assert torch.equal(out[:, :588].float(), ref) and float(out[:, 588:].abs().max()) == 0.0
+    x = rnd(2, 80, 300, seed=47)
+    t = ops.transpose_pad(x, 1)
+    assert torch.equal(t[:, 1:-1], x.transpose(1, 2)) and float(t[:, 0].abs().max()) == 0 and float(t[:, -1].abs().max()) == 0
+    a, add = rnd(514, 1024, seed=48), rnd(257, 1024, seed=49)
+    y = torch.empty_like(a)
+    ops.add_rows(a, add, y)
+    assert rel_err(y, a.float() + add.float().repeat(2, 1)) < 3e-3
+
+
+def test_align_softmax_and_fixup():
+    ops = _ops()
+    R, V = 37, 32000
+    scores = torch.randn(R, V, device=DEV) * 3
+    stats = torch.randn(R, 2, device=DEV)
+    P = torch.empty(R, V, device=DEV, dtype=torch.bfloat16)
+    psum, pext = ops.align_softmax(scores, stats, P, V)
+    full = torch.cat([scores + stats[:, :1], stats[:, 1:2], torch.zeros(R, 1, device=DEV)], dim=1)
+    pr = torch.softmax(full, dim=-1)
+    assert rel_err(P, pr[:, :V]) < 3e-3
+    assert rel_err(psum, pr[:, :V].sum(-1)) < 1e-5 and rel_err(pext, pr[:, V]) < 1e-5
+
+
+def test_ce_loss():
+    ops = _ops()
+    B, T, V = 3, 21, 5000
+    logits = rnd(B, T, V, scale=3.0, seed=50)
+    labels = torch.randint(0, V, (B, T), device=DEV)
+    labels[:, :5] = -100
+    loss = ops.ce_loss(logits, labels)
+    ref = torch.nn.functional.cross_entropy(logits[:, :-1].float().reshape(-1, V), labels[:, 1:].reshape(-1))
+    assert abs(float(loss) - float(ref)) < 1e-3 * abs(float(ref))
