@@ -1,0 +1,375 @@
+#!/usr/bin/env python
+"""Benchmark of record: multimodal prefill tokens/sec of the MM_LLMs forward (BASELINE.json metric).
+
+  python bench.py --gpus N --steps K --warmup W            # this repo's sm_100a path (one rank per GPU under torchrun)
+  python bench.py --impl reference --gpus N --steps K ...  # the reference algorithm on the host CPUs (oracle port)
+
+Workload (config.workload): BASELINE config 4 — image + audio + text, CLIP ViT-L/14-224 + Whisper-base encoder +
+alignment (32000 x 4096 table, 16 heads) + LLaMA-7B, global batch 32, L = 512 text tokens -> T = 528 positions,
+random-init weights, synthetic inputs, labels=None, logits for all positions.  A "step" is one forward over the
+global batch; with N ranks the global batch is split by sample (strong scaling, no collective on the data path).
+
+One JSON line is printed by rank 0 (see the field list in DESIGN.md §Measurement).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+METRIC = "multimodal prefill tokens/sec (img+audio+text->LLaMA)"
+UNIT = "tokens/s"
+
+
+# ---------------------------------------------------------------------------------------------------- configs
+def real_configs(small: bool = False):
+    from transformers import CLIPConfig, LlamaConfig, WhisperConfig
+
+    if small:  # CI-sized stand-in used by tests (same code path, kernel-compatible widths)
+        from tests.golden import gen
+
+        return gen.build_configs(gen.TINY), dict(n_frames=gen.TINY["n_frames"], attention_heads=gen.TINY["attention_heads"])
+    clip = CLIPConfig(  # openai/clip-vit-large-patch14
+        text_config=dict(hidden_size=768, intermediate_size=3072, num_hidden_layers=12, num_attention_heads=12,
+                         projection_dim=768),
+        vision_config=dict(hidden_size=1024, intermediate_size=4096, num_hidden_layers=24, num_attention_heads=16,
+                           image_size=224, patch_size=14, projection_dim=768, hidden_act="quick_gelu"),
+        projection_dim=768)
+    whisper = WhisperConfig(  # openai/whisper-base
+        d_model=512, encoder_layers=6, encoder_attention_heads=8, encoder_ffn_dim=2048, decoder_layers=6,
+        decoder_attention_heads=8, decoder_ffn_dim=2048, num_mel_bins=80, max_source_positions=1500, vocab_size=51865)
+    llama = LlamaConfig(hidden_size=4096, intermediate_size=11008, num_hidden_layers=32, num_attention_heads=32,
+                        vocab_size=32000, rms_norm_eps=1e-6, max_position_embeddings=2048, pad_token_id=0,
+                        bos_token_id=1, eos_token_id=2)
+    return (clip, whisper, llama), dict(n_frames=6, attention_heads=8)
+
+
+def synth_inputs(B, L, V, img, mel_T, seed, dtype=torch.bfloat16, pin=True):
+    """Seeded synthetic host inputs of the reference's `inputs` dict."""
+    g = torch.Generator().manual_seed(seed)
+    d = dict(videos=None)
+    d["images"] = torch.randn(B, 3, img, img, generator=g).to(dtype)
+    d["audios"] = torch.randn(B, 80, mel_T, generator=g).to(dtype)
+    ids = torch.randint(3, V - 6, (B, L), generator=g)
+    ids[:, 0] = 1
+    d["input_ids"] = ids
+    d["attention_mask"] = torch.ones(B, L, dtype=torch.int64)
+    sp = [V - 6 + i for i in range(6)]
+    for i, name in enumerate(("image", "audio", "video")):
+        d[f"{name}_starts"] = torch.full((B,), sp[2 * i], dtype=torch.int32)
+        d[f"{name}_ends"] = torch.full((B,), sp[2 * i + 1], dtype=torch.int32)
+    if pin and torch.cuda.is_available():
+        d = {k: (v.pin_memory() if isinstance(v, torch.Tensor) else v) for k, v in d.items()}
+    return d
+
+
+# ---------------------------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    """nvidia-smi sampling during the timed region (B200_PROFILING.md clocks line)."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.index), "-lms", "200"], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=self._pump, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx = float(f[1])
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": (statistics.median(sm) if sm else None), "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------------- reference arm
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return d.get("hbm_gbs", 6650.0), d.get("bf16_tflops", 1590.0), d.get("bf16_tflops_sustained", 1400.0), "measured"
+    return 6650.0, 1590.0, 1400.0, "fallback"
+
+
+def cpu_oracle_sample(cfgs, hyper, L, steps, warmup, seed=1234, state_dict=None, budget_s=240.0):
+    """Time the CPU oracle (a port of the reference's algorithm, oracle/macaw_oracle.py) on a bounded sample of the
+    workload: ONE sample (B=1) image+audio+text, full model depth, fp32, all host threads.  The reference is linear in
+    B (every term is per-sample), so tokens/s of one sample is its tokens/s at any batch."""
+    from oracle import macaw_oracle as O
+    from macaw_llm_b200.modeling import MM_LLMs_Config
+
+    clip, whisper, llama = cfgs
+    cfg = MM_LLMs_Config(clip_config=clip, whisper_config=whisper, llm_config=llama, **hyper)
+    hp = O.hp_from_config(cfg)
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    if state_dict is None:
+        # identical family of random weights, generated on the host (the oracle only needs a state_dict)
+        from macaw_llm_b200.modeling import MM_LLMs
+
+        with torch.device("meta"):
+            shapes = {k: tuple(v.shape) for k, v in MM_LLMs(cfg).state_dict().items()}
+        g = torch.Generator().manual_seed(0)
+        state_dict = {}
+        for k, shp in shapes.items():
+            if k.endswith("inv_freq") or k.endswith("position_ids"):
+                continue
+            if len(shp) == 1 and "norm" in k.lower() and k.endswith("weight"):
+                state_dict[k] = torch.ones(shp)
+            elif len(shp) <= 1:
+                state_dict[k] = torch.zeros(shp)
+            else:
+                state_dict[k] = torch.empty(shp).normal_(0.0, 0.02, generator=g)
+    else:
+        state_dict = {k: v.detach().to("cpu", torch.float32) for k, v in state_dict.items()}
+    V = llama.vocab_size
+    inp = synth_inputs(1, L, V, clip.vision_config.image_size, 2 * whisper.max_source_positions, seed, torch.float32,
+                       pin=False)
+    times, T = [], None
+    t_begin = time.perf_counter()
+    done = 0
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        out = O.forward(inp, state_dict, hp, dtype=torch.float32)
+        dt = time.perf_counter() - t0
+        T = out["logits"].shape[1]
+        if i >= warmup:
+            times.append(dt)
+            done += 1
+        # keep the whole arm within the budget: stop early once at least one timed step exists
+        if (time.perf_counter() - t_begin) + dt > budget_s and done >= 1:
+            break
+    sec = sum(times) / len(times)
+    return dict(value=T / sec, unit=UNIT, cores=cores, kind="port", steps_timed=len(times), sec_per_step=sec,
+                sample=f"1 sample (B=1) image+audio+text, L={L} -> T={T}, full depth, fp32, oracle/macaw_oracle.py; "
+                       f"reference cost is linear in B")
+
+
+# ---------------------------------------------------------------------------------------------------- main
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--global-batch", type=int, default=32)
+    ap.add_argument("--seq-len", type=int, default=512)
+    ap.add_argument("--scaling", default="strong", choices=["strong", "weak"])
+    ap.add_argument("--small", action="store_true", help="tiny stand-in model (tests only; the result is not a bench value)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    cfgs, hyper = real_configs(args.small)
+    clip, whisper, llama = cfgs
+    L, V = args.seq_len, llama.vocab_size
+    workload = (f"cfg4 image+audio+text: CLIP ViT-L/14-224 + Whisper-base + alignment(V={V},E={llama.hidden_size},"
+                f"{hyper['attention_heads'] * 2} heads) + LLaMA-7B, global_batch={args.global_batch}, L={L}")
+    if args.small:
+        workload = "SMALL stand-in (tests only) " + workload
+
+    # ------------------------------------------------------------------ reference arm: host CPUs only
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        steps = max(1, min(args.steps, 5))
+        warm = min(args.warmup, 1)
+        cb = cpu_oracle_sample(cfgs, hyper, L, steps, warm)
+        line = {
+            "impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus,
+            "steps": cb["steps_timed"], "warmup": warm, "ms_per_step": cb["sec_per_step"] * 1e3,
+            "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": workload, "sample": cb["sample"]},
+            "cpu_baseline": {"value": cb["value"], "unit": UNIT, "cores": cb["cores"], "kind": cb["kind"],
+                             "sample": cb["sample"]},
+            "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0,
+        }
+        print(json.dumps(line), flush=True)
+        return
+
+    # ------------------------------------------------------------------ B200 arm
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the B200 path has no CPU fallback (use --impl reference for the CPU arm)")
+    import torch.distributed as dist
+
+    from macaw_llm_b200 import ops
+    from macaw_llm_b200.modeling import MM_LLMs, MM_LLMs_Config
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    if args.scaling == "strong":
+        assert args.global_batch % world == 0, "global batch must divide by the number of ranks"
+        B_local, B_global = args.global_batch // world, args.global_batch
+    else:
+        B_local, B_global = args.global_batch, args.global_batch * world
+
+    cfg = MM_LLMs_Config(clip_config=clip, whisper_config=whisper, llm_config=llama, **hyper)
+    model = MM_LLMs.build_random(cfg, device=dev, dtype=torch.bfloat16, seed=0)  # same seed -> identical replicas
+    host = synth_inputs(B_local, L, V, clip.vision_config.image_size, 2 * whisper.max_source_positions, 1234 + rank)
+    dev_in = {k: (v.to(dev) if isinstance(v, torch.Tensor) else v) for k, v in host.items()}
+
+    def step_resident():
+        return model(dev_in).logits
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # warm-up (also builds the derived-weight cache)
+    for _ in range(max(args.warmup, 3)):
+        logits = step_resident()
+    T = logits.shape[1]
+    barrier()
+
+    # ---- timed region 1: inputs resident in HBM ("value"), per-launch GEMM events for the live roofline
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ops.PROFILE = []
+    ops.launch_count_reset()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        logits = step_resident()
+    e1.record()
+    barrier()
+    launches = ops.launch_count()
+    ms = e0.elapsed_time(e1)
+    prof, ops.PROFILE = ops.PROFILE, None
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    value = B_global * T * args.steps / (ms_max / 1e3)
+
+    # ---- timed region 2: end to end through the public call with HOST (pinned) buffers: H2D of every input + forward
+    #      + D2H of the step's result (next-token logits of every sample)
+    out_host = torch.empty((B_local, V), dtype=torch.bfloat16).pin_memory()
+
+    def step_e2e():
+        d = {k: (v.to(dev, non_blocking=True) if isinstance(v, torch.Tensor) else v) for k, v in host.items()}
+        lg = model(d).logits
+        out_host.copy_(lg[:, -1, :], non_blocking=True)
+
+    step_e2e()
+    barrier()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record()
+    for _ in range(args.steps):
+        step_e2e()
+    f1.record()
+    barrier()
+    t2 = torch.tensor([f0.elapsed_time(f1)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t2, op=dist.ReduceOp.MAX)
+    e2e_value = B_global * T * args.steps / (float(t2.item()) / 1e3)
+    h2d = sum(v.numel() * v.element_size() for v in host.values() if isinstance(v, torch.Tensor)) * world
+    d2h = out_host.numel() * out_host.element_size() * world
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- live roofline of the dominant kernel (the tcgen05 GEMM): algorithmic FLOPs / CUDA-event time, all launches
+    hbm_peak, tf_burst, tf_sust, peak_src = load_peaks()
+    by_tag = {}
+    for tag, flops, a, b in prof:
+        d = by_tag.setdefault(tag, [0.0, 0.0, 0])
+        d[0] += flops
+        d[1] += a.elapsed_time(b) * 1e-3
+        d[2] += 1
+    tot_f = sum(v[0] for v in by_tag.values())
+    tot_s = sum(v[1] for v in by_tag.values())
+    achieved = tot_f / tot_s / 1e12 if tot_s > 0 else 0.0
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    if os.path.exists(tp):
+        try:
+            traffic = json.load(open(tp)).get("gemm_dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+    roofline = {
+        "kernel": "mm::gemm_bf16_kernel (tcgen05 + TMA), all launches of the step",
+        "bound": "tensor", "achieved": achieved, "peak": tf_sust, "unit": "TFLOP/s", "frac": achieved / tf_sust,
+        "peak_source": f"{peak_src} bf16_tflops_sustained (kernel timed inside a long step)", "traffic": traffic,
+        "share_of_step": tot_s / (ms / 1e3),
+        "by_section": {k: {"tflops": v[0] / v[1] / 1e12 if v[1] > 0 else 0.0, "ms_per_step": v[1] * 1e3 / args.steps,
+                           "launches_per_step": v[2] / args.steps} for k, v in sorted(by_tag.items())},
+    }
+
+    cpu = None
+    if not args.no_cpu_baseline and world == 1:
+        sd = model.state_dict() if args.small else None
+        cb = cpu_oracle_sample(cfgs, hyper, L, steps=1, warmup=0, state_dict=sd, budget_s=120.0)
+        cpu = {"value": cb["value"], "unit": UNIT, "cores": cb["cores"], "kind": cb["kind"], "sample": cb["sample"]}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
+        "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": workload, "global_batch": B_global, "per_gpu_batch": B_local, "seq_len": L, "T": T,
+                   "parallelism": f"dp{world}", "l2": "per-step working set (16 GB of weights) >> 126 MB L2; no flush needed"},
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "result": "next-token logits (B, V) bf16 read back to pinned host memory"},
+        "gpu_launches": launches,
+        "roofline": roofline,
+        "cpu_baseline": cpu,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,471 @@
+"""The MM_LLMs forward pass expressed over the sm_100a kernel library (ops.py -> libmacaw_b200.so).
+
+Every arithmetic step of the reference hot path (reference: /root/reference/modeling.py:941-1118 and the torch /
+transformers modules it delegates to) is executed by a hand-written kernel; torch only owns device memory.  The
+engine reads the parameters of an `MM_LLMs` module (modeling.py in this package) and keeps *derived* weights
+(fused QKV, interleaved gate/up, permuted conv filters, bf16 shadows) in a cache keyed by parameter version, so
+in-place weight updates are picked up.
+
+Data layout in HBM: activations are bf16, token-major `(tokens, channels)` with the residual stream updated in
+place by GEMM epilogues; all contractions accumulate in fp32 (TMEM / registers); scores of the alignment
+cross-attention are fp32.
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, Optional, Tuple
+
+import torch
+
+from . import ops
+
+BF16 = torch.bfloat16
+
+
+def _round_up(x: int, m: int) -> int:
+    return (x + m - 1) // m * m
+
+
+class Engine:
+    def __init__(self, model):
+        self.m = model
+        self._cache: Dict[str, Tuple[tuple, object]] = {}
+        self._rope: Dict[Tuple[int, int, str], Tuple[torch.Tensor, torch.Tensor]] = {}
+        self._pe: Dict[Tuple[int, int, str], torch.Tensor] = {}
+        self._zeros: Dict[Tuple[int, str], torch.Tensor] = {}
+
+    # ------------------------------------------------------------------------------------------------ weight cache
+    @staticmethod
+    def _stamp(*params) -> tuple:
+        return tuple((p.data_ptr(), p._version, p.dtype) for p in params)
+
+    def derived(self, key: str, params, fn):
+        st = self._stamp(*params)
+        hit = self._cache.get(key)
+        if hit is not None and hit[0] == st:
+            return hit[1]
+        with torch.no_grad():
+            val = fn()
+        self._cache[key] = (st, val)
+        return val
+
+    def w(self, p: torch.Tensor, key: str) -> torch.Tensor:
+        """bf16 CUDA view of a parameter (the parameter itself when it already is bf16)."""
+        if not p.is_cuda:
+            raise RuntimeError(
+                "macaw_b200: model parameters live on the CPU; move the model to a CUDA device "
+                "(there is no CPU execution path)")
+        if p.dtype == BF16:
+            return p.detach()
+        return self.derived("bf16:" + key, [p], lambda: p.detach().to(BF16))
+
+    def zeros(self, n: int, dev) -> torch.Tensor:
+        k = (n, str(dev))
+        z = self._zeros.get(k)
+        if z is None:
+            z = torch.zeros((1, n), device=dev, dtype=BF16)
+            self._zeros[k] = z
+        return z
+
+    # ------------------------------------------------------------------------------------------------ generic blocks
+    def _self_attn_block(self, x, B, T, D, H, ln1, wqkv, bqkv, wo, bo, ln2, fc1, fc2, act, eps, scale):
+        """Pre-LN encoder layer (CLIP: modeling_clip.py CLIPEncoderLayer; Whisper: modeling_whisper.py WhisperEncoderLayer)."""
+        hd = D // H
+        h = ops.layernorm(x, ln1[0], ln1[1], eps)
+        qkv = ops.linear(h, wqkv, bqkv).view(B, T, 3, H, hd)
+        a = ops.attention(qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2], scale=scale)
+        ops.linear(a.view(B * T, D), wo, bo, residual=x, out=x)
+        h = ops.layernorm(x, ln2[0], ln2[1], eps)
+        f = ops.linear(h, fc1[0], fc1[1], act=act)
+        ops.linear(f, fc2[0], fc2[1], residual=x, out=x)
+        return x
+
+    # ------------------------------------------------------------------------------------------------ CLIP
+    def clip_tokens(self, images: torch.Tensor, which: str) -> torch.Tensor:
+        """visual_projection(vision_model(images)[0])[:, 1:, :] (reference modeling.py:1092 / :1073) -> (n_img, 256, P).
+
+        CLS rows are skipped by the projection GEMM itself (A starts at row 1 of every image)."""
+        ops.TAG = "clip"
+        clip = getattr(self.m, which)
+        vm = clip.vision_model
+        cfg = clip.config.vision_config
+        D, H, p = cfg.hidden_size, cfg.num_attention_heads, cfg.patch_size
+        eps = cfg.layer_norm_eps
+        act = {"quick_gelu": ops.ACT_QUICK_GELU, "gelu": ops.ACT_GELU}[cfg.hidden_act]
+        n_img = images.shape[0]
+        G = (images.shape[2] // p) * (images.shape[3] // p)
+        T = G + 1
+        dev = images.device
+        kp = _round_up(3 * p * p, 64)
+        pre = which + ".vision_model."
+        emb = vm.embeddings
+
+        def pack_patch():
+            wt = emb.patch_embedding.weight.detach().to(BF16).reshape(D, -1)
+            out = torch.zeros((D, kp), device=dev, dtype=BF16)
+            out[:, : wt.shape[1]] = wt
+            return out
+
+        w_patch = self.derived(pre + "patch", [emb.patch_embedding.weight], pack_patch)
+        pos = self.w(emb.position_embedding.weight, pre + "pos")
+        cls = self.w(emb.class_embedding, pre + "cls").view(1, D)
+
+        cols = ops.patchify(images, p, kp)  # (n_img * G, kp)
+        x = torch.empty((n_img, T, D), device=dev, dtype=BF16)
+        # patch embedding + position embedding, written to rows 1..G of every image
+        ops.gemm_raw(M=G, N=D, K=kp, batch=n_img, A=cols.data_ptr(), lda=kp, a_bs=G * kp, B=w_patch.data_ptr(), ldb=kp,
+                     b_bs=0, Cout=x.data_ptr() + D * 2, ldc=D, c_bs=T * D, residual=pos.data_ptr() + D * 2, ldr=D, r_bs=0)
+        # CLS row = class_embedding + pos[0]
+        ops.add_rows(cls.expand(n_img, D), pos[:1], x[:, 0, :])
+        x2 = x.view(n_img * T, D)
+        x2 = ops.layernorm(x2, self.w(vm.pre_layrnorm.weight, pre + "pln.w"), self.w(vm.pre_layrnorm.bias, pre + "pln.b"),
+                           eps)
+        for i, l in enumerate(vm.encoder.layers):
+            k = f"{pre}l{i}."
+            sa = l.self_attn
+            wqkv = self.derived(k + "wqkv", [sa.q_proj.weight, sa.k_proj.weight, sa.v_proj.weight],
+                                lambda sa=sa: torch.cat([sa.q_proj.weight, sa.k_proj.weight, sa.v_proj.weight], 0).detach().to(BF16).contiguous())
+            bqkv = self.derived(k + "bqkv", [sa.q_proj.bias, sa.k_proj.bias, sa.v_proj.bias],
+                                lambda sa=sa: torch.cat([sa.q_proj.bias, sa.k_proj.bias, sa.v_proj.bias], 0).detach().to(BF16).contiguous())
+            x2 = self._self_attn_block(
+                x2, n_img, T, D, H,
+                (self.w(l.layer_norm1.weight, k + "ln1w"), self.w(l.layer_norm1.bias, k + "ln1b")),
+                wqkv, bqkv, self.w(sa.out_proj.weight, k + "wo"), self.w(sa.out_proj.bias, k + "bo"),
+                (self.w(l.layer_norm2.weight, k + "ln2w"), self.w(l.layer_norm2.bias, k + "ln2b")),
+                (self.w(l.mlp.fc1.weight, k + "fc1w"), self.w(l.mlp.fc1.bias, k + "fc1b")),
+                (self.w(l.mlp.fc2.weight, k + "fc2w"), self.w(l.mlp.fc2.bias, k + "fc2b")),
+                act, eps, (D // H) ** -0.5)
+        wp = self.w(clip.visual_projection.weight, which + ".vproj")
+        P = wp.shape[0]
+        tok = torch.empty((n_img, G, P), device=dev, dtype=BF16)
+        ops.gemm_raw(M=G, N=P, K=D, batch=n_img, A=x2.data_ptr() + D * 2, lda=D, a_bs=T * D, B=wp.data_ptr(), ldb=D, b_bs=0,
+                     Cout=tok.data_ptr(), ldc=P, c_bs=G * P)
+        return tok
+
+    # ------------------------------------------------------------------------------------------------ Whisper
+    def whisper_encode(self, mel: torch.Tensor) -> torch.Tensor:
+        """audio_encoder.encoder(mel)[0] (reference modeling.py:1081-1083) -> (B, 1500, d_model).
+
+        Both stem convolutions run as GEMMs over overlapping row windows of a time-major, zero-padded buffer
+        (no im2col copy): conv1 k=3 s=1 p=1, conv2 k=3 s=2 p=1; GELU and the position embedding ride the epilogues."""
+        ops.TAG = "whisper"
+        enc = self.m.audio_encoder.encoder
+        cfg = self.m.audio_encoder.config
+        D, H = cfg.d_model, cfg.encoder_attention_heads
+        act = {"gelu": ops.ACT_GELU}[cfg.activation_function]
+        B, C, Tm = mel.shape
+        dev = mel.device
+        pre = "audio_encoder.encoder."
+        w1 = self.derived(pre + "conv1", [enc.conv1.weight],
+                          lambda: enc.conv1.weight.detach().to(BF16).permute(0, 2, 1).reshape(D, 3 * C).contiguous())
+        w2 = self.derived(pre + "conv2", [enc.conv2.weight],
+                          lambda: enc.conv2.weight.detach().to(BF16).permute(0, 2, 1).reshape(D, 3 * D).contiguous())
+        xt = ops.transpose_pad(mel, 1)  # (B, Tm + 2, C)
+        h1 = torch.empty((B, Tm + 2, D), device=dev, dtype=BF16)
+        z = self.zeros(D, dev)
+        ops.add_rows(z.expand(B, D), None, h1[:, 0, :])
+        ops.add_rows(z.expand(B, D), None, h1[:, Tm + 1, :])
+        ops.gemm_raw(M=Tm, N=D, K=3 * C, batch=B, A=xt.data_ptr(), lda=C, a_bs=(Tm + 2) * C, B=w1.data_ptr(), ldb=3 * C, b_bs=0,
+                     Cout=h1.data_ptr() + D * 2, ldc=D, c_bs=(Tm + 2) * D, bias=self.w(enc.conv1.bias, pre + "b1").data_ptr(),
+                     act=ops.ACT_GELU)
+        T = Tm // 2
+        pos = self.w(enc.embed_positions.weight, pre + "pos")
+        x = torch.empty((B, T, D), device=dev, dtype=BF16)
+        ops.gemm_raw(M=T, N=D, K=3 * D, batch=B, A=h1.data_ptr(), lda=2 * D, a_bs=(Tm + 2) * D, B=w2.data_ptr(), ldb=3 * D,
+                     b_bs=0, Cout=x.data_ptr(), ldc=D, c_bs=T * D, bias=self.w(enc.conv2.bias, pre + "b2").data_ptr(),
+                     act=ops.ACT_GELU, residual=pos.data_ptr(), ldr=D, r_bs=0)
+        x2 = x.view(B * T, D)
+        for i, l in enumerate(enc.layers):
+            k = f"{pre}l{i}."
+            sa = l.self_attn
+            wqkv = self.derived(k + "wqkv", [sa.q_proj.weight, sa.k_proj.weight, sa.v_proj.weight],
+                                lambda sa=sa: torch.cat([sa.q_proj.weight, sa.k_proj.weight, sa.v_proj.weight], 0).detach().to(BF16).contiguous())
+            bqkv = self.derived(k + "bqkv", [sa.q_proj.bias, sa.v_proj.bias],
+                                lambda sa=sa: torch.cat([sa.q_proj.bias, torch.zeros_like(sa.q_proj.bias), sa.v_proj.bias], 0).detach().to(BF16).contiguous())
+            x2 = self._self_attn_block(
+                x2, B, T, D, H,
+                (self.w(l.self_attn_layer_norm.weight, k + "ln1w"), self.w(l.self_attn_layer_norm.bias, k + "ln1b")),
+                wqkv, bqkv, self.w(sa.out_proj.weight, k + "wo"), self.w(sa.out_proj.bias, k + "bo"),
+                (self.w(l.final_layer_norm.weight, k + "ln2w"), self.w(l.final_layer_norm.bias, k + "ln2b")),
+                (self.w(l.fc1.weight, k + "fc1w"), self.w(l.fc1.bias, k + "fc1b")),
+                (self.w(l.fc2.weight, k + "fc2w"), self.w(l.fc2.bias, k + "fc2b")),
+                act, 1e-5, (D // H) ** -0.5)
+        x2 = ops.layernorm(x2, self.w(enc.layer_norm.weight, pre + "lnw"), self.w(enc.layer_norm.bias, pre + "lnb"), 1e-5)
+        return x2.view(B, T, D)
+
+    # ------------------------------------------------------------------------------------------------ video-long
+    def video_pe(self, L: int, h: int, dev) -> torch.Tensor:
+        """Sinusoid table of create_positional_encoding (reference modeling.py:1095-1106), built once per shape on the
+        host with the reference's exact fp32 arithmetic (exponent 2*i with i already even) instead of its O(L*h)
+        python loop per forward."""
+        key = (L, h, str(dev))
+        pe = self._pe.get(key)
+        if pe is None:
+            arg = torch.tensor([-(math.log(10000.0) / h * (2 * i)) for i in range(0, h, 2)], dtype=torch.float32)
+            div = torch.exp(arg)
+            pos = torch.arange(L, dtype=torch.float32)[:, None]
+            t = torch.zeros(L, h, dtype=torch.float32)
+            t[:, 0::2] = torch.sin(pos * div)
+            t[:, 1::2] = torch.cos(pos * div)
+            pe = t.to(BF16).to(dev)
+            self._pe[key] = pe
+        return pe
+
+    def encode_video_long(self, videos: torch.Tensor) -> torch.Tensor:
+        """reference modeling.py:1070-1079 -> (B, F*256, P)."""
+        m = self.m
+        F_ = m.config.n_frames
+        frames = videos.reshape(-1, *videos.shape[-3:])
+        tok = self.clip_tokens(frames, "video_encoder")  # (B*F, G, P)
+        B = frames.shape[0] // F_
+        G, P = tok.shape[1], tok.shape[2]
+        N = F_ * G
+        dev = videos.device
+        ops.TAG = "video_long"
+        x = tok.view(B * N, P)
+        pe = self.video_pe(N, P, dev)
+        xp = torch.empty_like(x)
+        ops.add_rows(x, pe, xp)
+        mha = m.video_long_self_attention
+        H = mha.num_heads
+        hd = P // H
+        pre = "video_long_self_attention."
+        w_in = self.w(mha.in_proj_weight, pre + "win")
+        b_in = self.w(mha.in_proj_bias, pre + "bin")
+        qkv = torch.empty((B, N + 2, 3 * P), device=dev, dtype=BF16)
+        ops.gemm_raw(M=N, N=3 * P, K=P, batch=B, A=xp.data_ptr(), lda=P, a_bs=N * P, B=w_in.data_ptr(), ldb=P, b_bs=0,
+                     Cout=qkv.data_ptr(), ldc=3 * P, c_bs=(N + 2) * 3 * P, bias=b_in.data_ptr())
+        # synthetic keys: row N = (bias_k, bias_v) appended un-projected, row N+1 = zeros (functional.py:6531-6537, 6585-6602)
+        bk = self.w(mha.bias_k, pre + "bk").view(1, P)
+        bv = self.w(mha.bias_v, pre + "bv").view(1, P)
+        z = self.zeros(P, dev)
+        ops.add_rows(bk.expand(B, P), None, qkv[:, N, P:2 * P])
+        ops.add_rows(bv.expand(B, P), None, qkv[:, N, 2 * P:])
+        ops.add_rows(z.expand(B, P), None, qkv[:, N + 1, P:2 * P])
+        ops.add_rows(z.expand(B, P), None, qkv[:, N + 1, 2 * P:])
+        q5 = qkv.view(B, N + 2, 3, H, hd)
+        a = ops.attention(q5[:, :N, 0], q5[:, :, 1], q5[:, :, 2], scale=hd ** -0.5)
+        out = ops.linear(a.view(B * N, P), self.w(mha.out_proj.weight, pre + "wo"), self.w(mha.out_proj.bias, pre + "bo"))
+        return out.view(B, N, P)
+
+    # ------------------------------------------------------------------------------------------------ alignment
+    def align(self, feats: torch.Tensor, name: str, table: torch.Tensor, prefix: torch.Tensor, row_off: int) -> int:
+        """One modality of reference modeling.py:982-987 / 999-1008 / 1022-1026 in ABSORBED form:
+        the keys/values are never projected — q is pushed through W_k per head and both big contractions
+        (scores = q~ . table^T over E, ctx~ = P . table over V) stream tiles of the raw embedding table through TMA.
+
+        feats (B, N, C) bf16 with unit channel stride and row stride C (sample stride free); writes the Lq aligned
+        rows into prefix[:, row_off : row_off + Lq] and returns Lq."""
+        ops.TAG = "align.proj"
+        m = self.m
+        conv = getattr(m, f"project_{name}")
+        lin = getattr(m, f"transform_{name}_to_hidden")
+        mha = getattr(m, f"{name}_align_attention")
+        B, N, C = feats.shape
+        assert feats.stride(2) == 1 and feats.stride(1) == C
+        kk, ss = conv.kernel_size[0], conv.stride[0]
+        Lq = (N - kk) // ss + 1
+        Nq = B * Lq
+        E = table.shape[1]
+        V = table.shape[0]
+        H = mha.num_heads
+        hd = E // H
+        dev = feats.device
+        pre = f"{name}_align."
+        # ---- Conv1d over the token axis == GEMM on overlapping row windows (window = kk*C contiguous elements), split over K
+        wc = self.derived(pre + "conv", [conv.weight],
+                          lambda: conv.weight.detach().to(BF16).permute(0, 2, 1).reshape(C, kk * C).contiguous())
+        K = kk * C
+        S = 1
+        for cand in (16, 12, 9, 8, 6, 4, 3, 2):
+            if K % (cand * 64) == 0:
+                S = cand
+                break
+        Kc = K // S
+        part = torch.empty((S, Nq, C), device=dev, dtype=torch.float32)
+        ops.gemm_raw(M=Lq, N=C, K=Kc, batch=S, batch2=B, A=feats.data_ptr(), lda=ss * C, a_bs=Kc, a_bs2=feats.stride(0),
+                     B=wc.data_ptr(), ldb=K, b_bs=Kc, b_bs2=0, Cout=part.data_ptr(), ldc=C, c_bs=Nq * C, c_bs2=Lq * C,
+                     c_fp32=True)
+        y = torch.empty((Nq, C), device=dev, dtype=BF16)
+        ops.splitk_reduce(part, self.w(conv.bias, pre + "convb"), y)
+        # ---- Linear C -> E, then the MHA query projection
+        z = ops.linear(y, self.w(lin.weight, pre + "lw"), self.w(lin.bias, pre + "lb"))
+        w_in = self.w(mha.in_proj_weight, pre + "win")
+        b_in = self.w(mha.in_proj_bias, pre + "bin")
+        q = ops.linear(z, w_in[:E], b_in[:E])  # (Nq, E); the 1/sqrt(hd) scale is applied downstream (alpha)
+        w_k, w_v = w_in[E:2 * E], w_in[2 * E:]
+        bk2 = self.derived(pre + "bk2", [mha.in_proj_bias, mha.bias_k],
+                           lambda: torch.stack([mha.in_proj_bias.detach()[E:2 * E].to(BF16),
+                                                mha.bias_k.detach().reshape(E).to(BF16)], 0).contiguous())
+        b_v = b_in[2 * E:]
+        bias_v = self.w(mha.bias_v, pre + "biasv").view(E)
+        scale = 1.0 / math.sqrt(hd)
+        Vp = _round_up(V, 8)
+        ctx = torch.empty((Nq, E), device=dev, dtype=BF16)
+        # bound the fp32 score buffer (R x V) to ~2 GiB by chunking query rows
+        max_nq = max(1, (1 << 31) // (H * Vp * 4))
+        for n0 in range(0, Nq, max_nq):
+            n1 = min(Nq, n0 + max_nq)
+            nq = n1 - n0
+            R = H * nq
+            qs = q[n0:n1]
+            # per-row constants: q_h . b_k[h] (added to every real key) and q_h . bias_k[h] (the bias_k key's score)
+            stats = torch.empty((H, nq, 2), device=dev, dtype=torch.float32)
+            ops.gemm_raw(M=nq, N=2, K=hd, batch=H, A=qs.data_ptr(), lda=E, a_bs=hd, B=bk2.data_ptr(), ldb=E, b_bs=hd,
+                         Cout=stats.data_ptr(), ldc=2, c_bs=nq * 2, c_fp32=True, alpha=scale)
+            # q~[h] = (q_h / sqrt(hd)) W_k[h]   (B operand = W_k rows of head h, N-contiguous -> MN-major UMMA descriptor)
+            qt = torch.empty((H, nq, E), device=dev, dtype=BF16)
+            ops.gemm_raw(M=nq, N=E, K=hd, batch=H, A=qs.data_ptr(), lda=E, a_bs=hd, B=w_k.data_ptr(), ldb=E, b_bs=hd * E,
+                         b_mn_major=True, Cout=qt.data_ptr(), ldc=E, c_bs=nq * E, alpha=scale)
+            # scores = q~ . table^T  (R x V, fp32)
+            scores = torch.empty((R, Vp), device=dev, dtype=torch.float32)
+            ops.TAG = "align.scores"
+            ops.gemm_raw(M=R, N=V, K=E, A=qt.data_ptr(), lda=E, B=table.data_ptr(), ldb=E, Cout=scores.data_ptr(), ldc=Vp,
+                         c_fp32=True)
+            P = torch.empty((R, Vp), device=dev, dtype=BF16)
+            psum, pext = ops.align_softmax(scores, stats.view(R, 2), P, V)
+            del scores
+            # ctx~ = P . table   (K = V runs down the table rows: MN-major B straight from the table, no transpose copy)
+            ctxt = torch.empty((H, nq, E), device=dev, dtype=BF16)
+            ops.TAG = "align.pv"
+            ops.gemm_raw(M=R, N=E, K=V, A=P.data_ptr(), lda=Vp, B=table.data_ptr(), ldb=E, b_mn_major=True,
+                         Cout=ctxt.data_ptr(), ldc=E)
+            del P
+            # ctx[:, h] = ctx~[h] W_v[h]^T, then the two value-bias terms
+            cs = ctx[n0:n1]
+            ops.TAG = "align.proj"
+            ops.gemm_raw(M=nq, N=hd, K=E, batch=H, A=ctxt.data_ptr(), lda=E, a_bs=nq * E, B=w_v.data_ptr(), ldb=E,
+                         b_bs=hd * E, Cout=cs.data_ptr(), ldc=E, c_bs=hd)
+            ops.align_ctx_fixup(cs, psum, pext, b_v, bias_v, hd)
+        # ---- out_proj straight into the prefix block of every sample
+        Ptot = prefix.shape[1]
+        ops.gemm_raw(M=Lq, N=E, K=E, batch=B, A=ctx.data_ptr(), lda=E, a_bs=Lq * E,
+                     B=self.w(mha.out_proj.weight, pre + "wo").data_ptr(), ldb=E, b_bs=0,
+                     Cout=prefix.data_ptr() + row_off * E * 2, ldc=E, c_bs=Ptot * E,
+                     bias=self.w(mha.out_proj.bias, pre + "bo").data_ptr())
+        return Lq
+
+    @staticmethod
+    def align_len(n_tokens: int, kernel: int, stride: int) -> int:
+        return (n_tokens - kernel) // stride + 1
+
+    # ------------------------------------------------------------------------------------------------ input preparation
+    def _to_dev_bf16(self, t: torch.Tensor, dev) -> torch.Tensor:
+        if t.device != dev:
+            t = t.to(dev, non_blocking=True)
+        if t.dtype != BF16:
+            t = t.to(BF16)
+        return t.contiguous()
+
+    def prepare_inputs(self, inputs: dict):
+        """MM_LLMs.prepare_inputs_for_generation (reference modeling.py:965-1048)."""
+        m = self.m
+        table = self.w(m.llm.model.embed_tokens.weight, "llm.embed")
+        dev = table.device
+        E = table.shape[1]
+        ids = inputs["input_ids"].to(dev)
+        B, L = ids.shape
+        feats = {}
+        if inputs.get("images") is not None:
+            feats["image"] = self.clip_tokens(self._to_dev_bf16(inputs["images"], dev), "image_encoder")
+        if inputs.get("audios") is not None:
+            feats["audio"] = self.whisper_encode(self._to_dev_bf16(inputs["audios"], dev))
+        if inputs.get("videos") is not None:
+            feats["video"] = self.encode_video_long(self._to_dev_bf16(inputs["videos"], dev))
+        # final layout [BOS, <image> img </image>, <audio> aud </audio>, <video> vid </video>, text[1:]]: each block is
+        # spliced right after BOS in the order video, audio, image (reference modeling.py:978-1034), so image ends up first
+        lens = {}
+        for name in ("image", "audio", "video"):
+            if name in feats:
+                conv = getattr(m, f"project_{name}")
+                lens[name] = self.align_len(feats[name].shape[1], conv.kernel_size[0], conv.stride[0])
+        n_prefix = sum(v + 2 for v in lens.values())
+        prefix = None
+        if n_prefix > 0:
+            prefix = torch.empty((B, n_prefix, E), device=dev, dtype=BF16)
+            off = 0
+            for name in ("image", "audio", "video"):
+                if name not in feats:
+                    continue
+                Lq = lens[name]
+                ops.embed_gather(table, inputs[f"{name}_starts"].to(dev), out=prefix[:, off, :])
+                got = self.align(feats[name], name, table, prefix, off + 1)
+                assert got == Lq
+                ops.embed_gather(table, inputs[f"{name}_ends"].to(dev), out=prefix[:, off + 1 + Lq, :])
+                off += Lq + 2
+        text = ops.embed_gather(table, ids).view(B, L, E)
+        mask_in = inputs["attention_mask"].to(dev) if "attention_mask" in inputs else None
+        labels_in = inputs["labels"].to(dev) if inputs.get("labels") is not None else None
+        return ops.splice_prefix(text, prefix, mask_in, labels_in)
+
+    # ------------------------------------------------------------------------------------------------ LLaMA
+    def rope_tables(self, T: int, hd: int, dev):
+        """cos/sin (T, hd/2) fp32.  Always rebuilt from the closed form (base 1e4, reference modeling.py:97-107): the
+        reference caches cos/sin at construction in fp32, so a later `.half()` / `.to(bf16)` of the `inv_freq`
+        buffer must not change the angles."""
+        key = (T, hd, str(dev))
+        t = self._rope.get(key)
+        if t is None:
+            inv = (1.0 / (10000 ** (torch.arange(0, hd, 2).float() / hd))).to(dev)
+            fr = torch.arange(T, device=dev, dtype=torch.float32)[:, None] * inv[None, :]
+            t = (fr.cos().contiguous(), fr.sin().contiguous())
+            self._rope[key] = t
+        return t
+
+    def llama_forward(self, embeds: torch.Tensor, attention_mask: Optional[torch.Tensor]) -> torch.Tensor:
+        """Vendored LlamaModel + lm_head of the reference (modeling.py:397-522, 597) -> bf16 logits (B, T, V).
+
+        RoPE is applied in the QKV GEMM epilogue, SwiGLU in the gate/up GEMM epilogue, both residual adds in the
+        o_proj / down_proj epilogues (in place on the residual stream)."""
+        ops.TAG = "llama"
+        llm = self.m.llm
+        cfg = llm.config
+        E, H = cfg.hidden_size, cfg.num_attention_heads
+        hd = E // H
+        if hd != 128:
+            raise NotImplementedError(f"macaw_b200: LLaMA head_dim {hd} unsupported (RoPE epilogue is specialised for 128)")
+        I = cfg.intermediate_size
+        if I % 32 != 0:
+            raise NotImplementedError("macaw_b200: intermediate_size must be a multiple of 32")
+        eps = cfg.rms_norm_eps
+        B, T, _ = embeds.shape
+        dev = embeds.device
+        x = embeds.reshape(B * T, E)
+        if not x.is_contiguous():
+            x = x.contiguous()
+        kmask = None
+        if attention_mask is not None:
+            kmask = attention_mask.to(device=dev, dtype=torch.int32).contiguous()
+        layers = llm.model.layers
+        cos, sin = self.rope_tables(T, hd, dev)
+        scale = 1.0 / math.sqrt(hd)
+        for i, l in enumerate(layers):
+            k = f"llm.l{i}."
+            sa, mlp = l.self_attn, l.mlp
+            wqkv = self.derived(k + "wqkv", [sa.q_proj.weight, sa.k_proj.weight, sa.v_proj.weight],
+                                lambda sa=sa: torch.cat([sa.q_proj.weight, sa.k_proj.weight, sa.v_proj.weight], 0).detach().to(BF16).contiguous())
+            wgu = self.derived(k + "wgu", [mlp.gate_proj.weight, mlp.up_proj.weight],
+                               lambda mlp=mlp: torch.stack([mlp.gate_proj.weight.detach().to(BF16).view(I // 32, 32, E),
+                                                            mlp.up_proj.weight.detach().to(BF16).view(I // 32, 32, E)], 1)
+                               .reshape(2 * I, E).contiguous())
+            h = ops.rmsnorm(x, self.w(l.input_layernorm.weight, k + "ln1"), eps)
+            qkv = ops.linear(h, wqkv, epi=ops.EPI_ROPE, rope=(cos, sin, T, 2 * E)).view(B, T, 3, H, hd)
+            a = ops.attention(qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2], scale=scale, causal=True, key_mask=kmask)
+            ops.linear(a.view(B * T, E), self.w(sa.o_proj.weight, k + "wo"), residual=x, out=x)
+            h = ops.rmsnorm(x, self.w(l.post_attention_layernorm.weight, k + "ln2"), eps)
+            g = ops.linear(h, wgu, epi=ops.EPI_SWIGLU)
+            ops.linear(g, self.w(mlp.down_proj.weight, k + "wd"), residual=x, out=x)
+        h = ops.rmsnorm(x, self.w(llm.model.norm.weight, "llm.norm"), eps)
+        wl = self.w(llm.lm_head.weight, "llm.lm_head")
+        ops.TAG = "lm_head"
+        logits = ops.linear(h, wl)
+        return logits.view(B, T, wl.shape[0])
+
+    # ------------------------------------------------------------------------------------------------ whole forward
+    def forward(self, inputs: dict):
+        """MM_LLMs.forward (reference modeling.py:941-963), prefill branch -> (loss | None, logits (B, T, V) bf16)."""
+        with torch.no_grad():
+            embeds, mask, labels = self.prepare_inputs(inputs)
+            logits = self.llama_forward(embeds, mask)
+            loss = ops.ce_loss(logits, labels) if labels is not None else None
+        return loss, logits, embeds, mask, labels

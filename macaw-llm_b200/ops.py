@@ -40,6 +40,12 @@ def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
     return None if t is None else t.data_ptr()
 
 
+# Optional per-launch CUDA-event profiling of the GEMM kernel (bench.py's live roofline): when PROFILE is a list, every
+# mm_gemm_fwd launch appends (TAG, flops, start_event, end_event) recorded on the launching stream.
+PROFILE = None
+TAG = "gemm"
+
+
 def launch_count() -> int:
     return int(_lib.load().mm_launch_count())
 
@@ -57,7 +63,14 @@ def gemm_raw(*, M, N, K, A, lda, B, ldb, Cout, ldc, batch=1, a_bs=0, b_bs=0, c_b
     a = GemmArgs(M, N, K, batch, batch2, A, lda, a_bs, a_bs2, B, ldb, b_bs, b_bs2, int(b_mn_major), Cout, ldc, c_bs,
                  c_bs2, int(c_fp32), epi, act, float(alpha), bias, bias_bs, row_scale, residual, ldr, r_bs, r_bs2,
                  res_row_mod, rope_cos, rope_sin, rope_T, rope_cols)
+    if PROFILE is None:
+        _check(_lib.load().mm_gemm_fwd(C.byref(a), _stream()), "mm_gemm_fwd")
+        return
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
     _check(_lib.load().mm_gemm_fwd(C.byref(a), _stream()), "mm_gemm_fwd")
+    e1.record()
+    PROFILE.append((TAG, 2.0 * M * N * K * batch * max(1, batch2), e0, e1))
 
 
 def linear(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, *, act: int = ACT_NONE,

@@ -181,8 +181,9 @@ def video_positional_encoding(L: int, h: int, dtype=torch.float32) -> Tensor:
     """create_positional_encoding (modeling.py:1095-1106), vectorised.  The reference computes, in fp32,
     div = exp(-(ln(10000)/h) * (2*i)) for even i (note 2*i with i already even — a non-standard frequency ladder),
     pe[pos, i] = sin(pos * div), pe[pos, i+1] = cos(pos * div).  Computed in fp32 exactly as written, then cast."""
-    i = torch.arange(0, h, 2, dtype=torch.float32)
-    div = torch.exp(-(math.log(10000.0) / h * (2 * i)))  # python double scalar * fp32 tensor -> fp32, as torch.tensor(.) does
+    # the exponent is a python double rounded to fp32 by torch.tensor(.), then exp() runs in fp32 (modeling.py:1102)
+    arg = torch.tensor([-(math.log(10000.0) / h * (2 * i)) for i in range(0, h, 2)], dtype=torch.float32)
+    div = torch.exp(arg)
     pos = torch.arange(L, dtype=torch.float32)[:, None]
     pe = torch.zeros(L, h, dtype=torch.float32)
     pe[:, 0::2] = torch.sin(pos * div)

@@ -32,8 +32,13 @@ def import_reference():
     from transformers import PretrainedConfig, PreTrainedModel
 
     mu.PretrainedConfig = PretrainedConfig  # shim 1
-    sys.path.insert(0, "/root/reference")
-    import modeling  # noqa
+    # load under a private module name so the repo's own drop-in `modeling` module is not shadowed
+    import importlib.util
+
+    spec = importlib.util.spec_from_file_location("_macaw_reference_modeling", "/root/reference/modeling.py")
+    modeling = importlib.util.module_from_spec(spec)
+    sys.modules["_macaw_reference_modeling"] = modeling
+    spec.loader.exec_module(modeling)
 
     _orig = PreTrainedModel.init_weights
 
@@ -62,7 +67,8 @@ CASES = [
     ("all3", 2, 16, ("image", "audio", "video"), 3, True),
     ("image", 1, 12, ("image",), 0, False),
     ("audio", 2, 10, ("audio",), 0, True),
-    ("text", 2, 9, (), 2, True),
+    # text-only WITH labels crashes in the reference itself (modeling.py:1043: empty float tensor cat -> float labels)
+    ("text", 2, 9, (), 2, False),
 ]
 
 
@@ -88,13 +94,14 @@ def main():
         o = O.forward(inp64, sd64, hp, dtype=torch.float64)
         e_emb = float((o["embeds"] - emb_r).abs().max())
         e_log = float((o["logits"] - out_r.logits).abs().max())
-        assert e_emb < 1e-9 and e_log < 1e-8, (name, e_emb, e_log)
+        # the reference softmaxes in fp32 even when run in fp64 (HF eager attention; modeling.py:214), hence 1e-6 not 1e-12
+        assert e_emb < 1e-6 and e_log < 1e-5, (name, e_emb, e_log)
         assert (mask_r is None) == (o["attention_mask"] is None) and (lab_r is None) == (o["labels"] is None)
         if mask_r is not None:
             assert torch.equal(mask_r.long(), o["attention_mask"])
         if lab_r is not None:
             assert torch.equal(lab_r.long(), o["labels"])
-            assert abs(float(out_r.loss) - float(o["loss"])) < 1e-9
+            assert abs(float(out_r.loss) - float(o["loss"])) < 1e-6
         print(f"[golden] {name}: oracle vs reference fp64 max|d| embeds {e_emb:.2e} logits {e_log:.2e}  T={emb_r.shape[1]}")
         np.savez_compressed(
             os.path.join(HERE, f"tiny_{name}.npz"),

@@ -1,0 +1,156 @@
+"""End-to-end parity of the CUDA path on the B200 against (a) the golden vectors minted from the unmodified reference
+and (b) the CPU oracle run on the SAME bf16-rounded weights and inputs.
+
+Tolerances (norm-wise relative error, ||ours - ref|| / ||ref||):
+  * int64 attention-mask / label prefix and the sequence layout: bit-exact.
+  * embeds (prefix + text) and logits vs the fp32 oracle on bf16-rounded weights: the CUDA path stores activations in
+    bf16 (one rounding = 2^-9 ~ 2e-3 per element, ~1.1e-3 norm-wise), so a chain of k bf16-stored stages cannot be
+    better than ~sqrt(k) * 1.1e-3.  Bars: 1e-2 on the aligned prefix rows, 3e-2 on logits; the measured values are
+    printed and recorded in DESIGN.md.
+  * vs the golden fixtures (fp32 reference, unrounded weights) the bf16 weight rounding adds to that; bar 5e-2.
+"""
+import pytest
+import torch
+
+from tests import helpers as H
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def tiny():
+    model, spec, hp, weights = H.build_tiny_model("cuda", torch.bfloat16)
+    return model, spec, hp, weights
+
+
+def _to_bf16_inputs(inp):
+    out = {}
+    for k, v in inp.items():
+        if isinstance(v, torch.Tensor) and v.is_floating_point():
+            out[k] = v.to(torch.bfloat16)
+        else:
+            out[k] = v
+    return out
+
+
+@pytest.mark.parametrize("name", ["all3", "image", "audio", "text"])
+def test_forward_vs_golden_and_oracle(tiny, name):
+    from oracle import macaw_oracle as O
+
+    model, spec, hp, weights = tiny
+    case = H.load_case(name)
+    inp = _to_bf16_inputs(H.case_inputs(spec, case))
+    dev_inp = {k: (v.cuda() if isinstance(v, torch.Tensor) else v) for k, v in inp.items()}
+    out = model(dev_inp)
+    emb, mask, labels = model.prepare_inputs_for_generation(dev_inp)
+    torch.cuda.synchronize()
+
+    # ---- layout / integer side: bit-exact against the reference fixture
+    g_emb = torch.from_numpy(case["embeds"])
+    assert tuple(emb.shape) == tuple(g_emb.shape)
+    assert torch.equal(mask.cpu(), torch.from_numpy(case["attention_mask"]))
+    if int(case["with_labels"]):
+        assert torch.equal(labels.cpu(), torch.from_numpy(case["labels"]))
+    else:
+        assert labels is None and out.loss is None
+    # text rows of the splice are pure gathers of bf16 table rows: bit-exact vs the bf16-rounded table
+    table = weights["llm.model.embed_tokens.weight"].to(torch.bfloat16)
+    n_prefix = emb.shape[1] - int(case["L"])
+    ids = inp["input_ids"]
+    assert torch.equal(emb[:, 0].cpu(), table[ids[:, 0]])
+    assert torch.equal(emb[:, 1 + n_prefix:].cpu(), table[ids[:, 1:]])
+
+    # ---- floating point: oracle on the same bf16-rounded weights / inputs
+    sd = H.bf16_round(weights)
+    o = O.forward({k: (v.float() if isinstance(v, torch.Tensor) and v.is_floating_point() else v) for k, v in inp.items()},
+                  sd, hp, dtype=torch.float32)
+    e_emb = H.rel_err(emb, o["embeds"])
+    e_pre = H.rel_err(emb[:, 1:1 + n_prefix], o["embeds"][:, 1:1 + n_prefix]) if n_prefix else 0.0
+    valid = torch.from_numpy(case["attention_mask"]).bool()
+    e_log = H.rel_err(out.logits.cpu()[valid], o["logits"][valid])
+    e_gold = H.rel_err(out.logits.cpu()[valid], torch.from_numpy(case["logits"])[valid])
+    print(f"\n[parity:{name}] prefix {e_pre:.3e}  embeds {e_emb:.3e}  logits {e_log:.3e}  logits-vs-golden {e_gold:.3e}")
+    assert e_pre < 1e-2 and e_emb < 1e-2
+    assert e_log < 3e-2
+    assert e_gold < 5e-2
+    if int(case["with_labels"]):
+        assert abs(float(out.loss) - float(o["loss"])) < 2e-2 * abs(float(o["loss"]))
+
+
+def test_encoders_vs_oracle(tiny):
+    from oracle import macaw_oracle as O
+
+    model, spec, hp, weights = tiny
+    sd = O._SD(H.bf16_round(weights))
+    inp = _to_bf16_inputs(H.case_inputs(spec, H.load_case("all3")))
+    img = model.encode_image(inp["images"].cuda())
+    aud = model.encode_audio(inp["audios"].cuda())
+    vid = model.encode_video_long(inp["videos"].cuda())
+    torch.cuda.synchronize()
+    r_img = O.clip_tokens(inp["images"].float(), sd.sub("image_encoder."), hp)
+    r_aud = O.whisper_encode(inp["audios"].float(), sd.sub("audio_encoder.encoder."), hp)
+    r_vid = O.encode_video_long(inp["videos"].float(), sd, hp)
+    e = (H.rel_err(img, r_img), H.rel_err(aud, r_aud), H.rel_err(vid, r_vid))
+    print(f"\n[parity:encoders] image {e[0]:.3e} audio {e[1]:.3e} video {e[2]:.3e}")
+    assert max(e) < 1e-2
+
+
+def test_video_pe_matches_reference_loop(tiny):
+    import numpy as np
+    import os
+
+    model = tiny[0]
+    pe = model.engine.video_pe(40, 24, torch.device("cuda"))
+    ref = torch.from_numpy(np.load(os.path.join(H.GOLDEN, "video_pe_40x24.npz"))["pe"])
+    assert torch.equal(pe.cpu(), ref.to(torch.bfloat16))
+
+
+def test_no_cpu_fallback():
+    model, spec, hp, weights = H.build_tiny_model("cpu", torch.bfloat16)
+    inp = H.case_inputs(spec, H.load_case("text"))
+    with pytest.raises(RuntimeError, match="no CPU"):
+        model(inp)
+
+
+def test_real_width_alignment_block():
+    """BASELINE config 1 shape on the GPU: 1 x 50 x 768 visual feats against a 32000 x 4096 table, 16 heads."""
+    from macaw_llm_b200 import ops
+    from macaw_llm_b200.engine import Engine
+    from oracle import macaw_oracle as O
+
+    torch.manual_seed(0)
+    E, V, C, H = 4096, 32000, 768, 16
+
+    class M(torch.nn.Module):
+        pass
+
+    m = M()
+    m.project_image = torch.nn.Conv1d(C, C, 48, 36)
+    m.transform_image_to_hidden = torch.nn.Linear(C, E)
+    m.image_align_attention = torch.nn.MultiheadAttention(E, H, dropout=0.1, add_bias_kv=True, add_zero_attn=True)
+    with torch.no_grad():
+        for p in m.parameters():
+            if p.dim() > 1:
+                p.normal_(0, 0.02)
+            else:
+                p.normal_(0, 0.02)
+        m.image_align_attention.in_proj_weight.mul_(3.0)
+    m = m.cuda().to(torch.bfloat16).eval()
+    table = (torch.randn(V, E) * 0.5).cuda().to(torch.bfloat16)
+    feats = torch.randn(1, 50, C).cuda().to(torch.bfloat16)
+    eng = Engine(m)
+    prefix = torch.zeros(1, 3, E, device="cuda", dtype=torch.bfloat16)
+    Lq = eng.align(feats, "image", table, prefix, 1)
+    torch.cuda.synchronize()
+    assert Lq == 1
+    sd = O._SD({k: v.detach().float().cpu() for k, v in m.state_dict().items()})
+    ref = O.align_block(feats.float().cpu(), table.float().cpu(), sd.sub("project_image."),
+                        sd.sub("transform_image_to_hidden."), sd.sub("image_align_attention."), 36, H)
+    e = H_rel(prefix[:, 1:2], ref)
+    print(f"\n[parity:align 32000x4096] {e:.3e}")
+    assert e < 1e-2
+    assert float(prefix[:, 0].abs().max()) == 0 and float(prefix[:, 2].abs().max()) == 0
+
+
+def H_rel(a, b):
+    return H.rel_err(a, b)

@@ -1,0 +1,92 @@
+"""CPU tier: the oracle (oracle/macaw_oracle.py) against the golden vectors minted from the unmodified reference, and
+— when /root/reference exists (build container) — against the live reference in-process."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import macaw_oracle as O
+from tests import helpers as H
+from tests.golden import gen
+
+
+@pytest.fixture(scope="module")
+def tiny_weights():
+    spec, hp, shapes = H.load_shapes()
+    return spec, hp, gen.make_weights(shapes, seed=0)
+
+
+@pytest.mark.parametrize("name", ["all3", "image", "audio", "text"])
+def test_oracle_matches_golden(tiny_weights, name):
+    spec, hp, weights = tiny_weights
+    case = H.load_case(name)
+    o = O.forward(H.case_inputs(spec, case), weights, hp, dtype=torch.float32)
+    g_emb, g_log = torch.from_numpy(case["embeds"]), torch.from_numpy(case["logits"])
+    assert tuple(o["embeds"].shape) == tuple(g_emb.shape)
+    assert H.rel_err(o["embeds"], g_emb) < 1e-5
+    assert H.rel_err(o["logits"], g_log) < 1e-4
+    # integer side is bit-exact
+    assert torch.equal(o["attention_mask"], torch.from_numpy(case["attention_mask"]))
+    if int(case["with_labels"]):
+        assert torch.equal(o["labels"], torch.from_numpy(case["labels"]))
+        assert abs(float(o["loss"]) - float(case["loss"])) < 1e-4 * abs(float(case["loss"]))
+    else:
+        assert o["labels"] is None and o["loss"] is None
+
+
+def test_layout_order_and_prefix_lengths(tiny_weights):
+    """[BOS, <image> img </image>, <audio> aud </audio>, <video> vid </video>, text[1:]]."""
+    spec, hp, weights = tiny_weights
+    case = H.load_case("all3")
+    inp = H.case_inputs(spec, case)
+    emb, mask, labels = O.prepare_inputs(inp, weights, hp)
+    table = weights["llm.model.embed_tokens.weight"]
+    n_img = (256 - 48) // 36 + 1
+    n_aud = (1500 - 240) // 220 + 1
+    n_vid = (spec["n_frames"] * 256 - 36) // 30 + 1
+    pos = 1
+    for name, n in (("image", n_img), ("audio", n_aud), ("video", n_vid)):
+        assert torch.equal(emb[:, pos], table[inp[f"{name}_starts"].long()])
+        assert torch.equal(emb[:, pos + n + 1], table[inp[f"{name}_ends"].long()])
+        pos += n + 2
+    assert emb.shape[1] == pos + inp["input_ids"].shape[1] - 1
+    assert torch.equal(emb[:, pos:], table[inp["input_ids"][:, 1:]])
+    assert torch.equal(mask[:, : pos - 1], torch.ones(2, pos - 1, dtype=torch.int64))
+    assert torch.equal(labels[:, : pos - 1], torch.full((2, pos - 1), -100))
+
+
+def test_video_pe_fixture():
+    ref = np.load(os.path.join(H.GOLDEN, "video_pe_40x24.npz"))["pe"]
+    assert np.array_equal(O.video_positional_encoding(40, 24).numpy(), ref)
+
+
+def test_mha_restatement_vs_torch_module():
+    """nn.MultiheadAttention (installed torch) vs the restatement, fp64 — the alignment shape in miniature."""
+    torch.manual_seed(0)
+    E, Hh, V, B, Lq = 32, 4, 50, 3, 5
+    mha = torch.nn.MultiheadAttention(E, Hh, dropout=0.1, add_bias_kv=True, add_zero_attn=True).double().eval()
+    with torch.no_grad():
+        mha.in_proj_bias.normal_()
+        mha.out_proj.bias.normal_()
+    table = torch.randn(V, E, dtype=torch.float64)
+    q = torch.randn(Lq, B, E, dtype=torch.float64)
+    kv = table.unsqueeze(1).repeat(1, B, 1)
+    ref = mha(q, kv, kv)[0]
+    got = O.mha_forward(q, kv, kv, O._SD(dict(mha.state_dict()), torch.float64), Hh)
+    assert float((ref - got).abs().max()) < 1e-12
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference"), reason="reference tree only exists in the build container")
+def test_oracle_vs_live_reference():
+    from tests.golden import make_golden as MG
+
+    modeling = MG.import_reference()
+    cfg, model, shapes, weights = MG.build_reference(modeling, gen.TINY)
+    hp = O.hp_from_config(cfg)
+    inp = gen.make_inputs(gen.TINY, 2, 11, seed=7, modalities=("image", "audio"), pad_tail=2)
+    with torch.no_grad():
+        out = model(inp)
+    o = O.forward(inp, {k: v for k, v in model.state_dict().items()}, hp)
+    assert H.rel_err(o["logits"], out.logits) < 1e-4
+    assert abs(float(o["loss"]) - float(out.loss)) < 1e-4

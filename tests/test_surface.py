@@ -1,0 +1,102 @@
+"""CPU tier: the drop-in class surface — constructor kwargs, attribute / state_dict names,
+config round trip, loud failure without CUDA, batch sharding under a world_size-2 gloo group."""
+import os
+import sys
+
+import pytest
+import torch
+
+from tests import helpers as H
+from tests.golden import gen
+
+
+def _tiny_cfg():
+    from macaw_llm_b200.modeling import MM_LLMs_Config
+
+    clip, whisper, llama = gen.build_configs(gen.TINY)
+    return MM_LLMs_Config(n_frames=2, attention_heads=2, clip_config=clip, whisper_config=whisper, llm_config=llama)
+
+
+def test_state_dict_keys_and_shapes_match_reference():
+    from macaw_llm_b200.modeling import MM_LLMs
+
+    _, _, shapes = H.load_shapes()  # keys/shapes of the live reference model (tests/golden/make_golden.py)
+    sd = MM_LLMs(_tiny_cfg()).state_dict()
+    assert set(sd) == set(shapes)
+    assert all(tuple(sd[k].shape) == shapes[k] for k in shapes)
+
+
+def test_config_surface_roundtrip(tmp_path):
+    import modeling  # root-level drop-in module name used by the reference's callers
+
+    cfg = _tiny_cfg()
+    assert modeling.MM_LLMs_Config is modeling.MM_LLMsConfig
+    assert cfg.model_type == "mm_llms" and cfg.hidden_size == 256
+    d = cfg.to_dict()
+    for k in ("image_config", "audio_config", "llm_config", "n_frames", "attention_heads", "image_conv_kernel",
+              "image_conv_stride", "video_conv_kernel", "video_conv_stride", "audio_conv_kernel", "audio_conv_stride",
+              "hidden_size", "model_type"):
+        assert k in d
+    cfg.save_pretrained(tmp_path)
+    c2 = modeling.MM_LLMs_Config.from_pretrained(tmp_path)
+    assert (c2.n_frames, c2.attention_heads, c2.audio_conv_kernel) == (2, 2, 240)
+    assert c2.llm_config.hidden_size == 256 and c2.image_config.projection_dim == 192
+    dflt = modeling.MM_LLMs_Config(clip_config=cfg.image_config, whisper_config=cfg.audio_config, llm_config=cfg.llm_config)
+    assert (dflt.n_frames, dflt.attention_heads, dflt.image_conv_kernel, dflt.image_conv_stride, dflt.video_conv_kernel,
+            dflt.video_conv_stride, dflt.audio_conv_kernel, dflt.audio_conv_stride) == (6, 8, 48, 36, 36, 30, 240, 220)
+
+
+def test_reference_caller_surface():
+    """What run_clm_llms.py / llm_trainer.py reach for."""
+    from macaw_llm_b200.modeling import MM_LLMs
+
+    m = MM_LLMs(_tiny_cfg())
+    for attr in ("image_encoder", "video_encoder", "audio_encoder", "llm", "prepare_inputs_for_generation",
+                 "encode_image", "encode_audio", "encode_video_long"):
+        assert hasattr(m, attr)
+    m.llm.resize_token_embeddings(512 + 7)  # run_clm_llms.py:495
+    assert m.llm.model.embed_tokens.weight.shape[0] == 519 and m.llm.lm_head.weight.shape[0] == 519
+    frozen = [n for n, _ in m.named_parameters() if "encoder" in n]  # run_clm_llms.py:390-393 name test
+    assert frozen and all(n.split(".")[0] in ("image_encoder", "video_encoder", "audio_encoder") or "encoder" in n for n in frozen)
+    with pytest.raises(NotImplementedError):
+        m({"inference": True})
+
+
+def test_cpu_parameters_raise():
+    model, spec, hp, _ = H.build_tiny_model("cpu", torch.bfloat16)
+    with pytest.raises(RuntimeError, match="no CPU"):
+        model(H.case_inputs(spec, H.load_case("text")))
+
+
+def _gloo_worker(rank, world, port, q):
+    import torch.distributed as dist
+
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    from macaw_llm_b200 import dist as D
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    inp = gen.make_inputs(gen.TINY, 5, 9, seed=3, modalities=("image",))
+    sh = D.shard_inputs(inp, rank, world)
+    lo, hi = D.shard_range(5, rank, world)
+    ok = torch.equal(sh["input_ids"], inp["input_ids"][lo:hi]) and sh["images"].shape[0] == hi - lo and sh["videos"] is None
+    ms = D.max_over_ranks(10.0 + rank)
+    loss = D.weighted_mean_loss(float(rank + 1) * (hi - lo), hi - lo)
+    q.put((rank, ok, lo, hi, ms, loss))
+    dist.destroy_process_group()
+
+
+def test_sharding_and_reductions_world2_gloo():
+    import torch.multiprocessing as mp
+
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + os.getpid() % 1000
+    ps = [ctx.Process(target=_gloo_worker, args=(r, 2, port, q)) for r in range(2)]
+    [p.start() for p in ps]
+    res = sorted(q.get(timeout=120) for _ in ps)
+    [p.join(60) for p in ps]
+    assert [r[1] for r in res] == [True, True]
+    assert (res[0][2], res[0][3], res[1][2], res[1][3]) == (0, 3, 3, 5)      # contiguous cover of the global batch
+    assert res[0][4] == res[1][4] == 11.0                                      # max over ranks
+    assert abs(res[0][5] - (1 * 3 + 2 * 2) / 5) < 1e-12                        # token-weighted global mean
