@@ -134,7 +134,6 @@ def test_real_width_alignment_block():
                 p.normal_(0, 0.02)
             else:
                 p.normal_(0, 0.02)
-        m.image_align_attention.in_proj_weight.mul_(3.0)
     m = m.cuda().to(torch.bfloat16).eval()
     table = (torch.randn(V, E) * 0.5).cuda().to(torch.bfloat16)
     feats = torch.randn(1, 50, C).cuda().to(torch.bfloat16)
