@@ -132,6 +132,18 @@ def load_peaks():
     return 6650.0, 1590.0, 1400.0, "fallback"
 
 
+def usable_cores() -> int:
+    """Host threads this process may actually use: min(affinity, cgroup v2 cpu.max quota)."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        quota, period = open("/sys/fs/cgroup/cpu.max").read().split()
+        if quota != "max":
+            n = min(n, max(1, int(int(quota) / int(period))))
+    except Exception:
+        pass
+    return n
+
+
 def cpu_oracle_sample(cfgs, hyper, L, steps, warmup, seed=1234, state_dict=None, budget_s=240.0):
     """Time the CPU oracle (a port of the reference's algorithm, oracle/macaw_oracle.py) on a bounded sample of the
     workload: ONE sample (B=1) image+audio+text, full model depth, fp32, all host threads.  The reference is linear in
@@ -142,7 +154,7 @@ def cpu_oracle_sample(cfgs, hyper, L, steps, warmup, seed=1234, state_dict=None,
     clip, whisper, llama = cfgs
     cfg = MM_LLMs_Config(clip_config=clip, whisper_config=whisper, llm_config=llama, **hyper)
     hp = O.hp_from_config(cfg)
-    cores = os.cpu_count() or 1
+    cores = usable_cores()
     torch.set_num_threads(cores)
     if state_dict is None:
         # identical family of random weights, generated on the host (the oracle only needs a state_dict)

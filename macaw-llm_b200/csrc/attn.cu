@@ -53,16 +53,15 @@ __device__ __forceinline__ void mma_bf16_16816(float (&c)[4], const uint32_t (&a
 }
 
 constexpr int kQTile = 64;
-constexpr int kKTile = 64;
 
-template <int HD>
+template <int HD, int ROWS>
 __device__ __forceinline__ void load_tile(bf16* sdst, const bf16* gbase, long long row_stride, int row0, int nrows_valid,
                                           int tid) {
-  // 64 rows x HD bf16, padded row stride HD + 8; 16-byte chunks
+  // ROWS rows x HD bf16, padded row stride HD + 8; 16-byte chunks
   constexpr int LDS = HD + 8;
   constexpr int CPR = HD / 8;  // chunks per row
 #pragma unroll
-  for (int c = tid; c < kKTile * CPR; c += 128) {
+  for (int c = tid; c < ROWS * CPR; c += 128) {
     const int r = c / CPR, cc = c % CPR;
     const bool ok = (row0 + r) < nrows_valid;
     const bf16* src = gbase + static_cast<long long>(ok ? (row0 + r) : 0) * row_stride + cc * 8;
@@ -70,8 +69,10 @@ __device__ __forceinline__ void load_tile(bf16* sdst, const bf16* gbase, long lo
   }
 }
 
-template <int HD>
-__global__ void __launch_bounds__(128) flash_attn_kernel(const AttnKParams p) {
+// KT = keys per tile, MINB = CTAs per SM the register allocation must allow
+template <int HD, int KT, int MINB>
+__global__ void __launch_bounds__(128, MINB) flash_attn_kernel(const AttnKParams p) {
+  constexpr int kKTile = KT;
   constexpr int LDS = HD + 8;
   constexpr int KC = HD / 16;  // k-chunks of the QK^T contraction
   constexpr int NB = HD / 8;   // n-blocks of the output
@@ -79,6 +80,7 @@ __global__ void __launch_bounds__(128) flash_attn_kernel(const AttnKParams p) {
   bf16* sQ = reinterpret_cast<bf16*>(smem_raw_attn);
   bf16* sK = sQ + kQTile * LDS;
   bf16* sV = sK + 2 * kKTile * LDS;
+  int* sM = reinterpret_cast<int*>(sV + 2 * kKTile * LDS);  // key-mask tile, double-buffered
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int m0 = blockIdx.x * kQTile, h = blockIdx.y, b = blockIdx.z;
@@ -92,12 +94,13 @@ __global__ void __launch_bounds__(128) flash_attn_kernel(const AttnKParams p) {
   if (p.causal) kv_end = min(p.Tk, m0 + kQTile + shift);
   const int n_tiles = kv_end > 0 ? (kv_end + kKTile - 1) / kKTile : 0;
 
-  load_tile<HD>(sQ, qg, p.q_ts, m0, p.Tq, tid);
+  load_tile<HD, kQTile>(sQ, qg, p.q_ts, m0, p.Tq, tid);
   if (n_tiles > 0) {
-    load_tile<HD>(sK, kg, p.k_ts, 0, p.Tk, tid);
-    load_tile<HD>(sV, vg, p.v_ts, 0, p.Tk, tid);
+    load_tile<HD, KT>(sK, kg, p.k_ts, 0, p.Tk, tid);
+    load_tile<HD, KT>(sV, vg, p.v_ts, 0, p.Tk, tid);
   }
   cp_async_commit();
+  if (kmask != nullptr && tid < KT) sM[tid] = (tid < p.Tk) ? kmask[tid] : 0;
 
   uint32_t qf[KC][4];
   float o[NB][4];
@@ -110,9 +113,13 @@ __global__ void __launch_bounds__(128) flash_attn_kernel(const AttnKParams p) {
   for (int j = 0; j < n_tiles; ++j) {
     const int buf = j & 1;
     if (j + 1 < n_tiles) {
-      load_tile<HD>(sK + (buf ^ 1) * kKTile * LDS, kg, p.k_ts, (j + 1) * kKTile, p.Tk, tid);
-      load_tile<HD>(sV + (buf ^ 1) * kKTile * LDS, vg, p.v_ts, (j + 1) * kKTile, p.Tk, tid);
+      load_tile<HD, KT>(sK + (buf ^ 1) * kKTile * LDS, kg, p.k_ts, (j + 1) * kKTile, p.Tk, tid);
+      load_tile<HD, KT>(sV + (buf ^ 1) * kKTile * LDS, vg, p.v_ts, (j + 1) * kKTile, p.Tk, tid);
       cp_async_commit();
+      if (kmask != nullptr && tid < KT) {
+        const int key = (j + 1) * kKTile + tid;
+        sM[(buf ^ 1) * KT + tid] = (key < p.Tk) ? kmask[key] : 0;
+      }
       cp_async_wait<1>();
     } else {
       cp_async_wait<0>();
@@ -127,15 +134,16 @@ __global__ void __launch_bounds__(128) flash_attn_kernel(const AttnKParams p) {
       }
     }
 
-    // ---- S = Q K^T (16 x 64 per warp)
-    float s[8][4];
+    // ---- S = Q K^T (16 x KT per warp)
+    constexpr int SB = KT / 8;  // 8-key score blocks
+    float s[SB][4];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) s[i][0] = s[i][1] = s[i][2] = s[i][3] = 0.f;
+    for (int i = 0; i < SB; ++i) s[i][0] = s[i][1] = s[i][2] = s[i][3] = 0.f;
     const bf16* kt = sK + buf * kKTile * LDS;
 #pragma unroll
     for (int kc = 0; kc < KC; ++kc) {
 #pragma unroll
-      for (int np = 0; np < 4; ++np) {  // pairs of 8-key blocks
+      for (int np = 0; np < SB / 2; ++np) {  // pairs of 8-key blocks
         uint32_t b0, b1, b2, b3;
         const bf16* a = kt + (np * 16 + (lane & 7) + (lane >> 4) * 8) * LDS + kc * 16 + ((lane >> 3) & 1) * 8;
         ldsm_x4(smem_u32(a), b0, b1, b2, b3);
@@ -148,14 +156,14 @@ __global__ void __launch_bounds__(128) flash_attn_kernel(const AttnKParams p) {
     const int key0 = j * kKTile + (lane & 3) * 2;
     float mx[2] = {-INFINITY, -INFINITY};
 #pragma unroll
-    for (int nb = 0; nb < 8; ++nb) {
+    for (int nb = 0; nb < SB; ++nb) {
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         const int key = key0 + nb * 8 + (e & 1);
         const int qrow = qrow0 + (e >> 1) * 8;
         bool ok = key < p.Tk;
         if (p.causal) ok = ok && (key <= qrow + shift);
-        if (kmask != nullptr && ok) ok = kmask[key] != 0;
+        if (kmask != nullptr && ok) ok = sM[buf * KT + (key - j * kKTile)] != 0;
         const float v = ok ? s[nb][e] * p.scale_log2 : -INFINITY;
         s[nb][e] = v;
         mx[e >> 1] = fmaxf(mx[e >> 1], v);
@@ -174,7 +182,7 @@ __global__ void __launch_bounds__(128) flash_attn_kernel(const AttnKParams p) {
     }
     float ls[2] = {0.f, 0.f};
 #pragma unroll
-    for (int nb = 0; nb < 8; ++nb) {
+    for (int nb = 0; nb < SB; ++nb) {
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         const float pv = exp2f(s[nb][e] - mx[e >> 1]);
@@ -245,13 +253,13 @@ __global__ void __launch_bounds__(128) flash_attn_kernel(const AttnKParams p) {
   }
 }
 
-template <int HD>
+template <int HD, int KT, int MINB>
 static int launch_attn(const AttnKParams& p, cudaStream_t st) {
-  constexpr size_t smem = static_cast<size_t>(kQTile + 4 * kKTile) * (HD + 8) * sizeof(bf16);
+  constexpr size_t smem = static_cast<size_t>(kQTile + 4 * KT) * (HD + 8) * sizeof(bf16) + 2 * KT * sizeof(int);
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e =
-        cudaFuncSetAttribute(flash_attn_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+        cudaFuncSetAttribute(flash_attn_kernel<HD, KT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     if (e != cudaSuccess) {
       set_error("mm_attn_fwd: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
       return 2;
@@ -259,7 +267,7 @@ static int launch_attn(const AttnKParams& p, cudaStream_t st) {
     attr_set = true;
   }
   dim3 grid((p.Tq + kQTile - 1) / kQTile, p.H, p.B);
-  flash_attn_kernel<HD><<<grid, 128, smem, st>>>(p);
+  flash_attn_kernel<HD, KT, MINB><<<grid, 128, smem, st>>>(p);
   return check_launch("mm_attn_fwd");
 }
 
@@ -289,8 +297,8 @@ extern "C" int32_t mm_attn_fwd(const mm_attn_args* a, void* stream) {
   p.scale_log2 = a->scale * 1.4426950408889634f;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   switch (a->head_dim) {
-    case 64: return launch_attn<64>(p, st);
-    case 96: return launch_attn<96>(p, st);
-    default: return launch_attn<128>(p, st);
+    case 64: return launch_attn<64, 64, 4>(p, st);
+    case 96: return launch_attn<96, 64, 3>(p, st);
+    default: return launch_attn<128, 32, 4>(p, st);
   }
 }
