@@ -107,6 +107,7 @@ typedef struct mm_attn_args {
   const int32_t* key_mask;
   int32_t causal;
   float scale;
+  int32_t impl; /* 0 = auto (tcgen05 kernel for head_dim 64/128, mma.sync kernel for 96); 1 = force the mma.sync kernel */
 } mm_attn_args;
 int32_t mm_attn_fwd(const mm_attn_args* args, void* stream);
 

@@ -40,7 +40,7 @@ class AttnArgs(C.Structure):
         ("k_bs", c_i64), ("k_ts", c_i64), ("k_hs", c_i64),
         ("v_bs", c_i64), ("v_ts", c_i64), ("v_hs", c_i64),
         ("o_bs", c_i64), ("o_ts", c_i64), ("o_hs", c_i64),
-        ("key_mask", c_vp), ("causal", c_i32), ("scale", c_f32),
+        ("key_mask", c_vp), ("causal", c_i32), ("scale", c_f32), ("impl", c_i32),
     ]
 
 

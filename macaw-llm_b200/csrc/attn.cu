@@ -273,6 +273,9 @@ static int launch_attn(const AttnKParams& p, cudaStream_t st) {
 
 }  // namespace mm
 
+namespace mm {
+int attn_tcgen05_dispatch(const mm_attn_args* a, cudaStream_t st);
+}
 using namespace mm;
 
 extern "C" int32_t mm_attn_fwd(const mm_attn_args* a, void* stream) {
@@ -286,6 +289,9 @@ extern "C" int32_t mm_attn_fwd(const mm_attn_args* a, void* stream) {
   MM_REQUIRE(((uintptr_t)a->q % 16 == 0) && ((uintptr_t)a->k % 16 == 0) && ((uintptr_t)a->v % 16 == 0) &&
                  ((uintptr_t)a->out % 16 == 0),
              "mm_attn_fwd: pointers must be 16-byte aligned");
+  // head_dim 64 / 128: tcgen05 kernel (attn_tcgen05.cu); impl == 1 forces the mma.sync kernel below (tests)
+  if ((a->head_dim == 64 || a->head_dim == 128) && a->scale > 0.f && a->impl != 1)
+    return attn_tcgen05_dispatch(a, reinterpret_cast<cudaStream_t>(stream));
   AttnKParams p;
   p.q = (const bf16*)a->q; p.k = (const bf16*)a->k; p.v = (const bf16*)a->v; p.out = (bf16*)a->out;
   p.B = a->B; p.H = a->H; p.Tq = a->Tq; p.Tk = a->Tk;

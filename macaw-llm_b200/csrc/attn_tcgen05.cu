@@ -1,0 +1,403 @@
+// Flash attention on the 5th-gen tensor cores (tcgen05 + TMEM + TMA) for head_dim 64 / 128.
+//
+// One CTA = 128 queries of one (batch, head).  Warp roles:
+//   warp 0      : TMA producer — Q once, then K / V tiles of 128 keys into 2-stage rings (128B swizzle)
+//   warp 1      : single-thread tcgen05.mma issuer:  S_j = Q K_j^T (TMEM, double-buffered)  and  O += P_j V_j (TMEM)
+//   warps 2..5  : softmax — ONE THREAD PER QUERY ROW (tcgen05.ld 32x32b gives each thread its row, so the row max /
+//                 row sum need no shuffles); writes P_j as bf16 into a 128B-swizzled smem tile that is the A operand
+//                 of the PV MMA; V is consumed as an MN-major B operand straight from its row-major layout.
+// S_{j+2} and PV_j are issued while the softmax warps work on S_{j+1}, so tensor pipe and MUFU overlap.
+// O stays in TMEM across key tiles; it is rescaled (tcgen05.ld -> scale -> tcgen05.st) only when a row's running max
+// grows by more than 2^8 since the max the accumulator is expressed in ("lazy rescale"); P and the row sums use that
+// same reference max, so the final O / l is exact.
+//
+// Masking: causal (key j visible to query i iff j <= i + Tk - Tq), key padding mask, and the Tk bound, evaluated as
+// 32-bit masks per 32-key chunk.  Rows with every key masked produce zeros (see DESIGN.md "unspecified rows").
+//
+// Reference call sites replaced: see include/macaw_b200.h (mm_attn_fwd); the mma.sync kernel in attn.cu remains for
+// head_dim 96 (video-long self-attention).
+#include "common.cuh"
+#include "ptx.cuh"
+#include "../../include/macaw_b200.h"
+
+namespace mm {
+
+struct FaParams {
+  bf16* out;
+  int B, H, Tq, Tk;
+  long long o_bs, o_ts, o_hs;
+  const int* key_mask;
+  int causal;
+  float scale_log2;
+};
+
+constexpr int kFaMQ = 128;  // queries per CTA
+constexpr int kFaKT = 128;  // keys per tile
+constexpr float kFaTau = 8.0f;  // lazy-rescale threshold (log2 domain)
+
+template <int HD>
+__host__ __device__ constexpr size_t fa_smem_bytes() {
+  // Q + 2 K stages + 2 V stages + 2 P buffers + barriers + alignment slack
+  return 1024 + (size_t)(HD / 64) * 16384 * 5 + 2 * 32768 + 256;
+}
+
+template <int HD>
+__global__ void __launch_bounds__(192, 1)
+fa_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                  const __grid_constant__ CUtensorMap tmV, const FaParams p) {
+  constexpr int KB = HD / 64;                 // 64-column blocks of the head dim
+  constexpr uint32_t QB = KB * 16384;         // bytes of Q, and of one K / V stage
+  constexpr uint32_t IDESC_S = make_idesc_bf16(kFaMQ, kFaKT, false, false);
+  constexpr uint32_t IDESC_O = make_idesc_bf16(kFaMQ, HD, false, true);
+  constexpr uint32_t S_COL = 0, O_COL = 256;  // TMEM columns: S0 [0,128), S1 [128,256), O [256, 256+HD)
+
+  extern __shared__ uint8_t fa_smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(fa_smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;
+  uint8_t* sK = sQ + QB;
+  uint8_t* sV = sK + 2 * QB;
+  uint8_t* sP = sV + 2 * QB;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * 32768);
+  uint64_t* bar_q = bars;            // 1
+  uint64_t* bar_k = bars + 1;        // 2
+  uint64_t* bar_v = bars + 3;        // 2
+  uint64_t* bar_kfree = bars + 5;    // 2
+  uint64_t* bar_vfree = bars + 7;    // 2
+  uint64_t* bar_s = bars + 9;        // 2
+  uint64_t* bar_sfree = bars + 11;   // 2
+  uint64_t* bar_p = bars + 13;       // 2
+  uint64_t* bar_pfree = bars + 15;   // 2
+  uint64_t* bar_o = bars + 17;       // 1
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 18);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int mt = gridDim.x - 1 - blockIdx.x;  // heavy (late, causal) tiles first
+  const int m0 = mt * kFaMQ, h = blockIdx.y, b = blockIdx.z;
+  const int shift = p.Tk - p.Tq;
+  int kv_end = p.Tk;
+  if (p.causal) kv_end = min(p.Tk, m0 + kFaMQ + shift);
+  const int n_tiles = kv_end > 0 ? (kv_end + kFaKT - 1) / kFaKT : 0;
+
+  if (warp == 0 && elect_one()) {
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmK);
+    tma_prefetch_desc(&tmV);
+  }
+  if (warp == 1) {
+    if (elect_one()) {
+      mbar_init(bar_q, 1);
+      mbar_init(bar_o, 1);
+      for (int i = 0; i < 2; ++i) {
+        mbar_init(&bar_k[i], 1);
+        mbar_init(&bar_v[i], 1);
+        mbar_init(&bar_kfree[i], 1);
+        mbar_init(&bar_vfree[i], 1);
+        mbar_init(&bar_s[i], 1);
+        mbar_init(&bar_sfree[i], 4);
+        mbar_init(&bar_p[i], 4);
+        mbar_init(&bar_pfree[i], 1);
+      }
+      fence_mbar_init();
+    }
+    __syncwarp();
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (elect_one() && n_tiles > 0) {
+      mbar_arrive_expect_tx(bar_q, QB);
+#pragma unroll
+      for (int kb = 0; kb < KB; ++kb) tma_load_4d(&tmQ, bar_q, sQ + kb * 16384, kb * 64, m0, h, b);
+      for (int j = 0; j < n_tiles; ++j) {
+        const int st = j & 1;
+        const uint32_t par = ((j >> 1) - 1) & 1;  // parity of the (j-2)-th use of this stage
+        if (j >= 2) mbar_wait(&bar_kfree[st], par);
+        mbar_arrive_expect_tx(&bar_k[st], QB);
+#pragma unroll
+        for (int kb = 0; kb < KB; ++kb)
+          tma_load_4d(&tmK, &bar_k[st], sK + st * QB + kb * 16384, kb * 64, j * kFaKT, h, b);
+        if (j >= 2) mbar_wait(&bar_vfree[st], par);
+        mbar_arrive_expect_tx(&bar_v[st], QB);
+#pragma unroll
+        for (int kb = 0; kb < KB; ++kb)
+          tma_load_4d(&tmV, &bar_v[st], sV + st * QB + kb * 16384, kb * 64, j * kFaKT, h, b);
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (elect_one() && n_tiles > 0) {
+      auto issue_s = [&](int jj) {
+        const int st = jj & 1;
+        mbar_wait(&bar_k[st], (jj >> 1) & 1);
+        if (jj >= 2) mbar_wait(&bar_sfree[st], ((jj >> 1) - 1) & 1);
+        tc_fence_after();
+        const uint32_t qa = smem_u32(sQ), ka = smem_u32(sK + st * QB);
+#pragma unroll
+        for (int k = 0; k < HD / 16; ++k) {
+          const uint64_t ad = make_sdesc_sw128(qa + (k >> 2) * 16384 + (k & 3) * 32, 16, 1024);
+          const uint64_t bd = make_sdesc_sw128(ka + (k >> 2) * 16384 + (k & 3) * 32, 16, 1024);
+          umma_bf16(tmem_base + S_COL + st * kFaKT, ad, bd, IDESC_S, k != 0 ? 1u : 0u);
+        }
+        umma_commit(&bar_s[st]);
+        umma_commit(&bar_kfree[st]);
+      };
+      mbar_wait(bar_q, 0);
+      issue_s(0);
+      if (n_tiles > 1) issue_s(1);
+      for (int j = 0; j < n_tiles; ++j) {
+        const int st = j & 1;
+        mbar_wait(&bar_p[st], (j >> 1) & 1);
+        mbar_wait(&bar_v[st], (j >> 1) & 1);
+        tc_fence_after();
+        const uint32_t pa = smem_u32(sP + st * 32768), va = smem_u32(sV + st * QB);
+#pragma unroll
+        for (int k = 0; k < kFaKT / 16; ++k) {
+          const uint64_t ad = make_sdesc_sw128(pa + (k >> 2) * 16384 + (k & 3) * 32, 16, 1024);
+          // V: MN-major B (head dim contiguous); 64-column blocks 16 KiB apart (LBO), 8-key groups 1 KiB apart (SBO)
+          const uint64_t bd = make_sdesc_sw128(va + k * 2048, 16384, 1024);
+          umma_bf16(tmem_base + O_COL, ad, bd, IDESC_O, (j | k) != 0 ? 1u : 0u);
+        }
+        umma_commit(&bar_pfree[st]);
+        umma_commit(&bar_vfree[st]);
+        if (j + 2 < n_tiles) issue_s(j + 2);
+      }
+      umma_commit(bar_o);
+    }
+  } else {
+    // ------------------------------------------------------------------ softmax warps: one thread per query row
+    const int q = warp & 3;
+    const int r = q * 32 + lane;  // row within the tile == TMEM lane
+    const int qrow = m0 + r;
+    const uint32_t lane_base = static_cast<uint32_t>(q * 32) << 16;
+    const int* kmask = p.key_mask ? p.key_mask + static_cast<long long>(b) * p.Tk : nullptr;
+    float m_used = -INFINITY;  // reference max the accumulator / row sum are expressed in (log2 domain)
+    float l = 0.f;
+    const int sw = r & 7;
+
+    for (int j = 0; j < n_tiles; ++j) {
+      const int st = j & 1;
+      mbar_wait(&bar_s[st], (j >> 1) & 1);
+      tc_fence_after();
+      const uint32_t s_addr = tmem_base + lane_base + S_COL + st * kFaKT;
+      const int key0 = j * kFaKT;
+      // per-32-key validity bits: Tk bound + key padding mask (warp-cooperative) & causal limit (per row)
+      uint32_t okb[4];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const int key = key0 + c * 32 + lane;
+        bool ok = key < p.Tk;
+        if (ok && kmask != nullptr) ok = kmask[key] != 0;
+        uint32_t bits = __ballot_sync(0xffffffffu, ok);
+        if (p.causal) {
+          const int lim = qrow + shift - (key0 + c * 32);  // keys with index <= lim inside this chunk are visible
+          bits &= lim >= 31 ? 0xffffffffu : (lim < 0 ? 0u : ((2u << lim) - 1u));
+        }
+        okb[c] = bits;
+      }
+      // ---- pass 1: row max
+      float mx = -INFINITY;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        uint32_t v[32];
+        tmem_ld32(s_addr + c * 32, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+          if (okb[c] & (1u << i)) mx = fmaxf(mx, __uint_as_float(v[i]));
+      }
+      mx *= p.scale_log2;  // scale > 0, so max commutes with the scaling
+      // ---- decide the reference max for this tile
+      float alpha = 1.0f;
+      bool rescale = false;
+      if (mx > m_used + kFaTau || m_used == -INFINITY) {
+        if (mx != -INFINITY) {
+          if (m_used != -INFINITY) {
+            alpha = exp2f(m_used - mx);
+            rescale = true;
+          }
+          m_used = mx;
+        }
+      }
+      const float m_ref = (m_used == -INFINITY) ? 0.f : m_used;
+      // ---- pass 2: P = exp2(s * scale - m_ref) -> bf16 -> swizzled smem (A operand of the PV MMA)
+      if (j >= 2) mbar_wait(&bar_pfree[st], ((j >> 1) - 1) & 1);  // PV_{j-2} has finished reading this P buffer
+      uint8_t* prow = sP + st * 32768 + r * 128;
+      float psum = 0.f;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        uint32_t v[32];
+        tmem_ld32(s_addr + c * 32, v);
+        tmem_ld_wait();
+        float e[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const float x = exp2f(fmaf(__uint_as_float(v[i]), p.scale_log2, -m_ref));
+          e[i] = (okb[c] & (1u << i)) ? x : 0.f;
+          psum += e[i];
+        }
+        uint8_t* blk = prow + (c >> 1) * 16384;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          uint4 u;
+          u.x = pack_bf16x2(e[8 * i + 0], e[8 * i + 1]);
+          u.y = pack_bf16x2(e[8 * i + 2], e[8 * i + 3]);
+          u.z = pack_bf16x2(e[8 * i + 4], e[8 * i + 5]);
+          u.w = pack_bf16x2(e[8 * i + 6], e[8 * i + 7]);
+          *reinterpret_cast<uint4*>(blk + ((((c & 1) * 4 + i) ^ sw) << 4)) = u;
+        }
+      }
+      l = l * alpha + psum;
+      // S_j fully consumed: the MMA warp may overwrite this S buffer with S_{j+2}
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bar_sfree[st]);
+      // ---- lazy rescale of the TMEM accumulator (rare): needs PV_{j-1} complete, must finish before PV_j starts
+      if (__any_sync(0xffffffffu, rescale)) {
+        if (j >= 1) mbar_wait(&bar_pfree[(j - 1) & 1], ((j - 1) >> 1) & 1);
+        tc_fence_after();
+#pragma unroll 1
+        for (int c = 0; c < HD / 32; ++c) {
+          uint32_t v[32];
+          tmem_ld32(tmem_base + lane_base + O_COL + c * 32, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * alpha);
+          tmem_st32(tmem_base + lane_base + O_COL + c * 32, v);
+        }
+        tmem_st_wait();
+        tc_fence_before();
+      }
+      fence_proxy_async_smem();  // P (generic-proxy stores) -> visible to the tensor core's async proxy
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bar_p[st]);
+    }
+
+    // ---- epilogue: O / l -> bf16 -> per-warp swizzled staging (reuses P buffer 0) -> coalesced stores
+    if (n_tiles > 0) {
+      mbar_wait(bar_o, 0);
+      tc_fence_after();
+    }
+    const float inv = l > 0.f ? 1.0f / l : 0.f;
+    uint8_t* stg = sP + (warp - 2) * 8192;  // 32 rows x 256 B
+    uint8_t* srow = stg + lane * 256;
+#pragma unroll 1
+    for (int c = 0; c < HD / 32; ++c) {
+      uint32_t v[32];
+      if (n_tiles > 0) {
+        tmem_ld32(tmem_base + lane_base + O_COL + c * 32, v);
+        tmem_ld_wait();
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = 0u;
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        uint4 u;
+        u.x = pack_bf16x2(__uint_as_float(v[8 * i + 0]) * inv, __uint_as_float(v[8 * i + 1]) * inv);
+        u.y = pack_bf16x2(__uint_as_float(v[8 * i + 2]) * inv, __uint_as_float(v[8 * i + 3]) * inv);
+        u.z = pack_bf16x2(__uint_as_float(v[8 * i + 4]) * inv, __uint_as_float(v[8 * i + 5]) * inv);
+        u.w = pack_bf16x2(__uint_as_float(v[8 * i + 6]) * inv, __uint_as_float(v[8 * i + 7]) * inv);
+        *reinterpret_cast<uint4*>(srow + (((c * 4 + i) ^ sw) << 4)) = u;
+      }
+    }
+    __syncwarp();
+    constexpr int CPR = HD / 8;        // 16-byte chunks per output row
+    constexpr int RPI = 32 / CPR;      // rows written per warp instruction
+    bf16* og = p.out + static_cast<long long>(b) * p.o_bs + static_cast<long long>(h) * p.o_hs;
+#pragma unroll 4
+    for (int it = 0; it < 32 / RPI; ++it) {
+      const int rr = it * RPI + lane / CPR, ch = lane % CPR;
+      const int gq = m0 + q * 32 + rr;
+      if (gq < p.Tq)
+        *reinterpret_cast<uint4*>(og + static_cast<long long>(gq) * p.o_ts + ch * 8) =
+            *reinterpret_cast<const uint4*>(stg + rr * 256 + ((ch ^ (rr & 7)) << 4));
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+typedef CUresult (*EncodeTiledFn2)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static int fa_make_map(CUtensorMap* m, const void* ptr, int hd, int T, int H, int B, int64_t ts, int64_t hs, int64_t bs,
+                       uint32_t box_rows) {
+  static EncodeTiledFn2 fn = nullptr;
+  if (fn == nullptr) {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn2>(f);
+  }
+  if (fn == nullptr) {
+    set_error("cuTensorMapEncodeTiled entry point unavailable");
+    return 1;
+  }
+  // a size-1 dimension may carry any stride; keep every stride a positive multiple of 16 bytes
+  if (hs <= 0) hs = static_cast<int64_t>(hd);
+  if (bs <= 0) bs = static_cast<int64_t>(T) * ts;
+  cuuint64_t dims[4] = {static_cast<cuuint64_t>(hd), static_cast<cuuint64_t>(T), static_cast<cuuint64_t>(H),
+                        static_cast<cuuint64_t>(B)};
+  cuuint64_t strides[3] = {static_cast<cuuint64_t>(ts) * 2, static_cast<cuuint64_t>(hs) * 2,
+                           static_cast<cuuint64_t>(bs) * 2};
+  cuuint32_t box[4] = {64, box_rows, 1, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("mm_attn_fwd: cuTensorMapEncodeTiled failed (%d) hd=%d T=%d H=%d B=%d ts=%lld hs=%lld bs=%lld",
+              static_cast<int>(r), hd, T, H, B, (long long)ts, (long long)hs, (long long)bs);
+    return 1;
+  }
+  return 0;
+}
+
+template <int HD>
+static int launch_fa(const mm_attn_args* a, cudaStream_t st) {
+  static bool attr_set = false;
+  constexpr size_t smem = fa_smem_bytes<HD>();
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(fa_tcgen05_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         static_cast<int>(smem));
+    if (e != cudaSuccess) {
+      set_error("mm_attn_fwd: cudaFuncSetAttribute(%zu) failed: %s", smem, cudaGetErrorString(e));
+      return 2;
+    }
+    attr_set = true;
+  }
+  CUtensorMap tq, tk, tv;
+  if (fa_make_map(&tq, a->q, HD, a->Tq, a->H, a->B, a->q_ts, a->q_hs, a->q_bs, kFaMQ)) return 1;
+  if (fa_make_map(&tk, a->k, HD, a->Tk, a->H, a->B, a->k_ts, a->k_hs, a->k_bs, kFaKT)) return 1;
+  if (fa_make_map(&tv, a->v, HD, a->Tk, a->H, a->B, a->v_ts, a->v_hs, a->v_bs, kFaKT)) return 1;
+  FaParams p;
+  p.out = reinterpret_cast<bf16*>(a->out);
+  p.B = a->B; p.H = a->H; p.Tq = a->Tq; p.Tk = a->Tk;
+  p.o_bs = a->o_bs; p.o_ts = a->o_ts; p.o_hs = a->o_hs;
+  p.key_mask = a->key_mask;
+  p.causal = a->causal;
+  p.scale_log2 = a->scale * 1.4426950408889634f;
+  dim3 grid((a->Tq + kFaMQ - 1) / kFaMQ, a->H, a->B);
+  fa_tcgen05_kernel<HD><<<grid, 192, smem, st>>>(tq, tk, tv, p);
+  return check_launch("mm_attn_fwd(tcgen05)");
+}
+
+// called from mm_attn_fwd (attn.cu) for head_dim 64 / 128 when scale > 0
+int attn_tcgen05_dispatch(const mm_attn_args* a, cudaStream_t st) {
+  return a->head_dim == 64 ? launch_fa<64>(a, st) : launch_fa<128>(a, st);
+}
+
+}  // namespace mm

@@ -2,7 +2,14 @@
 //
 //   warp 0      : TMA producer  (cp.async.bulk.tensor -> 128B-swizzled smem ring, mbarrier complete_tx)
 //   warp 1      : TMEM allocator + single-thread tcgen05.mma issuer (accumulators live in TMEM, 2 buffers)
-//   warps 2..5  : epilogue (tcgen05.ld -> registers -> bias/activation/residual/RoPE/SwiGLU -> global)
+//   warps 2..9  : epilogue (tcgen05.ld -> registers -> bias/activation/residual/RoPE/SwiGLU -> global); two warps per
+//                 TMEM lane quarter, each taking half of the tile's columns (the epilogue is issue-bound: with one
+//                 warp per SM sub-partition short-K GEMMs (CLIP / Whisper) were epilogue-limited)
+//
+// Epilogue note (measured, round 1): staging C through shared memory for fully coalesced stores was tried and is
+// SLOWER (LLaMA GEMMs 1384 -> 1240 TFLOP/s, CLIP 315 -> 228): with cta_group::1 and a 128x256 tile the tensor core
+// already reads 96 B/cycle/SM of the 128 B/cycle shared-memory bandwidth, so any extra smem traffic stalls the MMA.
+// Accumulator rows therefore go registers -> global directly (each thread owns one row: 64 B contiguous per chunk).
 //
 // Tile = 128 (M) x BN (N) x 64 (K) per stage; UMMA shape 128 x BN x 16.  Two TMEM accumulator buffers let the
 // epilogue of tile i overlap the main loop of tile i+1.  One CTA per SM, static round-robin tile schedule with
@@ -49,8 +56,7 @@ __host__ __device__ constexpr uint32_t gemm_tmem_cols(int BN) {
   return 2 * BN <= 32 ? 32 : (2 * BN <= 64 ? 64 : (2 * BN <= 128 ? 128 : (2 * BN <= 256 ? 256 : 512)));
 }
 __host__ __device__ constexpr size_t gemm_smem_bytes(int BN) {
-  return 1024 /*align slack*/ + (size_t)gemm_stages(BN) * (kABytes + BN * kBlockK * 2) + 256 /*barriers*/ +
-         4 * 32 * 256 /*epilogue staging*/;
+  return 1024 /*align slack*/ + (size_t)gemm_stages(BN) * (kABytes + BN * kBlockK * 2) + 256 /*barriers*/;
 }
 
 struct TileCoord {
@@ -78,87 +84,50 @@ __device__ __forceinline__ float apply_act(float x, int act) {
     case MM_ACT_GELU:
       return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f));
     case MM_ACT_QUICK_GELU:
-      return x / (1.0f + __expf(-1.702f * x));
+      return __fdividef(x, 1.0f + __expf(-1.702f * x));
     case MM_ACT_SILU:
-      return x / (1.0f + __expf(-x));
+      return __fdividef(x, 1.0f + __expf(-x));
     default:
       return x;
   }
 }
 
-constexpr uint32_t kStageBytesPerWarp = 32 * 256;  // 32 rows x 256 B, XOR-swizzled 16 B chunks
-
-// Write one staged pass (this warp's 32 rows x `pass_cols` output columns starting at global column `col_base`) to
-// global memory with coalesced row segments.  Staging holds fp32 (64 columns / row) or bf16 (128 columns / row);
-// chunk c of row r lives at r * 256 + ((c ^ (r & 7)) << 4).  With fp32 staging the residual is added here (fp32,
-// coalesced reads) before the single rounding to the output type.
-template <bool STAGE_F32>
-__device__ __forceinline__ void flush_pass(const GemmKParams& p, const uint8_t* stg, int lane, int row0, int col_base,
-                                           int pass_cols, int n_out_total, char* cmat, const bf16* rmat) {
-  constexpr int EPC = STAGE_F32 ? 4 : 8;  // elements per 16-byte chunk
-  const int ch = lane & 15;
-  const int col = col_base + ch * EPC;
-  if (ch * EPC >= pass_cols || col >= n_out_total) return;
-#pragma unroll 4
-  for (int it = 0; it < 16; ++it) {
-    const int r = it * 2 + (lane >> 4);
-    const int grow = row0 + r;
-    if (grow >= p.M) continue;
-    const uint4 raw = *reinterpret_cast<const uint4*>(stg + r * 256 + ((ch ^ (r & 7)) << 4));
-    if constexpr (STAGE_F32) {
-      float v[4] = {__uint_as_float(raw.x), __uint_as_float(raw.y), __uint_as_float(raw.z), __uint_as_float(raw.w)};
-      const bool full = p.vec_ok && (col + 4 <= n_out_total);
-      if (rmat != nullptr) {
-        const int rr = p.res_row_mod > 0 ? grow % p.res_row_mod : grow;
-        const bf16* rp = rmat + static_cast<long long>(rr) * p.ldr + col;
-        if (full) {
-          const uint2 u = *reinterpret_cast<const uint2*>(rp);
-          v[0] += bf16lo(u.x); v[1] += bf16hi(u.x); v[2] += bf16lo(u.y); v[3] += bf16hi(u.y);
-        } else {
+// Store 32 consecutive outputs of one row (columns col0..col0+31), masked by N.
+__device__ __forceinline__ void store_row32(const GemmKParams& p, void* crow, int col0, int ncols_total,
+                                            const float (&v)[32]) {
+  if (p.c_fp32) {
+    float* c = reinterpret_cast<float*>(crow) + col0;
+    if (p.vec_ok && col0 + 32 <= ncols_total) {
 #pragma unroll
-          for (int i = 0; i < 4; ++i)
-            if (col + i < n_out_total) v[i] += __bfloat162float(rp[i]);
-        }
-      }
-      if (p.c_fp32) {
-        float* cp = reinterpret_cast<float*>(cmat) + static_cast<long long>(grow) * p.ldc + col;
-        if (full) {
-          *reinterpret_cast<float4*>(cp) = make_float4(v[0], v[1], v[2], v[3]);
-        } else {
+      for (int i = 0; i < 8; ++i)
+        reinterpret_cast<float4*>(c)[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+    } else {
 #pragma unroll
-          for (int i = 0; i < 4; ++i)
-            if (col + i < n_out_total) cp[i] = v[i];
-        }
-      } else {
-        bf16* cp = reinterpret_cast<bf16*>(cmat) + static_cast<long long>(grow) * p.ldc + col;
-        if (full) {
-          uint2 u;
-          u.x = pack_bf16x2(v[0], v[1]);
-          u.y = pack_bf16x2(v[2], v[3]);
-          *reinterpret_cast<uint2*>(cp) = u;
-        } else {
+      for (int i = 0; i < 32; ++i)
+        if (col0 + i < ncols_total) c[i] = v[i];
+    }
+  } else {
+    bf16* c = reinterpret_cast<bf16*>(crow) + col0;
+    if (p.vec_ok && col0 + 32 <= ncols_total) {
 #pragma unroll
-          for (int i = 0; i < 4; ++i)
-            if (col + i < n_out_total) cp[i] = __float2bfloat16(v[i]);
-        }
+      for (int i = 0; i < 4; ++i) {
+        uint4 u;
+        u.x = pack_bf16x2(v[8 * i + 0], v[8 * i + 1]);
+        u.y = pack_bf16x2(v[8 * i + 2], v[8 * i + 3]);
+        u.z = pack_bf16x2(v[8 * i + 4], v[8 * i + 5]);
+        u.w = pack_bf16x2(v[8 * i + 6], v[8 * i + 7]);
+        reinterpret_cast<uint4*>(c)[i] = u;
       }
     } else {
-      bf16* cp = reinterpret_cast<bf16*>(cmat) + static_cast<long long>(grow) * p.ldc + col;
-      if (p.vec_ok && col + 8 <= n_out_total) {
-        *reinterpret_cast<uint4*>(cp) = raw;
-      } else {
-        const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
 #pragma unroll
-        for (int i = 0; i < 8; ++i)
-          if (col + i < n_out_total)
-            cp[i] = __ushort_as_bfloat16(static_cast<unsigned short>((i & 1) ? (w[i >> 1] >> 16) : (w[i >> 1] & 0xFFFF)));
-      }
+      for (int i = 0; i < 32; ++i)
+        if (col0 + i < ncols_total) c[i] = __float2bfloat16(v[i]);
     }
   }
 }
 
 template <int BN, int EPI, bool B_MN>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(320, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const GemmKParams p) {
   constexpr int STAGES = gemm_stages(BN);
@@ -175,7 +144,6 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   uint64_t* tfull_bar = empty_bar + STAGES;
   uint64_t* tempty_bar = tfull_bar + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
-  uint8_t* stage_base = reinterpret_cast<uint8_t*>(full_bar) + 256;  // 4 x 8 KiB epilogue staging (16 B aligned)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -193,7 +161,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       }
       for (int s = 0; s < 2; ++s) {
         mbar_init(&tfull_bar[s], 1);
-        mbar_init(&tempty_bar[s], 4);
+        mbar_init(&tempty_bar[s], 8);
       }
       fence_mbar_init();
     }
@@ -275,144 +243,117 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
   } else {
     // ------------------------------------------------------------------ epilogue warps
-    // TMEM -> registers (one accumulator row per thread) -> epilogue math -> per-warp smem staging (XOR-swizzled
-    // 16 B chunks, 256 B per row) -> coalesced global stores (16 lanes cover 256 contiguous bytes of one row).
-    const int q = warp & 3;  // TMEM lane quarter this warp may access
-    uint8_t* stg = stage_base + (warp - 2) * kStageBytesPerWarp;
+    const int q = warp & 3;            // TMEM lane quarter this warp may access
+    const int half = (warp - 2) >> 2;  // which half of the tile's columns this warp handles
     int acc = 0;
     uint32_t acc_phase = 0;
     const int n_out_total = (EPI == MM_EPI_SWIGLU) ? p.N / 2 : p.N;
-    const bool stage_f32 = (EPI == MM_EPI_STD) && (p.c_fp32 != 0 || p.residual != nullptr);
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const TileCoord t = tile_coord(tile, p);
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
-      const int row0 = t.m_blk * kBlockM + q * 32;  // first row of this warp's slice
-      const int row = row0 + lane;
+      const int row = t.m_blk * kBlockM + q * 32 + lane;
       const bool row_ok = row < p.M;
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN;
-      char* cmat = reinterpret_cast<char*>(p.C) +
-                   (static_cast<long long>(t.b_lo) * p.c_bs + static_cast<long long>(t.b_hi) * p.c_bs2) *
-                       (p.c_fp32 ? 4 : 2);
-      const bf16* rmat = p.residual
-                             ? p.residual + static_cast<long long>(t.b_lo) * p.r_bs +
-                                   static_cast<long long>(t.b_hi) * p.r_bs2
-                             : nullptr;
+      char* crow = reinterpret_cast<char*>(p.C) +
+                   (static_cast<long long>(t.b_lo) * p.c_bs + static_cast<long long>(t.b_hi) * p.c_bs2 +
+                    static_cast<long long>(row) * p.ldc) * (p.c_fp32 ? 4 : 2);
       float rs = 1.0f;
       if (p.row_scale != nullptr && row_ok) rs = p.row_scale[static_cast<long long>(t.b) * p.M + row];
       rs *= p.alpha;
-      uint8_t* srow = stg + lane * 256;
-      const int sw = lane & 7;
 
       if constexpr (EPI == MM_EPI_STD) {
         const bf16* bias = p.bias ? p.bias + static_cast<long long>(t.b_lo) * p.bias_bs : nullptr;
-        const int cpp = stage_f32 ? 64 : 128;  // accumulator columns per staging pass
+        const bf16* rrow = nullptr;
+        if (p.residual != nullptr && row_ok) {
+          const int rr = p.res_row_mod > 0 ? row % p.res_row_mod : row;
+          rrow = p.residual + static_cast<long long>(t.b_lo) * p.r_bs + static_cast<long long>(t.b_hi) * p.r_bs2 +
+                 static_cast<long long>(rr) * p.ldr;
+        }
+        constexpr int CPH = BN >= 64 ? BN / 64 : 1;  // 32-column chunks per half
 #pragma unroll 1
-        for (int c0 = 0; c0 < BN; c0 += cpp) {
-          if (t.n_blk * BN + c0 >= p.N) break;  // warp-uniform
-#pragma unroll 1
-          for (int cc = 0; cc * 32 < cpp && c0 + cc * 32 < BN; ++cc) {
-            uint32_t r[32];
-            tmem_ld32(taddr + c0 + cc * 32, r);
-            tmem_ld_wait();
-            const int col0 = t.n_blk * BN + c0 + cc * 32;
-            float v[32];
+        for (int c = half * CPH; c < (half + 1) * CPH && c < BN / 32; ++c) {
+          uint32_t r[32];
+          tmem_ld32(taddr + c * 32, r);
+          tmem_ld_wait();
+          const int col0 = t.n_blk * BN + c * 32;
+          if (col0 >= p.N) continue;  // warp-uniform
+          float v[32];
 #pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]) * rs;
-            if (bias != nullptr) {
-              if (p.vec_ok && col0 + 32 <= p.N) {
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                  const uint4 u = __ldg(reinterpret_cast<const uint4*>(bias + col0) + i);
-                  v[8 * i + 0] += bf16lo(u.x); v[8 * i + 1] += bf16hi(u.x);
-                  v[8 * i + 2] += bf16lo(u.y); v[8 * i + 3] += bf16hi(u.y);
-                  v[8 * i + 4] += bf16lo(u.z); v[8 * i + 5] += bf16hi(u.z);
-                  v[8 * i + 6] += bf16lo(u.w); v[8 * i + 7] += bf16hi(u.w);
-                }
-              } else {
-#pragma unroll
-                for (int i = 0; i < 32; ++i)
-                  if (col0 + i < p.N) v[i] += __bfloat162float(bias[col0 + i]);
-              }
-            }
-            if (p.act != MM_ACT_NONE) {
-#pragma unroll
-              for (int i = 0; i < 32; ++i) v[i] = apply_act(v[i], p.act);
-            }
-            if (stage_f32) {
-#pragma unroll
-              for (int i = 0; i < 8; ++i)
-                *reinterpret_cast<float4*>(srow + (((cc * 8 + i) ^ sw) << 4)) =
-                    make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-            } else {
+          for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]) * rs;
+          const bool full = p.vec_ok && (col0 + 32 <= p.N);
+          if (bias != nullptr) {
+            if (full) {
 #pragma unroll
               for (int i = 0; i < 4; ++i) {
-                uint4 u;
-                u.x = pack_bf16x2(v[8 * i + 0], v[8 * i + 1]);
-                u.y = pack_bf16x2(v[8 * i + 2], v[8 * i + 3]);
-                u.z = pack_bf16x2(v[8 * i + 4], v[8 * i + 5]);
-                u.w = pack_bf16x2(v[8 * i + 6], v[8 * i + 7]);
-                *reinterpret_cast<uint4*>(srow + (((cc * 4 + i) ^ sw) << 4)) = u;
+                const uint4 u = __ldg(reinterpret_cast<const uint4*>(bias + col0) + i);
+                v[8 * i + 0] += bf16lo(u.x); v[8 * i + 1] += bf16hi(u.x);
+                v[8 * i + 2] += bf16lo(u.y); v[8 * i + 3] += bf16hi(u.y);
+                v[8 * i + 4] += bf16lo(u.z); v[8 * i + 5] += bf16hi(u.z);
+                v[8 * i + 6] += bf16lo(u.w); v[8 * i + 7] += bf16hi(u.w);
               }
+            } else {
+#pragma unroll
+              for (int i = 0; i < 32; ++i)
+                if (col0 + i < p.N) v[i] += __bfloat162float(bias[col0 + i]);
             }
           }
-          __syncwarp();
-          const int pass_cols = min(cpp, BN - c0);
-          if (stage_f32)
-            flush_pass<true>(p, stg, lane, row0, t.n_blk * BN + c0, pass_cols, n_out_total, cmat, rmat);
-          else
-            flush_pass<false>(p, stg, lane, row0, t.n_blk * BN + c0, pass_cols, n_out_total, cmat, nullptr);
-          __syncwarp();
+          if (p.act != MM_ACT_NONE) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = apply_act(v[i], p.act);
+          }
+          if (rrow != nullptr) {
+            if (full) {
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const uint4 u = *(reinterpret_cast<const uint4*>(rrow + col0) + i);
+                v[8 * i + 0] += bf16lo(u.x); v[8 * i + 1] += bf16hi(u.x);
+                v[8 * i + 2] += bf16lo(u.y); v[8 * i + 3] += bf16hi(u.y);
+                v[8 * i + 4] += bf16lo(u.z); v[8 * i + 5] += bf16hi(u.z);
+                v[8 * i + 6] += bf16lo(u.w); v[8 * i + 7] += bf16hi(u.w);
+              }
+            } else {
+#pragma unroll
+              for (int i = 0; i < 32; ++i)
+                if (col0 + i < p.N) v[i] += __bfloat162float(rrow[col0 + i]);
+            }
+          }
+          if (row_ok) store_row32(p, crow, col0, n_out_total, v);
         }
       } else if constexpr (EPI == MM_EPI_SWIGLU) {
-        // 64 accumulator columns = [32 gate | 32 up] -> 32 outputs; one bf16 pass holds 128 outputs (256 acc columns)
 #pragma unroll 1
-        for (int c0 = 0; c0 < BN; c0 += 256) {
-          if (t.n_blk * BN + c0 >= p.N) break;
-#pragma unroll 1
-          for (int cc = 0; cc < 4 && c0 + cc * 64 < BN; ++cc) {
-            uint32_t g[32], u[32];
-            tmem_ld32(taddr + c0 + cc * 64, g);
-            tmem_ld32(taddr + c0 + cc * 64 + 32, u);
-            tmem_ld_wait();
-            float v[32];
+        for (int c = half * (BN / 128); c < (half + 1) * (BN / 128); ++c) {
+          uint32_t g[32], u[32];
+          tmem_ld32(taddr + c * 64, g);
+          tmem_ld32(taddr + c * 64 + 32, u);
+          tmem_ld_wait();
+          const int col_in = t.n_blk * BN + c * 64;
+          if (col_in >= p.N) continue;
+          float v[32];
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
-              const float gg = __uint_as_float(g[i]) * rs;
-              const float uu = __uint_as_float(u[i]) * rs;
-              v[i] = gg / (1.0f + __expf(-gg)) * uu;
-            }
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              uint4 w;
-              w.x = pack_bf16x2(v[8 * i + 0], v[8 * i + 1]);
-              w.y = pack_bf16x2(v[8 * i + 2], v[8 * i + 3]);
-              w.z = pack_bf16x2(v[8 * i + 4], v[8 * i + 5]);
-              w.w = pack_bf16x2(v[8 * i + 6], v[8 * i + 7]);
-              *reinterpret_cast<uint4*>(srow + (((cc * 4 + i) ^ sw) << 4)) = w;
-            }
+          for (int i = 0; i < 32; ++i) {
+            const float gg = __uint_as_float(g[i]) * rs;
+            const float uu = __uint_as_float(u[i]) * rs;
+            v[i] = __fdividef(gg, 1.0f + __expf(-gg)) * uu;
           }
-          __syncwarp();
-          flush_pass<false>(p, stg, lane, row0, (t.n_blk * BN + c0) / 2, min(128, (BN - c0) / 2), n_out_total, cmat,
-                            nullptr);
-          __syncwarp();
+          if (row_ok) store_row32(p, crow, col_in / 2, n_out_total, v);
         }
-      } else {  // MM_EPI_ROPE, head_dim 128: pairs (i, i + 64) within each head; one head = one 128-column pass
+      } else {  // MM_EPI_ROPE, head_dim 128: pairs (i, i + 64) within each head
         const int pos = row_ok ? (row % p.rope_T) : 0;
         const float* cs = p.rope_cos + static_cast<long long>(pos) * 64;
         const float* sn = p.rope_sin + static_cast<long long>(pos) * 64;
 #pragma unroll 1
-        for (int h = 0; h < BN / 128; ++h) {
-          const int colh = t.n_blk * BN + h * 128;
-          if (colh >= p.N) break;
-#pragma unroll 1
-          for (int hc = 0; hc < 2; ++hc) {
+        for (int un = half * (BN / 128); un < (half + 1) * (BN / 128); ++un) {
+          {
+            const int h = un >> 1, hc = un & 1;
             uint32_t x1[32], x2[32];
             tmem_ld32(taddr + h * 128 + hc * 32, x1);
             tmem_ld32(taddr + h * 128 + 64 + hc * 32, x2);
             tmem_ld_wait();
+            const int col1 = t.n_blk * BN + h * 128 + hc * 32;
+            if (col1 >= p.N) continue;
             float o1[32], o2[32];
-            if (colh < p.rope_cols) {
+            if (col1 < p.rope_cols) {
 #pragma unroll
               for (int i = 0; i < 8; ++i) {
                 const float4 c4 = __ldg(reinterpret_cast<const float4*>(cs + hc * 32) + i);
@@ -434,20 +375,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 o2[i] = __uint_as_float(x2[i]) * rs;
               }
             }
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              uint4 w1, w2;
-              w1.x = pack_bf16x2(o1[8 * i + 0], o1[8 * i + 1]); w1.y = pack_bf16x2(o1[8 * i + 2], o1[8 * i + 3]);
-              w1.z = pack_bf16x2(o1[8 * i + 4], o1[8 * i + 5]); w1.w = pack_bf16x2(o1[8 * i + 6], o1[8 * i + 7]);
-              w2.x = pack_bf16x2(o2[8 * i + 0], o2[8 * i + 1]); w2.y = pack_bf16x2(o2[8 * i + 2], o2[8 * i + 3]);
-              w2.z = pack_bf16x2(o2[8 * i + 4], o2[8 * i + 5]); w2.w = pack_bf16x2(o2[8 * i + 6], o2[8 * i + 7]);
-              *reinterpret_cast<uint4*>(srow + (((hc * 4 + i) ^ sw) << 4)) = w1;       // columns hc*32 .. +31
-              *reinterpret_cast<uint4*>(srow + (((8 + hc * 4 + i) ^ sw) << 4)) = w2;   // columns 64 + hc*32 ..
+            if (row_ok) {
+              store_row32(p, crow, col1, n_out_total, o1);
+              store_row32(p, crow, col1 + 64, n_out_total, o2);
             }
           }
-          __syncwarp();
-          flush_pass<false>(p, stg, lane, row0, colh, 128, n_out_total, cmat, nullptr);
-          __syncwarp();
         }
       }
       // release this accumulator buffer back to the MMA warp
@@ -540,7 +472,7 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmK
   }
   const int total = p.batch * p.batch2 * p.m_tiles * p.n_tiles;
   const int grid = total < num_sms() ? total : num_sms();
-  gemm_bf16_kernel<BN, EPI, B_MN><<<grid, 192, smem, st>>>(ta, tb, p);
+  gemm_bf16_kernel<BN, EPI, B_MN><<<grid, 320, smem, st>>>(ta, tb, p);
   return check_launch("mm_gemm_fwd");
 }
 

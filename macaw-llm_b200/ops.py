@@ -111,7 +111,7 @@ def splitk_reduce(partial: torch.Tensor, bias: Optional[torch.Tensor], out: torc
 
 # ---------------------------------------------------------------------------------------------------- attention
 def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, *, scale: float, causal: bool = False,
-              key_mask: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+              key_mask: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None, impl: int = 0) -> torch.Tensor:
     """q (B, Tq, H, hd), k/v (B, Tk, H, hd) bf16 views (hd contiguous, arbitrary other strides) -> (B, Tq, H, hd)."""
     for n, t in (("q", q), ("k", k), ("v", v)):
         _cuda(t, _BF16, n)
@@ -126,7 +126,7 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, *, scale: float
     a = AttnArgs(q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), B, H, Tq, Tk, hd,
                  q.stride(0), q.stride(1), q.stride(2), k.stride(0), k.stride(1), k.stride(2),
                  v.stride(0), v.stride(1), v.stride(2), out.stride(0), out.stride(1), out.stride(2),
-                 _ptr(key_mask), int(causal), float(scale))
+                 _ptr(key_mask), int(causal), float(scale), int(impl))
     _check(_lib.load().mm_attn_fwd(C.byref(a), _stream()), "mm_attn_fwd")
     return out
 

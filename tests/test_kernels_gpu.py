@@ -22,6 +22,20 @@ def rel_err(a: torch.Tensor, b: torch.Tensor) -> float:
     return float((a - b).norm() / (b.norm() + 1e-20))
 
 
+def test_attention_lazy_rescale_large_scores():
+    """Scores with a large dynamic range (row max grows by >> 2^8 between key tiles) exercise the TMEM rescale path."""
+    ops = _ops()
+    B, H, T, hd = 1, 2, 512, 128
+    q = rnd(B, T, H, hd, scale=2.0, seed=60)
+    k = rnd(B, T, H, hd, scale=2.0, seed=61)
+    v = rnd(B, T, H, hd, seed=62)
+    # make later keys systematically larger so the running max keeps jumping
+    k = (k.float() * torch.linspace(0.2, 3.0, T, device=DEV)[None, :, None, None]).to(torch.bfloat16)
+    out = ops.attention(q, k, v, scale=hd ** -0.5)
+    ref = _attn_ref(q, k, v, hd ** -0.5, False, None)
+    assert rel_err(out, ref) < 1e-2
+
+
 def rnd(*shape, scale=1.0, seed=0):
     g = torch.Generator(device="cpu").manual_seed(seed)
     return (torch.randn(*shape, generator=g) * scale).to(DEV).to(torch.bfloat16)
@@ -200,9 +214,14 @@ def _attn_ref(q, k, v, scale, causal, key_mask):
         (2, 4, 130, 130, 128, True, True),     # LLaMA causal + right padding
         (1, 2, 64, 64, 128, True, False),
         (1, 2, 1, 70, 64, False, False),
+        (2, 32, 528, 528, 128, True, True),    # cfg4 LLaMA shape: 5 query tiles, lazy-rescale path, padding
+        (1, 3, 300, 300, 64, True, False),
     ],
 )
-def test_attention(B, H, Tq, Tk, hd, causal, masked):
+@pytest.mark.parametrize("impl", [0, 1])
+def test_attention(B, H, Tq, Tk, hd, causal, masked, impl):
+    if hd == 96 and impl == 1:
+        pytest.skip("head_dim 96 always runs the mma.sync kernel")
     ops = _ops()
     # q/k/v as strided views of one fused (B, T, 3, H, hd) projection output, as the engine uses them
     qkv_q = rnd(B, Tq, 3, H, hd, seed=30)
@@ -213,7 +232,7 @@ def test_attention(B, H, Tq, Tk, hd, causal, masked):
         km = torch.ones(B, Tk, dtype=torch.int32, device=DEV)
         km[0, Tk - 17:] = 0
     scale = hd ** -0.5
-    out = ops.attention(q, k, v, scale=scale, causal=causal, key_mask=km)
+    out = ops.attention(q, k, v, scale=scale, causal=causal, key_mask=km, impl=impl)
     ref = _attn_ref(q, k, v, scale, causal, km)
     if masked:  # rows whose own key is padding are unspecified; compare valid query rows only
         valid = km.bool()[:, -Tq:]
