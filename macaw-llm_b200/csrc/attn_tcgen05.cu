@@ -1,7 +1,8 @@
 // Flash attention on the 5th-gen tensor cores (tcgen05 + TMEM + TMA) for head_dim 64 / 128.
 //
-// One CTA = 128 queries of one (batch, head).  Warp roles:
-//   warp 0      : TMA producer — Q once, then K / V tiles of 128 keys into 2-stage rings (128B swizzle)
+// One CTA = 128 queries of one (batch, head); key tiles of KT = 64 keys so that TWO CTAs fit per SM (smem <= 113 KB,
+// 256 TMEM columns each): one CTA's prologue / epilogue / softmax latency hides behind the other's MMAs.  Warp roles:
+//   warp 0      : TMA producer — Q once, then K / V tiles of KT keys into 2-stage rings (128B swizzle)
 //   warp 1      : single-thread tcgen05.mma issuer:  S_j = Q K_j^T (TMEM, double-buffered)  and  O += P_j V_j (TMEM)
 //   warps 2..5  : softmax — ONE THREAD PER QUERY ROW (tcgen05.ld 32x32b gives each thread its row, so the row max /
 //                 row sum need no shuffles); writes P_j as bf16 into a 128B-swizzled smem tile that is the A operand
@@ -32,32 +33,44 @@ struct FaParams {
 };
 
 constexpr int kFaMQ = 128;  // queries per CTA
-constexpr int kFaKT = 128;  // keys per tile
 constexpr float kFaTau = 8.0f;  // lazy-rescale threshold (log2 domain)
 
-template <int HD>
-__host__ __device__ constexpr size_t fa_smem_bytes() {
-  // Q + 2 K stages + 2 V stages + 2 P buffers + barriers + alignment slack
-  return 1024 + (size_t)(HD / 64) * 16384 * 5 + 2 * 32768 + 256;
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
 }
 
-template <int HD>
-__global__ void __launch_bounds__(192, 1)
+// HD head dim (64 | 128), KT keys per tile (64 | 128), NPB number of P buffers (1 | 2)
+template <int HD, int KT, int NPB>
+__host__ __device__ constexpr size_t fa_smem_bytes() {
+  // Q + 2 K stages + 2 V stages + NPB P buffers + barriers (the dynamic smem window itself is 1024-byte aligned)
+  return (size_t)(HD / 64) * 16384 + 4 * (size_t)(HD / 64) * KT * 128 + (size_t)NPB * 128 * KT * 2 + 256;
+}
+
+template <int HD, int KT, int NPB>
+__global__ void __launch_bounds__(192, 2)
 fa_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                   const __grid_constant__ CUtensorMap tmV, const FaParams p) {
+  constexpr int kFaKT = KT;
   constexpr int KB = HD / 64;                 // 64-column blocks of the head dim
-  constexpr uint32_t QB = KB * 16384;         // bytes of Q, and of one K / V stage
-  constexpr uint32_t IDESC_S = make_idesc_bf16(kFaMQ, kFaKT, false, false);
+  constexpr uint32_t QBYTES = KB * 16384;     // bytes of the Q tile
+  constexpr uint32_t QB = KB * KT * 128;      // bytes of one K / V stage
+  constexpr uint32_t PB = 128 * KT * 2;       // bytes of one P buffer
+  constexpr int NCH = KT / 32;                // 32-key chunks per tile
+  constexpr uint32_t IDESC_S = make_idesc_bf16(kFaMQ, KT, false, false);
   constexpr uint32_t IDESC_O = make_idesc_bf16(kFaMQ, HD, false, true);
-  constexpr uint32_t S_COL = 0, O_COL = 256;  // TMEM columns: S0 [0,128), S1 [128,256), O [256, 256+HD)
+  constexpr uint32_t S_COL = 0, O_COL = 2 * KT;  // TMEM columns: S0 [0,KT), S1 [KT,2KT), O [2KT, 2KT+HD)
+  constexpr uint32_t TMEM_COLS = (2 * KT + HD) <= 256 ? 256 : 512;
+  static_assert(2 * KT + HD <= 512, "TMEM budget");
 
-  extern __shared__ uint8_t fa_smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(fa_smem_raw) + 1023) & ~uintptr_t(1023));
+  extern __shared__ __align__(1024) uint8_t smem[];
+  if ((smem_u32(smem) & 1023u) != 0) __trap();  // 128B-swizzled TMA / UMMA tiles need 1024-byte alignment
   uint8_t* sQ = smem;
-  uint8_t* sK = sQ + QB;
+  uint8_t* sK = sQ + QBYTES;
   uint8_t* sV = sK + 2 * QB;
   uint8_t* sP = sV + 2 * QB;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * 32768);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + NPB * PB);
   uint64_t* bar_q = bars;            // 1
   uint64_t* bar_k = bars + 1;        // 2
   uint64_t* bar_v = bars + 3;        // 2
@@ -100,7 +113,7 @@ fa_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
       fence_mbar_init();
     }
     __syncwarp();
-    tmem_alloc(tmem_slot, 512);
+    tmem_alloc(tmem_slot, TMEM_COLS);
     tmem_relinquish();
   }
   tc_fence_before();
@@ -111,7 +124,7 @@ fa_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
     if (elect_one() && n_tiles > 0) {
-      mbar_arrive_expect_tx(bar_q, QB);
+      mbar_arrive_expect_tx(bar_q, QBYTES);
 #pragma unroll
       for (int kb = 0; kb < KB; ++kb) tma_load_4d(&tmQ, bar_q, sQ + kb * 16384, kb * 64, m0, h, b);
       for (int j = 0; j < n_tiles; ++j) {
@@ -121,12 +134,12 @@ fa_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
         mbar_arrive_expect_tx(&bar_k[st], QB);
 #pragma unroll
         for (int kb = 0; kb < KB; ++kb)
-          tma_load_4d(&tmK, &bar_k[st], sK + st * QB + kb * 16384, kb * 64, j * kFaKT, h, b);
+          tma_load_4d(&tmK, &bar_k[st], sK + st * QB + kb * (KT * 128), kb * 64, j * kFaKT, h, b);
         if (j >= 2) mbar_wait(&bar_vfree[st], par);
         mbar_arrive_expect_tx(&bar_v[st], QB);
 #pragma unroll
         for (int kb = 0; kb < KB; ++kb)
-          tma_load_4d(&tmV, &bar_v[st], sV + st * QB + kb * 16384, kb * 64, j * kFaKT, h, b);
+          tma_load_4d(&tmV, &bar_v[st], sV + st * QB + kb * (KT * 128), kb * 64, j * kFaKT, h, b);
       }
     }
   } else if (warp == 1) {
@@ -141,7 +154,7 @@ fa_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
 #pragma unroll
         for (int k = 0; k < HD / 16; ++k) {
           const uint64_t ad = make_sdesc_sw128(qa + (k >> 2) * 16384 + (k & 3) * 32, 16, 1024);
-          const uint64_t bd = make_sdesc_sw128(ka + (k >> 2) * 16384 + (k & 3) * 32, 16, 1024);
+          const uint64_t bd = make_sdesc_sw128(ka + (k >> 2) * (KT * 128) + (k & 3) * 32, 16, 1024);
           umma_bf16(tmem_base + S_COL + st * kFaKT, ad, bd, IDESC_S, k != 0 ? 1u : 0u);
         }
         umma_commit(&bar_s[st]);
@@ -152,18 +165,19 @@ fa_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
       if (n_tiles > 1) issue_s(1);
       for (int j = 0; j < n_tiles; ++j) {
         const int st = j & 1;
-        mbar_wait(&bar_p[st], (j >> 1) & 1);
+        const int pb = (NPB == 2) ? st : 0;
+        if (NPB == 2) mbar_wait(&bar_p[st], (j >> 1) & 1); else mbar_wait(&bar_p[0], j & 1);
         mbar_wait(&bar_v[st], (j >> 1) & 1);
         tc_fence_after();
-        const uint32_t pa = smem_u32(sP + st * 32768), va = smem_u32(sV + st * QB);
+        const uint32_t pa = smem_u32(sP + pb * PB), va = smem_u32(sV + st * QB);
 #pragma unroll
         for (int k = 0; k < kFaKT / 16; ++k) {
           const uint64_t ad = make_sdesc_sw128(pa + (k >> 2) * 16384 + (k & 3) * 32, 16, 1024);
-          // V: MN-major B (head dim contiguous); 64-column blocks 16 KiB apart (LBO), 8-key groups 1 KiB apart (SBO)
-          const uint64_t bd = make_sdesc_sw128(va + k * 2048, 16384, 1024);
+          // V: MN-major B (head dim contiguous); 64-column blocks KT*128 B apart (LBO), 8-key groups 1 KiB apart (SBO)
+          const uint64_t bd = make_sdesc_sw128(va + k * 2048, KT * 128, 1024);
           umma_bf16(tmem_base + O_COL, ad, bd, IDESC_O, (j | k) != 0 ? 1u : 0u);
         }
-        umma_commit(&bar_pfree[st]);
+        umma_commit(&bar_pfree[pb]);
         umma_commit(&bar_vfree[st]);
         if (j + 2 < n_tiles) issue_s(j + 2);
       }
@@ -187,9 +201,9 @@ fa_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
       const uint32_t s_addr = tmem_base + lane_base + S_COL + st * kFaKT;
       const int key0 = j * kFaKT;
       // per-32-key validity bits: Tk bound + key padding mask (warp-cooperative) & causal limit (per row)
-      uint32_t okb[4];
+      uint32_t okb[NCH];
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
+      for (int c = 0; c < NCH; ++c) {
         const int key = key0 + c * 32 + lane;
         bool ok = key < p.Tk;
         if (ok && kmask != nullptr) ok = kmask[key] != 0;
@@ -200,17 +214,21 @@ fa_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
         }
         okb[c] = bits;
       }
-      // ---- pass 1: row max
+      // ---- the whole score row of this tile into registers (all loads in flight, one wait)
+      uint32_t v[NCH][32];
+#pragma unroll
+      for (int c = 0; c < NCH; ++c) tmem_ld32(s_addr + c * 32, v[c]);
+      tmem_ld_wait();
+      // S_j is in registers: the MMA warp may overwrite this S buffer with S_{j+2}
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bar_sfree[st]);
       float mx = -INFINITY;
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        uint32_t v[32];
-        tmem_ld32(s_addr + c * 32, v);
-        tmem_ld_wait();
+      for (int c = 0; c < NCH; ++c)
 #pragma unroll
         for (int i = 0; i < 32; ++i)
-          if (okb[c] & (1u << i)) mx = fmaxf(mx, __uint_as_float(v[i]));
-      }
+          if (okb[c] & (1u << i)) mx = fmaxf(mx, __uint_as_float(v[c][i]));
       mx *= p.scale_log2;  // scale > 0, so max commutes with the scaling
       // ---- decide the reference max for this tile
       float alpha = 1.0f;
@@ -218,48 +236,48 @@ fa_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
       if (mx > m_used + kFaTau || m_used == -INFINITY) {
         if (mx != -INFINITY) {
           if (m_used != -INFINITY) {
-            alpha = exp2f(m_used - mx);
+            alpha = ex2_approx(m_used - mx);
             rescale = true;
           }
           m_used = mx;
         }
       }
       const float m_ref = (m_used == -INFINITY) ? 0.f : m_used;
-      // ---- pass 2: P = exp2(s * scale - m_ref) -> bf16 -> swizzled smem (A operand of the PV MMA)
-      if (j >= 2) mbar_wait(&bar_pfree[st], ((j >> 1) - 1) & 1);  // PV_{j-2} has finished reading this P buffer
-      uint8_t* prow = sP + st * 32768 + r * 128;
+      // ---- P = exp2(s * scale - m_ref) -> bf16 -> swizzled smem (A operand of the PV MMA)
+      const int pb = (NPB == 2) ? st : 0;
+      if (NPB == 2) {
+        if (j >= 2) mbar_wait(&bar_pfree[st], ((j >> 1) - 1) & 1);  // PV_{j-2} has finished reading this P buffer
+      } else {
+        if (j >= 1) mbar_wait(&bar_pfree[0], (j - 1) & 1);          // PV_{j-1} has finished reading the P buffer
+      }
+      uint8_t* prow = sP + pb * PB + r * 128;
       float psum = 0.f;
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        uint32_t v[32];
-        tmem_ld32(s_addr + c * 32, v);
-        tmem_ld_wait();
-        float e[32];
+      for (int c = 0; c < NCH; ++c) {
+        uint32_t pk[16];
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const float x = exp2f(fmaf(__uint_as_float(v[i]), p.scale_log2, -m_ref));
-          e[i] = (okb[c] & (1u << i)) ? x : 0.f;
-          psum += e[i];
+        for (int i = 0; i < 16; ++i) {
+          float e0 = ex2_approx(fmaf(__uint_as_float(v[c][2 * i]), p.scale_log2, -m_ref));
+          float e1 = ex2_approx(fmaf(__uint_as_float(v[c][2 * i + 1]), p.scale_log2, -m_ref));
+          e0 = (okb[c] & (1u << (2 * i))) ? e0 : 0.f;
+          e1 = (okb[c] & (1u << (2 * i + 1))) ? e1 : 0.f;
+          psum += e0 + e1;
+          pk[i] = pack_bf16x2(e0, e1);
         }
         uint8_t* blk = prow + (c >> 1) * 16384;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          uint4 u;
-          u.x = pack_bf16x2(e[8 * i + 0], e[8 * i + 1]);
-          u.y = pack_bf16x2(e[8 * i + 2], e[8 * i + 3]);
-          u.z = pack_bf16x2(e[8 * i + 4], e[8 * i + 5]);
-          u.w = pack_bf16x2(e[8 * i + 6], e[8 * i + 7]);
-          *reinterpret_cast<uint4*>(blk + ((((c & 1) * 4 + i) ^ sw) << 4)) = u;
-        }
+        for (int i = 0; i < 4; ++i)
+          *reinterpret_cast<uint4*>(blk + ((((c & 1) * 4 + i) ^ sw) << 4)) =
+              make_uint4(pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
       }
       l = l * alpha + psum;
-      // S_j fully consumed: the MMA warp may overwrite this S buffer with S_{j+2}
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&bar_sfree[st]);
       // ---- lazy rescale of the TMEM accumulator (rare): needs PV_{j-1} complete, must finish before PV_j starts
       if (__any_sync(0xffffffffu, rescale)) {
-        if (j >= 1) mbar_wait(&bar_pfree[(j - 1) & 1], ((j - 1) >> 1) & 1);
+        if (NPB == 2) {
+          if (j >= 1) mbar_wait(&bar_pfree[(j - 1) & 1], ((j - 1) >> 1) & 1);
+        } else {
+          if (j >= 1) mbar_wait(&bar_pfree[0], (j - 1) & 1);
+        }
         tc_fence_after();
 #pragma unroll 1
         for (int c = 0; c < HD / 32; ++c) {
@@ -275,7 +293,7 @@ fa_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
       }
       fence_proxy_async_smem();  // P (generic-proxy stores) -> visible to the tensor core's async proxy
       __syncwarp();
-      if (lane == 0) mbar_arrive(&bar_p[st]);
+      if (lane == 0) mbar_arrive(&bar_p[pb]);
     }
 
     // ---- epilogue: O / l -> bf16 -> per-warp swizzled staging (reuses P buffer 0) -> coalesced stores
@@ -284,7 +302,7 @@ fa_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
       tc_fence_after();
     }
     const float inv = l > 0.f ? 1.0f / l : 0.f;
-    uint8_t* stg = sP + (warp - 2) * 8192;  // 32 rows x 256 B
+    uint8_t* stg = sK + (warp - 2) * 8192;  // 32 rows x 256 B; the K ring is idle once bar_o has fired
     uint8_t* srow = stg + lane * 256;
 #pragma unroll 1
     for (int c = 0; c < HD / 32; ++c) {
@@ -324,7 +342,7 @@ fa_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 512);
+    tmem_dealloc(tmem_base, TMEM_COLS);
   }
 }
 
@@ -366,12 +384,12 @@ static int fa_make_map(CUtensorMap* m, const void* ptr, int hd, int T, int H, in
   return 0;
 }
 
-template <int HD>
+template <int HD, int KT, int NPB>
 static int launch_fa(const mm_attn_args* a, cudaStream_t st) {
   static bool attr_set = false;
-  constexpr size_t smem = fa_smem_bytes<HD>();
+  constexpr size_t smem = fa_smem_bytes<HD, KT, NPB>();
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(fa_tcgen05_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(fa_tcgen05_kernel<HD, KT, NPB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          static_cast<int>(smem));
     if (e != cudaSuccess) {
       set_error("mm_attn_fwd: cudaFuncSetAttribute(%zu) failed: %s", smem, cudaGetErrorString(e));
@@ -381,8 +399,8 @@ static int launch_fa(const mm_attn_args* a, cudaStream_t st) {
   }
   CUtensorMap tq, tk, tv;
   if (fa_make_map(&tq, a->q, HD, a->Tq, a->H, a->B, a->q_ts, a->q_hs, a->q_bs, kFaMQ)) return 1;
-  if (fa_make_map(&tk, a->k, HD, a->Tk, a->H, a->B, a->k_ts, a->k_hs, a->k_bs, kFaKT)) return 1;
-  if (fa_make_map(&tv, a->v, HD, a->Tk, a->H, a->B, a->v_ts, a->v_hs, a->v_bs, kFaKT)) return 1;
+  if (fa_make_map(&tk, a->k, HD, a->Tk, a->H, a->B, a->k_ts, a->k_hs, a->k_bs, KT)) return 1;
+  if (fa_make_map(&tv, a->v, HD, a->Tk, a->H, a->B, a->v_ts, a->v_hs, a->v_bs, KT)) return 1;
   FaParams p;
   p.out = reinterpret_cast<bf16*>(a->out);
   p.B = a->B; p.H = a->H; p.Tq = a->Tq; p.Tk = a->Tk;
@@ -391,13 +409,13 @@ static int launch_fa(const mm_attn_args* a, cudaStream_t st) {
   p.causal = a->causal;
   p.scale_log2 = a->scale * 1.4426950408889634f;
   dim3 grid((a->Tq + kFaMQ - 1) / kFaMQ, a->H, a->B);
-  fa_tcgen05_kernel<HD><<<grid, 192, smem, st>>>(tq, tk, tv, p);
+  fa_tcgen05_kernel<HD, KT, NPB><<<grid, 192, smem, st>>>(tq, tk, tv, p);
   return check_launch("mm_attn_fwd(tcgen05)");
 }
 
 // called from mm_attn_fwd (attn.cu) for head_dim 64 / 128 when scale > 0
 int attn_tcgen05_dispatch(const mm_attn_args* a, cudaStream_t st) {
-  return a->head_dim == 64 ? launch_fa<64>(a, st) : launch_fa<128>(a, st);
+  return a->head_dim == 64 ? launch_fa<64, 64, 2>(a, st) : launch_fa<128, 64, 1>(a, st);
 }
 
 }  // namespace mm

@@ -153,3 +153,44 @@ def test_real_width_alignment_block():
 
 def H_rel(a, b):
     return H.rel_err(a, b)
+
+
+def test_real_width_reduced_depth_video_audio():
+    """BASELINE config 5 shapes at REAL widths (CLIP-L/14 width, Whisper-base width, LLaMA-7B width, V=32000, 16 frames
+    -> 4096 video tokens -> Lq=136, head_dim 96 video self-attention) with the DEPTHS cut to 2/1/1 layers so the CPU
+    oracle finishes in seconds.  Exercises every real-width code path of video + audio + text, B=2, L=64."""
+    import bench
+    from macaw_llm_b200.modeling import MM_LLMs, MM_LLMs_Config
+    from oracle import macaw_oracle as O
+
+    (clip, whisper, llama), hyper = bench.real_configs()
+    clip.vision_config.num_hidden_layers = 2
+    whisper.encoder_layers = 1
+    llama.num_hidden_layers = 1
+    hyper = dict(hyper, n_frames=16)
+    cfg = MM_LLMs_Config(clip_config=clip, whisper_config=whisper, llm_config=llama, **hyper)
+    model = MM_LLMs.build_random(cfg, device="cuda", dtype=torch.bfloat16, seed=1)
+    g = torch.Generator().manual_seed(5)
+    B, L, V = 2, 64, llama.vocab_size
+    inp = dict(images=None,
+               audios=torch.randn(B, 80, 3000, generator=g).to(torch.bfloat16),
+               videos=torch.randn(B, 16, 3, 224, 224, generator=g).to(torch.bfloat16),
+               input_ids=torch.randint(3, V - 6, (B, L), generator=g), attention_mask=torch.ones(B, L, dtype=torch.int64))
+    inp["input_ids"][:, 0] = 1
+    for i, name in enumerate(("image", "audio", "video")):
+        inp[f"{name}_starts"] = torch.full((B,), V - 6 + 2 * i, dtype=torch.int32)
+        inp[f"{name}_ends"] = torch.full((B,), V - 5 + 2 * i, dtype=torch.int32)
+    out = model({k: (v.cuda() if isinstance(v, torch.Tensor) else v) for k, v in inp.items()})
+    emb, mask, _ = model.prepare_inputs_for_generation({k: (v.cuda() if isinstance(v, torch.Tensor) else v) for k, v in inp.items()})
+    torch.cuda.synchronize()
+    T = 8 + 138 + L  # audio block 6+2, video block 136+2
+    assert tuple(out.logits.shape) == (B, T, V) and tuple(emb.shape) == (B, T, 4096)
+    assert torch.equal(mask.cpu(), torch.ones(B, T, dtype=torch.int64))
+    sd = {k: v.detach().float().cpu() for k, v in model.state_dict().items()}
+    hp = O.hp_from_config(cfg)
+    o = O.forward({k: (v.float() if isinstance(v, torch.Tensor) and v.is_floating_point() else v) for k, v in inp.items()},
+                  sd, hp, dtype=torch.float32)
+    e_pre = H.rel_err(emb[:, 1:147], o["embeds"][:, 1:147])
+    e_log = H.rel_err(out.logits, o["logits"])
+    print(f"\n[parity:real-width video+audio] prefix {e_pre:.3e} logits {e_log:.3e}")
+    assert e_pre < 1e-2 and e_log < 3e-2
