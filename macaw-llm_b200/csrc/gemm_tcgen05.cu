@@ -530,15 +530,25 @@ extern "C" int32_t mm_gemm_fwd(const mm_gemm_args* a, void* stream) {
     const long long t256 = (long long)a->batch * batch2 * p.m_tiles * ((a->N + 255) / 256);
     BN = (t256 >= sms) ? 256 : 128;
   } else {
+    // Cost model (cycles per 64-deep k-block of one tile, cta_group::1): the MMA needs 2*BN cycles, shared memory must
+    // deliver 16 KiB of A + 128*BN bytes of B at 128 B/cycle -> 128 + BN cycles; BN = 128 sits exactly on the smem
+    // limit (measured slower than the model, hence the 10 % penalty).  Waves = ceil(tiles / SMs).
     const int cands[4] = {256, 128, 64, 32};
+    const long long kcost[4] = {512, 282, 192, 160};
+    long long best = -1;
     BN = 32;
     for (int i = 0; i < 4; ++i) {
       const int bn = cands[i];
       if (a->b_mn_major && bn < 64) continue;
       if (bn > 32 && a->N <= bn / 2) continue;  // do not waste more than half a tile on padding
       const long long tiles = (long long)a->batch * batch2 * p.m_tiles * ((a->N + bn - 1) / bn);
-      BN = bn;
-      if (tiles >= sms) break;
+      const long long waves = (tiles + sms - 1) / sms;
+      // + a per-tile constant for the epilogue / pipeline fill (in k-block units of the same cost scale)
+      const long long cost = waves * ((long long)p.num_k * kcost[i] + 2 * kcost[i]);
+      if (best < 0 || cost < best) {
+        best = cost;
+        BN = bn;
+      }
     }
     if (a->b_mn_major && BN < 64) BN = 64;
   }
