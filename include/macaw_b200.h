@@ -114,6 +114,10 @@ int32_t mm_attn_fwd(const mm_attn_args* args, void* stream);
 /* ------------------------------------------------------------------------------------------------ norms
  * LlamaRMSNorm modeling.py:311-319 (fp32 variance);  y = x * rsqrt(mean(x^2) + eps) * w.  x, y bf16 [rows][cols]. */
 int32_t mm_rmsnorm_fwd(const void* x, const void* w, void* y, int32_t rows, int32_t cols, float eps, void* stream);
+/* rstd[r] = rsqrt(mean(x[r]^2) + eps) (fp32): the row statistic of LlamaRMSNorm.  With the gain folded into the next
+ * Linear's weight (W' = W * diag(g)) the norm itself becomes the `row_scale` of that GEMM's epilogue:
+ * RMSNorm(x) W^T = rstd * (x W'^T), so the normalised activations are never written to HBM. */
+int32_t mm_rms_rstd(const void* x, float* rstd, int32_t rows, int32_t cols, float eps, void* stream);
 /* nn.LayerNorm of the CLIP / Whisper encoders (transformers modeling_clip.py:CLIPEncoderLayer, modeling_whisper.py). */
 int32_t mm_layernorm_fwd(const void* x, int64_t ldx, const void* w, const void* b, void* y, int64_t ldy, int32_t rows,
                          int32_t cols, float eps, void* stream);

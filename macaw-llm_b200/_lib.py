@@ -55,6 +55,7 @@ SIGNATURES = {
     "mm_splitk_reduce": (c_i32, [c_vp, c_i32, c_i32, c_i32, c_vp, c_vp, c_i64, c_vp]),
     "mm_attn_fwd": (c_i32, [C.POINTER(AttnArgs), c_vp]),
     "mm_rmsnorm_fwd": (c_i32, [c_vp, c_vp, c_vp, c_i32, c_i32, c_f32, c_vp]),
+    "mm_rms_rstd": (c_i32, [c_vp, c_vp, c_i32, c_i32, c_f32, c_vp]),
     "mm_layernorm_fwd": (c_i32, [c_vp, c_i64, c_vp, c_vp, c_vp, c_i64, c_i32, c_i32, c_f32, c_vp]),
     "mm_embed_gather": (c_i32, [c_vp, c_i32, c_i32, c_vp, c_i64, c_vp, c_i64, c_vp]),
     "mm_splice_prefix": (c_i32, [c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp]),

@@ -81,6 +81,24 @@ __global__ void __launch_bounds__(256) rmsnorm_kernel(const bf16* __restrict__ x
   }
 }
 
+// rstd[row] = rsqrt(mean(x^2) + eps): the only part of RMSNorm that cannot ride a GEMM epilogue.  One warp per row.
+__global__ void __launch_bounds__(256) rms_rstd_kernel(const bf16* __restrict__ x, float* __restrict__ rstd, int rows,
+                                                       int cols, float eps) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int lane = threadIdx.x & 31;
+  const uint4* xr = reinterpret_cast<const uint4*>(x + static_cast<long long>(row) * cols);
+  float ss = 0.f;
+  for (int c = lane; c < (cols >> 3); c += 32) {
+    float f[8];
+    unpack8(xr[c], f);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) ss += f[i] * f[i];
+  }
+  ss = warp_sum(ss);
+  if (lane == 0) rstd[row] = rsqrtf(ss / static_cast<float>(cols) + eps);
+}
+
 // ------------------------------------------------------------------------------------------------ LayerNorm
 __global__ void __launch_bounds__(256) layernorm_kernel(const bf16* __restrict__ x, long long ldx,
                                                         const bf16* __restrict__ w, const bf16* __restrict__ b,
@@ -369,6 +387,12 @@ extern "C" int32_t mm_rmsnorm_fwd(const void* x, const void* w, void* y, int32_t
   MM_REQUIRE(AL16(x) && AL16(w) && AL16(y), "mm_rmsnorm_fwd: pointers must be 16-byte aligned");
   rmsnorm_kernel<<<rows, 256, 0, ST(stream)>>>((const bf16*)x, (const bf16*)w, (bf16*)y, cols, eps);
   return check_launch("mm_rmsnorm_fwd");
+}
+
+extern "C" int32_t mm_rms_rstd(const void* x, float* rstd, int32_t rows, int32_t cols, float eps, void* stream) {
+  MM_REQUIRE(x && rstd && rows > 0 && cols > 0 && cols % 8 == 0 && AL16(x), "mm_rms_rstd: bad arguments");
+  rms_rstd_kernel<<<(rows + 7) / 8, 256, 0, ST(stream)>>>((const bf16*)x, rstd, rows, cols, eps);
+  return check_launch("mm_rms_rstd");
 }
 
 extern "C" int32_t mm_layernorm_fwd(const void* x, int64_t ldx, const void* w, const void* b, void* y, int64_t ldy,

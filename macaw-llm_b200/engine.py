@@ -442,23 +442,29 @@ class Engine:
         for i, l in enumerate(layers):
             k = f"llm.l{i}."
             sa, mlp = l.self_attn, l.mlp
-            wqkv = self.derived(k + "wqkv", [sa.q_proj.weight, sa.k_proj.weight, sa.v_proj.weight],
-                                lambda sa=sa: torch.cat([sa.q_proj.weight, sa.k_proj.weight, sa.v_proj.weight], 0).detach().to(BF16).contiguous())
-            wgu = self.derived(k + "wgu", [mlp.gate_proj.weight, mlp.up_proj.weight],
-                               lambda mlp=mlp: torch.stack([mlp.gate_proj.weight.detach().to(BF16).view(I // 32, 32, E),
-                                                            mlp.up_proj.weight.detach().to(BF16).view(I // 32, 32, E)], 1)
+            g1, g2 = l.input_layernorm.weight, l.post_attention_layernorm.weight
+            # RMSNorm gains folded into the consuming weights (fp32 product, one bf16 rounding): RMSNorm(x) W^T = rstd * (x (W diag g)^T)
+            wqkv = self.derived(k + "wqkv", [sa.q_proj.weight, sa.k_proj.weight, sa.v_proj.weight, g1],
+                                lambda sa=sa, g1=g1: (torch.cat([sa.q_proj.weight, sa.k_proj.weight, sa.v_proj.weight], 0).detach().float()
+                                                      * g1.detach().float()[None, :]).to(BF16).contiguous())
+            wgu = self.derived(k + "wgu", [mlp.gate_proj.weight, mlp.up_proj.weight, g2],
+                               lambda mlp=mlp, g2=g2: torch.stack(
+                                   [(mlp.gate_proj.weight.detach().float() * g2.detach().float()[None, :]).to(BF16).view(I // 32, 32, E),
+                                    (mlp.up_proj.weight.detach().float() * g2.detach().float()[None, :]).to(BF16).view(I // 32, 32, E)], 1)
                                .reshape(2 * I, E).contiguous())
-            h = ops.rmsnorm(x, self.w(l.input_layernorm.weight, k + "ln1"), eps)
-            qkv = ops.linear(h, wqkv, epi=ops.EPI_ROPE, rope=(cos, sin, T, 2 * E)).view(B, T, 3, H, hd)
+            rstd = ops.rms_rstd(x, eps)
+            qkv = ops.linear(x, wqkv, epi=ops.EPI_ROPE, rope=(cos, sin, T, 2 * E), row_scale=rstd).view(B, T, 3, H, hd)
             a = ops.attention(qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2], scale=scale, causal=True, key_mask=kmask)
             ops.linear(a.view(B * T, E), self.w(sa.o_proj.weight, k + "wo"), residual=x, out=x)
-            h = ops.rmsnorm(x, self.w(l.post_attention_layernorm.weight, k + "ln2"), eps)
-            g = ops.linear(h, wgu, epi=ops.EPI_SWIGLU)
+            rstd = ops.rms_rstd(x, eps)
+            g = ops.linear(x, wgu, epi=ops.EPI_SWIGLU, row_scale=rstd)
             ops.linear(g, self.w(mlp.down_proj.weight, k + "wd"), residual=x, out=x)
-        h = ops.rmsnorm(x, self.w(llm.model.norm.weight, "llm.norm"), eps)
-        wl = self.w(llm.lm_head.weight, "llm.lm_head")
+        gn = llm.model.norm.weight
+        wl = self.derived("llm.lm_head_g", [llm.lm_head.weight, gn],
+                          lambda: (llm.lm_head.weight.detach().float() * gn.detach().float()[None, :]).to(BF16).contiguous())
+        rstd = ops.rms_rstd(x, eps)
         ops.TAG = "lm_head"
-        logits = ops.linear(h, wl)
+        logits = ops.linear(x, wl, row_scale=rstd)
         return logits.view(B, T, wl.shape[0])
 
     # ------------------------------------------------------------------------------------------------ whole forward

@@ -144,6 +144,17 @@ def rmsnorm(x: torch.Tensor, w: torch.Tensor, eps: float, out: Optional[torch.Te
     return out
 
 
+def rms_rstd(x: torch.Tensor, eps: float) -> torch.Tensor:
+    """fp32 rsqrt(mean(x^2) + eps) per row of a contiguous bf16 (rows, cols) tensor."""
+    _cuda(x, _BF16, "x")
+    assert x.is_contiguous()
+    cols = x.shape[-1]
+    rows = x.numel() // cols
+    out = torch.empty((rows,), device=x.device, dtype=torch.float32)
+    _check(_lib.load().mm_rms_rstd(x.data_ptr(), out.data_ptr(), rows, cols, float(eps), _stream()), "mm_rms_rstd")
+    return out
+
+
 def layernorm(x: torch.Tensor, w: torch.Tensor, b: torch.Tensor, eps: float,
               out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """x (rows, cols) bf16 with unit inner stride (row stride free)."""

@@ -310,3 +310,17 @@ def test_ce_loss():
     loss = ops.ce_loss(logits, labels)
     ref = torch.nn.functional.cross_entropy(logits[:, :-1].float().reshape(-1, V), labels[:, 1:].reshape(-1))
     assert abs(float(loss) - float(ref)) < 1e-3 * abs(float(ref))
+
+
+def test_rms_rstd_and_fused_norm_linear():
+    """RMSNorm folded into the next GEMM: rstd * (x (W diag g)^T) == RMSNorm(x) W^T."""
+    ops = _ops()
+    M, K, N = 300, 4096, 512
+    x, g, w = rnd(M, K, seed=70), (1.0 + 0.1 * torch.randn(K)).to(DEV).to(torch.bfloat16), rnd(N, K, scale=K ** -0.5, seed=71)
+    rstd = ops.rms_rstd(x, 1e-6)
+    ref_rstd = torch.rsqrt(x.float().pow(2).mean(-1) + 1e-6)
+    assert rel_err(rstd, ref_rstd) < 1e-5
+    wg = (w.float() * g.float()[None, :]).to(torch.bfloat16)
+    out = ops.linear(x, wg, row_scale=rstd)
+    ref = (x.float() * ref_rstd[:, None] * g.float()) @ w.float().t()
+    assert rel_err(out, ref) < 5e-3
