@@ -33,6 +33,9 @@ class Engine:
         self._rope: Dict[Tuple[int, int, str], Tuple[torch.Tensor, torch.Tensor]] = {}
         self._pe: Dict[Tuple[int, int, str], torch.Tensor] = {}
         self._zeros: Dict[Tuple[int, str], torch.Tensor] = {}
+        self._graphs: Dict[tuple, tuple] = {}
+        self._graphs_on = False
+        self._params = None
 
     # ------------------------------------------------------------------------------------------------ weight cache
     @staticmethod
@@ -468,10 +471,73 @@ class Engine:
         return logits.view(B, T, wl.shape[0])
 
     # ------------------------------------------------------------------------------------------------ whole forward
-    def forward(self, inputs: dict):
-        """MM_LLMs.forward (reference modeling.py:941-963), prefill branch -> (loss | None, logits (B, T, V) bf16)."""
+    def _forward_eager(self, inputs: dict):
         with torch.no_grad():
             embeds, mask, labels = self.prepare_inputs(inputs)
             logits = self.llama_forward(embeds, mask)
             loss = ops.ce_loss(logits, labels) if labels is not None else None
         return loss, logits, embeds, mask, labels
+
+    def forward(self, inputs: dict):
+        """MM_LLMs.forward (reference modeling.py:941-963), prefill branch -> (loss | None, logits (B, T, V) bf16, ...)."""
+        if self._graphs_on:
+            return self._forward_graphed(inputs)
+        return self._forward_eager(inputs)
+
+    # ---- CUDA-graph replay of the whole forward (opt-in) -----------------------------------------------------
+    def enable_cuda_graphs(self, flag: bool = True) -> None:
+        """Capture the ~480 kernel launches of one forward into a CUDA graph per input signature and replay it.
+
+        Removes per-launch host overhead (matters at small per-GPU batch).  Opt-in because the returned tensors are
+        STATIC buffers: a later call with the same input signature overwrites them.  Graphs are re-captured when
+        any parameter's version changes."""
+        self._graphs_on = bool(flag)
+        if not flag:
+            self._graphs.clear()
+
+    _TENSOR_KEYS = ("images", "audios", "videos", "input_ids", "attention_mask", "labels", "image_starts", "image_ends",
+                    "audio_starts", "audio_ends", "video_starts", "video_ends")
+
+    def _forward_graphed(self, inputs: dict):
+        dev = self.w(self.m.llm.model.embed_tokens.weight, "llm.embed").device
+        if self._params is None:
+            self._params = list(self.m.parameters())
+        stamp = sum(p._version for p in self._params)
+        present = tuple((k, tuple(inputs[k].shape)) for k in self._TENSOR_KEYS
+                        if isinstance(inputs.get(k), torch.Tensor))
+        key = (present, str(dev))
+        ent = self._graphs.get(key)
+        if ent is not None and ent[3] != stamp:
+            ent = None
+        if ent is None:
+            static_in = {k: v for k, v in inputs.items() if not isinstance(v, torch.Tensor)}
+            for k, _ in present:
+                v = inputs[k]
+                dt = BF16 if v.is_floating_point() else v.dtype
+                static_in[k] = torch.empty(v.shape, device=dev, dtype=dt)
+                static_in[k].copy_(v, non_blocking=True)
+            cur = torch.cuda.current_stream()
+            side = torch.cuda.Stream(device=dev)
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):
+                for _ in range(2):  # populate weight caches / function attributes before capture
+                    self._forward_eager(static_in)
+            cur.wait_stream(side)
+            torch.cuda.synchronize(dev)
+            g = torch.cuda.CUDAGraph()
+            prof, ops.PROFILE = ops.PROFILE, None  # event timing cannot live inside a capture
+            try:
+                with torch.cuda.graph(g, capture_error_mode="thread_local"):
+                    out = self._forward_eager(static_in)
+            finally:
+                ops.PROFILE = prof
+            ent = (g, static_in, out, stamp)
+            self._graphs[key] = ent
+        else:
+            static_in = ent[1]
+            for k, _ in present:
+                v = inputs[k]
+                if v.data_ptr() != static_in[k].data_ptr():
+                    static_in[k].copy_(v, non_blocking=True)
+        ent[0].replay()
+        return ent[2]

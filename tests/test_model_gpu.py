@@ -194,3 +194,29 @@ def test_real_width_reduced_depth_video_audio():
     e_log = H.rel_err(out.logits, o["logits"])
     print(f"\n[parity:real-width video+audio] prefix {e_pre:.3e} logits {e_log:.3e}")
     assert e_pre < 1e-2 and e_log < 3e-2
+
+
+def test_cuda_graph_replay_matches_eager(tiny):
+    model, spec, hp, weights = tiny
+    inp = _to_bf16_inputs(H.case_inputs(spec, H.load_case("all3")))
+    dev_inp = {k: (v.cuda() if isinstance(v, torch.Tensor) else v) for k, v in inp.items()}
+    ref = model(dev_inp)
+    ref_logits, ref_loss = ref.logits.clone(), float(ref.loss)
+    model.engine.enable_cuda_graphs(True)
+    try:
+        for _ in range(3):  # capture, then two replays
+            out = model(inp)  # host tensors: copied into the graph's static inputs
+            torch.cuda.synchronize()
+            assert torch.equal(out.logits, ref_logits), float((out.logits.float() - ref_logits.float()).abs().max())
+            assert abs(float(out.loss) - ref_loss) < 1e-5 * abs(ref_loss)  # CE uses float atomics: order-dependent last bits
+        # different values, same signature -> same graph, new result
+        inp2 = dict(inp)
+        inp2["input_ids"] = inp["input_ids"].clone()
+        inp2["input_ids"][:, 3] = 7
+        out2 = model(inp2)
+        torch.cuda.synchronize()
+        assert not torch.equal(out2.logits, ref_logits)
+    finally:
+        model.engine.enable_cuda_graphs(False)
+    eager2 = model({k: (v.cuda() if isinstance(v, torch.Tensor) else v) for k, v in inp2.items()})
+    assert torch.equal(eager2.logits, out2.logits), float((eager2.logits.float() - out2.logits.float()).abs().max())
