@@ -19,6 +19,7 @@
 #include "common.cuh"
 #include "ptx.cuh"
 #include "../../include/macaw_b200.h"
+#include <stdlib.h>
 
 namespace mm {
 
@@ -62,8 +63,8 @@ __host__ __device__ constexpr size_t gemm_smem_bytes(int BN) {
 struct TileCoord {
   int b, b_lo, b_hi, m_blk, n_blk;  // b = b_hi * batch + b_lo
 };
-__device__ __forceinline__ TileCoord tile_coord(int idx, const GemmKParams& p) {
-  const int per_batch = p.m_tiles * p.n_tiles;
+__device__ __forceinline__ TileCoord tile_coord(int idx, const GemmKParams& p, int m_units) {
+  const int per_batch = m_units * p.n_tiles;
   TileCoord t;
   t.b = idx / per_batch;
   t.b_hi = t.b / p.batch;
@@ -72,7 +73,7 @@ __device__ __forceinline__ TileCoord tile_coord(int idx, const GemmKParams& p) {
   const int in_group = kGroupM * p.n_tiles;
   const int g = r / in_group;
   const int first_m = g * kGroupM;
-  const int gsz = min(p.m_tiles - first_m, kGroupM);
+  const int gsz = min(m_units - first_m, kGroupM);
   const int rr = r - g * in_group;
   t.m_blk = first_m + rr % gsz;
   t.n_blk = rr / gsz;
@@ -126,7 +127,10 @@ __device__ __forceinline__ void store_row32(const GemmKParams& p, void* crow, in
   }
 }
 
-template <int BN, int EPI, bool B_MN>
+// MC = true: clusters of 2 CTAs work on vertically adjacent tiles (m_blk = 2u, 2u+1; same n_blk) and share the B tile:
+// each CTA TMA-loads half of it and multicasts to both, cutting L2->SM operand traffic per CTA from 48 to 32 KiB per
+// k-block.  A smem slot is free only when BOTH CTAs' MMAs have retired (they both receive the peer's multicast).
+template <int BN, int EPI, bool B_MN, bool MC>
 __global__ void __launch_bounds__(320, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const GemmKParams p) {
@@ -147,7 +151,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int total_tiles = p.batch * p.batch2 * p.m_tiles * p.n_tiles;
+  const int cta_rank = MC ? static_cast<int>(cluster_ctarank()) : 0;
+  const int worker = MC ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
+  const int n_workers = MC ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
+  const int m_units = MC ? (p.m_tiles + 1) / 2 : p.m_tiles;
+  const int total_tiles = p.batch * p.batch2 * m_units * p.n_tiles;
 
   if (warp == 0 && elect_one()) {
     tma_prefetch_desc(&tmA);
@@ -157,7 +165,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     if (elect_one()) {
       for (int s = 0; s < STAGES; ++s) {
         mbar_init(&full_bar[s], 1);
-        mbar_init(&empty_bar[s], 1);
+        mbar_init(&empty_bar[s], MC ? 2 : 1);
       }
       for (int s = 0; s < 2; ++s) {
         mbar_init(&tfull_bar[s], 1);
@@ -170,7 +178,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     tmem_relinquish();
   }
   tc_fence_before();
-  __syncthreads();
+  if constexpr (MC) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -179,15 +187,29 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const TileCoord t = tile_coord(tile, p);
+      for (int tile = worker; tile < total_tiles; tile += n_workers) {
+        TileCoord t = tile_coord(tile, p, m_units);
+        if constexpr (MC) t.m_blk = 2 * t.m_blk + cta_rank;
         const int bb = p.b_shared ? 0 : t.b_lo;
         const int bh = p.b2_shared ? 0 : t.b_hi;
         for (int kb = 0; kb < p.num_k; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           mbar_arrive_expect_tx(&full_bar[stage], kABytes + B_BYTES);
           tma_load_4d(&tmA, &full_bar[stage], sA + stage * kABytes, kb * kBlockK, t.m_blk * kBlockM, t.b_lo, t.b_hi);
-          if constexpr (!B_MN) {
+          if constexpr (MC) {
+            // this CTA fetches its half of the B tile and multicasts it to both CTAs of the pair
+            if constexpr (!B_MN) {
+              tma_load_4d_mc(&tmB, &full_bar[stage], sB + stage * B_BYTES + cta_rank * (BN / 2) * 128, kb * kBlockK,
+                             t.n_blk * BN + cta_rank * (BN / 2), bb, bh, 3);
+            } else {
+#pragma unroll
+              for (int jj = 0; jj < BN / 128; ++jj) {
+                const int j = cta_rank * (BN / 128) + jj;
+                tma_load_4d_mc(&tmB, &full_bar[stage], sB + stage * B_BYTES + j * 8192, t.n_blk * BN + j * 64,
+                               kb * kBlockK, bb, bh, 3);
+              }
+            }
+          } else if constexpr (!B_MN) {
             tma_load_4d(&tmB, &full_bar[stage], sB + stage * B_BYTES, kb * kBlockK, t.n_blk * BN, bb, bh);
           } else {
 #pragma unroll
@@ -209,7 +231,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int tile = worker; tile < total_tiles; tile += n_workers) {
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
@@ -228,7 +250,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             const uint64_t b_k = b_desc + static_cast<uint64_t>(B_MN ? kk * 128 : kk * 2);  // +2048 B | +32 B
             umma_bf16(d_tmem, a_k, b_k, IDESC, (kb | kk) != 0 ? 1u : 0u);
           }
-          umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs retire
+          // frees the smem slot once these MMAs retire (in both CTAs of a multicast pair)
+          if constexpr (MC) umma_commit_mc(&empty_bar[stage], 3); else umma_commit(&empty_bar[stage]);
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1;
@@ -248,8 +271,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     int acc = 0;
     uint32_t acc_phase = 0;
     const int n_out_total = (EPI == MM_EPI_SWIGLU) ? p.N / 2 : p.N;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      const TileCoord t = tile_coord(tile, p);
+    for (int tile = worker; tile < total_tiles; tile += n_workers) {
+      TileCoord t = tile_coord(tile, p, m_units);
+      if constexpr (MC) t.m_blk = 2 * t.m_blk + cta_rank;
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
       const int row = t.m_blk * kBlockM + q * 32 + lane;
@@ -394,7 +418,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   }
 
   tc_fence_before();
-  __syncthreads();
+  if constexpr (MC) cluster_sync_all(); else __syncthreads();  // a pair exits together: the peer may still signal us
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, TMEM_COLS);
@@ -457,22 +481,44 @@ static int num_sms() {
   return n;
 }
 
-template <int BN, int EPI, bool B_MN>
+template <int BN, int EPI, bool B_MN, bool MC>
 static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmKParams& p, cudaStream_t st) {
   static bool attr_set = false;
   constexpr size_t smem = gemm_smem_bytes(BN);
+  auto kern = gemm_bf16_kernel<BN, EPI, B_MN, MC>;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_bf16_kernel<BN, EPI, B_MN>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     if (e != cudaSuccess) {
       set_error("cudaFuncSetAttribute(smem=%zu) failed: %s", smem, cudaGetErrorString(e));
       return 2;
     }
     attr_set = true;
   }
-  const int total = p.batch * p.batch2 * p.m_tiles * p.n_tiles;
-  const int grid = total < num_sms() ? total : num_sms();
-  gemm_bf16_kernel<BN, EPI, B_MN><<<grid, 320, smem, st>>>(ta, tb, p);
+  const int m_units = MC ? (p.m_tiles + 1) / 2 : p.m_tiles;
+  const int total = p.batch * p.batch2 * m_units * p.n_tiles;
+  if constexpr (MC) {
+    const int pairs = total < num_sms() / 2 ? total : num_sms() / 2;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * pairs);
+    cfg.blockDim = dim3(320);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, ta, tb, p);
+    if (e != cudaSuccess) {
+      set_error("mm_gemm_fwd: cluster launch failed: %s", cudaGetErrorString(e));
+      return 2;
+    }
+  } else {
+    const int grid = total < num_sms() ? total : num_sms();
+    kern<<<grid, 320, smem, st>>>(ta, tb, p);
+  }
   return check_launch("mm_gemm_fwd");
 }
 
@@ -554,19 +600,32 @@ extern "C" int32_t mm_gemm_fwd(const mm_gemm_args* a, void* stream) {
   }
   p.n_tiles = (a->N + BN - 1) / BN;
 
+  // multicast pairs: wide tiles, several waves of work, and at most ~3 % of rows lost to an odd number of M tiles
+  static const int mc_env = []() { const char* e = getenv("MACAW_B200_GEMM_MC"); return e ? atoi(e) : 1; }();
+  const long long tiles256 = (long long)a->batch * batch2 * p.m_tiles * p.n_tiles;
+  // (measured A/B on one box, cfg4: LLaMA GEMMs 1282 -> 1325 TFLOP/s; short-K CLIP GEMMs do not gain, hence K >= 2048)
+  const bool use_mc = mc_env != 0 && BN == 256 && p.m_tiles >= 2 && p.num_k >= 32 && tiles256 >= 2LL * sms &&
+                      (((p.m_tiles + 1) / 2) * 2 - p.m_tiles) * 32 <= p.m_tiles;
   CUtensorMap ta, tb;
   if (make_map(&ta, a->A, a->K, a->M, a->batch, batch2, a->lda, a->a_bs, a->a_bs2, kBlockM)) return 1;
   const uint64_t b_batch = p.b_shared ? 1 : a->batch;
   const uint64_t b_batch2 = p.b2_shared ? 1 : batch2;
   if (!a->b_mn_major) {
-    if (make_map(&tb, a->B, a->K, a->N, b_batch, b_batch2, a->ldb, a->b_bs, a->b_bs2, BN)) return 1;
+    if (make_map(&tb, a->B, a->K, a->N, b_batch, b_batch2, a->ldb, a->b_bs, a->b_bs2, use_mc ? BN / 2 : BN)) return 1;
   } else {
     MM_REQUIRE(a->epi == MM_EPI_STD, "mm_gemm_fwd: MN-major B only with the standard epilogue");
     if (make_map(&tb, a->B, a->N, a->K, b_batch, b_batch2, a->ldb, a->b_bs, a->b_bs2, 64)) return 1;
   }
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
 
-#define MM_LAUNCH(BN_, EPI_, MN_) return launch_gemm<BN_, EPI_, MN_>(ta, tb, p, st)
+#define MM_LAUNCH(BN_, EPI_, MN_) return launch_gemm<BN_, EPI_, MN_, false>(ta, tb, p, st)
+#define MM_LAUNCH_MC(EPI_, MN_) return launch_gemm<256, EPI_, MN_, true>(ta, tb, p, st)
+  if (use_mc) {
+    if (a->epi == MM_EPI_ROPE) MM_LAUNCH_MC(MM_EPI_ROPE, false);
+    if (a->epi == MM_EPI_SWIGLU) MM_LAUNCH_MC(MM_EPI_SWIGLU, false);
+    if (a->b_mn_major) MM_LAUNCH_MC(MM_EPI_STD, true);
+    MM_LAUNCH_MC(MM_EPI_STD, false);
+  }
   if (a->epi == MM_EPI_ROPE) {
     if (BN == 256) MM_LAUNCH(256, MM_EPI_ROPE, false);
     MM_LAUNCH(128, MM_EPI_ROPE, false);
@@ -585,6 +644,7 @@ extern "C" int32_t mm_gemm_fwd(const mm_gemm_args* a, void* stream) {
   if (BN == 64) MM_LAUNCH(64, MM_EPI_STD, false);
   MM_LAUNCH(32, MM_EPI_STD, false);
 #undef MM_LAUNCH
+#undef MM_LAUNCH_MC
 }
 
 // ------------------------------------------------------------------------------------------------ split-K reduce

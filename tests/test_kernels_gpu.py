@@ -324,3 +324,57 @@ def test_rms_rstd_and_fused_norm_linear():
     out = ops.linear(x, wg, row_scale=rstd)
     ref = (x.float() * ref_rstd[:, None] * g.float()) @ w.float().t()
     assert rel_err(out, ref) < 5e-3
+
+
+@pytest.mark.parametrize(
+    "M,N,K,kind",
+    [
+        (4224, 4096, 512, "std"),      # 33 M tiles (odd): last pair has an idle half
+        (4096, 2560, 1024, "bias_res"),
+        (4096, 4096, 1024, "rope"),
+        (4096, 5504, 1024, "swiglu"),
+        (3072, 4096, 3001, "mn"),      # P x table shape, MN-major B, ragged K
+        (16896, 4096, 4096, "std"),    # cfg4 o_proj
+    ],
+)
+def test_gemm_multicast_pairs(M, N, K, kind):
+    """Shapes large enough to take the 2-CTA TMA-multicast path (BN = 256, >= 2 waves)."""
+    ops = _ops()
+    x = rnd(M, K, seed=80)
+    if kind == "mn":
+        P = rnd(M, 3008, seed=81).abs()
+        P[:, K:] = 0
+        tab = rnd(K, N, seed=82)
+        out = torch.empty(M, N, device=DEV, dtype=torch.bfloat16)
+        ops.gemm_raw(M=M, N=N, K=K, A=P.data_ptr(), lda=P.stride(0), B=tab.data_ptr(), ldb=N, b_mn_major=True,
+                     Cout=out.data_ptr(), ldc=N)
+        assert rel_err(out, P[:, :K].float() @ tab.float()) < 4e-3
+        return
+    if kind == "swiglu":
+        I = N // 2
+        wg, wu = rnd(I, K, scale=K ** -0.5, seed=83), rnd(I, K, scale=K ** -0.5, seed=84)
+        wgu = torch.stack([wg.view(I // 32, 32, K), wu.view(I // 32, 32, K)], dim=1).reshape(2 * I, K).contiguous()
+        out = ops.linear(x, wgu, epi=ops.EPI_SWIGLU)
+        ref = torch.nn.functional.silu(x.float() @ wg.float().t()) * (x.float() @ wu.float().t())
+        assert rel_err(out, ref) < 4e-3
+        return
+    w = rnd(N, K, scale=K ** -0.5, seed=85)
+    if kind == "rope":
+        T = 128
+        inv = 1.0 / (10000 ** (torch.arange(0, 128, 2, device=DEV).float() / 128))
+        ang = torch.arange(T, device=DEV).float()[:, None] * inv[None, :]
+        cos, sin = ang.cos().contiguous(), ang.sin().contiguous()
+        out = ops.linear(x, w, epi=ops.EPI_ROPE, rope=(cos, sin, T, N))
+        y = (x.float() @ w.float().t()).view(M // T, T, N // 128, 128)
+        c = torch.cat([cos, cos], -1)[None, :, None, :]
+        s_ = torch.cat([sin, sin], -1)[None, :, None, :]
+        ref = (y * c + torch.cat([-y[..., 64:], y[..., :64]], -1) * s_).reshape(M, N)
+        assert rel_err(out, ref) < 4e-3
+        return
+    if kind == "bias_res":
+        b, res = rnd(N, seed=86), rnd(M, N, seed=87)
+        out = ops.linear(x, w, b, residual=res)
+        assert rel_err(out, x.float() @ w.float().t() + b.float() + res.float()) < 4e-3
+        return
+    out = ops.linear(x, w)
+    assert rel_err(out, x.float() @ w.float().t()) < 4e-3
