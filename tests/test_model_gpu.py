@@ -220,3 +220,50 @@ def test_cuda_graph_replay_matches_eager(tiny):
         model.engine.enable_cuda_graphs(False)
     eager2 = model({k: (v.cuda() if isinstance(v, torch.Tensor) else v) for k, v in inp2.items()})
     assert torch.equal(eager2.logits, out2.logits), float((eager2.logits.float() - out2.logits.float()).abs().max())
+
+
+def test_resized_vocab_not_multiple_of_8():
+    """The real pipeline resizes the table to 32007 rows (run_clm_llms.py:495): V % 8 != 0 exercises the padded score
+    buffer, the ragged-K P.table GEMM and the unaligned (scalar-store) lm_head epilogue.  Tiny model, V = 512 + 7."""
+    from oracle import macaw_oracle as O
+
+    model, spec, hp, weights = H.build_tiny_model("cpu", torch.float32)
+    model.llm.resize_token_embeddings(519)
+    g = torch.Generator().manual_seed(11)
+    with torch.no_grad():
+        model.llm.model.embed_tokens.weight[512:].copy_(torch.randn(7, 256, generator=g) * 0.5)
+        model.llm.lm_head.weight[512:].copy_(torch.randn(7, 256, generator=g) / 16)
+    model = model.cuda().to(torch.bfloat16).eval()
+    inp = _to_bf16_inputs(H.case_inputs(spec, H.load_case("all3")))
+    for i, name in enumerate(("image", "audio", "video")):  # modal tokens live in the appended rows, as in the reference
+        inp[f"{name}_starts"] = torch.full((2,), 513 + 2 * i, dtype=torch.int32)
+        inp[f"{name}_ends"] = torch.full((2,), 514 + 2 * i, dtype=torch.int32)
+    out = model({k: (v.cuda() if isinstance(v, torch.Tensor) else v) for k, v in inp.items()})
+    torch.cuda.synchronize()
+    assert out.logits.shape[-1] == 519
+    sd = {k: v.detach().float().cpu() for k, v in model.state_dict().items()}
+    hp2 = dict(hp, llama=dict(hp["llama"], vocab=519))
+    o = O.forward({k: (v.float() if isinstance(v, torch.Tensor) and v.is_floating_point() else v) for k, v in inp.items()},
+                  sd, hp2, dtype=torch.float32)
+    valid = o["attention_mask"].bool()
+    e = H.rel_err(out.logits.cpu()[valid], o["logits"][valid])
+    print(f"\n[parity:V=519] logits {e:.3e} loss {float(out.loss):.4f} vs {float(o['loss']):.4f}")
+    assert e < 3e-2 and abs(float(out.loss) - float(o["loss"])) < 2e-2 * abs(float(o["loss"]))
+
+
+def test_batch1_no_mask_no_labels(tiny):
+    """Smallest call shapes: B=1, no attention_mask key, no labels (reference returns mask=None, labels=None)."""
+    from oracle import macaw_oracle as O
+
+    model, spec, hp, weights = tiny
+    inp = _to_bf16_inputs(H.case_inputs(spec, H.load_case("image")))
+    inp.pop("attention_mask")
+    inp.pop("labels", None)
+    emb, mask, labels = model.prepare_inputs_for_generation({k: (v.cuda() if isinstance(v, torch.Tensor) else v) for k, v in inp.items()})
+    out = model({k: (v.cuda() if isinstance(v, torch.Tensor) else v) for k, v in inp.items()})
+    torch.cuda.synchronize()
+    assert mask is None and labels is None and out.loss is None
+    o = O.forward({k: (v.float() if isinstance(v, torch.Tensor) and v.is_floating_point() else v) for k, v in inp.items()},
+                  H.bf16_round(weights), hp, dtype=torch.float32)
+    assert o["attention_mask"] is None
+    assert H.rel_err(out.logits, o["logits"]) < 3e-2
