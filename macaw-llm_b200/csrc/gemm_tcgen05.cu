@@ -80,16 +80,37 @@ __device__ __forceinline__ TileCoord tile_coord(int idx, const GemmKParams& p, i
   return t;
 }
 
-__device__ __forceinline__ float apply_act(float x, int act) {
-  switch (act) {
-    case MM_ACT_GELU:
-      return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f));
-    case MM_ACT_QUICK_GELU:
-      return __fdividef(x, 1.0f + __expf(-1.702f * x));
-    case MM_ACT_SILU:
-      return __fdividef(x, 1.0f + __expf(-x));
-    default:
-      return x;
+__device__ __forceinline__ float tanh_approx(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// sigmoid(x) = 0.5 tanh(0.5 x) + 0.5: one MUFU op (tanh.approx.f32, rel. error ~2^-11 — far below the bf16 output rounding)
+__device__ __forceinline__ float sigmoid_fast(float x) { return fmaf(0.5f, tanh_approx(0.5f * x), 0.5f); }
+// exact-GELU's erf via Abramowitz-Stegun 7.1.26 (|error| <= 1.5e-7): 2 MUFU + ~10 FMA, branch-free
+__device__ __forceinline__ float gelu_erf(float x) {
+  const float z = fabsf(x) * 0.70710678118654752f;
+  const float t = __frcp_rn(fmaf(0.3275911f, z, 1.0f));
+  float poly = fmaf(1.061405429f, t, -1.453152027f);
+  poly = fmaf(poly, t, 1.421413741f);
+  poly = fmaf(poly, t, -0.284496736f);
+  poly = fmaf(poly, t, 0.254829592f);
+  poly *= t;
+  const float e = 1.0f - poly * exp2f(-1.4426950408889634f * z * z);  // erf(|x| / sqrt 2)
+  return 0.5f * x + 0.5f * fabsf(x) * e;                                 // 0.5 x (1 + sign(x) erf(|x|/sqrt2))
+}
+
+// Activation over a 32-wide chunk: the switch is hoisted so each case is a straight unrolled loop.
+__device__ __forceinline__ void apply_act32(float (&v)[32], int act) {
+  if (act == MM_ACT_QUICK_GELU) {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] *= sigmoid_fast(1.702f * v[i]);
+  } else if (act == MM_ACT_GELU) {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = gelu_erf(v[i]);
+  } else if (act == MM_ACT_SILU) {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] *= sigmoid_fast(v[i]);
   }
 }
 
@@ -322,10 +343,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 if (col0 + i < p.N) v[i] += __bfloat162float(bias[col0 + i]);
             }
           }
-          if (p.act != MM_ACT_NONE) {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = apply_act(v[i], p.act);
-          }
+          if (p.act != MM_ACT_NONE) apply_act32(v, p.act);
           if (rrow != nullptr) {
             if (full) {
 #pragma unroll
@@ -358,7 +376,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           for (int i = 0; i < 32; ++i) {
             const float gg = __uint_as_float(g[i]) * rs;
             const float uu = __uint_as_float(u[i]) * rs;
-            v[i] = __fdividef(gg, 1.0f + __expf(-gg)) * uu;
+            v[i] = gg * sigmoid_fast(gg) * uu;
           }
           if (row_ok) store_row32(p, crow, col_in / 2, n_out_total, v);
         }
