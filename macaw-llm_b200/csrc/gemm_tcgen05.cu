@@ -42,6 +42,7 @@ struct GemmKParams {
   const float* rope_sin;
   int rope_T, rope_cols;
   int vec_ok;
+  int group_m;  // rasterisation: M units per group
 };
 
 constexpr int kBlockM = 128;
@@ -70,10 +71,10 @@ __device__ __forceinline__ TileCoord tile_coord(int idx, const GemmKParams& p, i
   t.b_hi = t.b / p.batch;
   t.b_lo = t.b - t.b_hi * p.batch;
   int r = idx - t.b * per_batch;
-  const int in_group = kGroupM * p.n_tiles;
+  const int in_group = p.group_m * p.n_tiles;
   const int g = r / in_group;
-  const int first_m = g * kGroupM;
-  const int gsz = min(m_units - first_m, kGroupM);
+  const int first_m = g * p.group_m;
+  const int gsz = min(m_units - first_m, p.group_m);
   const int rr = r - g * in_group;
   t.m_blk = first_m + rr % gsz;
   t.n_blk = rr / gsz;
@@ -617,13 +618,21 @@ extern "C" int32_t mm_gemm_fwd(const mm_gemm_args* a, void* stream) {
     if (a->b_mn_major && BN < 64) BN = 64;
   }
   p.n_tiles = (a->N + BN - 1) / BN;
-
+  static const int gm_env = []() { const char* e = getenv("MACAW_B200_GEMM_GROUPM"); return e ? atoi(e) : 0; }();
   // multicast pairs: wide tiles, several waves of work, and at most ~3 % of rows lost to an odd number of M tiles
   static const int mc_env = []() { const char* e = getenv("MACAW_B200_GEMM_MC"); return e ? atoi(e) : 1; }();
   const long long tiles256 = (long long)a->batch * batch2 * p.m_tiles * p.n_tiles;
   // (measured A/B on one box, cfg4: LLaMA GEMMs 1282 -> 1325 TFLOP/s; short-K CLIP GEMMs do not gain, hence K >= 2048)
   const bool use_mc = mc_env != 0 && BN == 256 && p.m_tiles >= 2 && p.num_k >= 32 && tiles256 >= 2LL * sms &&
                       (((p.m_tiles + 1) / 2) * 2 - p.m_tiles) * 32 <= p.m_tiles;
+  // rasterisation: keep one group's A rows (~32 MiB) resident in the 126 MB L2 while its B tiles stream
+  // (measured on cfg4: 16 pairs at K=4096 is the optimum; 4 / 8 / 32 cost +5 % / +1 % / +9 % step time)
+  {
+    const long long unit_bytes = (long long)(use_mc ? 2 : 1) * kBlockM * a->K * 2;
+    long long g = ((32LL << 20) + unit_bytes / 2) / unit_bytes;
+    g = g < 2 ? 2 : (g > 32 ? 32 : g);
+    p.group_m = gm_env > 0 ? gm_env : static_cast<int>(g);
+  }
   CUtensorMap ta, tb;
   if (make_map(&ta, a->A, a->K, a->M, a->batch, batch2, a->lda, a->a_bs, a->a_bs2, kBlockM)) return 1;
   const uint64_t b_batch = p.b_shared ? 1 : a->batch;

@@ -138,6 +138,56 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const bf16* __restrict__
   }
 }
 
+// LayerNorm for narrow rows (cols <= 1024): one warp per row, the row lives in registers (single HBM read).
+template <int CH>  // 16-byte chunks per lane
+__global__ void __launch_bounds__(256) layernorm_warp_kernel(const bf16* __restrict__ x, long long ldx,
+                                                             const bf16* __restrict__ w, const bf16* __restrict__ b,
+                                                             bf16* __restrict__ y, long long ldy, int rows, int cols,
+                                                             float eps) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int lane = threadIdx.x & 31;
+  const int nch = cols >> 3;
+  const uint4* xr = reinterpret_cast<const uint4*>(x + static_cast<long long>(row) * ldx);
+  float f[CH][8];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < CH; ++i) {
+    const int c = lane + 32 * i;
+    if (c < nch) {
+      unpack8(xr[c], f[i]);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) s += f[i][k];
+    }
+  }
+  const float mean = warp_sum(s) / static_cast<float>(cols);
+  float vs = 0.f;
+#pragma unroll
+  for (int i = 0; i < CH; ++i) {
+    if (lane + 32 * i < nch) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const float d = f[i][k] - mean;
+        vs += d * d;
+      }
+    }
+  }
+  const float rstd = rsqrtf(warp_sum(vs) / static_cast<float>(cols) + eps);
+  uint4* yr = reinterpret_cast<uint4*>(y + static_cast<long long>(row) * ldy);
+#pragma unroll
+  for (int i = 0; i < CH; ++i) {
+    const int c = lane + 32 * i;
+    if (c < nch) {
+      float g[8], h[8];
+      unpack8(__ldg(reinterpret_cast<const uint4*>(w) + c), g);
+      unpack8(__ldg(reinterpret_cast<const uint4*>(b) + c), h);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) f[i][k] = (f[i][k] - mean) * rstd * g[k] + h[k];
+      yr[c] = pack8(f[i]);
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ gathers / copies
 __global__ void __launch_bounds__(128) embed_gather_kernel(const bf16* __restrict__ table, int vocab, int dim,
                                                            const long long* __restrict__ ids, bf16* __restrict__ out,
@@ -400,8 +450,16 @@ extern "C" int32_t mm_layernorm_fwd(const void* x, int64_t ldx, const void* w, c
   MM_REQUIRE(x && w && b && y && rows > 0 && cols > 0 && cols % 8 == 0 && ldx % 8 == 0 && ldy % 8 == 0,
              "mm_layernorm_fwd: bad arguments");
   MM_REQUIRE(AL16(x) && AL16(w) && AL16(b) && AL16(y), "mm_layernorm_fwd: pointers must be 16-byte aligned");
-  layernorm_kernel<<<rows, 128, 0, ST(stream)>>>((const bf16*)x, ldx, (const bf16*)w, (const bf16*)b, (bf16*)y, ldy,
-                                                 cols, eps);
+  if (cols <= 512) {
+    layernorm_warp_kernel<2><<<(rows + 7) / 8, 256, 0, ST(stream)>>>((const bf16*)x, ldx, (const bf16*)w, (const bf16*)b,
+                                                                     (bf16*)y, ldy, rows, cols, eps);
+  } else if (cols <= 1024) {
+    layernorm_warp_kernel<4><<<(rows + 7) / 8, 256, 0, ST(stream)>>>((const bf16*)x, ldx, (const bf16*)w, (const bf16*)b,
+                                                                     (bf16*)y, ldy, rows, cols, eps);
+  } else {
+    layernorm_kernel<<<rows, 128, 0, ST(stream)>>>((const bf16*)x, ldx, (const bf16*)w, (const bf16*)b, (bf16*)y, ldy,
+                                                   cols, eps);
+  }
   return check_launch("mm_layernorm_fwd");
 }
 

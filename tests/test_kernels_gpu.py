@@ -248,10 +248,11 @@ def test_rmsnorm_layernorm():
     xf = x.float()
     ref = xf * torch.rsqrt(xf.pow(2).mean(-1, keepdim=True) + 1e-6) * w.float()
     assert rel_err(y, ref) < 3e-3
-    x2 = rnd(514, 1024, seed=43)
-    y2 = ops.layernorm(x2, w[:1024].contiguous(), b[:1024].contiguous(), 1e-5)
-    ref2 = torch.nn.functional.layer_norm(x2.float(), (1024,), w[:1024].float(), b[:1024].float(), 1e-5)
-    assert rel_err(y2, ref2) < 3e-3
+    for cols in (128, 512, 1024, 2048):  # warp-per-row kernels (<= 1024) and the CTA-per-row kernel
+        x2 = rnd(517, cols, seed=43)
+        y2 = ops.layernorm(x2, w[:cols].contiguous(), b[:cols].contiguous(), 1e-5)
+        ref2 = torch.nn.functional.layer_norm(x2.float(), (cols,), w[:cols].float(), b[:cols].float(), 1e-5)
+        assert rel_err(y2, ref2) < 3e-3, cols
 
 
 def test_embed_gather_and_splice_bit_exact():
