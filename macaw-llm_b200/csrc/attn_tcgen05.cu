@@ -30,11 +30,18 @@ struct FaParams {
   const int* key_mask;
   int causal;
   float scale_log2;
+  int qpc;  // query tiles per CTA (walked heaviest first)
+  int rev;  // launch query-tile groups in descending order (heavier causal groups first)
 };
 
 constexpr int kFaMQ = 128;  // queries per CTA
 constexpr float kFaTau = 8.0f;  // lazy-rescale threshold (log2 domain)
 
+__device__ __forceinline__ float max3(float a, float b, float c) {  // one FMNMX3 on sm_100
+  float d;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+  return d;
+}
 __device__ __forceinline__ float ex2_approx(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -45,7 +52,7 @@ __device__ __forceinline__ float ex2_approx(float x) {
 template <int HD, int KT, int NPB>
 __host__ __device__ constexpr size_t fa_smem_bytes() {
   // Q + 2 K stages + 2 V stages + NPB P buffers + barriers (the dynamic smem window itself is 1024-byte aligned)
-  return (size_t)(HD / 64) * 16384 + 4 * (size_t)(HD / 64) * KT * 128 + (size_t)NPB * 128 * KT * 2 + 256;
+  return (size_t)(HD / 64) * 16384 + 4 * (size_t)(HD / 64) * KT * 128 + (size_t)NPB * 128 * KT * 2 + 256;  // 21 barriers + TMEM slot
 }
 
 template <int HD, int KT, int NPB>
@@ -71,25 +78,32 @@ fa_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
   uint8_t* sV = sK + 2 * QB;
   uint8_t* sP = sV + 2 * QB;
   uint64_t* bars = reinterpret_cast<uint64_t*>(sP + NPB * PB);
-  uint64_t* bar_q = bars;            // 1
-  uint64_t* bar_k = bars + 1;        // 2
-  uint64_t* bar_v = bars + 3;        // 2
-  uint64_t* bar_kfree = bars + 5;    // 2
-  uint64_t* bar_vfree = bars + 7;    // 2
-  uint64_t* bar_s = bars + 9;        // 2
-  uint64_t* bar_sfree = bars + 11;   // 2
-  uint64_t* bar_p = bars + 13;       // 2
-  uint64_t* bar_pfree = bars + 15;   // 2
-  uint64_t* bar_o = bars + 17;       // 1
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 18);
+  uint64_t* bar_q = bars;            // 1  Q tile landed
+  uint64_t* bar_k = bars + 1;        // 2  K stage landed
+  uint64_t* bar_v = bars + 3;        // 2  V stage landed
+  uint64_t* bar_kfree = bars + 5;    // 2  S MMA finished reading the K stage
+  uint64_t* bar_vfree = bars + 7;    // 2  PV MMA finished reading the V stage
+  uint64_t* bar_s = bars + 9;        // 2  S tile complete in TMEM
+  uint64_t* bar_sfree = bars + 11;   // 2  softmax has S in registers
+  uint64_t* bar_p = bars + 13;       // 2  P tile written to smem
+  uint64_t* bar_pfree = bars + 15;   // 2  PV MMA finished reading the P buffer
+  uint64_t* bar_o = bars + 17;       // 1  all PV of the current query tile complete
+  uint64_t* bar_qfree = bars + 18;   // 1  all S MMAs of the current query tile complete (Q may be replaced)
+  uint64_t* bar_ofree = bars + 19;   // 1  softmax warps have read O (next query tile may overwrite it)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int mt = gridDim.x - 1 - blockIdx.x;  // heavy (late, causal) tiles first
-  const int m0 = mt * kFaMQ, h = blockIdx.y, b = blockIdx.z;
+  const int h = blockIdx.y, b = blockIdx.z;
   const int shift = p.Tk - p.Tq;
-  int kv_end = p.Tk;
-  if (p.causal) kv_end = min(p.Tk, m0 + kFaMQ + shift);
-  const int n_tiles = kv_end > 0 ? (kv_end + kFaKT - 1) / kFaKT : 0;
+  // This CTA walks `p.qpc` consecutive query tiles of (b, h), heaviest first; heavy groups are launched first.
+  const int nq = (p.Tq + kFaMQ - 1) / kFaMQ;
+  const int grp = p.rev ? static_cast<int>(gridDim.x - 1 - blockIdx.x) : static_cast<int>(blockIdx.x);
+  const int q_lo = grp * p.qpc, q_hi = min(nq, q_lo + p.qpc);  // query tiles [q_lo, q_hi)
+  auto tiles_of = [&](int mt) {
+    int kv_end = p.Tk;
+    if (p.causal) kv_end = min(p.Tk, mt * kFaMQ + kFaMQ + shift);
+    return kv_end > 0 ? (kv_end + kFaKT - 1) / kFaKT : 0;
+  };
 
   if (warp == 0 && elect_one()) {
     tma_prefetch_desc(&tmQ);
@@ -100,6 +114,8 @@ fa_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
     if (elect_one()) {
       mbar_init(bar_q, 1);
       mbar_init(bar_o, 1);
+      mbar_init(bar_qfree, 1);
+      mbar_init(bar_ofree, 4);
       for (int i = 0; i < 2; ++i) {
         mbar_init(&bar_k[i], 1);
         mbar_init(&bar_v[i], 1);
@@ -121,220 +137,260 @@ fa_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
+  // Every role walks the same sequence: query tiles mt = q_hi-1 .. q_lo, key tiles j = 0 .. n-1 of each.
+  // G = running key-tile index across query tiles (ring stages / mbarrier parities), qa = running count of
+  // non-empty query tiles.
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
-    if (elect_one() && n_tiles > 0) {
-      mbar_arrive_expect_tx(bar_q, QBYTES);
+    if (elect_one()) {
+      int G = 0, qa = 0;
+      for (int mt = q_hi - 1; mt >= q_lo; --mt) {
+        const int n_tiles = tiles_of(mt);
+        if (n_tiles == 0) continue;
+        if (qa >= 1) mbar_wait(bar_qfree, (qa - 1) & 1);  // the previous query tile's S MMAs are done with sQ
+        mbar_arrive_expect_tx(bar_q, QBYTES);
 #pragma unroll
-      for (int kb = 0; kb < KB; ++kb) tma_load_4d(&tmQ, bar_q, sQ + kb * 16384, kb * 64, m0, h, b);
-      for (int j = 0; j < n_tiles; ++j) {
-        const int st = j & 1;
-        const uint32_t par = ((j >> 1) - 1) & 1;  // parity of the (j-2)-th use of this stage
-        if (j >= 2) mbar_wait(&bar_kfree[st], par);
-        mbar_arrive_expect_tx(&bar_k[st], QB);
+        for (int kb = 0; kb < KB; ++kb) tma_load_4d(&tmQ, bar_q, sQ + kb * 16384, kb * 64, mt * kFaMQ, h, b);
+        for (int j = 0; j < n_tiles; ++j, ++G) {
+          const int st = G & 1;
+          const uint32_t par = ((G >> 1) - 1) & 1;  // parity of the previous use of this stage
+          if (G >= 2) mbar_wait(&bar_kfree[st], par);
+          mbar_arrive_expect_tx(&bar_k[st], QB);
 #pragma unroll
-        for (int kb = 0; kb < KB; ++kb)
-          tma_load_4d(&tmK, &bar_k[st], sK + st * QB + kb * (KT * 128), kb * 64, j * kFaKT, h, b);
-        if (j >= 2) mbar_wait(&bar_vfree[st], par);
-        mbar_arrive_expect_tx(&bar_v[st], QB);
+          for (int kb = 0; kb < KB; ++kb)
+            tma_load_4d(&tmK, &bar_k[st], sK + st * QB + kb * (KT * 128), kb * 64, j * kFaKT, h, b);
+          if (G >= 2) mbar_wait(&bar_vfree[st], par);
+          mbar_arrive_expect_tx(&bar_v[st], QB);
 #pragma unroll
-        for (int kb = 0; kb < KB; ++kb)
-          tma_load_4d(&tmV, &bar_v[st], sV + st * QB + kb * (KT * 128), kb * 64, j * kFaKT, h, b);
+          for (int kb = 0; kb < KB; ++kb)
+            tma_load_4d(&tmV, &bar_v[st], sV + st * QB + kb * (KT * 128), kb * 64, j * kFaKT, h, b);
+        }
+        ++qa;
       }
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
-    if (elect_one() && n_tiles > 0) {
-      auto issue_s = [&](int jj) {
-        const int st = jj & 1;
-        mbar_wait(&bar_k[st], (jj >> 1) & 1);
-        if (jj >= 2) mbar_wait(&bar_sfree[st], ((jj >> 1) - 1) & 1);
-        tc_fence_after();
-        const uint32_t qa = smem_u32(sQ), ka = smem_u32(sK + st * QB);
+    if (elect_one()) {
+      int G0 = 0, qa = 0;
+      for (int mt = q_hi - 1; mt >= q_lo; --mt) {
+        const int n_tiles = tiles_of(mt);
+        if (n_tiles == 0) continue;
+        auto issue_s = [&](int jj) {
+          const int Gj = G0 + jj;
+          const int st = Gj & 1;
+          mbar_wait(&bar_k[st], (Gj >> 1) & 1);
+          if (Gj >= 2) mbar_wait(&bar_sfree[st], ((Gj >> 1) - 1) & 1);
+          tc_fence_after();
+          const uint32_t qa_ = smem_u32(sQ), ka = smem_u32(sK + st * QB);
 #pragma unroll
-        for (int k = 0; k < HD / 16; ++k) {
-          const uint64_t ad = make_sdesc_sw128(qa + (k >> 2) * 16384 + (k & 3) * 32, 16, 1024);
-          const uint64_t bd = make_sdesc_sw128(ka + (k >> 2) * (KT * 128) + (k & 3) * 32, 16, 1024);
-          umma_bf16(tmem_base + S_COL + st * kFaKT, ad, bd, IDESC_S, k != 0 ? 1u : 0u);
-        }
-        umma_commit(&bar_s[st]);
-        umma_commit(&bar_kfree[st]);
-      };
-      mbar_wait(bar_q, 0);
-      issue_s(0);
-      if (n_tiles > 1) issue_s(1);
-      for (int j = 0; j < n_tiles; ++j) {
-        const int st = j & 1;
-        const int pb = (NPB == 2) ? st : 0;
-        if (NPB == 2) mbar_wait(&bar_p[st], (j >> 1) & 1); else mbar_wait(&bar_p[0], j & 1);
-        mbar_wait(&bar_v[st], (j >> 1) & 1);
-        tc_fence_after();
-        const uint32_t pa = smem_u32(sP + pb * PB), va = smem_u32(sV + st * QB);
+          for (int k = 0; k < HD / 16; ++k) {
+            const uint64_t ad = make_sdesc_sw128(qa_ + (k >> 2) * 16384 + (k & 3) * 32, 16, 1024);
+            const uint64_t bd = make_sdesc_sw128(ka + (k >> 2) * (KT * 128) + (k & 3) * 32, 16, 1024);
+            umma_bf16(tmem_base + S_COL + st * kFaKT, ad, bd, IDESC_S, k != 0 ? 1u : 0u);
+          }
+          umma_commit(&bar_s[st]);
+          umma_commit(&bar_kfree[st]);
+          if (jj == n_tiles - 1) umma_commit(bar_qfree);  // last S of this query tile: sQ may be refilled
+        };
+        mbar_wait(bar_q, qa & 1);
+        issue_s(0);
+        if (n_tiles > 1) issue_s(1);
+        if (qa >= 1) mbar_wait(bar_ofree, (qa - 1) & 1);  // the previous query tile's O has been read out of TMEM
+        for (int j = 0; j < n_tiles; ++j) {
+          const int Gj = G0 + j;
+          const int st = Gj & 1;
+          const int pb = (NPB == 2) ? st : 0;
+          if (NPB == 2) mbar_wait(&bar_p[st], (Gj >> 1) & 1); else mbar_wait(&bar_p[0], Gj & 1);
+          mbar_wait(&bar_v[st], (Gj >> 1) & 1);
+          tc_fence_after();
+          const uint32_t pa = smem_u32(sP + pb * PB), va = smem_u32(sV + st * QB);
 #pragma unroll
-        for (int k = 0; k < kFaKT / 16; ++k) {
-          const uint64_t ad = make_sdesc_sw128(pa + (k >> 2) * 16384 + (k & 3) * 32, 16, 1024);
-          // V: MN-major B (head dim contiguous); 64-column blocks KT*128 B apart (LBO), 8-key groups 1 KiB apart (SBO)
-          const uint64_t bd = make_sdesc_sw128(va + k * 2048, KT * 128, 1024);
-          umma_bf16(tmem_base + O_COL, ad, bd, IDESC_O, (j | k) != 0 ? 1u : 0u);
+          for (int k = 0; k < kFaKT / 16; ++k) {
+            const uint64_t ad = make_sdesc_sw128(pa + (k >> 2) * 16384 + (k & 3) * 32, 16, 1024);
+            // V: MN-major B (head dim contiguous); 64-column blocks KT*128 B apart (LBO), 8-key groups 1 KiB apart (SBO)
+            const uint64_t bd = make_sdesc_sw128(va + k * 2048, KT * 128, 1024);
+            umma_bf16(tmem_base + O_COL, ad, bd, IDESC_O, (j | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&bar_pfree[pb]);
+          umma_commit(&bar_vfree[st]);
+          if (j + 2 < n_tiles) issue_s(j + 2);
         }
-        umma_commit(&bar_pfree[pb]);
-        umma_commit(&bar_vfree[st]);
-        if (j + 2 < n_tiles) issue_s(j + 2);
+        umma_commit(bar_o);
+        G0 += n_tiles;
+        ++qa;
       }
-      umma_commit(bar_o);
     }
   } else {
     // ------------------------------------------------------------------ softmax warps: one thread per query row
     const int q = warp & 3;
     const int r = q * 32 + lane;  // row within the tile == TMEM lane
-    const int qrow = m0 + r;
     const uint32_t lane_base = static_cast<uint32_t>(q * 32) << 16;
     const int* kmask = p.key_mask ? p.key_mask + static_cast<long long>(b) * p.Tk : nullptr;
-    float m_used = -INFINITY;  // reference max the accumulator / row sum are expressed in (log2 domain)
-    float l = 0.f;
     const int sw = r & 7;
-
-    for (int j = 0; j < n_tiles; ++j) {
-      const int st = j & 1;
-      mbar_wait(&bar_s[st], (j >> 1) & 1);
-      tc_fence_after();
-      const uint32_t s_addr = tmem_base + lane_base + S_COL + st * kFaKT;
-      const int key0 = j * kFaKT;
-      // per-32-key validity bits: Tk bound + key padding mask (warp-cooperative) & causal limit (per row)
-      uint32_t okb[NCH];
-#pragma unroll
-      for (int c = 0; c < NCH; ++c) {
-        const int key = key0 + c * 32 + lane;
-        bool ok = key < p.Tk;
-        if (ok && kmask != nullptr) ok = kmask[key] != 0;
-        uint32_t bits = __ballot_sync(0xffffffffu, ok);
-        if (p.causal) {
-          const int lim = qrow + shift - (key0 + c * 32);  // keys with index <= lim inside this chunk are visible
-          bits &= lim >= 31 ? 0xffffffffu : (lim < 0 ? 0u : ((2u << lim) - 1u));
-        }
-        okb[c] = bits;
-      }
-      // ---- the whole score row of this tile into registers (all loads in flight, one wait)
-      uint32_t v[NCH][32];
-#pragma unroll
-      for (int c = 0; c < NCH; ++c) tmem_ld32(s_addr + c * 32, v[c]);
-      tmem_ld_wait();
-      // S_j is in registers: the MMA warp may overwrite this S buffer with S_{j+2}
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&bar_sfree[st]);
-      float mx = -INFINITY;
-#pragma unroll
-      for (int c = 0; c < NCH; ++c)
-#pragma unroll
-        for (int i = 0; i < 32; ++i)
-          if (okb[c] & (1u << i)) mx = fmaxf(mx, __uint_as_float(v[c][i]));
-      mx *= p.scale_log2;  // scale > 0, so max commutes with the scaling
-      // ---- decide the reference max for this tile
-      float alpha = 1.0f;
-      bool rescale = false;
-      if (mx > m_used + kFaTau || m_used == -INFINITY) {
-        if (mx != -INFINITY) {
-          if (m_used != -INFINITY) {
-            alpha = ex2_approx(m_used - mx);
-            rescale = true;
-          }
-          m_used = mx;
-        }
-      }
-      const float m_ref = (m_used == -INFINITY) ? 0.f : m_used;
-      // ---- P = exp2(s * scale - m_ref) -> bf16 -> swizzled smem (A operand of the PV MMA)
-      const int pb = (NPB == 2) ? st : 0;
-      if (NPB == 2) {
-        if (j >= 2) mbar_wait(&bar_pfree[st], ((j >> 1) - 1) & 1);  // PV_{j-2} has finished reading this P buffer
-      } else {
-        if (j >= 1) mbar_wait(&bar_pfree[0], (j - 1) & 1);          // PV_{j-1} has finished reading the P buffer
-      }
-      uint8_t* prow = sP + pb * PB + r * 128;
-      float psum = 0.f;
-#pragma unroll
-      for (int c = 0; c < NCH; ++c) {
-        uint32_t pk[16];
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          float e0 = ex2_approx(fmaf(__uint_as_float(v[c][2 * i]), p.scale_log2, -m_ref));
-          float e1 = ex2_approx(fmaf(__uint_as_float(v[c][2 * i + 1]), p.scale_log2, -m_ref));
-          e0 = (okb[c] & (1u << (2 * i))) ? e0 : 0.f;
-          e1 = (okb[c] & (1u << (2 * i + 1))) ? e1 : 0.f;
-          psum += e0 + e1;
-          pk[i] = pack_bf16x2(e0, e1);
-        }
-        uint8_t* blk = prow + (c >> 1) * 16384;
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-          *reinterpret_cast<uint4*>(blk + ((((c & 1) * 4 + i) ^ sw) << 4)) =
-              make_uint4(pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
-      }
-      l = l * alpha + psum;
-      // ---- lazy rescale of the TMEM accumulator (rare): needs PV_{j-1} complete, must finish before PV_j starts
-      if (__any_sync(0xffffffffu, rescale)) {
-        if (NPB == 2) {
-          if (j >= 1) mbar_wait(&bar_pfree[(j - 1) & 1], ((j - 1) >> 1) & 1);
-        } else {
-          if (j >= 1) mbar_wait(&bar_pfree[0], (j - 1) & 1);
-        }
-        tc_fence_after();
-#pragma unroll 1
-        for (int c = 0; c < HD / 32; ++c) {
-          uint32_t v[32];
-          tmem_ld32(tmem_base + lane_base + O_COL + c * 32, v);
-          tmem_ld_wait();
-#pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * alpha);
-          tmem_st32(tmem_base + lane_base + O_COL + c * 32, v);
-        }
-        tmem_st_wait();
-        tc_fence_before();
-      }
-      fence_proxy_async_smem();  // P (generic-proxy stores) -> visible to the tensor core's async proxy
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&bar_p[pb]);
-    }
-
-    // ---- epilogue: O / l -> bf16 -> per-warp swizzled staging (reuses P buffer 0) -> coalesced stores
-    if (n_tiles > 0) {
-      mbar_wait(bar_o, 0);
-      tc_fence_after();
-    }
-    const float inv = l > 0.f ? 1.0f / l : 0.f;
-    uint8_t* stg = sK + (warp - 2) * 8192;  // 32 rows x 256 B; the K ring is idle once bar_o has fired
-    uint8_t* srow = stg + lane * 256;
-#pragma unroll 1
-    for (int c = 0; c < HD / 32; ++c) {
-      uint32_t v[32];
-      if (n_tiles > 0) {
-        tmem_ld32(tmem_base + lane_base + O_COL + c * 32, v);
-        tmem_ld_wait();
-      } else {
-#pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] = 0u;
-      }
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        uint4 u;
-        u.x = pack_bf16x2(__uint_as_float(v[8 * i + 0]) * inv, __uint_as_float(v[8 * i + 1]) * inv);
-        u.y = pack_bf16x2(__uint_as_float(v[8 * i + 2]) * inv, __uint_as_float(v[8 * i + 3]) * inv);
-        u.z = pack_bf16x2(__uint_as_float(v[8 * i + 4]) * inv, __uint_as_float(v[8 * i + 5]) * inv);
-        u.w = pack_bf16x2(__uint_as_float(v[8 * i + 6]) * inv, __uint_as_float(v[8 * i + 7]) * inv);
-        *reinterpret_cast<uint4*>(srow + (((c * 4 + i) ^ sw) << 4)) = u;
-      }
-    }
-    __syncwarp();
-    constexpr int CPR = HD / 8;        // 16-byte chunks per output row
-    constexpr int RPI = 32 / CPR;      // rows written per warp instruction
     bf16* og = p.out + static_cast<long long>(b) * p.o_bs + static_cast<long long>(h) * p.o_hs;
-#pragma unroll 4
-    for (int it = 0; it < 32 / RPI; ++it) {
-      const int rr = it * RPI + lane / CPR, ch = lane % CPR;
-      const int gq = m0 + q * 32 + rr;
-      if (gq < p.Tq)
-        *reinterpret_cast<uint4*>(og + static_cast<long long>(gq) * p.o_ts + ch * 8) =
-            *reinterpret_cast<const uint4*>(stg + rr * 256 + ((ch ^ (rr & 7)) << 4));
+    int G0 = 0, qa = 0;
+
+    for (int mt = q_hi - 1; mt >= q_lo; --mt) {
+      const int n_tiles = tiles_of(mt);
+      const int qrow = mt * kFaMQ + r;
+      float m_used = -INFINITY;  // reference max the accumulator / row sum are expressed in (log2 domain)
+      float l = 0.f;
+
+      for (int j = 0; j < n_tiles; ++j) {
+        const int Gj = G0 + j;
+        const int st = Gj & 1;
+        mbar_wait(&bar_s[st], (Gj >> 1) & 1);
+        tc_fence_after();
+        const uint32_t s_addr = tmem_base + lane_base + S_COL + st * kFaKT;
+        const int key0 = j * kFaKT;
+        // per-32-key validity bits: Tk bound + key padding mask (warp-cooperative) & causal limit (per row)
+        uint32_t okb[NCH];
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) {
+          const int key = key0 + c * 32 + lane;
+          bool ok = key < p.Tk;
+          if (ok && kmask != nullptr) ok = kmask[key] != 0;
+          uint32_t bits = __ballot_sync(0xffffffffu, ok);
+          if (p.causal) {
+            const int lim = qrow + shift - (key0 + c * 32);  // keys with index <= lim inside this chunk are visible
+            bits &= lim >= 31 ? 0xffffffffu : (lim < 0 ? 0u : ((2u << lim) - 1u));
+          }
+          okb[c] = bits;
+        }
+        // ---- the whole score row of this tile into registers (all loads in flight, one wait)
+        uint32_t v[NCH][32];
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) tmem_ld32(s_addr + c * 32, v[c]);
+        tmem_ld_wait();
+        // S_j is in registers: the MMA warp may overwrite this S buffer with S_{j+2}
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bar_sfree[st]);
+        // tiles without any masked element (the common case away from the causal diagonal / sequence end) take a
+        // select-free path: the softmax warps are ALU/MUFU-bound, every instruction per element counts
+        uint32_t allb = 0xffffffffu;
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) allb &= okb[c];
+        const bool full_tile = __all_sync(0xffffffffu, allb == 0xffffffffu);
+        float mx = -INFINITY;
+        if (full_tile) {
+#pragma unroll
+          for (int c = 0; c < NCH; ++c)
+#pragma unroll
+            for (int i = 0; i < 32; i += 2) mx = max3(mx, __uint_as_float(v[c][i]), __uint_as_float(v[c][i + 1]));
+        } else {
+#pragma unroll
+          for (int c = 0; c < NCH; ++c)
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (okb[c] & (1u << i)) mx = fmaxf(mx, __uint_as_float(v[c][i]));
+        }
+        mx *= p.scale_log2;  // scale > 0, so max commutes with the scaling
+        // ---- decide the reference max for this tile
+        float alpha = 1.0f;
+        bool rescale = false;
+        if (mx > m_used + kFaTau || m_used == -INFINITY) {
+          if (mx != -INFINITY) {
+            if (m_used != -INFINITY) {
+              alpha = ex2_approx(m_used - mx);
+              rescale = true;
+            }
+            m_used = mx;
+          }
+        }
+        const float m_ref = (m_used == -INFINITY) ? 0.f : m_used;
+        // ---- P = exp2(s * scale - m_ref) -> bf16 -> swizzled smem (A operand of the PV MMA)
+        const int pb = (NPB == 2) ? st : 0;
+        if (NPB == 2) {
+          if (Gj >= 2) mbar_wait(&bar_pfree[st], ((Gj >> 1) - 1) & 1);  // PV_{G-2} has finished reading this P buffer
+        } else {
+          if (Gj >= 1) mbar_wait(&bar_pfree[0], (Gj - 1) & 1);          // PV_{G-1} has finished reading the P buffer
+        }
+        uint8_t* prow = sP + pb * PB + r * 128;
+        float psum = 0.f;
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) {
+          uint32_t pk[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            float e0 = ex2_approx(fmaf(__uint_as_float(v[c][2 * i]), p.scale_log2, -m_ref));
+            float e1 = ex2_approx(fmaf(__uint_as_float(v[c][2 * i + 1]), p.scale_log2, -m_ref));
+            if (!full_tile) {
+              e0 = (okb[c] & (1u << (2 * i))) ? e0 : 0.f;
+              e1 = (okb[c] & (1u << (2 * i + 1))) ? e1 : 0.f;
+            }
+            psum += e0 + e1;
+            pk[i] = pack_bf16x2(e0, e1);
+          }
+          uint8_t* blk = prow + (c >> 1) * 16384;
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            *reinterpret_cast<uint4*>(blk + ((((c & 1) * 4 + i) ^ sw) << 4)) =
+                make_uint4(pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
+        }
+        l = l * alpha + psum;
+        // ---- lazy rescale of the TMEM accumulator (rare): needs PV_{j-1} complete, must finish before PV_j starts
+        if (__any_sync(0xffffffffu, rescale)) {
+          if (NPB == 2) {
+            if (Gj >= 1) mbar_wait(&bar_pfree[(Gj - 1) & 1], ((Gj - 1) >> 1) & 1);
+          } else {
+            if (Gj >= 1) mbar_wait(&bar_pfree[0], (Gj - 1) & 1);
+          }
+          tc_fence_after();
+#pragma unroll 1
+          for (int c = 0; c < HD / 32; ++c) {
+            uint32_t o[32];
+            tmem_ld32(tmem_base + lane_base + O_COL + c * 32, o);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+            tmem_st32(tmem_base + lane_base + O_COL + c * 32, o);
+          }
+          tmem_st_wait();
+          tc_fence_before();
+        }
+        fence_proxy_async_smem();  // P (generic-proxy stores) -> visible to the tensor core's async proxy
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bar_p[pb]);
+      }
+
+      // ---- epilogue of this query tile: O / l -> bf16 -> global (each thread owns one row: HD*2 contiguous bytes)
+      const float inv = l > 0.f ? 1.0f / l : 0.f;
+      if (n_tiles > 0) {
+        mbar_wait(bar_o, qa & 1);
+        tc_fence_after();
+      }
+      bf16* orow = og + static_cast<long long>(qrow) * p.o_ts;
+#pragma unroll 1
+      for (int c = 0; c < HD / 32; ++c) {
+        uint32_t o[32];
+        if (n_tiles > 0) {
+          tmem_ld32(tmem_base + lane_base + O_COL + c * 32, o);
+          tmem_ld_wait();
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) o[i] = 0u;
+        }
+        if (qrow < p.Tq) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            uint4 u;
+            u.x = pack_bf16x2(__uint_as_float(o[8 * i + 0]) * inv, __uint_as_float(o[8 * i + 1]) * inv);
+            u.y = pack_bf16x2(__uint_as_float(o[8 * i + 2]) * inv, __uint_as_float(o[8 * i + 3]) * inv);
+            u.z = pack_bf16x2(__uint_as_float(o[8 * i + 4]) * inv, __uint_as_float(o[8 * i + 5]) * inv);
+            u.w = pack_bf16x2(__uint_as_float(o[8 * i + 6]) * inv, __uint_as_float(o[8 * i + 7]) * inv);
+            *reinterpret_cast<uint4*>(orow + c * 32 + i * 8) = u;
+          }
+        }
+      }
+      if (n_tiles > 0) {
+        // O has left TMEM: the MMA warp may start the next query tile's PV (accumulate = 0 overwrites it)
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_ofree);
+        G0 += n_tiles;
+        ++qa;
+      }
     }
   }
 
@@ -408,7 +464,22 @@ static int launch_fa(const mm_attn_args* a, cudaStream_t st) {
   p.key_mask = a->key_mask;
   p.causal = a->causal;
   p.scale_log2 = a->scale * 1.4426950408889634f;
-  dim3 grid((a->Tq + kFaMQ - 1) / kFaMQ, a->H, a->B);
+  // query tiles per CTA: amortise the per-CTA prologue (TMEM alloc, barrier init, first TMA round trip) while keeping
+  // at least ~4 waves of CTAs (2 CTAs per SM) for balance
+  const int nq = (a->Tq + kFaMQ - 1) / kFaMQ;
+  int sms = 148;
+  {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  }
+  long long qpc = ((long long)nq * a->H * a->B) / (4LL * 2 * sms);
+  if (qpc < 1) qpc = 1;
+  if (qpc > nq) qpc = nq;
+  if (qpc > 8) qpc = 8;
+  p.qpc = static_cast<int>(qpc);
+  p.rev = (a->causal && nq % p.qpc == 0) ? 1 : 0;  // a trailing partial group is the light one: launch it last
+  dim3 grid((nq + p.qpc - 1) / p.qpc, a->H, a->B);
   fa_tcgen05_kernel<HD, KT, NPB><<<grid, 192, smem, st>>>(tq, tk, tv, p);
   return check_launch("mm_attn_fwd(tcgen05)");
 }
