@@ -47,7 +47,6 @@ struct GemmKParams {
 
 constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;
-constexpr int kGroupM = 16;
 constexpr uint32_t kABytes = kBlockM * kBlockK * 2;  // 16 KiB per stage
 
 __host__ __device__ constexpr int gemm_stages(int BN) {

@@ -23,11 +23,6 @@ def load_shapes():
     return d["spec"], d["hp"], {k: tuple(v) for k, v in d["shapes"].items()}
 
 
-def hp_fix(hp: dict) -> dict:
-    """json turns the (kernel, stride) tuples into lists; the oracle only indexes them."""
-    return hp
-
-
 def load_case(name: str) -> dict:
     z = np.load(os.path.join(GOLDEN, f"tiny_{name}.npz"))
     out = {k: z[k] for k in z.files}
