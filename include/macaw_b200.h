@@ -158,6 +158,15 @@ int32_t mm_align_softmax(const float* scores, int64_t lds, const float* row_bias
 int32_t mm_align_ctx_fixup(void* ctx, int64_t ldc, const float* p_sum_real, const float* p_extra, const void* b_v,
                            const void* bias_v, int32_t Nq, int32_t E, int32_t head_dim, void* stream);
 
+/* ------------------------------------------------------------------------------------------------ decode (generate branch)
+ * Greedy decoding behind inputs['inference'] = True (reference modeling.py:954-960 -> HF generate, vendored KV-cache
+ * logic modeling.py:190-195).  mm_kv_append copies the K and V thirds of a fused [q|k|v] activation (rows (b, t),
+ * row stride ld_qkv) into a per-layer cache (B, Tmax, 2, E) at time positions t0 .. t0 + T_new - 1.
+ * mm_argmax_rows: out[r] = argmax_c logits[r, c] (lowest index on ties), bf16 logits, int64 out. */
+int32_t mm_kv_append(const void* qkv, int64_t ld_qkv, int32_t B, int32_t T_new, int32_t E, void* cache, int32_t Tmax,
+                     int32_t t0, void* stream);
+int32_t mm_argmax_rows(const void* logits, int64_t ld, int32_t rows, int32_t V, int64_t* out, void* stream);
+
 /* ------------------------------------------------------------------------------------------------ loss
  * Shifted cross entropy of LlamaForCausalLM.forward modeling.py:600-610: logits bf16 (B, T, V), labels int64 (B, T);
  * position t predicts labels[t+1]; ignore_index -100; writes loss_sum[0] (fp32) and n_valid[0] (int32);

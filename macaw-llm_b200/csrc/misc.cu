@@ -391,6 +391,64 @@ __global__ void align_ctx_fixup_kernel(bf16* __restrict__ ctx, long long ldc, co
   }
 }
 
+// ------------------------------------------------------------------------------------------------ decode helpers
+// K / V rows of a fused QKV activation -> per-layer cache (B, Tmax, 2, E) at positions t0 .. t0 + T_new - 1
+__global__ void __launch_bounds__(128) kv_append_kernel(const bf16* __restrict__ qkv, long long ld_qkv, int T_new, int E,
+                                                        bf16* __restrict__ cache, int Tmax, int t0) {
+  const int b = blockIdx.x / T_new, t = blockIdx.x % T_new;
+  const bf16* src = qkv + (static_cast<long long>(b) * T_new + t) * ld_qkv + E;  // [q | k | v]: skip q
+  bf16* dst = cache + ((static_cast<long long>(b) * Tmax + t0 + t) * 2) * E;
+  const uint4* s4 = reinterpret_cast<const uint4*>(src);
+  uint4* d4 = reinterpret_cast<uint4*>(dst);
+  for (int c = threadIdx.x; c < (2 * E) >> 3; c += blockDim.x) d4[c] = s4[c];
+}
+
+// greedy next token: index of the largest logit per row (lowest index on ties), bf16 logits with row stride ld
+__global__ void __launch_bounds__(512) argmax_rows_kernel(const bf16* __restrict__ logits, long long ld, int V,
+                                                          long long* __restrict__ out) {
+  __shared__ float sv[16];
+  __shared__ int si[16];
+  const bf16* row = logits + static_cast<long long>(blockIdx.x) * ld;
+  float best = -INFINITY;
+  int bi = 0x7fffffff;
+  for (int c = threadIdx.x; c < V; c += blockDim.x) {
+    const float v = __bfloat162float(row[c]);
+    if (v > best || (v == best && c < bi)) {
+      best = v;
+      bi = c;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (ov > best || (ov == best && oi < bi)) {
+      best = ov;
+      bi = oi;
+    }
+  }
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  if (l == 0) {
+    sv[w] = best;
+    si[w] = bi;
+  }
+  __syncthreads();
+  if (w == 0) {
+    best = l < (blockDim.x >> 5) ? sv[l] : -INFINITY;
+    bi = l < (blockDim.x >> 5) ? si[l] : 0x7fffffff;
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (ov > best || (ov == best && oi < bi)) {
+        best = ov;
+        bi = oi;
+      }
+    }
+    if (l == 0) out[blockIdx.x] = bi;
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ CE loss
 __global__ void __launch_bounds__(512) ce_loss_kernel(const bf16* __restrict__ logits, const long long* __restrict__ labels,
                                                       int T, int V, float* __restrict__ loss_sum,
@@ -544,6 +602,21 @@ extern "C" int32_t mm_align_ctx_fixup(void* ctx, int64_t ldc, const float* p_sum
                                                                        (const bf16*)b_v, (const bf16*)bias_v, Nq, E,
                                                                        head_dim);
   return check_launch("mm_align_ctx_fixup");
+}
+
+extern "C" int32_t mm_kv_append(const void* qkv, int64_t ld_qkv, int32_t B, int32_t T_new, int32_t E, void* cache,
+                                int32_t Tmax, int32_t t0, void* stream) {
+  MM_REQUIRE(qkv && cache && B > 0 && T_new > 0 && E > 0 && E % 8 == 0 && ld_qkv % 8 == 0 && t0 >= 0 &&
+                 t0 + T_new <= Tmax && AL16(qkv) && AL16(cache),
+             "mm_kv_append: bad arguments");
+  kv_append_kernel<<<B * T_new, 128, 0, ST(stream)>>>((const bf16*)qkv, ld_qkv, T_new, E, (bf16*)cache, Tmax, t0);
+  return check_launch("mm_kv_append");
+}
+
+extern "C" int32_t mm_argmax_rows(const void* logits, int64_t ld, int32_t rows, int32_t V, int64_t* out, void* stream) {
+  MM_REQUIRE(logits && out && rows > 0 && V > 0 && ld >= V, "mm_argmax_rows: bad arguments");
+  argmax_rows_kernel<<<rows, 512, 0, ST(stream)>>>((const bf16*)logits, ld, V, (long long*)out);
+  return check_launch("mm_argmax_rows");
 }
 
 extern "C" int32_t mm_ce_loss(const void* logits, const int64_t* labels, int32_t B, int32_t T, int32_t V,

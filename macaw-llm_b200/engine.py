@@ -415,14 +415,24 @@ class Engine:
             self._rope[key] = t
         return t
 
-    def llama_forward(self, embeds: torch.Tensor, attention_mask: Optional[torch.Tensor]) -> torch.Tensor:
-        """Vendored LlamaModel + lm_head of the reference (modeling.py:397-522, 597) -> bf16 logits (B, T, V).
+    def _llama_weights(self, i: int, l, E: int, I: int):
+        """Derived weights of decoder layer i: fused [q;k;v] and 32-row-interleaved [gate|up], RMSNorm gains folded in
+        (fp32 product, one bf16 rounding): RMSNorm(x) W^T = rstd * (x (W diag g)^T)."""
+        k = f"llm.l{i}."
+        sa, mlp = l.self_attn, l.mlp
+        g1, g2 = l.input_layernorm.weight, l.post_attention_layernorm.weight
+        wqkv = self.derived(k + "wqkv", [sa.q_proj.weight, sa.k_proj.weight, sa.v_proj.weight, g1],
+                            lambda: (torch.cat([sa.q_proj.weight, sa.k_proj.weight, sa.v_proj.weight], 0).detach().float()
+                                     * g1.detach().float()[None, :]).to(BF16).contiguous())
+        wgu = self.derived(k + "wgu", [mlp.gate_proj.weight, mlp.up_proj.weight, g2],
+                           lambda: torch.stack(
+                               [(mlp.gate_proj.weight.detach().float() * g2.detach().float()[None, :]).to(BF16).view(I // 32, 32, E),
+                                (mlp.up_proj.weight.detach().float() * g2.detach().float()[None, :]).to(BF16).view(I // 32, 32, E)], 1)
+                           .reshape(2 * I, E).contiguous())
+        return wqkv, wgu, self.w(sa.o_proj.weight, k + "wo"), self.w(mlp.down_proj.weight, k + "wd")
 
-        RoPE is applied in the QKV GEMM epilogue, SwiGLU in the gate/up GEMM epilogue, both residual adds in the
-        o_proj / down_proj epilogues (in place on the residual stream)."""
-        ops.TAG = "llama"
-        llm = self.m.llm
-        cfg = llm.config
+    def _llama_dims(self):
+        cfg = self.m.llm.config
         E, H = cfg.hidden_size, cfg.num_attention_heads
         hd = E // H
         if hd != 128:
@@ -430,8 +440,58 @@ class Engine:
         I = cfg.intermediate_size
         if I % 32 != 0:
             raise NotImplementedError("macaw_b200: intermediate_size must be a multiple of 32")
-        eps = cfg.rms_norm_eps
-        B, T, _ = embeds.shape
+        return E, H, hd, I, cfg.rms_norm_eps
+
+    def _llama_layers(self, x: torch.Tensor, B: int, T: int, kmask, pos0: int = 0, cache=None, t_max: int = 0):
+        """The decoder stack on the residual stream x (B*T, E), updated in place.
+
+        pos0 = position of the first row of every sample (0 for prefill, the current length for a decode step).
+        With `cache` (per layer (B, Tmax, 2, E)) the new K/V rows are appended at pos0 and, for decode steps (pos0 > 0),
+        attention reads keys/values [0, pos0 + T) from the cache (reference KV-cache logic: modeling.py:190-195)."""
+        E, H, hd, I, eps = self._llama_dims()
+        dev = x.device
+        cos, sin = self.rope_tables(max(T, t_max), hd, dev)
+        scale = 1.0 / math.sqrt(hd)
+        rope = (cos, sin, T, 2 * E) if pos0 == 0 else (cos[pos0:], sin[pos0:], 1, 2 * E)
+        assert pos0 == 0 or T == 1
+        for i, l in enumerate(self.m.llm.model.layers):
+            wqkv, wgu, wo, wd = self._llama_weights(i, l, E, I)
+            rstd = ops.rms_rstd(x, eps)
+            qkv = ops.linear(x, wqkv, epi=ops.EPI_ROPE, rope=rope, row_scale=rstd)
+            q5 = qkv.view(B, T, 3, H, hd)
+            if cache is not None:
+                ops.kv_append(qkv, B, T, cache[i], pos0)
+            if pos0 == 0:
+                a = ops.attention(q5[:, :, 0], q5[:, :, 1], q5[:, :, 2], scale=scale, causal=True, key_mask=kmask)
+            else:
+                kv = cache[i][:, : pos0 + T].unflatten(-1, (H, hd))  # (B, Tk, 2, H, hd) view of the cache
+                a = ops.attention(q5[:, :, 0], kv[:, :, 0], kv[:, :, 1], scale=scale, causal=False, key_mask=kmask)
+            ops.linear(a.view(B * T, E), wo, residual=x, out=x)
+            rstd = ops.rms_rstd(x, eps)
+            g = ops.linear(x, wgu, epi=ops.EPI_SWIGLU, row_scale=rstd)
+            ops.linear(g, wd, residual=x, out=x)
+        return x
+
+    def _lm_head(self, x: torch.Tensor, rows: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """final RMSNorm (as the row scale of the GEMM) + lm_head on the rows of x (reference modeling.py:508, 597)."""
+        llm = self.m.llm
+        gn = llm.model.norm.weight
+        wl = self.derived("llm.lm_head_g", [llm.lm_head.weight, gn],
+                          lambda: (llm.lm_head.weight.detach().float() * gn.detach().float()[None, :]).to(BF16).contiguous())
+        rstd = ops.rms_rstd(x, llm.config.rms_norm_eps)
+        if rows is not None:  # strided row subset (last position of every sample)
+            x, rstd = rows, rstd.view(rows.shape[0], -1)[:, -1].contiguous()
+        ops.TAG = "lm_head"
+        return ops.linear(x, wl, row_scale=rstd)
+
+    def llama_forward(self, embeds: torch.Tensor, attention_mask: Optional[torch.Tensor]) -> torch.Tensor:
+        """Vendored LlamaModel + lm_head of the reference (modeling.py:397-522, 597) -> bf16 logits (B, T, V).
+
+        RMSNorm rides the consuming GEMM as a per-row scale (gain folded into the weights), RoPE is applied in the QKV
+        GEMM epilogue, SwiGLU in the gate/up GEMM epilogue, both residual adds in the o_proj / down_proj epilogues
+        (in place on the residual stream)."""
+        ops.TAG = "llama"
+        B, T, E = embeds.shape
         dev = embeds.device
         x = embeds.reshape(B * T, E)
         if not x.is_contiguous():
@@ -439,36 +499,45 @@ class Engine:
         kmask = None
         if attention_mask is not None:
             kmask = attention_mask.to(device=dev, dtype=torch.int32).contiguous()
-        layers = llm.model.layers
-        cos, sin = self.rope_tables(T, hd, dev)
-        scale = 1.0 / math.sqrt(hd)
-        for i, l in enumerate(layers):
-            k = f"llm.l{i}."
-            sa, mlp = l.self_attn, l.mlp
-            g1, g2 = l.input_layernorm.weight, l.post_attention_layernorm.weight
-            # RMSNorm gains folded into the consuming weights (fp32 product, one bf16 rounding): RMSNorm(x) W^T = rstd * (x (W diag g)^T)
-            wqkv = self.derived(k + "wqkv", [sa.q_proj.weight, sa.k_proj.weight, sa.v_proj.weight, g1],
-                                lambda sa=sa, g1=g1: (torch.cat([sa.q_proj.weight, sa.k_proj.weight, sa.v_proj.weight], 0).detach().float()
-                                                      * g1.detach().float()[None, :]).to(BF16).contiguous())
-            wgu = self.derived(k + "wgu", [mlp.gate_proj.weight, mlp.up_proj.weight, g2],
-                               lambda mlp=mlp, g2=g2: torch.stack(
-                                   [(mlp.gate_proj.weight.detach().float() * g2.detach().float()[None, :]).to(BF16).view(I // 32, 32, E),
-                                    (mlp.up_proj.weight.detach().float() * g2.detach().float()[None, :]).to(BF16).view(I // 32, 32, E)], 1)
-                               .reshape(2 * I, E).contiguous())
-            rstd = ops.rms_rstd(x, eps)
-            qkv = ops.linear(x, wqkv, epi=ops.EPI_ROPE, rope=(cos, sin, T, 2 * E), row_scale=rstd).view(B, T, 3, H, hd)
-            a = ops.attention(qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2], scale=scale, causal=True, key_mask=kmask)
-            ops.linear(a.view(B * T, E), self.w(sa.o_proj.weight, k + "wo"), residual=x, out=x)
-            rstd = ops.rms_rstd(x, eps)
-            g = ops.linear(x, wgu, epi=ops.EPI_SWIGLU, row_scale=rstd)
-            ops.linear(g, self.w(mlp.down_proj.weight, k + "wd"), residual=x, out=x)
-        gn = llm.model.norm.weight
-        wl = self.derived("llm.lm_head_g", [llm.lm_head.weight, gn],
-                          lambda: (llm.lm_head.weight.detach().float() * gn.detach().float()[None, :]).to(BF16).contiguous())
-        rstd = ops.rms_rstd(x, eps)
-        ops.TAG = "lm_head"
-        logits = ops.linear(x, wl, row_scale=rstd)
-        return logits.view(B, T, wl.shape[0])
+        x = self._llama_layers(x, B, T, kmask)
+        logits = self._lm_head(x)
+        return logits.view(B, T, logits.shape[-1])
+
+    # ------------------------------------------------------------------------------------------------ greedy decoding
+    def generate(self, inputs: dict, max_new_tokens: int = 128, eos_token_id: int = 2, pad_token_id: int = 32006):
+        """The `inference` branch of MM_LLMs.forward (reference modeling.py:954-960):
+        `llm.generate(inputs_embeds=..., max_new_tokens=128, eos_token_id=2, bos_token_id=1, pad_token_id=32006)` —
+        HF greedy search (no sampling, one beam) on the multimodal prefix.  As in the reference, NO attention mask is
+        handed to generate (padding positions are attended) and only the new tokens are returned.  Prefill runs the
+        normal forward kernels while filling a per-layer KV cache; every decode step is one pass of M = B GEMMs
+        (weight-streaming bound) and a Tq = 1 attention over the cache."""
+        with torch.no_grad():
+            embeds, _, _ = self.prepare_inputs({k: v for k, v in inputs.items() if k not in ("labels", "attention_mask")})
+            ops.TAG = "llama"
+            B, T, E = embeds.shape
+            dev = embeds.device
+            table = self.w(self.m.llm.model.embed_tokens.weight, "llm.embed")
+            n_layers = len(self.m.llm.model.layers)
+            t_max = T + max_new_tokens
+            cache = [torch.empty((B, t_max, 2, E), device=dev, dtype=BF16) for _ in range(n_layers)]
+            x = embeds.reshape(B * T, E).contiguous()
+            x = self._llama_layers(x, B, T, None, 0, cache, t_max)
+            logits = self._lm_head(x, rows=x.view(B, T, E)[:, -1, :])
+            out = torch.full((B, max_new_tokens), pad_token_id, device=dev, dtype=torch.int64)
+            finished = torch.zeros((B,), device=dev, dtype=torch.bool)
+            n = 0
+            for step in range(max_new_tokens):
+                tok = ops.argmax_rows(logits)
+                tok = torch.where(finished, torch.full_like(tok, pad_token_id), tok)  # HF: finished rows emit pad
+                out[:, step] = tok
+                n = step + 1
+                finished |= tok == eos_token_id
+                if step + 1 == max_new_tokens or bool(finished.all()):
+                    break
+                x = ops.embed_gather(table, tok)  # (B, E); ids beyond the table (pad of finished rows) are clamped
+                x = self._llama_layers(x, B, 1, None, T + step, cache, t_max)
+                logits = self._lm_head(x)
+        return out[:, :n]
 
     # ------------------------------------------------------------------------------------------------ whole forward
     def _forward_eager(self, inputs: dict):

@@ -266,11 +266,12 @@ class MM_LLMs(PreTrainedModel):
     def forward(self, inputs=None):
         """inputs: dict with images (B,3,H,W) | None, audios (B,80,3000) | None, videos (B,F,3,H,W) | None,
         input_ids (B,L), optional attention_mask (B,L), labels (B,L) | None, {image,audio,video}_{starts,ends} (B,),
-        optional inference flag (reference modeling.py:941-963, llm_trainer.py:366-381)."""
+        optional `inference: True` (greedy generation, returns token ids; `max_new_tokens` defaults to the reference's 128)
+        (reference modeling.py:941-963, llm_trainer.py:366-381)."""
         if inputs.get("inference") is True:
-            raise NotImplementedError(
-                "macaw_b200 implements the prefill forward; the generate branch (reference modeling.py:954-960) is "
-                "out of scope of this hot path (SURVEY.md §2 row 9)")
+            # generate branch (reference modeling.py:954-960): greedy decode, returns the new token ids (B, <= 128)
+            return self._engine.generate(inputs, max_new_tokens=int(inputs.get("max_new_tokens", 128)),
+                                         eos_token_id=2, pad_token_id=32006)
         loss, logits, _, _, _ = self._engine.forward(inputs)
         return CausalLMOutputWithPast(loss=loss, logits=logits)
 

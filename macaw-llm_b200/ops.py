@@ -263,6 +263,26 @@ def align_ctx_fixup(ctx: torch.Tensor, psum: torch.Tensor, pext: torch.Tensor, b
     return ctx
 
 
+# ---------------------------------------------------------------------------------------------------- decode helpers
+def kv_append(qkv: torch.Tensor, B: int, T_new: int, cache: torch.Tensor, t0: int) -> None:
+    """qkv (B*T_new, 3E) fused activation -> cache (B, Tmax, 2, E) at positions t0 .. t0+T_new-1 (K and V thirds)."""
+    _cuda(qkv, _BF16, "qkv"); _cuda(cache, _BF16, "cache")
+    E = cache.shape[-1]
+    assert qkv.shape == (B * T_new, 3 * E) and qkv.stride(1) == 1 and cache.is_contiguous() and cache.shape[2] == 2
+    _check(_lib.load().mm_kv_append(qkv.data_ptr(), qkv.stride(0), B, T_new, E, cache.data_ptr(), cache.shape[1], t0,
+                                    _stream()), "mm_kv_append")
+
+
+def argmax_rows(logits: torch.Tensor) -> torch.Tensor:
+    """Greedy token per row of bf16 logits (rows, V) with unit inner stride -> int64 (rows,)."""
+    _cuda(logits, _BF16, "logits")
+    assert logits.dim() == 2 and logits.stride(1) == 1
+    out = torch.empty((logits.shape[0],), device=logits.device, dtype=torch.int64)
+    _check(_lib.load().mm_argmax_rows(logits.data_ptr(), logits.stride(0), logits.shape[0], logits.shape[1],
+                                      out.data_ptr(), _stream()), "mm_argmax_rows")
+    return out
+
+
 # ---------------------------------------------------------------------------------------------------- loss
 def ce_loss(logits: torch.Tensor, labels: torch.Tensor) -> torch.Tensor:
     """Shifted CE (mean over labels != -100) of bf16 logits (B, T, V) against int64 labels (B, T); returns fp32 scalar."""

@@ -302,3 +302,30 @@ def forward(inputs: dict, sd_raw: Dict[str, Tensor], hp: dict, dtype=torch.float
         logits = llama_forward(embeds, mask, _SD(sd_raw, dtype), hp)
         loss = shifted_ce(logits, labels) if labels is not None else None
     return dict(loss=loss, logits=logits, embeds=embeds, attention_mask=mask, labels=labels)
+
+
+def generate_greedy(inputs: dict, sd_raw: Dict[str, Tensor], hp: dict, max_new_tokens: int = 128, eos_token_id: int = 2,
+                    pad_token_id: int = 32006, dtype=torch.float32, forced_tokens: Optional[Tensor] = None):
+    """The generate branch (modeling.py:954-960 -> HF greedy search on inputs_embeds, no attention mask, only new tokens
+    returned), restated WITHOUT a KV cache: the whole sequence is re-run every step.  With `forced_tokens` (B, n) the
+    given tokens are fed instead of the argmax (teacher forcing) and the per-step logits are returned as well."""
+    with torch.no_grad():
+        embeds, _, _ = prepare_inputs({k: v for k, v in inputs.items() if k not in ("labels", "attention_mask")}, sd_raw, hp, dtype)
+        sd = _SD(sd_raw, dtype)
+        table = sd("llm.model.embed_tokens.weight")
+        B = embeds.shape[0]
+        finished = torch.zeros(B, dtype=torch.bool)
+        out, step_logits = [], []
+        for step in range(max_new_tokens):
+            logits = llama_forward(embeds, None, sd, hp)[:, -1, :]
+            step_logits.append(logits)
+            tok = logits.argmax(-1)
+            if forced_tokens is not None:
+                tok = forced_tokens[:, step].to(tok.dtype)
+            tok = torch.where(finished, torch.full_like(tok, pad_token_id), tok)
+            out.append(tok)
+            finished |= tok == eos_token_id
+            if bool(finished.all()) or (forced_tokens is not None and step + 1 == forced_tokens.shape[1]):
+                break
+            embeds = torch.cat([embeds, table[tok.clamp(max=table.shape[0] - 1)].unsqueeze(1)], dim=1)
+    return torch.stack(out, dim=1), torch.stack(step_logits, dim=1)

@@ -267,3 +267,57 @@ def test_batch1_no_mask_no_labels(tiny):
                   H.bf16_round(weights), hp, dtype=torch.float32)
     assert o["attention_mask"] is None
     assert H.rel_err(out.logits, o["logits"]) < 3e-2
+
+
+def test_generate_greedy_vs_oracle(tiny):
+    """inputs['inference'] = True (reference modeling.py:954-960): greedy decoding with the KV cache.  bf16 vs fp32 can
+    flip an argmax between near-tied logits, so the check is teacher-forced: feeding the GPU's tokens to the oracle, every
+    GPU-chosen token must be the oracle's top-1 or within a small margin of it, and the first token must match exactly
+    when the oracle's top-2 gap is not a near-tie."""
+    from oracle import macaw_oracle as O
+
+    model, spec, hp, weights = tiny
+    inp = _to_bf16_inputs(H.case_inputs(spec, H.load_case("all3")))
+    inp.pop("labels", None)
+    n_new = 6
+    dev_inp = {k: (v.cuda() if isinstance(v, torch.Tensor) else v) for k, v in inp.items()}
+    toks = model(dict(dev_inp, inference=True, max_new_tokens=n_new))
+    torch.cuda.synchronize()
+    assert toks.dtype == torch.int64 and toks.shape[0] == 2 and 1 <= toks.shape[1] <= n_new
+    f32 = {k: (v.float() if isinstance(v, torch.Tensor) and v.is_floating_point() else v) for k, v in inp.items()}
+    o_toks, o_logits = O.generate_greedy(f32, H.bf16_round(weights), hp, max_new_tokens=toks.shape[1],
+                                         forced_tokens=toks.cpu())
+    for b in range(toks.shape[0]):
+        for s_ in range(toks.shape[1]):
+            t = int(toks[b, s_])
+            if t == 32006:  # pad after EOS
+                continue
+            row = o_logits[b, s_]
+            gap = float(row.max() - row[t])
+            assert gap <= 0.05 * float(row.std()) + 1e-3, (b, s_, t, int(row.argmax()), gap)
+
+
+def test_decode_step_matches_full_recompute(tiny):
+    """KV-cache consistency on the GPU itself: logits of a cached decode step == logits of a fresh prefill over the
+    extended sequence (both bf16 kernels; differences only from tile shapes / accumulation order)."""
+    from macaw_llm_b200 import ops
+
+    model, spec, hp, weights = tiny
+    eng = model.engine
+    inp = _to_bf16_inputs(H.case_inputs(spec, H.load_case("audio")))
+    dev_inp = {k: (v.cuda() if isinstance(v, torch.Tensor) else v) for k, v in inp.items() if k not in ("labels", "attention_mask")}
+    with torch.no_grad():
+        embeds, _, _ = eng.prepare_inputs(dev_inp)
+        B, T, E = embeds.shape
+        table = eng.w(model.llm.model.embed_tokens.weight, "llm.embed")
+        nxt = torch.tensor([5, 9], device="cuda")
+        ext = torch.cat([embeds, table[nxt].unsqueeze(1)], dim=1)
+        full = eng.llama_forward(ext.clone(), None)[:, -1, :]
+        cache = [torch.empty((B, T + 4, 2, E), device="cuda", dtype=torch.bfloat16) for _ in model.llm.model.layers]
+        x = embeds.reshape(B * T, E).clone()
+        eng._llama_layers(x, B, T, None, 0, cache, T + 4)
+        x1 = ops.embed_gather(table, nxt)
+        x1 = eng._llama_layers(x1, B, 1, None, T, cache, T + 4)
+        step = eng._lm_head(x1)
+    torch.cuda.synchronize()
+    assert H.rel_err(step, full) < 1e-2

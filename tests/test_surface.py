@@ -58,8 +58,9 @@ def test_reference_caller_surface():
     assert m.llm.model.embed_tokens.weight.shape[0] == 519 and m.llm.lm_head.weight.shape[0] == 519
     frozen = [n for n, _ in m.named_parameters() if "encoder" in n]  # run_clm_llms.py:390-393 name test
     assert frozen and all(n.split(".")[0] in ("image_encoder", "video_encoder", "audio_encoder") or "encoder" in n for n in frozen)
-    with pytest.raises(NotImplementedError):
-        m({"inference": True})
+    with pytest.raises(RuntimeError, match="no CPU"):  # the generate branch exists, but nothing executes on the CPU
+        m({"inference": True, "input_ids": torch.ones(1, 4, dtype=torch.long), "images": None, "audios": None,
+           "videos": None})
 
 
 def test_cpu_parameters_raise():
