@@ -2,6 +2,7 @@
 #include "common.cuh"
 #include "../../include/macaw_b200.h"
 #include <atomic>
+#include <stdlib.h>
 
 namespace mm {
 
@@ -15,6 +16,13 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+bool pdl_enabled() {
+  static const bool on = []() {
+    const char* e = getenv("MACAW_B200_PDL");
+    return e != nullptr && atoi(e) != 0;  // default OFF: measured slower (cfg4 B=4: 27.95 -> 28.8-29.4 ms/step)
+  }();
+  return on;
+}
 
 }  // namespace mm
 

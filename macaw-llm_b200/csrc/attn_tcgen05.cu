@@ -136,6 +136,8 @@ fa_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  griddep_launch();  // prologue done: the next kernel may begin its own
+  griddep_wait();    // q / k / v come from the previous kernel
 
   // Every role walks the same sequence: query tiles mt = q_hi-1 .. q_lo, key tiles j = 0 .. n-1 of each.
   // G = running key-tile index across query tiles (ring stages / mbarrier parities), qa = running count of
@@ -480,7 +482,11 @@ static int launch_fa(const mm_attn_args* a, cudaStream_t st) {
   p.qpc = static_cast<int>(qpc);
   p.rev = (a->causal && nq % p.qpc == 0) ? 1 : 0;  // a trailing partial group is the light one: launch it last
   dim3 grid((nq + p.qpc - 1) / p.qpc, a->H, a->B);
-  fa_tcgen05_kernel<HD, KT, NPB><<<grid, 192, smem, st>>>(tq, tk, tv, p);
+  cudaError_t e = launch_kernel(fa_tcgen05_kernel<HD, KT, NPB>, grid, dim3(192), smem, st, 1, tq, tk, tv, p);
+  if (e != cudaSuccess) {
+    set_error("mm_attn_fwd: launch failed: %s", cudaGetErrorString(e));
+    return 2;
+  }
   return check_launch("mm_attn_fwd(tcgen05)");
 }
 

@@ -31,4 +31,37 @@ inline int32_t check_launch(const char* what) {
 
 using bf16 = __nv_bfloat16;
 
+// Programmatic dependent launch: kernels call griddep_launch() once their prologue is done (lets the next kernel of the
+// stream start ITS prologue on SMs that free up) and griddep_wait() before their first global-memory access (returns
+// when every predecessor grid has completed and flushed).  The launch attribute is OPT-IN (MACAW_B200_PDL=1): on this
+// workload it measured slower than plain stream order under CUDA-graph replay (B=4: +3 %, B=32: +0.5 %), see DESIGN.md.
+bool pdl_enabled();
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_kernel(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                                 int cluster_x, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[2];
+  int n = 0;
+  if (cluster_x > 1) {
+    attr[n].id = cudaLaunchAttributeClusterDimension;
+    attr[n].val.clusterDim.x = cluster_x;
+    attr[n].val.clusterDim.y = 1;
+    attr[n].val.clusterDim.z = 1;
+    ++n;
+  }
+  if (pdl_enabled()) {
+    attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[n].val.programmaticStreamSerializationAllowed = 1;
+    ++n;
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = n;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
 }  // namespace mm

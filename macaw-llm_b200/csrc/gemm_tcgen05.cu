@@ -202,6 +202,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   if constexpr (MC) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // prologue done (barriers, TMEM, descriptors): let the next kernel start its own, then wait for our inputs
+  griddep_launch();
+  griddep_wait();
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
@@ -514,28 +517,17 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmK
   }
   const int m_units = MC ? (p.m_tiles + 1) / 2 : p.m_tiles;
   const int total = p.batch * p.batch2 * m_units * p.n_tiles;
+  cudaError_t e;
   if constexpr (MC) {
     const int pairs = total < num_sms() / 2 ? total : num_sms() / 2;
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(2 * pairs);
-    cfg.blockDim = dim3(320);
-    cfg.dynamicSmemBytes = smem;
-    cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 2;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, ta, tb, p);
-    if (e != cudaSuccess) {
-      set_error("mm_gemm_fwd: cluster launch failed: %s", cudaGetErrorString(e));
-      return 2;
-    }
+    e = launch_kernel(kern, dim3(2 * pairs), dim3(320), smem, st, 2, ta, tb, p);
   } else {
     const int grid = total < num_sms() ? total : num_sms();
-    kern<<<grid, 320, smem, st>>>(ta, tb, p);
+    e = launch_kernel(kern, dim3(grid), dim3(320), smem, st, 1, ta, tb, p);
+  }
+  if (e != cudaSuccess) {
+    set_error("mm_gemm_fwd: launch failed: %s", cudaGetErrorString(e));
+    return 2;
   }
   return check_launch("mm_gemm_fwd");
 }

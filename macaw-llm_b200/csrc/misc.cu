@@ -84,6 +84,8 @@ __global__ void __launch_bounds__(256) rmsnorm_kernel(const bf16* __restrict__ x
 // rstd[row] = rsqrt(mean(x^2) + eps): the only part of RMSNorm that cannot ride a GEMM epilogue.  One warp per row.
 __global__ void __launch_bounds__(256) rms_rstd_kernel(const bf16* __restrict__ x, float* __restrict__ rstd, int rows,
                                                        int cols, float eps) {
+  griddep_launch();
+  griddep_wait();
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
   const int lane = threadIdx.x & 31;
@@ -144,6 +146,8 @@ __global__ void __launch_bounds__(256) layernorm_warp_kernel(const bf16* __restr
                                                              const bf16* __restrict__ w, const bf16* __restrict__ b,
                                                              bf16* __restrict__ y, long long ldy, int rows, int cols,
                                                              float eps) {
+  griddep_launch();
+  griddep_wait();
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
   const int lane = threadIdx.x & 31;
@@ -499,7 +503,11 @@ extern "C" int32_t mm_rmsnorm_fwd(const void* x, const void* w, void* y, int32_t
 
 extern "C" int32_t mm_rms_rstd(const void* x, float* rstd, int32_t rows, int32_t cols, float eps, void* stream) {
   MM_REQUIRE(x && rstd && rows > 0 && cols > 0 && cols % 8 == 0 && AL16(x), "mm_rms_rstd: bad arguments");
-  rms_rstd_kernel<<<(rows + 7) / 8, 256, 0, ST(stream)>>>((const bf16*)x, rstd, rows, cols, eps);
+  if (launch_kernel(rms_rstd_kernel, dim3((rows + 7) / 8), dim3(256), 0, ST(stream), 1, (const bf16*)x, rstd, rows, cols,
+                    eps) != cudaSuccess) {
+    set_error("mm_rms_rstd: launch failed");
+    return 2;
+  }
   return check_launch("mm_rms_rstd");
 }
 
@@ -509,11 +517,11 @@ extern "C" int32_t mm_layernorm_fwd(const void* x, int64_t ldx, const void* w, c
              "mm_layernorm_fwd: bad arguments");
   MM_REQUIRE(AL16(x) && AL16(w) && AL16(b) && AL16(y), "mm_layernorm_fwd: pointers must be 16-byte aligned");
   if (cols <= 512) {
-    layernorm_warp_kernel<2><<<(rows + 7) / 8, 256, 0, ST(stream)>>>((const bf16*)x, ldx, (const bf16*)w, (const bf16*)b,
-                                                                     (bf16*)y, ldy, rows, cols, eps);
+    launch_kernel(layernorm_warp_kernel<2>, dim3((rows + 7) / 8), dim3(256), 0, ST(stream), 1, (const bf16*)x,
+                  (long long)ldx, (const bf16*)w, (const bf16*)b, (bf16*)y, (long long)ldy, rows, cols, eps);
   } else if (cols <= 1024) {
-    layernorm_warp_kernel<4><<<(rows + 7) / 8, 256, 0, ST(stream)>>>((const bf16*)x, ldx, (const bf16*)w, (const bf16*)b,
-                                                                     (bf16*)y, ldy, rows, cols, eps);
+    launch_kernel(layernorm_warp_kernel<4>, dim3((rows + 7) / 8), dim3(256), 0, ST(stream), 1, (const bf16*)x,
+                  (long long)ldx, (const bf16*)w, (const bf16*)b, (bf16*)y, (long long)ldy, rows, cols, eps);
   } else {
     layernorm_kernel<<<rows, 128, 0, ST(stream)>>>((const bf16*)x, ldx, (const bf16*)w, (const bf16*)b, (bf16*)y, ldy,
                                                    cols, eps);

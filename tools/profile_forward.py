@@ -22,15 +22,21 @@ def main():
     ap.add_argument("--warm", type=int, default=1)
     ap.add_argument("--steps", type=int, default=1)
     ap.add_argument("--layers", type=int, default=0, help="truncate LLaMA depth (profiling convenience only)")
+    ap.add_argument("--video-frames", type=int, default=0, help="add a video of F frames per sample and drop the image (BASELINE config 5: F=16)")
     a = ap.parse_args()
     from macaw_llm_b200.modeling import MM_LLMs, MM_LLMs_Config
 
     (clip, whisper, llama), hyper = bench.real_configs()
     if a.layers:
         llama.num_hidden_layers = a.layers
+    if a.video_frames:
+        hyper = dict(hyper, n_frames=a.video_frames)
     cfg = MM_LLMs_Config(clip_config=clip, whisper_config=whisper, llm_config=llama, **hyper)
     model = MM_LLMs.build_random(cfg, device="cuda", dtype=torch.bfloat16, seed=0)
     host = bench.synth_inputs(a.batch, a.seq_len, llama.vocab_size, 224, 3000, 1234)
+    if a.video_frames:
+        host["images"] = None
+        host["videos"] = torch.randn(a.batch, a.video_frames, 3, 224, 224).to(torch.bfloat16)
     dev_in = {k: (v.cuda() if isinstance(v, torch.Tensor) else v) for k, v in host.items()}
     for _ in range(a.warm):
         model(dev_in)
