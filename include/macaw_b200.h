@@ -79,6 +79,7 @@ typedef struct mm_gemm_args {
   const float* rope_cos;  /* fp32 [rope_T][64] */
   const float* rope_sin;
   int32_t rope_T, rope_cols;
+  const int32_t* rope_pos; /* NULL, or device int added to every row's position (decode steps replayed from a CUDA graph) */
 } mm_gemm_args;
 
 int32_t mm_gemm_fwd(const mm_gemm_args* args, void* stream);
@@ -108,6 +109,8 @@ typedef struct mm_attn_args {
   int32_t causal;
   float scale;
   int32_t impl; /* 0 = auto (tcgen05 kernel for head_dim 64/128, mma.sync kernel for 96); 1 = force the mma.sync kernel */
+  const int32_t* tk_dev; /* NULL, or device int holding the number of valid keys (<= Tk, which then is the capacity of
+                            k / v): lets one captured launch serve a growing KV cache (tcgen05 kernel only) */
 } mm_attn_args;
 int32_t mm_attn_fwd(const mm_attn_args* args, void* stream);
 
@@ -164,7 +167,7 @@ int32_t mm_align_ctx_fixup(void* ctx, int64_t ldc, const float* p_sum_real, cons
  * row stride ld_qkv) into a per-layer cache (B, Tmax, 2, E) at time positions t0 .. t0 + T_new - 1.
  * mm_argmax_rows: out[r] = argmax_c logits[r, c] (lowest index on ties), bf16 logits, int64 out. */
 int32_t mm_kv_append(const void* qkv, int64_t ld_qkv, int32_t B, int32_t T_new, int32_t E, void* cache, int32_t Tmax,
-                     int32_t t0, void* stream);
+                     int32_t t0, const int32_t* t0_dev, void* stream); /* t0_dev != NULL overrides t0 with a device int */
 int32_t mm_argmax_rows(const void* logits, int64_t ld, int32_t rows, int32_t V, int64_t* out, void* stream);
 
 /* ------------------------------------------------------------------------------------------------ loss

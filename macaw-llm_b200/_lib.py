@@ -26,7 +26,7 @@ class GemmArgs(C.Structure):
         ("bias", c_vp), ("bias_bs", c_i64),
         ("row_scale", c_vp),
         ("residual", c_vp), ("ldr", c_i64), ("r_bs", c_i64), ("r_bs2", c_i64), ("res_row_mod", c_i32),
-        ("rope_cos", c_vp), ("rope_sin", c_vp), ("rope_T", c_i32), ("rope_cols", c_i32),
+        ("rope_cos", c_vp), ("rope_sin", c_vp), ("rope_T", c_i32), ("rope_cols", c_i32), ("rope_pos", c_vp),
     ]
 
 
@@ -40,7 +40,7 @@ class AttnArgs(C.Structure):
         ("k_bs", c_i64), ("k_ts", c_i64), ("k_hs", c_i64),
         ("v_bs", c_i64), ("v_ts", c_i64), ("v_hs", c_i64),
         ("o_bs", c_i64), ("o_ts", c_i64), ("o_hs", c_i64),
-        ("key_mask", c_vp), ("causal", c_i32), ("scale", c_f32), ("impl", c_i32),
+        ("key_mask", c_vp), ("causal", c_i32), ("scale", c_f32), ("impl", c_i32), ("tk_dev", c_vp),
     ]
 
 
@@ -65,7 +65,7 @@ SIGNATURES = {
     "mm_copy_rows": (c_i32, [c_vp, c_i64, c_vp, c_i64, c_i32, c_i32, c_vp]),
     "mm_align_softmax": (c_i32, [c_vp, c_i64, c_vp, c_vp, c_i64, c_vp, c_i64, c_vp, c_vp, c_i32, c_i32, c_vp]),
     "mm_align_ctx_fixup": (c_i32, [c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_vp]),
-    "mm_kv_append": (c_i32, [c_vp, c_i64, c_i32, c_i32, c_i32, c_vp, c_i32, c_i32, c_vp]),
+    "mm_kv_append": (c_i32, [c_vp, c_i64, c_i32, c_i32, c_i32, c_vp, c_i32, c_i32, c_vp, c_vp]),
     "mm_argmax_rows": (c_i32, [c_vp, c_i64, c_i32, c_i32, c_vp, c_vp]),
     "mm_ce_loss": (c_i32, [c_vp, c_vp, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp]),
 }

@@ -292,6 +292,7 @@ extern "C" int32_t mm_attn_fwd(const mm_attn_args* a, void* stream) {
   // head_dim 64 / 128: tcgen05 kernel (attn_tcgen05.cu); impl == 1 forces the mma.sync kernel below (tests)
   if ((a->head_dim == 64 || a->head_dim == 128) && a->scale > 0.f && a->impl != 1)
     return attn_tcgen05_dispatch(a, reinterpret_cast<cudaStream_t>(stream));
+  MM_REQUIRE(a->tk_dev == nullptr, "mm_attn_fwd: device-side key length is only supported by the tcgen05 kernel");
   AttnKParams p;
   p.q = (const bf16*)a->q; p.k = (const bf16*)a->k; p.v = (const bf16*)a->v; p.out = (bf16*)a->out;
   p.B = a->B; p.H = a->H; p.Tq = a->Tq; p.Tk = a->Tk;

@@ -28,6 +28,7 @@ struct FaParams {
   int B, H, Tq, Tk;
   long long o_bs, o_ts, o_hs;
   const int* key_mask;
+  const int* tk_dev;  // optional device-side number of valid keys (<= Tk)
   int causal;
   float scale_log2;
   int qpc;  // query tiles per CTA (walked heaviest first)
@@ -94,14 +95,15 @@ fa_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int h = blockIdx.y, b = blockIdx.z;
-  const int shift = p.Tk - p.Tq;
+  int Tk = p.Tk;          // replaced below by the device-side length when one is given
+  int shift = Tk - p.Tq;  // causal: key j visible to query i iff j <= i + shift
   // This CTA walks `p.qpc` consecutive query tiles of (b, h), heaviest first; heavy groups are launched first.
   const int nq = (p.Tq + kFaMQ - 1) / kFaMQ;
   const int grp = p.rev ? static_cast<int>(gridDim.x - 1 - blockIdx.x) : static_cast<int>(blockIdx.x);
   const int q_lo = grp * p.qpc, q_hi = min(nq, q_lo + p.qpc);  // query tiles [q_lo, q_hi)
   auto tiles_of = [&](int mt) {
-    int kv_end = p.Tk;
-    if (p.causal) kv_end = min(p.Tk, mt * kFaMQ + kFaMQ + shift);
+    int kv_end = Tk;
+    if (p.causal) kv_end = min(Tk, mt * kFaMQ + kFaMQ + shift);
     return kv_end > 0 ? (kv_end + kFaKT - 1) / kFaKT : 0;
   };
 
@@ -137,7 +139,11 @@ fa_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   griddep_launch();  // prologue done: the next kernel may begin its own
-  griddep_wait();    // q / k / v come from the previous kernel
+  griddep_wait();    // q / k / v (and the device-side length) come from earlier kernels
+  if (p.tk_dev != nullptr) {
+    Tk = min(*p.tk_dev, p.Tk);
+    shift = Tk - p.Tq;
+  }
 
   // Every role walks the same sequence: query tiles mt = q_hi-1 .. q_lo, key tiles j = 0 .. n-1 of each.
   // G = running key-tile index across query tiles (ring stages / mbarrier parities), qa = running count of
@@ -250,7 +256,7 @@ fa_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
 #pragma unroll
         for (int c = 0; c < NCH; ++c) {
           const int key = key0 + c * 32 + lane;
-          bool ok = key < p.Tk;
+          bool ok = key < Tk;
           if (ok && kmask != nullptr) ok = kmask[key] != 0;
           uint32_t bits = __ballot_sync(0xffffffffu, ok);
           if (p.causal) {
@@ -464,6 +470,7 @@ static int launch_fa(const mm_attn_args* a, cudaStream_t st) {
   p.B = a->B; p.H = a->H; p.Tq = a->Tq; p.Tk = a->Tk;
   p.o_bs = a->o_bs; p.o_ts = a->o_ts; p.o_hs = a->o_hs;
   p.key_mask = a->key_mask;
+  p.tk_dev = a->tk_dev;
   p.causal = a->causal;
   p.scale_log2 = a->scale * 1.4426950408889634f;
   // query tiles per CTA: amortise the per-CTA prologue (TMEM alloc, barrier init, first TMA round trip) while keeping

@@ -41,6 +41,7 @@ struct GemmKParams {
   const float* rope_cos;
   const float* rope_sin;
   int rope_T, rope_cols;
+  const int* rope_pos;
   int vec_ok;
   int group_m;  // rasterisation: M units per group
 };
@@ -384,7 +385,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           if (row_ok) store_row32(p, crow, col_in / 2, n_out_total, v);
         }
       } else {  // MM_EPI_ROPE, head_dim 128: pairs (i, i + 64) within each head
-        const int pos = row_ok ? (row % p.rope_T) : 0;
+        const int pos = (row_ok ? (row % p.rope_T) : 0) + (p.rope_pos != nullptr ? __ldg(p.rope_pos) : 0);
         const float* cs = p.rope_cos + static_cast<long long>(pos) * 64;
         const float* sn = p.rope_sin + static_cast<long long>(pos) * 64;
 #pragma unroll 1
@@ -563,6 +564,7 @@ extern "C" int32_t mm_gemm_fwd(const mm_gemm_args* a, void* stream) {
   p.residual = reinterpret_cast<const bf16*>(a->residual); p.ldr = a->ldr; p.r_bs = a->r_bs; p.r_bs2 = a->r_bs2;
   p.res_row_mod = a->res_row_mod;
   p.rope_cos = a->rope_cos; p.rope_sin = a->rope_sin; p.rope_T = a->rope_T; p.rope_cols = a->rope_cols;
+  p.rope_pos = a->rope_pos;
 
   const int esz = a->c_fp32 ? 4 : 2;
   bool vec = (reinterpret_cast<uintptr_t>(a->C) % 16 == 0) && ((a->ldc * esz) % 16 == 0) &&

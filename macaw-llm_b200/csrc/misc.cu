@@ -398,7 +398,9 @@ __global__ void align_ctx_fixup_kernel(bf16* __restrict__ ctx, long long ldc, co
 // ------------------------------------------------------------------------------------------------ decode helpers
 // K / V rows of a fused QKV activation -> per-layer cache (B, Tmax, 2, E) at positions t0 .. t0 + T_new - 1
 __global__ void __launch_bounds__(128) kv_append_kernel(const bf16* __restrict__ qkv, long long ld_qkv, int T_new, int E,
-                                                        bf16* __restrict__ cache, int Tmax, int t0) {
+                                                        bf16* __restrict__ cache, int Tmax, int t0,
+                                                        const int* __restrict__ t0_dev) {
+  if (t0_dev != nullptr) t0 = *t0_dev;
   const int b = blockIdx.x / T_new, t = blockIdx.x % T_new;
   const bf16* src = qkv + (static_cast<long long>(b) * T_new + t) * ld_qkv + E;  // [q | k | v]: skip q
   bf16* dst = cache + ((static_cast<long long>(b) * Tmax + t0 + t) * 2) * E;
@@ -613,11 +615,11 @@ extern "C" int32_t mm_align_ctx_fixup(void* ctx, int64_t ldc, const float* p_sum
 }
 
 extern "C" int32_t mm_kv_append(const void* qkv, int64_t ld_qkv, int32_t B, int32_t T_new, int32_t E, void* cache,
-                                int32_t Tmax, int32_t t0, void* stream) {
+                                int32_t Tmax, int32_t t0, const int32_t* t0_dev, void* stream) {
   MM_REQUIRE(qkv && cache && B > 0 && T_new > 0 && E > 0 && E % 8 == 0 && ld_qkv % 8 == 0 && t0 >= 0 &&
                  t0 + T_new <= Tmax && AL16(qkv) && AL16(cache),
              "mm_kv_append: bad arguments");
-  kv_append_kernel<<<B * T_new, 128, 0, ST(stream)>>>((const bf16*)qkv, ld_qkv, T_new, E, (bf16*)cache, Tmax, t0);
+  kv_append_kernel<<<B * T_new, 128, 0, ST(stream)>>>((const bf16*)qkv, ld_qkv, T_new, E, (bf16*)cache, Tmax, t0, t0_dev);
   return check_launch("mm_kv_append");
 }
 

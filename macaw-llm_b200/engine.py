@@ -442,26 +442,37 @@ class Engine:
             raise NotImplementedError("macaw_b200: intermediate_size must be a multiple of 32")
         return E, H, hd, I, cfg.rms_norm_eps
 
-    def _llama_layers(self, x: torch.Tensor, B: int, T: int, kmask, pos0: int = 0, cache=None, t_max: int = 0):
+    def _llama_layers(self, x: torch.Tensor, B: int, T: int, kmask, pos0: int = 0, cache=None, t_max: int = 0,
+                      pos_dev: Optional[torch.Tensor] = None):
         """The decoder stack on the residual stream x (B*T, E), updated in place.
 
         pos0 = position of the first row of every sample (0 for prefill, the current length for a decode step).
         With `cache` (per layer (B, Tmax, 2, E)) the new K/V rows are appended at pos0 and, for decode steps (pos0 > 0),
-        attention reads keys/values [0, pos0 + T) from the cache (reference KV-cache logic: modeling.py:190-195)."""
+        attention reads keys/values [0, pos0 + T) from the cache (reference KV-cache logic: modeling.py:190-195).
+        `pos_dev` (int32 tensor [pos, pos + 1] on the device) replaces pos0 for a decode step whose launches are captured
+        in a CUDA graph: RoPE position, cache slot and key count are then read by the kernels themselves."""
         E, H, hd, I, eps = self._llama_dims()
         dev = x.device
         cos, sin = self.rope_tables(max(T, t_max), hd, dev)
         scale = 1.0 / math.sqrt(hd)
-        rope = (cos, sin, T, 2 * E) if pos0 == 0 else (cos[pos0:], sin[pos0:], 1, 2 * E)
-        assert pos0 == 0 or T == 1
+        dyn = pos_dev is not None
+        if dyn:
+            rope = (cos, sin, 1, 2 * E, pos_dev[0:1])
+        else:
+            rope = (cos, sin, T, 2 * E) if pos0 == 0 else (cos[pos0:], sin[pos0:], 1, 2 * E)
+        assert (pos0 == 0 and not dyn) or T == 1
         for i, l in enumerate(self.m.llm.model.layers):
             wqkv, wgu, wo, wd = self._llama_weights(i, l, E, I)
             rstd = ops.rms_rstd(x, eps)
             qkv = ops.linear(x, wqkv, epi=ops.EPI_ROPE, rope=rope, row_scale=rstd)
             q5 = qkv.view(B, T, 3, H, hd)
             if cache is not None:
-                ops.kv_append(qkv, B, T, cache[i], pos0)
-            if pos0 == 0:
+                ops.kv_append(qkv, B, T, cache[i], pos0, pos_dev[0:1] if dyn else None)
+            if dyn:
+                kv = cache[i].unflatten(-1, (H, hd))  # whole capacity; the kernel reads the valid length from pos_dev[1]
+                a = ops.attention(q5[:, :, 0], kv[:, :, 0], kv[:, :, 1], scale=scale, causal=False, key_mask=kmask,
+                                  tk_dev=pos_dev[1:2])
+            elif pos0 == 0:
                 a = ops.attention(q5[:, :, 0], q5[:, :, 1], q5[:, :, 2], scale=scale, causal=True, key_mask=kmask)
             else:
                 kv = cache[i][:, : pos0 + T].unflatten(-1, (H, hd))  # (B, Tk, 2, H, hd) view of the cache
@@ -519,24 +530,55 @@ class Engine:
             table = self.w(self.m.llm.model.embed_tokens.weight, "llm.embed")
             n_layers = len(self.m.llm.model.layers)
             t_max = T + max_new_tokens
-            cache = [torch.empty((B, t_max, 2, E), device=dev, dtype=BF16) for _ in range(n_layers)]
+            # zero-filled: the graph-replayed decode attention addresses the cache at full capacity and masks keys beyond
+            # the current length by score, so never-written V rows must be finite (0 * NaN would poison the PV product)
+            cache = [torch.zeros((B, t_max, 2, E), device=dev, dtype=BF16) for _ in range(n_layers)]
             x = embeds.reshape(B * T, E).contiguous()
             x = self._llama_layers(x, B, T, None, 0, cache, t_max)
             logits = self._lm_head(x, rows=x.view(B, T, E)[:, -1, :])
             out = torch.full((B, max_new_tokens), pad_token_id, device=dev, dtype=torch.int64)
             finished = torch.zeros((B,), device=dev, dtype=torch.bool)
-            n = 0
-            for step in range(max_new_tokens):
-                tok = ops.argmax_rows(logits)
-                tok = torch.where(finished, torch.full_like(tok, pad_token_id), tok)  # HF: finished rows emit pad
-                out[:, step] = tok
-                n = step + 1
-                finished |= tok == eos_token_id
-                if step + 1 == max_new_tokens or bool(finished.all()):
-                    break
-                x = ops.embed_gather(table, tok)  # (B, E); ids beyond the table (pad of finished rows) are clamped
-                x = self._llama_layers(x, B, 1, None, T + step, cache, t_max)
-                logits = self._lm_head(x)
+            pad = torch.full((B,), pad_token_id, device=dev, dtype=torch.int64)
+            tok = ops.argmax_rows(logits)
+            out[:, 0] = tok
+            finished |= tok == eos_token_id
+            n = 1
+            if max_new_tokens > 1 and not bool(finished.all()):
+                # One decode step = ~8 launches per layer: host-bound when launched one by one, so the step is captured
+                # ONCE in a CUDA graph whose kernels read position / cache slot / key count from `pos_dev`.
+                pos_dev = torch.tensor([T, T + 1], device=dev, dtype=torch.int32)
+                tok_in = tok.clone()
+
+                def decode_step():
+                    x1 = ops.embed_gather(table, tok_in)  # ids beyond the table (pad of finished rows) are clamped
+                    x1 = self._llama_layers(x1, B, 1, None, 1, cache, t_max, pos_dev)
+                    nxt = ops.argmax_rows(self._lm_head(x1))
+                    nxt = torch.where(finished, pad, nxt)  # HF: finished rows emit pad
+                    finished.logical_or_(nxt == eos_token_id)
+                    tok_in.copy_(nxt)
+                    pos_dev.add_(1)
+
+                decode_step()  # eager first step: fills caches / function attributes, and is a real step
+                out[:, 1] = tok_in
+                n = 2
+                graph = None
+                while n < max_new_tokens:
+                    if n % 8 == 2 and bool(finished.all()):  # host check every 8 steps (finished rows only emit pad)
+                        break
+                    if graph is None:
+                        graph = torch.cuda.CUDAGraph()
+                        prof, ops.PROFILE = ops.PROFILE, None
+                        try:
+                            with torch.cuda.graph(graph, capture_error_mode="thread_local"):
+                                decode_step()
+                        finally:
+                            ops.PROFILE = prof
+                    graph.replay()
+                    out[:, n] = tok_in
+                    n += 1
+                # trim trailing all-pad columns produced between two host checks
+                alive = (out[:, :n] != pad_token_id).any(dim=0)
+                n = int(alive.nonzero().max().item()) + 1 if bool(alive.any()) else 1
         return out[:, :n]
 
     # ------------------------------------------------------------------------------------------------ whole forward

@@ -58,11 +58,11 @@ def launch_count_reset() -> None:
 def gemm_raw(*, M, N, K, A, lda, B, ldb, Cout, ldc, batch=1, a_bs=0, b_bs=0, c_bs=0, batch2=1, a_bs2=0, b_bs2=0,
              c_bs2=0, b_mn_major=False, c_fp32=False, epi=EPI_STD, act=ACT_NONE, alpha=1.0, bias=None, bias_bs=0,
              row_scale=None, residual=None, ldr=0, r_bs=0, r_bs2=0, res_row_mod=0, rope_cos=None, rope_sin=None,
-             rope_T=0, rope_cols=0) -> None:
+             rope_T=0, rope_cols=0, rope_pos=None) -> None:
     """Direct binding of mm_gemm_fwd; pointers are ints (data_ptr() + byte offsets)."""
     a = GemmArgs(M, N, K, batch, batch2, A, lda, a_bs, a_bs2, B, ldb, b_bs, b_bs2, int(b_mn_major), Cout, ldc, c_bs,
                  c_bs2, int(c_fp32), epi, act, float(alpha), bias, bias_bs, row_scale, residual, ldr, r_bs, r_bs2,
-                 res_row_mod, rope_cos, rope_sin, rope_T, rope_cols)
+                 res_row_mod, rope_cos, rope_sin, rope_T, rope_cols, rope_pos)
     if PROFILE is None:
         _check(_lib.load().mm_gemm_fwd(C.byref(a), _stream()), "mm_gemm_fwd")
         return
@@ -93,8 +93,10 @@ def linear(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None
         assert residual.stride(-1) == 1
         kw.update(residual=residual.data_ptr(), ldr=residual.stride(0), res_row_mod=res_row_mod)
     if rope is not None:
-        cos, sin, T, cols = rope
+        cos, sin, T, cols = rope[:4]
         kw.update(rope_cos=cos.data_ptr(), rope_sin=sin.data_ptr(), rope_T=T, rope_cols=cols)
+        if len(rope) > 4 and rope[4] is not None:  # device-side position offset (int32 tensor)
+            kw.update(rope_pos=rope[4].data_ptr())
     gemm_raw(M=M, N=N, K=K, A=x.data_ptr(), lda=x.stride(0), B=w.data_ptr(), ldb=w.stride(0), Cout=out.data_ptr(),
              ldc=out.stride(0), c_fp32=out.dtype == torch.float32, epi=epi, act=act, alpha=alpha, bias=_ptr(bias),
              row_scale=_ptr(row_scale), **kw)
@@ -111,7 +113,8 @@ def splitk_reduce(partial: torch.Tensor, bias: Optional[torch.Tensor], out: torc
 
 # ---------------------------------------------------------------------------------------------------- attention
 def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, *, scale: float, causal: bool = False,
-              key_mask: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None, impl: int = 0) -> torch.Tensor:
+              key_mask: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None, impl: int = 0,
+              tk_dev: Optional[torch.Tensor] = None) -> torch.Tensor:
     """q (B, Tq, H, hd), k/v (B, Tk, H, hd) bf16 views (hd contiguous, arbitrary other strides) -> (B, Tq, H, hd)."""
     for n, t in (("q", q), ("k", k), ("v", v)):
         _cuda(t, _BF16, n)
@@ -126,7 +129,7 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, *, scale: float
     a = AttnArgs(q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), B, H, Tq, Tk, hd,
                  q.stride(0), q.stride(1), q.stride(2), k.stride(0), k.stride(1), k.stride(2),
                  v.stride(0), v.stride(1), v.stride(2), out.stride(0), out.stride(1), out.stride(2),
-                 _ptr(key_mask), int(causal), float(scale), int(impl))
+                 _ptr(key_mask), int(causal), float(scale), int(impl), _ptr(tk_dev))
     _check(_lib.load().mm_attn_fwd(C.byref(a), _stream()), "mm_attn_fwd")
     return out
 
@@ -264,13 +267,14 @@ def align_ctx_fixup(ctx: torch.Tensor, psum: torch.Tensor, pext: torch.Tensor, b
 
 
 # ---------------------------------------------------------------------------------------------------- decode helpers
-def kv_append(qkv: torch.Tensor, B: int, T_new: int, cache: torch.Tensor, t0: int) -> None:
+def kv_append(qkv: torch.Tensor, B: int, T_new: int, cache: torch.Tensor, t0: int,
+              t0_dev: Optional[torch.Tensor] = None) -> None:
     """qkv (B*T_new, 3E) fused activation -> cache (B, Tmax, 2, E) at positions t0 .. t0+T_new-1 (K and V thirds)."""
     _cuda(qkv, _BF16, "qkv"); _cuda(cache, _BF16, "cache")
     E = cache.shape[-1]
     assert qkv.shape == (B * T_new, 3 * E) and qkv.stride(1) == 1 and cache.is_contiguous() and cache.shape[2] == 2
     _check(_lib.load().mm_kv_append(qkv.data_ptr(), qkv.stride(0), B, T_new, E, cache.data_ptr(), cache.shape[1], t0,
-                                    _stream()), "mm_kv_append")
+                                    _ptr(t0_dev), _stream()), "mm_kv_append")
 
 
 def argmax_rows(logits: torch.Tensor) -> torch.Tensor:
