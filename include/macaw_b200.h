@@ -80,6 +80,9 @@ typedef struct mm_gemm_args {
   const float* rope_sin;
   int32_t rope_T, rope_cols;
   const int32_t* rope_pos; /* NULL, or device int added to every row's position (decode steps replayed from a CUDA graph) */
+  int32_t c_trans; /* 1: C and residual are addressed transposed (C[n][m], row stride ldc), bias is indexed by m, row_scale by n:
+                      lets a caller swap the operands (A = weight rows, B = a handful of activation rows) so that thin
+                      decode GEMMs fill the 128-row MMA tile with weights (standard epilogue, batch == 1) */
 } mm_gemm_args;
 
 int32_t mm_gemm_fwd(const mm_gemm_args* args, void* stream);
@@ -169,6 +172,13 @@ int32_t mm_align_ctx_fixup(void* ctx, int64_t ldc, const float* p_sum_real, cons
 int32_t mm_kv_append(const void* qkv, int64_t ld_qkv, int32_t B, int32_t T_new, int32_t E, void* cache, int32_t Tmax,
                      int32_t t0, const int32_t* t0_dev, void* stream); /* t0_dev != NULL overrides t0 with a device int */
 int32_t mm_argmax_rows(const void* logits, int64_t ld, int32_t rows, int32_t V, int64_t* out, void* stream);
+/* Thin-row companions of the swapped-operand decode GEMMs (mm_gemm_args.c_trans), whose epilogue cannot pair columns:
+ * mm_rope_rows: in-place rotate-half RoPE (head_dim 128, apply_rotary_pos_emb modeling.py:83-91) on the first rot_cols
+ * columns; position of row r = (*pos_dev if given) + r % rope_T.  mm_swiglu_rows: out[r, j] = silu(gate_j) * up_j from
+ * the [32 gate | 32 up]-interleaved product (LlamaMLP modeling.py:139-140). */
+int32_t mm_rope_rows(void* x, int64_t ld, int32_t rows, int32_t rot_cols, const float* cos_t, const float* sin_t,
+                     int32_t rope_T, const int32_t* pos_dev, void* stream);
+int32_t mm_swiglu_rows(const void* gu, int64_t ld, int32_t rows, int32_t I, void* out, int64_t ldo, void* stream);
 
 /* ------------------------------------------------------------------------------------------------ loss
  * Shifted cross entropy of LlamaForCausalLM.forward modeling.py:600-610: logits bf16 (B, T, V), labels int64 (B, T);

@@ -42,6 +42,7 @@ struct GemmKParams {
   const float* rope_sin;
   int rope_T, rope_cols;
   const int* rope_pos;
+  int c_trans;
   int vec_ok;
   int group_m;  // rasterisation: M units per group
 };
@@ -308,10 +309,46 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                    (static_cast<long long>(t.b_lo) * p.c_bs + static_cast<long long>(t.b_hi) * p.c_bs2 +
                     static_cast<long long>(row) * p.ldc) * (p.c_fp32 ? 4 : 2);
       float rs = 1.0f;
-      if (p.row_scale != nullptr && row_ok) rs = p.row_scale[static_cast<long long>(t.b) * p.M + row];
+      if (p.row_scale != nullptr && row_ok && !p.c_trans) rs = p.row_scale[static_cast<long long>(t.b) * p.M + row];
       rs *= p.alpha;
 
       if constexpr (EPI == MM_EPI_STD) {
+        if (p.c_trans) {
+          // "swap-AB" launches (few activation rows, many weight rows): the tile's rows are OUTPUT FEATURES (weights ride
+          // the 128-row A operand so every MMA row is useful) and its columns are the activation rows.  C / residual are
+          // addressed transposed, bias is per tile row, row_scale per tile column.  Outputs are tiny: scalar stores.
+          constexpr int CPH_T = BN >= 64 ? BN / 64 : 1;
+          const float bias_r = (p.bias != nullptr && row_ok) ? __bfloat162float(p.bias[row]) : 0.f;
+#pragma unroll 1
+          for (int c = half * CPH_T; c < (half + 1) * CPH_T && c < BN / 32; ++c) {
+            uint32_t r[32];
+            tmem_ld32(taddr + c * 32, r);
+            tmem_ld_wait();
+            const int col0 = t.n_blk * BN + c * 32;
+            if (col0 >= p.N || !row_ok) continue;
+            float v[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              const int col = col0 + i;
+              float cs = p.alpha;
+              if (p.row_scale != nullptr && col < p.N) cs *= p.row_scale[col];
+              v[i] = __uint_as_float(r[i]) * cs + bias_r;
+            }
+            if (p.act != MM_ACT_NONE) apply_act32(v, p.act);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              const int col = col0 + i;
+              if (col < p.N) {
+                float o = v[i];
+                if (p.residual != nullptr) o += __bfloat162float(p.residual[static_cast<long long>(col) * p.ldr + row]);
+                if (p.c_fp32)
+                  reinterpret_cast<float*>(p.C)[static_cast<long long>(col) * p.ldc + row] = o;
+                else
+                  reinterpret_cast<bf16*>(p.C)[static_cast<long long>(col) * p.ldc + row] = __float2bfloat16(o);
+              }
+            }
+          }
+        } else {
         const bf16* bias = p.bias ? p.bias + static_cast<long long>(t.b_lo) * p.bias_bs : nullptr;
         const bf16* rrow = nullptr;
         if (p.residual != nullptr && row_ok) {
@@ -366,6 +403,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           }
           if (row_ok) store_row32(p, crow, col0, n_out_total, v);
         }
+        }  // !c_trans
       } else if constexpr (EPI == MM_EPI_SWIGLU) {
 #pragma unroll 1
         for (int c = half * (BN / 128); c < (half + 1) * (BN / 128); ++c) {
@@ -565,6 +603,9 @@ extern "C" int32_t mm_gemm_fwd(const mm_gemm_args* a, void* stream) {
   p.res_row_mod = a->res_row_mod;
   p.rope_cos = a->rope_cos; p.rope_sin = a->rope_sin; p.rope_T = a->rope_T; p.rope_cols = a->rope_cols;
   p.rope_pos = a->rope_pos;
+  p.c_trans = a->c_trans;
+  MM_REQUIRE(!a->c_trans || (a->epi == MM_EPI_STD && a->batch == 1 && batch2 == 1),
+             "mm_gemm_fwd: c_trans needs the standard epilogue and no batching");
 
   const int esz = a->c_fp32 ? 4 : 2;
   bool vec = (reinterpret_cast<uintptr_t>(a->C) % 16 == 0) && ((a->ldc * esz) % 16 == 0) &&

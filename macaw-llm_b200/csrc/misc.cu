@@ -409,6 +409,39 @@ __global__ void __launch_bounds__(128) kv_append_kernel(const bf16* __restrict__
   for (int c = threadIdx.x; c < (2 * E) >> 3; c += blockDim.x) d4[c] = s4[c];
 }
 
+// rotate-half RoPE (head_dim 128) in place on the first `rot_cols` columns of thin rows (decode step): position of row r
+// = pos_base (+ *pos_dev) + r % rope_T.  Same arithmetic as the GEMM's RoPE epilogue (fp32, tables (T, 64)).
+__global__ void rope_rows_kernel(bf16* __restrict__ x, long long ld, int rows, int rot_cols, const float* __restrict__ cs,
+                                 const float* __restrict__ sn, int rope_T, const int* __restrict__ pos_dev) {
+  const int pairs_per_row = rot_cols / 2;
+  const long long total = static_cast<long long>(rows) * pairs_per_row;
+  const int pos0 = pos_dev != nullptr ? *pos_dev : 0;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int r = static_cast<int>(i / pairs_per_row), pi = static_cast<int>(i % pairs_per_row);
+    const int head = pi / 64, j = pi % 64;
+    const int pos = pos0 + r % rope_T;
+    bf16* p1 = x + r * ld + head * 128 + j;
+    const float a = __bfloat162float(p1[0]), b = __bfloat162float(p1[64]);
+    const float c = cs[static_cast<long long>(pos) * 64 + j], s = sn[static_cast<long long>(pos) * 64 + j];
+    p1[0] = __float2bfloat16(a * c - b * s);
+    p1[64] = __float2bfloat16(b * c + a * s);
+  }
+}
+
+// out[r, 32 q + i] = silu(gu[r, 64 q + i]) * gu[r, 64 q + 32 + i]: the [32 gate | 32 up] interleave of the fused weight
+__global__ void swiglu_rows_kernel(const bf16* __restrict__ gu, long long ld, int rows, int I, bf16* __restrict__ out,
+                                   long long ldo) {
+  const long long total = static_cast<long long>(rows) * I;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int r = static_cast<int>(i / I), c = static_cast<int>(i % I);
+    const bf16* g = gu + r * ld + (c / 32) * 64 + (c % 32);
+    const float a = __bfloat162float(g[0]), b = __bfloat162float(g[32]);
+    out[r * ldo + c] = __float2bfloat16(a / (1.0f + __expf(-a)) * b);
+  }
+}
+
 // greedy next token: index of the largest logit per row (lowest index on ties), bf16 logits with row stride ld
 __global__ void __launch_bounds__(512) argmax_rows_kernel(const bf16* __restrict__ logits, long long ld, int V,
                                                           long long* __restrict__ out) {
@@ -621,6 +654,21 @@ extern "C" int32_t mm_kv_append(const void* qkv, int64_t ld_qkv, int32_t B, int3
              "mm_kv_append: bad arguments");
   kv_append_kernel<<<B * T_new, 128, 0, ST(stream)>>>((const bf16*)qkv, ld_qkv, T_new, E, (bf16*)cache, Tmax, t0, t0_dev);
   return check_launch("mm_kv_append");
+}
+
+extern "C" int32_t mm_rope_rows(void* x, int64_t ld, int32_t rows, int32_t rot_cols, const float* cos_t, const float* sin_t,
+                                int32_t rope_T, const int32_t* pos_dev, void* stream) {
+  MM_REQUIRE(x && cos_t && sin_t && rows > 0 && rot_cols > 0 && rot_cols % 128 == 0 && rope_T > 0, "mm_rope_rows: bad arguments");
+  const long long total = static_cast<long long>(rows) * rot_cols / 2;
+  rope_rows_kernel<<<grid_for(total, 256), 256, 0, ST(stream)>>>((bf16*)x, ld, rows, rot_cols, cos_t, sin_t, rope_T, pos_dev);
+  return check_launch("mm_rope_rows");
+}
+
+extern "C" int32_t mm_swiglu_rows(const void* gu, int64_t ld, int32_t rows, int32_t I, void* out, int64_t ldo, void* stream) {
+  MM_REQUIRE(gu && out && rows > 0 && I > 0 && I % 32 == 0, "mm_swiglu_rows: bad arguments");
+  const long long total = static_cast<long long>(rows) * I;
+  swiglu_rows_kernel<<<grid_for(total, 256), 256, 0, ST(stream)>>>((const bf16*)gu, ld, rows, I, (bf16*)out, ldo);
+  return check_launch("mm_swiglu_rows");
 }
 
 extern "C" int32_t mm_argmax_rows(const void* logits, int64_t ld, int32_t rows, int32_t V, int64_t* out, void* stream) {

@@ -464,7 +464,12 @@ class Engine:
         for i, l in enumerate(self.m.llm.model.layers):
             wqkv, wgu, wo, wd = self._llama_weights(i, l, E, I)
             rstd = ops.rms_rstd(x, eps)
-            qkv = ops.linear(x, wqkv, epi=ops.EPI_ROPE, rope=rope, row_scale=rstd)
+            thin = T == 1 and B * T <= 64  # decode step: swap operands so the weights fill the 128-row MMA tiles
+            if thin:
+                qkv = ops.linear_thin(x, wqkv, row_scale=rstd)
+                ops.rope_rows(qkv, 2 * E, rope[0], rope[1], rope[2], rope[4] if len(rope) > 4 else None)
+            else:
+                qkv = ops.linear(x, wqkv, epi=ops.EPI_ROPE, rope=rope, row_scale=rstd)
             q5 = qkv.view(B, T, 3, H, hd)
             if cache is not None:
                 ops.kv_append(qkv, B, T, cache[i], pos0, pos_dev[0:1] if dyn else None)
@@ -477,10 +482,16 @@ class Engine:
             else:
                 kv = cache[i][:, : pos0 + T].unflatten(-1, (H, hd))  # (B, Tk, 2, H, hd) view of the cache
                 a = ops.attention(q5[:, :, 0], kv[:, :, 0], kv[:, :, 1], scale=scale, causal=False, key_mask=kmask)
-            ops.linear(a.view(B * T, E), wo, residual=x, out=x)
-            rstd = ops.rms_rstd(x, eps)
-            g = ops.linear(x, wgu, epi=ops.EPI_SWIGLU, row_scale=rstd)
-            ops.linear(g, wd, residual=x, out=x)
+            if thin:
+                ops.linear_thin(a.view(B * T, E), wo, residual=x, out=x)
+                rstd = ops.rms_rstd(x, eps)
+                g = ops.swiglu_rows(ops.linear_thin(x, wgu, row_scale=rstd), I)
+                ops.linear_thin(g, wd, residual=x, out=x)
+            else:
+                ops.linear(a.view(B * T, E), wo, residual=x, out=x)
+                rstd = ops.rms_rstd(x, eps)
+                g = ops.linear(x, wgu, epi=ops.EPI_SWIGLU, row_scale=rstd)
+                ops.linear(g, wd, residual=x, out=x)
         return x
 
     def _lm_head(self, x: torch.Tensor, rows: Optional[torch.Tensor] = None) -> torch.Tensor:
@@ -493,6 +504,8 @@ class Engine:
         if rows is not None:  # strided row subset (last position of every sample)
             x, rstd = rows, rstd.view(rows.shape[0], -1)[:, -1].contiguous()
         ops.TAG = "lm_head"
+        if x.shape[0] <= 64:
+            return ops.linear_thin(x, wl, row_scale=rstd)
         return ops.linear(x, wl, row_scale=rstd)
 
     def llama_forward(self, embeds: torch.Tensor, attention_mask: Optional[torch.Tensor]) -> torch.Tensor:

@@ -58,11 +58,11 @@ def launch_count_reset() -> None:
 def gemm_raw(*, M, N, K, A, lda, B, ldb, Cout, ldc, batch=1, a_bs=0, b_bs=0, c_bs=0, batch2=1, a_bs2=0, b_bs2=0,
              c_bs2=0, b_mn_major=False, c_fp32=False, epi=EPI_STD, act=ACT_NONE, alpha=1.0, bias=None, bias_bs=0,
              row_scale=None, residual=None, ldr=0, r_bs=0, r_bs2=0, res_row_mod=0, rope_cos=None, rope_sin=None,
-             rope_T=0, rope_cols=0, rope_pos=None) -> None:
+             rope_T=0, rope_cols=0, rope_pos=None, c_trans=False) -> None:
     """Direct binding of mm_gemm_fwd; pointers are ints (data_ptr() + byte offsets)."""
     a = GemmArgs(M, N, K, batch, batch2, A, lda, a_bs, a_bs2, B, ldb, b_bs, b_bs2, int(b_mn_major), Cout, ldc, c_bs,
                  c_bs2, int(c_fp32), epi, act, float(alpha), bias, bias_bs, row_scale, residual, ldr, r_bs, r_bs2,
-                 res_row_mod, rope_cos, rope_sin, rope_T, rope_cols, rope_pos)
+                 res_row_mod, rope_cos, rope_sin, rope_T, rope_cols, rope_pos, int(c_trans))
     if PROFILE is None:
         _check(_lib.load().mm_gemm_fwd(C.byref(a), _stream()), "mm_gemm_fwd")
         return
@@ -100,6 +100,30 @@ def linear(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None
     gemm_raw(M=M, N=N, K=K, A=x.data_ptr(), lda=x.stride(0), B=w.data_ptr(), ldb=w.stride(0), Cout=out.data_ptr(),
              ldc=out.stride(0), c_fp32=out.dtype == torch.float32, epi=epi, act=act, alpha=alpha, bias=_ptr(bias),
              row_scale=_ptr(row_scale), **kw)
+    return out
+
+
+def linear_thin(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, *, act: int = ACT_NONE,
+                residual: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None,
+                row_scale: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """out = epilogue(x @ w.T) for a THIN x (a few rows, e.g. one decode step): operands are swapped so the weight rows
+    fill the 128-row MMA tile (weight-streaming regime) and the epilogue stores transposed.  Same semantics as `linear`
+    with the standard epilogue: row_scale scales rows of x, bias is per output feature, residual/out are (M, N)."""
+    _cuda(x, _BF16, "x"); _cuda(w, _BF16, "w")
+    M, K = x.shape
+    N = w.shape[0]
+    assert x.stride(1) == 1 and w.stride(1) == 1 and w.shape[1] == K
+    if out is None:
+        out = torch.empty((M, N), device=x.device, dtype=_BF16)
+    assert out.shape == (M, N) and out.stride(1) == 1
+    kw = {}
+    if residual is not None:
+        assert residual.stride(1) == 1
+        kw.update(residual=residual.data_ptr(), ldr=residual.stride(0))
+    # swapped problem: M' = N (weight rows), N' = M (activation rows)
+    gemm_raw(M=N, N=M, K=K, A=w.data_ptr(), lda=w.stride(0), B=x.data_ptr(), ldb=x.stride(0), Cout=out.data_ptr(),
+             ldc=out.stride(0), c_fp32=out.dtype == torch.float32, act=act, bias=_ptr(bias), row_scale=_ptr(row_scale),
+             c_trans=True, **kw)
     return out
 
 
@@ -275,6 +299,26 @@ def kv_append(qkv: torch.Tensor, B: int, T_new: int, cache: torch.Tensor, t0: in
     assert qkv.shape == (B * T_new, 3 * E) and qkv.stride(1) == 1 and cache.is_contiguous() and cache.shape[2] == 2
     _check(_lib.load().mm_kv_append(qkv.data_ptr(), qkv.stride(0), B, T_new, E, cache.data_ptr(), cache.shape[1], t0,
                                     _ptr(t0_dev), _stream()), "mm_kv_append")
+
+
+def rope_rows(x: torch.Tensor, rot_cols: int, cos: torch.Tensor, sin: torch.Tensor, rope_T: int,
+              pos_dev: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """In-place rotate-half RoPE (head_dim 128) on the first rot_cols columns of thin bf16 rows."""
+    _cuda(x, _BF16, "x")
+    assert x.dim() == 2 and x.stride(1) == 1
+    _check(_lib.load().mm_rope_rows(x.data_ptr(), x.stride(0), x.shape[0], rot_cols, cos.data_ptr(), sin.data_ptr(), rope_T,
+                                    _ptr(pos_dev), _stream()), "mm_rope_rows")
+    return x
+
+
+def swiglu_rows(gu: torch.Tensor, I: int) -> torch.Tensor:
+    """(rows, 2I) [32 gate | 32 up]-interleaved product -> (rows, I) silu(gate) * up."""
+    _cuda(gu, _BF16, "gu")
+    assert gu.dim() == 2 and gu.stride(1) == 1 and gu.shape[1] == 2 * I
+    out = torch.empty((gu.shape[0], I), device=gu.device, dtype=_BF16)
+    _check(_lib.load().mm_swiglu_rows(gu.data_ptr(), gu.stride(0), gu.shape[0], I, out.data_ptr(), out.stride(0),
+                                      _stream()), "mm_swiglu_rows")
+    return out
 
 
 def argmax_rows(logits: torch.Tensor) -> torch.Tensor:

@@ -379,3 +379,43 @@ def test_gemm_multicast_pairs(M, N, K, kind):
         return
     out = ops.linear(x, w)
     assert rel_err(out, x.float() @ w.float().t()) < 4e-3
+
+
+@pytest.mark.parametrize("M", [1, 8, 32, 50])
+def test_linear_thin_swapped_operands(M):
+    """Decode-step GEMMs: operands swapped (weights on the 128-row side), transposed epilogue."""
+    ops = _ops()
+    K, N = 1024, 1536
+    x, w, b = rnd(M, K, seed=90), rnd(N, K, scale=K ** -0.5, seed=91), rnd(N, seed=92)
+    res = rnd(M, N, seed=93)
+    rs = torch.rand(M, device=DEV) + 0.5
+    out = ops.linear_thin(x, w, b, act=ops.ACT_GELU, residual=res, row_scale=rs)
+    ref = torch.nn.functional.gelu((x.float() @ w.float().t()) * rs[:, None] + b.float()) + res.float()
+    assert rel_err(out, ref) < 4e-3
+    h = res.clone()
+    ops.linear_thin(x, w, residual=h, out=h)  # in-place residual stream update
+    assert rel_err(h, x.float() @ w.float().t() + res.float()) < 4e-3
+
+
+def test_rope_rows_and_swiglu_rows():
+    ops = _ops()
+    B, E, I = 8, 512, 1376
+    x = rnd(B, 3 * E, seed=94)
+    T = 40
+    inv = 1.0 / (10000 ** (torch.arange(0, 128, 2, device=DEV).float() / 128))
+    ang = torch.arange(T, device=DEV).float()[:, None] * inv[None, :]
+    cos, sin = ang.cos().contiguous(), ang.sin().contiguous()
+    pos = torch.tensor([17], device=DEV, dtype=torch.int32)
+    y = x.clone()
+    ops.rope_rows(y, 2 * E, cos, sin, 1, pos)
+    xf = x.float().view(B, 3, E // 128, 128)
+    c = torch.cat([cos[17], cos[17]])[None, None, None, :]
+    s_ = torch.cat([sin[17], sin[17]])[None, None, None, :]
+    rot = torch.cat([-xf[..., 64:], xf[..., :64]], -1)
+    ref = xf.clone()
+    ref[:, :2] = (xf * c + rot * s_)[:, :2]
+    assert rel_err(y, ref.view(B, 3 * E)) < 3e-3
+    g, u = rnd(B, I, seed=95), rnd(B, I, seed=96)
+    gu = torch.stack([g.view(B, I // 32, 32), u.view(B, I // 32, 32)], dim=2).reshape(B, 2 * I).contiguous()
+    out = ops.swiglu_rows(gu, I)
+    assert rel_err(out, torch.nn.functional.silu(g.float()) * u.float()) < 3e-3
