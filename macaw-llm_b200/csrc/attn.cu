@@ -5,8 +5,9 @@
 // registers; softmax reductions are warp-shuffle (quad) reductions in fp32; P is re-packed to bf16 in registers and
 // fed straight back to the tensor cores (mma.sync.m16n8k16 bf16, fp32 accumulate).
 //
-// Self-attention is ~2 % of the forward FLOPs at the BASELINE configs, so this kernel uses the
-// register-fragment tensor path; the GEMMs, where the FLOPs are, use tcgen05 (gemm_tcgen05.cu).
+// This register-fragment (mma.sync) kernel serves head_dim 96 — the video-long self-attention with its two synthetic
+// keys — and stays selectable (mm_attn_args.impl = 1) as an independent second implementation for the tests.  Head
+// dims 64 / 128 (CLIP, Whisper, LLaMA) run on the tcgen05 kernel in attn_tcgen05.cu, to which mm_attn_fwd dispatches.
 //
 // Reference call sites replaced: see include/macaw_b200.h (mm_attn_fwd).
 #include "common.cuh"

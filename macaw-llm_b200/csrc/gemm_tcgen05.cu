@@ -15,6 +15,9 @@
 // epilogue of tile i overlap the main loop of tile i+1.  One CTA per SM, static round-robin tile schedule with
 // grouped rasterisation for L2 reuse.
 //
+// Thin problems (decode steps) are launched with the operands swapped and `c_trans` set: the weight matrix takes the
+// 128-row A side, the few activation rows the narrow B side, and the standard epilogue stores transposed.
+//
 // Reference call sites replaced: see include/macaw_b200.h (mm_gemm_fwd).
 #include "common.cuh"
 #include "ptx.cuh"
