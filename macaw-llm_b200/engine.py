@@ -35,6 +35,7 @@ class Engine:
         self._zeros: Dict[Tuple[int, str], torch.Tensor] = {}
         self._graphs: Dict[tuple, tuple] = {}
         self._graphs_on = False
+        self.align_max_rows = None  # test hook: cap on query rows per alignment chunk (default: ~2 GiB of fp32 scores)
         self._params = None
 
     # ------------------------------------------------------------------------------------------------ weight cache
@@ -307,6 +308,8 @@ class Engine:
         ctx = torch.empty((Nq, E), device=dev, dtype=BF16)
         # bound the fp32 score buffer (R x V) to ~2 GiB by chunking query rows
         max_nq = max(1, (1 << 31) // (H * Vp * 4))
+        if self.align_max_rows:
+            max_nq = min(max_nq, int(self.align_max_rows))
         for n0 in range(0, Nq, max_nq):
             n1 = min(Nq, n0 + max_nq)
             nq = n1 - n0

@@ -321,3 +321,40 @@ def test_decode_step_matches_full_recompute(tiny):
         step = eng._lm_head(x1)
     torch.cuda.synchronize()
     assert H.rel_err(step, full) < 1e-2
+
+
+def test_alignment_row_chunking(tiny):
+    """The alignment scores buffer is chunked over query rows (video at large batch); force tiny chunks and compare."""
+    model, spec, hp, weights = tiny
+    inp = _to_bf16_inputs(H.case_inputs(spec, H.load_case("all3")))
+    dev_inp = {k: (v.cuda() if isinstance(v, torch.Tensor) else v) for k, v in inp.items()}
+    ref, _, _ = model.prepare_inputs_for_generation(dev_inp)
+    model.engine.align_max_rows = 5  # video: Nq = 32 rows -> 7 chunks; image / audio: 12 rows -> 3 chunks
+    try:
+        got, _, _ = model.prepare_inputs_for_generation(dev_inp)
+    finally:
+        model.engine.align_max_rows = None
+    torch.cuda.synchronize()
+    assert H.rel_err(got, ref) < 2e-3
+
+
+def test_fp32_and_fp16_parameter_models_use_bf16_shadows():
+    """Reference users call model.half() (llm_trainer.py:366-368): non-bf16 parameters are shadowed to bf16 once per
+    weight version; results equal the bf16 model built from the same (bf16-representable) weights."""
+    model_bf16, spec, hp, weights = H.build_tiny_model("cuda", torch.bfloat16)
+    model_f32, _, _, _ = H.build_tiny_model("cuda", torch.float32)
+    with torch.no_grad():
+        for (n, p32), (_, p16) in zip(model_f32.named_parameters(), model_bf16.named_parameters()):
+            p32.copy_(p16.float())
+    inp = _to_bf16_inputs(H.case_inputs(spec, H.load_case("image")))
+    dev_inp = {k: (v.cuda() if isinstance(v, torch.Tensor) else v) for k, v in inp.items()}
+    a = model_bf16(dev_inp).logits
+    b = model_f32(dev_inp).logits
+    torch.cuda.synchronize()
+    assert torch.equal(a, b)
+    # an in-place weight update must invalidate the shadow
+    with torch.no_grad():
+        model_f32.llm.lm_head.weight.mul_(2.0)
+    c = model_f32(dev_inp).logits
+    torch.cuda.synchronize()
+    assert H.rel_err(c, 2.0 * a.float()) < 1e-2
