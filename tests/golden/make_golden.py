@@ -51,8 +51,12 @@ def import_reference():
 
 def build_reference(modeling, spec):
     clip, whisper, llama = gen.build_configs(spec)
+    extra = {}
+    for name in ("image", "video", "audio"):
+        if f"{name}_conv" in spec:
+            extra[f"{name}_conv_kernel"], extra[f"{name}_conv_stride"] = spec[f"{name}_conv"]
     cfg = modeling.MM_LLMs_Config(n_frames=spec["n_frames"], attention_heads=spec["attention_heads"],
-                                  clip_config=clip, whisper_config=whisper, llm_config=llama)
+                                  clip_config=clip, whisper_config=whisper, llm_config=llama, **extra)
     model = modeling.MM_LLMs(cfg).eval()
     shapes = {k: tuple(v.shape) for k, v in model.state_dict().items()}
     weights = gen.make_weights(shapes, seed=0)
@@ -112,6 +116,28 @@ def main():
             labels=(lab_r.long().numpy() if lab_r is not None else np.zeros(0, dtype=np.int64)),
             loss=(float(out_r.loss) if out_r.loss is not None else np.nan),
         )
+
+    # second shape family (gen.ALT): oracle pinned on the reference in fp64, fixture replayed by tests/test_oracle.py
+    cfg2, model2, shapes2, _ = build_reference(modeling, gen.ALT)
+    hp2 = O.hp_from_config(cfg2)
+    with open(os.path.join(HERE, "alt_shapes.json"), "w") as f:
+        json.dump({"spec": gen.ALT, "hp": hp2, "shapes": {k: list(v) for k, v in shapes2.items()}}, f, indent=0,
+                  sort_keys=True)
+    model2 = model2.double()
+    sd2 = {k: v.double() for k, v in model2.state_dict().items()}
+    inp = gen.make_inputs(gen.ALT, 2, 13, seed=321, pad_tail=4)
+    inp64 = {k: (v.double() if isinstance(v, torch.Tensor) and v.is_floating_point() else v) for k, v in inp.items()}
+    with torch.no_grad():
+        emb_r, mask_r, lab_r = model2.prepare_inputs_for_generation(inp64)
+        out_r = model2(inp64)
+    o = O.forward(inp64, sd2, hp2, dtype=torch.float64)
+    e_emb, e_log = float((o["embeds"] - emb_r).abs().max()), float((o["logits"] - out_r.logits).abs().max())
+    assert e_emb < 1e-6 and e_log < 1e-5, (e_emb, e_log)
+    assert torch.equal(mask_r.long(), o["attention_mask"]) and torch.equal(lab_r.long(), o["labels"])
+    print(f"[golden] alt family: oracle vs reference fp64 max|d| embeds {e_emb:.2e} logits {e_log:.2e}  T={emb_r.shape[1]}")
+    np.savez_compressed(os.path.join(HERE, "alt_all3.npz"), B=2, L=13, seed=321, pad_tail=4,
+                        embeds=emb_r.float().numpy(), logits=out_r.logits.float().numpy(),
+                        attention_mask=mask_r.long().numpy(), labels=lab_r.long().numpy(), loss=float(out_r.loss))
 
     # stand-alone pieces with their own fixtures: video PE table (python double loop in the reference) and one MHA
     pe_ref = modeling.create_positional_encoding(40, 24)

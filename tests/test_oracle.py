@@ -35,6 +35,27 @@ def test_oracle_matches_golden(tiny_weights, name):
         assert o["labels"] is None and o["loss"] is None
 
 
+def test_oracle_matches_golden_alt_family():
+    """Second shape family (different widths, head counts, 3 frames, non-default Conv1d kernels / strides)."""
+    import json
+
+    with open(os.path.join(H.GOLDEN, "alt_shapes.json")) as f:
+        d = json.load(f)
+    spec, hp, shapes = d["spec"], d["hp"], {k: tuple(v) for k, v in d["shapes"].items()}
+    weights = gen.make_weights(shapes, seed=0)
+    z = np.load(os.path.join(H.GOLDEN, "alt_all3.npz"))
+    inp = gen.make_inputs(spec, int(z["B"]), int(z["L"]), seed=int(z["seed"]), pad_tail=int(z["pad_tail"]))
+    o = O.forward(inp, weights, hp, dtype=torch.float32)
+    assert H.rel_err(o["embeds"], torch.from_numpy(z["embeds"])) < 1e-5
+    assert H.rel_err(o["logits"], torch.from_numpy(z["logits"])) < 1e-4
+    assert torch.equal(o["attention_mask"], torch.from_numpy(z["attention_mask"]))
+    assert torch.equal(o["labels"], torch.from_numpy(z["labels"]))
+    assert abs(float(o["loss"]) - float(z["loss"])) < 1e-4 * abs(float(z["loss"]))
+    # prefix lengths follow (tokens - kernel) // stride + 1 with the non-default hyper-parameters
+    n_img, n_aud, n_vid = (256 - 40) // 24 + 1, (1500 - 300) // 200 + 1, (3 * 256 - 50) // 45 + 1
+    assert o["embeds"].shape[1] == 13 + (n_img + 2) + (n_aud + 2) + (n_vid + 2)
+
+
 def test_layout_order_and_prefix_lengths(tiny_weights):
     """[BOS, <image> img </image>, <audio> aud </audio>, <video> vid </video>, text[1:]]."""
     spec, hp, weights = tiny_weights
