@@ -66,3 +66,18 @@ def test_errors_are_reported_not_thrown():
     a.M, a.N, a.K, a.batch = 0, 8, 8, 1
     assert lib.mm_gemm_fwd(ctypes.byref(a), None) != 0 and b"bad shape" in lib.mm_last_error()
     assert lib.mm_rmsnorm_fwd(None, None, None, 1, 7, 1e-6, None) != 0
+
+
+def test_integration_md_stub_matches_abi():
+    """The ctypes stub shown to reference maintainers in INTEGRATION.md must mirror mm_gemm_args exactly."""
+    import ctypes
+
+    from macaw_llm_b200 import _lib
+
+    src = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    block = src[src.index("class GemmArgs(C.Structure)"):src.index("def b200_linear")]
+    ns = {}
+    exec("import ctypes as C\n" + block, ns)
+    doc = ns["GemmArgs"]
+    assert [f[0] for f in doc._fields_] == [f[0] for f in _lib.GemmArgs._fields_]
+    assert ctypes.sizeof(doc) == ctypes.sizeof(_lib.GemmArgs)
