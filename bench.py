@@ -2,7 +2,7 @@
 """Benchmark of record: multimodal prefill tokens/sec of the MM_LLMs forward (BASELINE.json metric).
 
   python bench.py --gpus N --steps K --warmup W            # this repo's sm_100a path (one rank per GPU under torchrun)
-  python bench.py --impl reference --gpus N --steps K ...  # the reference algorithm on the host CPUs (oracle port)
+  python bench.py --impl reference --gpus N --steps K ...  # the UNMODIFIED reference modeling.py on the host CPUs (oracle/_ref)
 
 Workload (config.workload): BASELINE config 4 — image + audio + text, CLIP ViT-L/14-224 + Whisper-base encoder +
 alignment (32000 x 4096 table, 16 heads) + LLaMA-7B, global batch 32, L = 512 text tokens -> T = 528 positions,
@@ -144,58 +144,95 @@ def usable_cores() -> int:
     return n
 
 
-def cpu_oracle_sample(cfgs, hyper, L, steps, warmup, seed=1234, state_dict=None, budget_s=240.0):
-    """Time the CPU oracle (a port of the reference's algorithm, oracle/macaw_oracle.py) on a bounded sample of the
-    workload: ONE sample (B=1) image+audio+text, full model depth, fp32, all host threads.  The reference is linear in
-    B (every term is per-sample), so tokens/s of one sample is its tokens/s at any batch."""
-    from oracle import macaw_oracle as O
-    from macaw_llm_b200.modeling import MM_LLMs_Config
+def physical_cores_one_socket() -> int:
+    """Physical cores of socket 0 (hyper-threads and the second socket make the fp32 CPU arm SLOWER: round 1 measured
+    56.6 tok/s on a 96-thread box vs 66.4 on a 16-thread one)."""
+    try:
+        cores, phys, core = set(), None, None
+        for ln in open("/proc/cpuinfo"):
+            if ln.startswith("physical id"):
+                phys = ln.split(":")[1].strip()
+            elif ln.startswith("core id"):
+                core = ln.split(":")[1].strip()
+            elif not ln.strip():
+                if phys == "0" and core is not None:
+                    cores.add(core)
+                phys = core = None
+        return len(cores) or (os.cpu_count() or 1)
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def cpu_threads() -> int:
+    return max(1, min(usable_cores(), physical_cores_one_socket()))
+
+
+def cpu_reference_sample(cfgs, hyper, L, steps, warmup, seed=1234, state_dict=None, inputs=None, budget_s=240.0):
+    """Time the reference's own CPU implementation of the path on a bounded sample of the workload: ONE sample (B=1)
+    image+audio+text, full model depth, fp32.
+
+    kind "reference": the UNMODIFIED /root/reference/modeling.py staged under oracle/_ref (oracle/make_ref.py) —
+    `MM_LLMs.forward` through its stock code path (per-sample K/V projection of the whole table included).
+    kind "port": oracle/macaw_oracle.py, only when oracle/_ref is absent.
+    The reference is linear in B (every term is per-sample), so tokens/s of one sample is its tokens/s at
+    any batch.  Returns timing + the sample's outputs (for the bench line's `parity` block)."""
+    import copy
+
+    from oracle import ref_runner as R
 
     clip, whisper, llama = cfgs
-    cfg = MM_LLMs_Config(clip_config=clip, whisper_config=whisper, llm_config=llama, **hyper)
-    hp = O.hp_from_config(cfg)
-    cores = usable_cores()
+    cores = cpu_threads()
     torch.set_num_threads(cores)
-    if state_dict is None:
-        # identical family of random weights, generated on the host (the oracle only needs a state_dict)
-        from macaw_llm_b200.modeling import MM_LLMs
-
-        with torch.device("meta"):
-            shapes = {k: tuple(v.shape) for k, v in MM_LLMs(cfg).state_dict().items()}
-        g = torch.Generator().manual_seed(0)
-        state_dict = {}
-        for k, shp in shapes.items():
-            if k.endswith("inv_freq") or k.endswith("position_ids"):
-                continue
-            if len(shp) == 1 and "norm" in k.lower() and k.endswith("weight"):
-                state_dict[k] = torch.ones(shp)
-            elif len(shp) <= 1:
-                state_dict[k] = torch.zeros(shp)
-            else:
-                state_dict[k] = torch.empty(shp).normal_(0.0, 0.02, generator=g)
-    else:
-        state_dict = {k: v.detach().to("cpu", torch.float32) for k, v in state_dict.items()}
     V = llama.vocab_size
-    inp = synth_inputs(1, L, V, clip.vision_config.image_size, 2 * whisper.max_source_positions, seed, torch.float32,
-                       pin=False)
-    times, T = [], None
+    if inputs is None:
+        inputs = synth_inputs(1, L, V, clip.vision_config.image_size, 2 * whisper.max_source_positions, seed,
+                              torch.float32, pin=False)
+    inputs = {k: (v.float() if isinstance(v, torch.Tensor) and v.is_floating_point() else v) for k, v in inputs.items()}
+    if R.available():
+        kind = "reference"
+        model = R.build_model(copy.deepcopy(clip), copy.deepcopy(whisper), copy.deepcopy(llama), dict(hyper),
+                              state_dict=state_dict)
+
+        def run():
+            with torch.no_grad():
+                emb, _, _ = model.prepare_inputs_for_generation(inputs)
+                out = model(inputs)
+            return out.logits, emb
+        what = "oracle/_ref/modeling.py (unmodified reference, MM_LLMs.forward)"
+    else:
+        kind = "port"
+        from macaw_llm_b200.modeling import MM_LLMs, MM_LLMs_Config
+        from oracle import macaw_oracle as O
+
+        cfg = MM_LLMs_Config(clip_config=clip, whisper_config=whisper, llm_config=llama, **hyper)
+        hp = O.hp_from_config(cfg)
+        if state_dict is None:
+            with torch.device("meta"):
+                meta = MM_LLMs(cfg)
+            state_dict = R.random_state_dict(meta)
+        sd = {k: v.detach().to("cpu", torch.float32) for k, v in state_dict.items() if v.is_floating_point()}
+
+        def run():
+            o = O.forward(inputs, sd, hp, dtype=torch.float32)
+            return o["logits"], o["embeds"]
+        what = "oracle/macaw_oracle.py (port; oracle/_ref absent)"
+    times, T, out = [], None, None
     t_begin = time.perf_counter()
-    done = 0
     for i in range(warmup + steps):
         t0 = time.perf_counter()
-        out = O.forward(inp, state_dict, hp, dtype=torch.float32)
+        out = run()
         dt = time.perf_counter() - t0
-        T = out["logits"].shape[1]
+        T = out[0].shape[1]
         if i >= warmup:
             times.append(dt)
-            done += 1
         # keep the whole arm within the budget: stop early once at least one timed step exists
-        if (time.perf_counter() - t_begin) + dt > budget_s and done >= 1:
+        if (time.perf_counter() - t_begin) + dt > budget_s and times:
             break
     sec = sum(times) / len(times)
-    return dict(value=T / sec, unit=UNIT, cores=cores, kind="port", steps_timed=len(times), sec_per_step=sec,
-                sample=f"1 sample (B=1) image+audio+text, L={L} -> T={T}, full depth, fp32, oracle/macaw_oracle.py; "
-                       f"reference cost is linear in B")
+    return dict(value=T / sec, unit=UNIT, cores=cores, kind=kind, steps_timed=len(times), sec_per_step=sec,
+                logits=out[0], embeds=out[1],
+                sample=f"1 sample (B=1) image+audio+text, L={L} -> T={T}, full depth, fp32, {what}; "
+                       f"reference cost is linear in B; {cores} threads (physical cores of one socket, capped by the cgroup)")
 
 
 # ---------------------------------------------------------------------------------------------------- main
@@ -230,7 +267,7 @@ def main():
             return
         steps = max(1, min(args.steps, 5))
         warm = min(args.warmup, 1)
-        cb = cpu_oracle_sample(cfgs, hyper, L, steps, warm)
+        cb = cpu_reference_sample(cfgs, hyper, L, steps, warm)
         line = {
             "impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus,
             "steps": cb["steps_timed"], "warmup": warm, "ms_per_step": cb["sec_per_step"] * 1e3,
@@ -376,11 +413,34 @@ def main():
                            "launches_per_step": v[2] / args.steps} for k, v in sorted(by_tag.items())},
     }
 
-    cpu = None
+    # ---- CPU arm on the SAME weights and the same sample 0 as the GPU arm: a timing baseline AND a full-depth parity
+    #      check of the benchmarked configuration (the GPU side re-runs sample 0 alone, eager launches)
+    cpu = parity = None
     if not args.no_cpu_baseline and world == 1:
-        sd = model.state_dict() if args.small else None
-        cb = cpu_oracle_sample(cfgs, hyper, L, steps=1, warmup=0, state_dict=sd, budget_s=120.0)
+        one = {k: (v[:1].clone() if isinstance(v, torch.Tensor) else v) for k, v in host.items()}
+        model.engine.enable_cuda_graphs(False)
+        with torch.no_grad():
+            g_emb, _, _ = model.prepare_inputs_for_generation({k: (v.to(dev) if isinstance(v, torch.Tensor) else v)
+                                                               for k, v in one.items()})
+            g_log = model({k: (v.to(dev) if isinstance(v, torch.Tensor) else v) for k, v in one.items()}).logits
+        g_emb, g_log = g_emb.float().cpu(), g_log.float().cpu()
+        cb = cpu_reference_sample(cfgs, hyper, L, steps=1, warmup=0, state_dict=model.state_dict(), inputs=one,
+                                  budget_s=120.0)
         cpu = {"value": cb["value"], "unit": UNIT, "cores": cb["cores"], "kind": cb["kind"], "sample": cb["sample"]}
+        r_log, r_emb = cb["logits"].float(), cb["embeds"].float()
+        n_prefix = r_emb.shape[1] - L
+
+        def rel(a, b):
+            return float((a - b).norm() / (b.norm() + 1e-30))
+
+        parity = {
+            "vs": cb["kind"] + " fp32 on the GPU arm's bf16 weights, rank-0 sample 0, full depth",
+            "embeds_rel": rel(g_emb, r_emb), "prefix_rel": rel(g_emb[:, 1:1 + n_prefix], r_emb[:, 1:1 + n_prefix]),
+            "logits_rel": rel(g_log, r_log),
+            "argmax_agree": float((g_log.argmax(-1) == r_log.argmax(-1)).float().mean()),
+            "layout_exact": bool(torch.equal(g_emb[:, 1 + n_prefix:], r_emb[:, 1 + n_prefix:].to(torch.bfloat16).float())),
+            "metric": "norm-wise relative error ||gpu - ref|| / ||ref||",
+        }
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
@@ -395,6 +455,7 @@ def main():
         "gpu_launches": launches,  # kernels of libmacaw_b200.so per timed region (counted on the eager pass; the graph replays the same nodes)
         "roofline": roofline,
         "cpu_baseline": cpu,
+        "parity": parity,
     }
     print(json.dumps(line), flush=True)
     if world > 1:

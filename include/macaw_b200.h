@@ -26,6 +26,9 @@ extern "C" {
 /* ------------------------------------------------------------------------------------------------ meta */
 const char* mm_last_error(void);
 int32_t mm_abi_version(void);
+/* Content hash of the kernel sources + this header the library was built from (the loader compares it with the sources
+ * on disk and rebuilds on mismatch, so a stale library never meets a newer struct layout). */
+const char* mm_build_hash(void);
 /* Number of kernel launches issued through this library by the calling process since the last reset. */
 int64_t mm_launch_count(void);
 void mm_launch_count_reset(void);

@@ -49,6 +49,7 @@ class AttnArgs(C.Structure):
 SIGNATURES = {
     "mm_last_error": (C.c_char_p, []),
     "mm_abi_version": (c_i32, []),
+    "mm_build_hash": (C.c_char_p, []),
     "mm_launch_count": (c_i64, []),
     "mm_launch_count_reset": (None, []),
     "mm_gemm_fwd": (c_i32, [C.POINTER(GemmArgs), c_vp]),
@@ -73,6 +74,7 @@ SIGNATURES = {
 }
 
 _lib = None
+ABI_VERSION = 2
 
 
 def load(build_if_missing: bool = True) -> C.CDLL:
@@ -80,20 +82,26 @@ def load(build_if_missing: bool = True) -> C.CDLL:
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(LIB_PATH):
-        if not build_if_missing:
-            raise RuntimeError(f"{LIB_PATH} is missing; run `python macaw-llm_b200/build.py`")
-        import importlib.util
+    import importlib.util
 
-        spec = importlib.util.spec_from_file_location("_macaw_b200_build", os.path.join(HERE, "build.py"))
-        mod = importlib.util.module_from_spec(spec)
-        spec.loader.exec_module(mod)
+    spec = importlib.util.spec_from_file_location("_macaw_b200_build", os.path.join(HERE, "build.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    want = mod.source_hash()
+    # stale or missing library: (re)build under build.py's file lock (safe when several ranks arrive at once)
+    if not os.path.exists(LIB_PATH) or mod.built_hash() != want:
+        if not build_if_missing:
+            raise RuntimeError(f"{LIB_PATH} is missing or older than csrc/; run `python macaw-llm_b200/build.py`")
         mod.build()
     lib = C.CDLL(LIB_PATH)
     for name, (res, args) in SIGNATURES.items():
         fn = getattr(lib, name)  # AttributeError here == ABI drift; fail loudly
         fn.restype = res
         fn.argtypes = args
+    got = lib.mm_build_hash().decode()
+    if got != want or lib.mm_abi_version() != ABI_VERSION:
+        raise RuntimeError(f"libmacaw_b200.so was built from other sources (library {got}, csrc {want}; ABI "
+                           f"{lib.mm_abi_version()} vs {ABI_VERSION}): rebuild with `python macaw-llm_b200/build.py --force`")
     _lib = lib
     return lib
 

@@ -24,11 +24,26 @@ bool pdl_enabled() {
   return on;
 }
 
+int num_sms() {
+  static int cache[kMaxDevices] = {0};
+  const int dev = current_device();
+  if (cache[dev] == 0) {
+    int n = 0;
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    cache[dev] = n > 0 ? n : 148;
+  }
+  return cache[dev];
+}
+
 }  // namespace mm
 
 extern "C" {
 const char* mm_last_error(void) { return mm::g_err; }
-int32_t mm_abi_version(void) { return 1; }
+int32_t mm_abi_version(void) { return 2; }
+#ifndef MM_SRC_HASH
+#define MM_SRC_HASH "unknown"
+#endif
+const char* mm_build_hash(void) { return MM_SRC_HASH; }
 int64_t mm_launch_count(void) { return mm::g_launches.load(); }
 void mm_launch_count_reset(void) { mm::g_launches.store(0); }
 }

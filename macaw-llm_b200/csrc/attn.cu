@@ -257,16 +257,8 @@ __global__ void __launch_bounds__(128, MINB) flash_attn_kernel(const AttnKParams
 template <int HD, int KT, int MINB>
 static int launch_attn(const AttnKParams& p, cudaStream_t st) {
   constexpr size_t smem = static_cast<size_t>(kQTile + 4 * KT) * (HD + 8) * sizeof(bf16) + 2 * KT * sizeof(int);
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e =
-        cudaFuncSetAttribute(flash_attn_kernel<HD, KT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-    if (e != cudaSuccess) {
-      set_error("mm_attn_fwd: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
-      return 2;
-    }
-    attr_set = true;
-  }
+  static bool attr_set[kMaxDevices] = {};
+  if (int rc = ensure_smem_attr(flash_attn_kernel<HD, KT, MINB>, smem, attr_set, "mm_attn_fwd")) return rc;
   dim3 grid((p.Tq + kQTile - 1) / kQTile, p.H, p.B);
   flash_attn_kernel<HD, KT, MINB><<<grid, 128, smem, st>>>(p);
   return check_launch("mm_attn_fwd");

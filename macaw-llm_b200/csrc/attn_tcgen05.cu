@@ -450,17 +450,9 @@ static int fa_make_map(CUtensorMap* m, const void* ptr, int hd, int T, int H, in
 
 template <int HD, int KT, int NPB>
 static int launch_fa(const mm_attn_args* a, cudaStream_t st) {
-  static bool attr_set = false;
+  static bool attr_set[kMaxDevices] = {};
   constexpr size_t smem = fa_smem_bytes<HD, KT, NPB>();
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(fa_tcgen05_kernel<HD, KT, NPB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         static_cast<int>(smem));
-    if (e != cudaSuccess) {
-      set_error("mm_attn_fwd: cudaFuncSetAttribute(%zu) failed: %s", smem, cudaGetErrorString(e));
-      return 2;
-    }
-    attr_set = true;
-  }
+  if (int rc = ensure_smem_attr(fa_tcgen05_kernel<HD, KT, NPB>, smem, attr_set, "mm_attn_fwd")) return rc;
   CUtensorMap tq, tk, tv;
   if (fa_make_map(&tq, a->q, HD, a->Tq, a->H, a->B, a->q_ts, a->q_hs, a->q_bs, kFaMQ)) return 1;
   if (fa_make_map(&tk, a->k, HD, a->Tk, a->H, a->B, a->k_ts, a->k_hs, a->k_bs, KT)) return 1;
@@ -476,12 +468,7 @@ static int launch_fa(const mm_attn_args* a, cudaStream_t st) {
   // query tiles per CTA: amortise the per-CTA prologue (TMEM alloc, barrier init, first TMA round trip) while keeping
   // at least ~4 waves of CTAs (2 CTAs per SM) for balance
   const int nq = (a->Tq + kFaMQ - 1) / kFaMQ;
-  int sms = 148;
-  {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  }
+  const int sms = num_sms();
   long long qpc = ((long long)nq * a->H * a->B) / (4LL * 2 * sms);
   if (qpc < 1) qpc = 1;
   if (qpc > nq) qpc = nq;

@@ -31,6 +31,31 @@ inline int32_t check_launch(const char* what) {
 
 using bf16 = __nv_bfloat16;
 
+// Per-DEVICE caches (function attributes and the SM count are properties of a device, not of the process: a second GPU
+// used from the same process must get its own cudaFuncSetAttribute call).
+constexpr int kMaxDevices = 64;
+inline int current_device() {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  return (dev >= 0 && dev < kMaxDevices) ? dev : 0;
+}
+int num_sms();  // SM count of the current device (cached per device)
+
+// Opt a kernel into `smem` bytes of dynamic shared memory on the current device, once per (kernel instantiation, device).
+// `flags` is a zero-initialised static array owned by the calling template instantiation.
+template <typename K>
+inline int ensure_smem_attr(K kern, size_t smem, bool (&flags)[kMaxDevices], const char* what) {
+  const int dev = current_device();
+  if (flags[dev]) return 0;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+  if (e != cudaSuccess) {
+    set_error("%s: cudaFuncSetAttribute(smem=%zu) failed: %s", what, smem, cudaGetErrorString(e));
+    return 2;
+  }
+  flags[dev] = true;
+  return 0;
+}
+
 // Programmatic dependent launch: kernels call griddep_launch() once their prologue is done (lets the next kernel of the
 // stream start ITS prologue on SMs that free up) and griddep_wait() before their first global-memory access (returns
 // when every predecessor grid has completed and flushed).  The launch attribute is OPT-IN (MACAW_B200_PDL=1): on this

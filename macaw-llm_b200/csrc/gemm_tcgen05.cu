@@ -533,30 +533,12 @@ static int make_map(CUtensorMap* m, const void* ptr, uint64_t inner, uint64_t ro
   return 0;
 }
 
-static int num_sms() {
-  static int n = 0;
-  if (n == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-    if (n <= 0) n = 148;
-  }
-  return n;
-}
-
 template <int BN, int EPI, bool B_MN, bool MC>
 static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmKParams& p, cudaStream_t st) {
-  static bool attr_set = false;
+  static bool attr_set[kMaxDevices] = {};
   constexpr size_t smem = gemm_smem_bytes(BN);
   auto kern = gemm_bf16_kernel<BN, EPI, B_MN, MC>;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-    if (e != cudaSuccess) {
-      set_error("cudaFuncSetAttribute(smem=%zu) failed: %s", smem, cudaGetErrorString(e));
-      return 2;
-    }
-    attr_set = true;
-  }
+  if (int rc = ensure_smem_attr(kern, smem, attr_set, "mm_gemm_fwd")) return rc;
   const int m_units = MC ? (p.m_tiles + 1) / 2 : p.m_tiles;
   const int total = p.batch * p.batch2 * m_units * p.n_tiles;
   cudaError_t e;

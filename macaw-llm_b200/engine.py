@@ -36,7 +36,6 @@ class Engine:
         self._graphs: Dict[tuple, tuple] = {}
         self._graphs_on = False
         self.align_max_rows = None  # test hook: cap on query rows per alignment chunk (default: ~2 GiB of fp32 scores)
-        self._params = None
 
     # ------------------------------------------------------------------------------------------------ weight cache
     @staticmethod
@@ -112,6 +111,9 @@ class Engine:
 
         w_patch = self.derived(pre + "patch", [emb.patch_embedding.weight], pack_patch)
         pos = self.w(emb.position_embedding.weight, pre + "pos")
+        if T != pos.shape[0] or images.shape[1] != 3:  # HF CLIPVisionEmbeddings raises on a size mismatch
+            raise ValueError(f"Input image size ({images.shape[2]}*{images.shape[3]}) doesn't match model "
+                             f"({cfg.image_size}*{cfg.image_size}).")
         cls = self.w(emb.class_embedding, pre + "cls").view(1, D)
 
         cols = ops.patchify(images, p, kp)  # (n_img * G, kp)
@@ -174,6 +176,9 @@ class Engine:
                      act=ops.ACT_GELU)
         T = Tm // 2
         pos = self.w(enc.embed_positions.weight, pre + "pos")
+        if T != pos.shape[0]:  # HF WhisperEncoder.forward raises on any other mel length; the GEMM reads pos by raw pointer
+            raise ValueError(f"Whisper expects the mel input features to be of length {2 * pos.shape[0]}, but found {Tm}. "
+                             f"Make sure to pad the input mel features to {2 * pos.shape[0]}.")
         x = torch.empty((B, T, D), device=dev, dtype=BF16)
         ops.gemm_raw(M=T, N=D, K=3 * D, batch=B, A=h1.data_ptr(), lda=2 * D, a_bs=(Tm + 2) * D, B=w2.data_ptr(), ldb=3 * D,
                      b_bs=0, Cout=x.data_ptr(), ldc=D, c_bs=T * D, bias=self.w(enc.conv2.bias, pre + "b2").data_ptr(),
@@ -369,7 +374,18 @@ class Engine:
         table = self.w(m.llm.model.embed_tokens.weight, "llm.embed")
         dev = table.device
         E = table.shape[1]
-        ids = inputs["input_ids"].to(dev)
+        ids = inputs["input_ids"]
+        V_rows = table.shape[0]
+        for k in ("input_ids", "image_starts", "image_ends", "audio_starts", "audio_ends", "video_starts", "video_ends"):
+            t = inputs.get(k)
+            # nn.Embedding raises on out-of-range ids; the gather kernel clamps, so host-resident ids are validated here
+            # (device-resident ids would need a sync: they stay clamped, as documented in include/macaw_b200.h)
+            if isinstance(t, torch.Tensor) and not t.is_cuda and t.numel() > 0:
+                lo, hi = int(t.min()), int(t.max())
+                if lo < 0 or hi >= V_rows:
+                    raise IndexError(f"{k}: token id out of range for the {V_rows}-row embedding table (min {lo}, max {hi}); "
+                                     f"call model.llm.resize_token_embeddings(len(tokenizer)) first")
+        ids = ids.to(dev)
         B, L = ids.shape
         feats = {}
         if inputs.get("images") is not None:
@@ -627,9 +643,9 @@ class Engine:
 
     def _forward_graphed(self, inputs: dict):
         dev = self.w(self.m.llm.model.embed_tokens.weight, "llm.embed").device
-        if self._params is None:
-            self._params = list(self.m.parameters())
-        stamp = sum(p._version for p in self._params)
+        # graphs bake parameter ADDRESSES in: any replaced Parameter (resize_token_embeddings), `.data` swap (model.to)
+        # or in-place update (optimizer step) must drop them — same key the derived-weight cache uses
+        stamp = self._stamp(*self.m.parameters())
         present = tuple((k, tuple(inputs[k].shape)) for k in self._TENSOR_KEYS
                         if isinstance(inputs.get(k), torch.Tensor))
         key = (present, str(dev))

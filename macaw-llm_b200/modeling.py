@@ -62,14 +62,27 @@ class MM_LLMs_Config(PretrainedConfig):
 
     @classmethod
     def from_pretrained(cls, pretrained_model_name_or_path, **kwargs):
+        """Reference modeling.py:853-861, plus the `return_unused_kwargs` contract of PretrainedConfig.from_pretrained
+        that `PreTrainedModel.from_pretrained(dir)` (no `config=`) relies on: it then expects `(config, unused_kwargs)`."""
+        return_unused = bool(kwargs.pop("return_unused_kwargs", False))
         d, kwargs = cls.get_config_dict(pretrained_model_name_or_path, **kwargs)
-        hyper = {k: d[k] for k in ("n_frames", "attention_heads", "image_conv_kernel", "image_conv_stride",
-                                   "video_conv_kernel", "video_conv_stride", "audio_conv_kernel", "audio_conv_stride")
-                 if k in d}
-        hyper.update(kwargs)
-        return cls(clip_config=CLIPConfig.from_dict(d["image_config"]),
-                   whisper_config=WhisperConfig.from_dict(d["audio_config"]),
-                   llm_config=LlamaConfig.from_dict(d["llm_config"]), **hyper)
+        names = ("n_frames", "attention_heads", "image_conv_kernel", "image_conv_stride", "video_conv_kernel",
+                 "video_conv_stride", "audio_conv_kernel", "audio_conv_stride")
+        hyper = {k: d[k] for k in names if k in d}
+        unused = {}
+        for k, v in kwargs.items():  # explicit overrides of our own hyper-parameters are applied, the rest handed back
+            if k in names:
+                hyper[k] = v
+            else:
+                unused[k] = v
+        cfg = cls(clip_config=CLIPConfig.from_dict(d["image_config"]),
+                  whisper_config=WhisperConfig.from_dict(d["audio_config"]),
+                  llm_config=LlamaConfig.from_dict(d["llm_config"]), **hyper)
+        if return_unused:
+            return cfg, unused
+        for k, v in unused.items():  # reference behaviour: remaining kwargs become config attributes (PretrainedConfig(**kwargs))
+            setattr(cfg, k, v)
+        return cfg
 
 
 MM_LLMsConfig = MM_LLMs_Config  # BASELINE.json spells it this way
@@ -153,6 +166,25 @@ class LlamaModel(_LlamaPreTrained):
         self.embed_tokens = value
 
 
+class _EngineRef:
+    """Weak handle from the LLaMA container to the owning MM_LLMs engine that copies / pickles as an EMPTY handle (the
+    copy's owner attaches its own engine)."""
+
+    def __init__(self, eng=None):
+        import weakref
+
+        self._r = weakref.ref(eng) if eng is not None else None
+
+    def __call__(self):
+        return self._r() if self._r is not None else None
+
+    def __deepcopy__(self, memo):
+        return _EngineRef()
+
+    def __reduce__(self):
+        return (_EngineRef, ())
+
+
 class LlamaForCausalLM(_LlamaPreTrained):
     """Parameter container with the reference's names; `forward(inputs_embeds=..., attention_mask=..., labels=...)`
     runs on the owning MM_LLMs engine (reference modeling.py:555-622)."""
@@ -161,7 +193,7 @@ class LlamaForCausalLM(_LlamaPreTrained):
         super().__init__(config)
         self.model = LlamaModel(config)
         self.lm_head = nn.Linear(config.hidden_size, config.vocab_size, bias=False)
-        self._engine_ref = None
+        self._engine_ref = _EngineRef()
         self.post_init()
 
     def get_input_embeddings(self):
@@ -177,9 +209,9 @@ class LlamaForCausalLM(_LlamaPreTrained):
         self.lm_head = new_embeddings
 
     def forward(self, input_ids=None, attention_mask=None, inputs_embeds=None, labels=None, **unused):
-        if self._engine_ref is None:
-            raise RuntimeError("LlamaForCausalLM must be owned by an MM_LLMs module to run (engine not attached)")
         eng = self._engine_ref()
+        if eng is None:
+            raise RuntimeError("LlamaForCausalLM must be owned by an MM_LLMs module to run (engine not attached)")
         from . import ops
 
         if (input_ids is None) == (inputs_embeds is None):
@@ -240,16 +272,37 @@ class MM_LLMs(PreTrainedModel):
         self.logit_scale = nn.Parameter(torch.ones([]) * math.log(1 / 0.07))
         self.layer_norm = nn.LayerNorm(P)
 
-        self._engine = Engine(self)
-        import weakref
-
-        self.llm._engine_ref = weakref.ref(self._engine)
+        self._attach_engine()
         self.post_init()
 
-    # the engine is not a sub-module and must not be (de)serialised or deep-copied with the parameters
+    # the engine is not a sub-module and must not be (de)serialised or deep-copied with the parameters: a copy of the
+    # model gets its OWN engine (weight caches and CUDA graphs are keyed by the parameters of the owning module)
     @property
     def engine(self) -> Engine:
         return self._engine
+
+    def _attach_engine(self):
+        self.__dict__["_engine"] = Engine(self)
+        self.llm._engine_ref = _EngineRef(self._engine)
+
+    def __deepcopy__(self, memo):
+        cls = self.__class__
+        new = cls.__new__(cls)
+        memo[id(self)] = new
+        for k, v in self.__dict__.items():
+            if k != "_engine":
+                new.__dict__[k] = copy.deepcopy(v, memo)
+        new._attach_engine()
+        return new
+
+    def __getstate__(self):
+        st = dict(self.__dict__)
+        st.pop("_engine", None)
+        return st
+
+    def __setstate__(self, st):
+        self.__dict__.update(st)
+        self._attach_engine()
 
     def _init_weights(self, module):
         if isinstance(module, (nn.Linear, nn.Conv1d, nn.Conv2d)):
@@ -272,8 +325,16 @@ class MM_LLMs(PreTrainedModel):
             # generate branch (reference modeling.py:954-960): greedy decode, returns the new token ids (B, <= 128)
             return self._engine.generate(inputs, max_new_tokens=int(inputs.get("max_new_tokens", 128)),
                                          eos_token_id=2, pad_token_id=32006)
+        if self.training and torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            return self._forward_train(inputs)
         loss, logits, _, _, _ = self._engine.forward(inputs)
         return CausalLMOutputWithPast(loss=loss, logits=logits)
+
+    def _forward_train(self, inputs):
+        raise NotImplementedError(
+            "macaw_b200: MM_LLMs.forward was called in train() mode with gradients enabled, but this build only "
+            "implements the inference forward (no autograd graph is recorded by the sm_100a kernels). Call model.eval() "
+            "/ torch.no_grad() for evaluation.")
 
     def prepare_inputs_for_generation(self, inputs):
         return self._engine.prepare_inputs(inputs)

@@ -33,6 +33,10 @@ def _cuda(t: torch.Tensor, dtype=None, name: str = "tensor") -> torch.Tensor:
         raise RuntimeError(f"macaw_b200: {name} must be a CUDA tensor (no CPU fallback exists)")
     if dtype is not None and t.dtype != dtype:
         raise TypeError(f"macaw_b200: {name} must be {dtype}, got {t.dtype}")
+    if t.device.index != torch.cuda.current_device():
+        # kernels are launched on the CURRENT device's stream: a tensor of another GPU would be used with the wrong stream
+        raise RuntimeError(f"macaw_b200: {name} lives on {t.device} but the current CUDA device is "
+                           f"cuda:{torch.cuda.current_device()}; wrap the call in torch.cuda.device(...)")
     return t
 
 

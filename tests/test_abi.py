@@ -25,7 +25,7 @@ def test_header_library_and_ctypes_agree():
     out = subprocess.run(["nm", "-D", "--defined-only", _lib.LIB_PATH], capture_output=True, text=True).stdout
     exported = set(re.findall(r" T (mm_[a-z0-9_]+)", out))
     assert syms <= exported, syms - exported
-    assert lib.mm_abi_version() == 1
+    assert lib.mm_abi_version() == _lib.ABI_VERSION
     assert isinstance(lib.mm_launch_count(), int)
 
 

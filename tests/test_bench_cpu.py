@@ -7,6 +7,7 @@ import sys
 
 import torch
 
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
@@ -23,7 +24,11 @@ def test_reference_arm_json_contract_small():
         assert k in d, k
     assert d["impl"] == "reference" and d["unit"] == "tokens/s" and d["higher_is_better"] is True
     assert d["value"] > 0 and d["vs_baseline"] is None and d["gpu_launches"] == 0
-    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and "sample" in d["cpu_baseline"]
+    # the arm drives the unmodified reference when oracle/_ref is staged (build container, GPU box), else the port
+    from oracle import ref_runner
+
+    assert d["cpu_baseline"]["kind"] == ("reference" if ref_runner.available() else "port")
+    assert d["cpu_baseline"]["cores"] >= 1 and "sample" in d["cpu_baseline"]
     assert d["e2e"] == {"value": d["value"], "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
 
 
@@ -45,6 +50,7 @@ def test_synth_inputs_and_cores():
     assert d["input_ids"].shape == (3, 20) and int(d["input_ids"][:, 0].max()) == 1
     assert len({int(d[f"{m}_{s}"][0]) for m in ("image", "audio", "video") for s in ("starts", "ends")}) == 6
     assert 1 <= bench.usable_cores() <= (os.cpu_count() or 1)
+    assert 1 <= bench.cpu_threads() <= bench.usable_cores()
     (clip, whisper, llama), hyper = bench.real_configs()
     assert (llama.hidden_size, llama.num_hidden_layers, llama.vocab_size) == (4096, 32, 32000)
     assert (clip.vision_config.hidden_size, clip.projection_dim, whisper.d_model) == (1024, 768, 512)
