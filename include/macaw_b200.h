@@ -86,14 +86,30 @@ typedef struct mm_gemm_args {
   int32_t c_trans; /* 1: C and residual are addressed transposed (C[n][m], row stride ldc), bias is indexed by m, row_scale by n:
                       lets a caller swap the operands (A = weight rows, B = a handful of activation rows) so that thin
                       decode GEMMs fill the 128-row MMA tile with weights (standard epilogue, batch == 1) */
+  /* 16-bit operand formats: 0 = bf16 (default), 1 = fp16 (IEEE half).  A and B must agree: the instruction descriptor has
+   * independent format fields, but sm_100a raises an illegal-instruction fault for f16 x bf16 (measured, round 2).
+   * The alignment chain runs in fp16 (11-bit significand: one stored stage costs 1.4e-4 norm-wise instead of bf16's
+   * 1.1e-3) against fp16 COPIES of its weights and of the embedding table (exact conversions of the bf16 values). */
+  int32_t a_fp16, b_fp16;
+  int32_t c_fp16; /* 1: C is fp16 (c_fp32 must be 0) */
+  /* MM_EPI_STD only: out += bias_rs[b*M + m] * bias[n] (when bias_rs != NULL the bias term is scaled per row) and
+   * out += bias2_rs[b*M + m] * bias2[n].  Value-side bias terms of the absorbed alignment attention
+   * (functional.py:6531-6537: b_v rides on every real key, bias_v on the appended key). bias2 shares bias_bs. */
+  const float* bias_rs;
+  const void* bias2;
+  const float* bias2_rs;
+  /* 1: A is given as [batch][K][M] (M contiguous, row stride lda) — the transpose of a row-major activation.  With
+   * b_mn_major this is the weight-gradient product dW[n][k] = sum_m dY[m][n] X[m][k] on the tensors as stored
+   * (reference: autograd of every nn.Linear on the path; llm_trainer.py:184-188 -> loss.backward()). */
+  int32_t a_mn_major;
 } mm_gemm_args;
 
 int32_t mm_gemm_fwd(const mm_gemm_args* args, void* stream);
 
-/* Sum fp32 partials [splits][M][N] (+ bf16 bias[N]) -> bf16 [M][N] (row stride ldo).  Split-K tail of the
- * Conv1d down-samplers (modeling.py:982, 999, 1022). */
+/* Sum fp32 partials [splits][M][N] (+ bf16 bias[N]) -> bf16 (or fp16 when out_fp16 != 0) [M][N] (row stride ldo).
+ * Split-K tail of the Conv1d down-samplers (modeling.py:982, 999, 1022). */
 int32_t mm_splitk_reduce(const float* partial, int32_t splits, int32_t M, int32_t N, const void* bias, void* out,
-                         int64_t ldo, void* stream);
+                         int64_t ldo, int32_t out_fp16, void* stream);
 
 /* ------------------------------------------------------------------------------------------------ attention
  * out[b,t,h,:] = softmax(scale * q k^T + mask) v, flash-style (no T x T tensor in HBM).
@@ -114,7 +130,7 @@ typedef struct mm_attn_args {
   const int32_t* key_mask;
   int32_t causal;
   float scale;
-  int32_t impl; /* 0 = auto (tcgen05 kernel for head_dim 64/128, mma.sync kernel for 96); 1 = force the mma.sync kernel */
+  int32_t impl; /* 0 = tcgen05 kernel (head_dim 64 / 96 / 128); 1 = force the legacy mma.sync kernel (tests only) */
   const int32_t* tk_dev; /* NULL, or device int holding the number of valid keys (<= Tk, which then is the capacity of
                             k / v): lets one captured launch serve a growing KV cache (tcgen05 kernel only) */
 } mm_attn_args;
@@ -151,8 +167,47 @@ int32_t mm_transpose_pad(const void* x, int32_t B, int32_t C, int32_t T, int32_t
 /* y[r,:] = x[r,:] + add[r % add_rows,:]  (bf16; CLIP class/position embeddings, video sinusoid PE modeling.py:1108-1118) */
 int32_t mm_add_rows(const void* x, int64_t ldx, const void* add, int64_t lda, int32_t add_rows, void* y, int64_t ldy,
                     int32_t rows, int32_t cols, void* stream);
+/* bf16 rows -> fp16 rows (modal features entering the fp16 alignment chain; exact within fp16's normal range) */
+int32_t mm_cast_bf16_f16(const void* x, int64_t ldx, void* y, int64_t ldy, int32_t rows, int32_t cols, void* stream);
 /* generic strided 2-D copy of bf16 rows (concats, CLS drop) */
 int32_t mm_copy_rows(const void* x, int64_t ldx, void* y, int64_t ldy, int32_t rows, int32_t cols, void* stream);
+
+/* ------------------------------------------------------------------------------------------------ fused alignment attention
+ * The cross-modal alignment attention of reference modeling.py:986-987 / 1007-1008 / 1025-1026
+ * (nn.MultiheadAttention with K = V = the whole embedding table, add_bias_kv, add_zero_attn; torch functional.py:6531-6672)
+ * in ABSORBED form: for the R = H * Nq per-head query rows q~ = (q_h / sqrt(hd)) W_k[h] (fp16, width E)
+ *     out[r, :]      = sum_{v < V} P[r, v] * table[v, :]                               (fp16, R x E; "ctx~")
+ *     P[r, :]        = softmax over the S = V + 2 keys of { q~[r] . table[v] + row_bias[r] (v < V), extra[r], 0 }
+ *     p_sum_real[r]  = sum_{v < V} P[r, v]        p_extra[r] = P of the appended bias_k key
+ * ONE persistent kernel: phase 1 streams K-major table tiles through TMA into tcgen05 (S = q~ . table^T) and its
+ * epilogue writes the un-normalised probabilities once, in fp16 (no fp32 score tensor, no softmax kernel); phase 2
+ * streams the SAME table rows as an MN-major operand (O = P' . table) and normalises in its epilogue.  The caller
+ * finishes with ctx_h = ctx~_h W_v[h]^T + p_sum_real * b_v[h] + p_extra * bias_v[h] (mm_gemm_fwd with row-scaled biases).
+ * row_bias[r] = q_h . b_k[h] / sqrt(hd) and extra[r] = q_h . bias_k[h] / sqrt(hd) are read at index r * stat_stride.
+ * P: scratch fp16 [R][ldp], ldp >= V rounded up to 8.  workspace: mm_align_workspace_bytes(R, V) bytes, 16-byte aligned
+ * (zeroed by the call).  mode 0: one cooperative launch with grid-wide barriers between the phases; mode 1: the same
+ * kernel launched three times in stream order (phase 1, conditional redo, phase 2). */
+typedef struct mm_align_args {
+  const void* table; /* fp16 [V][ldt] (exact fp16 copy of the bf16 embedding table) */
+  int32_t V, E;
+  int64_t ldt;
+  const void* qt; /* fp16 [R][ldq] */
+  int32_t R;
+  int64_t ldq;
+  const float* row_bias;
+  const float* extra;
+  int64_t stat_stride;
+  void* out; /* fp16 [R][ldo] */
+  int64_t ldo;
+  float* p_sum_real;
+  float* p_extra;
+  void* P;
+  int64_t ldp;
+  void* workspace;
+  int32_t mode;
+} mm_align_args;
+int32_t mm_align_fwd(const mm_align_args* args, void* stream);
+int64_t mm_align_workspace_bytes(int32_t R, int32_t V);
 
 /* ------------------------------------------------------------------------------------------------ alignment softmax
  * Row softmax of the absorbed-form alignment scores (torch F.multi_head_attention_forward: softmax over S = V + 2 keys,
@@ -189,6 +244,35 @@ int32_t mm_swiglu_rows(const void* gu, int64_t ld, int32_t rows, int32_t I, void
  * both must be zeroed by the caller. */
 int32_t mm_ce_loss(const void* logits, const int64_t* labels, int32_t B, int32_t T, int32_t V, float* loss_sum,
                    int32_t* n_valid, void* stream);
+
+/* ------------------------------------------------------------------------------------------------ training step
+ * Backward halves of the HBM-bound ops + the optimizer.  The reference trains through autograd of
+ * modeling.py driven by llm_trainer.py:184-188 (compute_loss -> backward) with AdamW (train.sh, fp32 master weights in
+ * DeepSpeed).  All contractions of the backward pass are mm_gemm_fwd calls (dX: MN-major B; dW: MN-major A and B).
+ *
+ * mm_rmsnorm_bwd: y = x * rstd * g (LlamaRMSNorm modeling.py:311-319).  dx = rstd*(g*dy) - rstd^3/cols * x * sum(g*dy*x)
+ *   (+ dres when given: the residual branch's gradient), dg[c] += sum_r dy*x*rstd (fp32, accumulated with atomics). */
+int32_t mm_rmsnorm_bwd(const void* dy, const void* x, const float* rstd, const void* g, const void* dres, void* dx,
+                       float* dg, int32_t rows, int32_t cols, void* stream);
+/* LlamaMLP modeling.py:139-140 on separate gate / up activations: h = silu(gate) * up over n contiguous elements. */
+int32_t mm_swiglu_fwd(const void* gate, const void* up, void* h, int64_t n, void* stream);
+int32_t mm_swiglu_bwd(const void* dh, const void* gate, const void* up, void* dgate, void* dup, int64_t n, void* stream);
+/* Attention backward through the softmax (LlamaAttention modeling.py:197-215; nn.MultiheadAttention): S = q.k^T (pre-scale)
+ * and dP = dO.v^T, fp32 [B][H][Tq][ld]; writes P = softmax(scale*S + mask) and dS = scale * P * (dP - sum_j P_j dP_j) as
+ * bf16 with the same layout.  Masks as in mm_attn_fwd. */
+int32_t mm_attn_softmax_bwd(const float* S, const float* dP, void* P, void* dS, int32_t B, int32_t H, int32_t Tq,
+                            int32_t Tk, int64_t ld, float scale, int32_t causal, const int32_t* key_mask, void* stream);
+/* Gradient of mm_ce_loss w.r.t. the logits (modeling.py:600-610), times grad_scale / n_valid; may run in place. */
+int32_t mm_ce_bwd(const void* logits, const int64_t* labels, void* dlogits, int32_t B, int32_t T, int32_t V,
+                  const int32_t* n_valid, float grad_scale, void* stream);
+/* Gradient of mm_embed_gather: dtable[ids[i], :] += dx[i, :] (bf16x2 atomics). */
+int32_t mm_embed_scatter_add(const void* dx, int64_t ldx, const int64_t* ids, int64_t n, int32_t dim, int32_t vocab,
+                             void* dtable, void* stream);
+/* out[c] += sum_r x[r, c]  (bias gradients; fp32 atomics) */
+int32_t mm_colsum(const void* x, int64_t ldx, int32_t rows, int32_t cols, float* out, void* stream);
+/* Fused AdamW step on one parameter tensor: bf16 working copy p, bf16 gradient g (times grad_scale), fp32 master / m / v. */
+int32_t mm_adamw(void* p, const void* g, float* master, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
+                 float eps, float weight_decay, int32_t step, float grad_scale, void* stream);
 
 #ifdef __cplusplus
 }

@@ -27,6 +27,8 @@ class GemmArgs(C.Structure):
         ("row_scale", c_vp),
         ("residual", c_vp), ("ldr", c_i64), ("r_bs", c_i64), ("r_bs2", c_i64), ("res_row_mod", c_i32),
         ("rope_cos", c_vp), ("rope_sin", c_vp), ("rope_T", c_i32), ("rope_cols", c_i32), ("rope_pos", c_vp), ("c_trans", c_i32),
+        ("a_fp16", c_i32), ("b_fp16", c_i32), ("c_fp16", c_i32),
+        ("bias_rs", c_vp), ("bias2", c_vp), ("bias2_rs", c_vp), ("a_mn_major", c_i32),
     ]
 
 
@@ -44,6 +46,18 @@ class AttnArgs(C.Structure):
     ]
 
 
+class AlignArgs(C.Structure):
+    """Mirror of `mm_align_args` (include/macaw_b200.h)."""
+
+    _fields_ = [
+        ("table", c_vp), ("V", c_i32), ("E", c_i32), ("ldt", c_i64),
+        ("qt", c_vp), ("R", c_i32), ("ldq", c_i64),
+        ("row_bias", c_vp), ("extra", c_vp), ("stat_stride", c_i64),
+        ("out", c_vp), ("ldo", c_i64), ("p_sum_real", c_vp), ("p_extra", c_vp),
+        ("P", c_vp), ("ldp", c_i64), ("workspace", c_vp), ("mode", c_i32),
+    ]
+
+
 # name -> (restype, argtypes).  Every symbol declared in include/macaw_b200.h must appear here
 # (tests/test_abi.py cross-checks the header against this table and against the built library).
 SIGNATURES = {
@@ -53,7 +67,7 @@ SIGNATURES = {
     "mm_launch_count": (c_i64, []),
     "mm_launch_count_reset": (None, []),
     "mm_gemm_fwd": (c_i32, [C.POINTER(GemmArgs), c_vp]),
-    "mm_splitk_reduce": (c_i32, [c_vp, c_i32, c_i32, c_i32, c_vp, c_vp, c_i64, c_vp]),
+    "mm_splitk_reduce": (c_i32, [c_vp, c_i32, c_i32, c_i32, c_vp, c_vp, c_i64, c_i32, c_vp]),
     "mm_attn_fwd": (c_i32, [C.POINTER(AttnArgs), c_vp]),
     "mm_rmsnorm_fwd": (c_i32, [c_vp, c_vp, c_vp, c_i32, c_i32, c_f32, c_vp]),
     "mm_rms_rstd": (c_i32, [c_vp, c_vp, c_i32, c_i32, c_f32, c_vp]),
@@ -63,13 +77,24 @@ SIGNATURES = {
     "mm_patchify": (c_i32, [c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp, c_i64, c_vp]),
     "mm_transpose_pad": (c_i32, [c_vp, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp]),
     "mm_add_rows": (c_i32, [c_vp, c_i64, c_vp, c_i64, c_i32, c_vp, c_i64, c_i32, c_i32, c_vp]),
+    "mm_cast_bf16_f16": (c_i32, [c_vp, c_i64, c_vp, c_i64, c_i32, c_i32, c_vp]),
     "mm_copy_rows": (c_i32, [c_vp, c_i64, c_vp, c_i64, c_i32, c_i32, c_vp]),
+    "mm_align_fwd": (c_i32, [C.POINTER(AlignArgs), c_vp]),
+    "mm_align_workspace_bytes": (c_i64, [c_i32, c_i32]),
     "mm_align_softmax": (c_i32, [c_vp, c_i64, c_vp, c_vp, c_i64, c_vp, c_i64, c_vp, c_vp, c_i32, c_i32, c_vp]),
     "mm_align_ctx_fixup": (c_i32, [c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_vp]),
     "mm_kv_append": (c_i32, [c_vp, c_i64, c_i32, c_i32, c_i32, c_vp, c_i32, c_i32, c_vp, c_vp]),
     "mm_argmax_rows": (c_i32, [c_vp, c_i64, c_i32, c_i32, c_vp, c_vp]),
     "mm_rope_rows": (c_i32, [c_vp, c_i64, c_i32, c_i32, c_vp, c_vp, c_i32, c_vp, c_vp]),
     "mm_swiglu_rows": (c_i32, [c_vp, c_i64, c_i32, c_i32, c_vp, c_i64, c_vp]),
+    "mm_rmsnorm_bwd": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_vp]),
+    "mm_swiglu_fwd": (c_i32, [c_vp, c_vp, c_vp, c_i64, c_vp]),
+    "mm_swiglu_bwd": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp]),
+    "mm_attn_softmax_bwd": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_i64, c_f32, c_i32, c_vp, c_vp]),
+    "mm_ce_bwd": (c_i32, [c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_vp, c_f32, c_vp]),
+    "mm_embed_scatter_add": (c_i32, [c_vp, c_i64, c_vp, c_i64, c_i32, c_i32, c_vp, c_vp]),
+    "mm_colsum": (c_i32, [c_vp, c_i64, c_i32, c_i32, c_vp, c_vp]),
+    "mm_adamw": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_f32, c_f32, c_f32, c_f32, c_f32, c_i32, c_f32, c_vp]),
     "mm_ce_loss": (c_i32, [c_vp, c_vp, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp]),
 }
 

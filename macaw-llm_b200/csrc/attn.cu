@@ -282,8 +282,8 @@ extern "C" int32_t mm_attn_fwd(const mm_attn_args* a, void* stream) {
   MM_REQUIRE(((uintptr_t)a->q % 16 == 0) && ((uintptr_t)a->k % 16 == 0) && ((uintptr_t)a->v % 16 == 0) &&
                  ((uintptr_t)a->out % 16 == 0),
              "mm_attn_fwd: pointers must be 16-byte aligned");
-  // head_dim 64 / 128: tcgen05 kernel (attn_tcgen05.cu); impl == 1 forces the mma.sync kernel below (tests)
-  if ((a->head_dim == 64 || a->head_dim == 128) && a->scale > 0.f && a->impl != 1)
+  // tcgen05 kernel (attn_tcgen05.cu) for every supported head_dim; impl == 1 forces the mma.sync kernel below (tests)
+  if (a->scale > 0.f && a->impl != 1)
     return attn_tcgen05_dispatch(a, reinterpret_cast<cudaStream_t>(stream));
   MM_REQUIRE(a->tk_dev == nullptr, "mm_attn_fwd: device-side key length is only supported by the tcgen05 kernel");
   AttnKParams p;

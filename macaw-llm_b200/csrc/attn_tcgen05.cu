@@ -1,4 +1,4 @@
-// Flash attention on the 5th-gen tensor cores (tcgen05 + TMEM + TMA) for head_dim 64 / 128.
+// Flash attention on the 5th-gen tensor cores (tcgen05 + TMEM + TMA) for head_dim 64 / 96 / 128.
 //
 // One CTA = 128 queries of one (batch, head); key tiles of KT = 64 keys so that TWO CTAs fit per SM (smem <= 113 KB,
 // 256 TMEM columns each): one CTA's prologue / epilogue / softmax latency hides behind the other's MMAs.  Warp roles:
@@ -15,8 +15,10 @@
 // Masking: causal (key j visible to query i iff j <= i + Tk - Tq), key padding mask, and the Tk bound, evaluated as
 // 32-bit masks per 32-key chunk.  Rows with every key masked produce zeros (see DESIGN.md "unspecified rows").
 //
-// Reference call sites replaced: see include/macaw_b200.h (mm_attn_fwd); the mma.sync kernel in attn.cu remains for
-// head_dim 96 (video-long self-attention).
+// Reference call sites replaced: see include/macaw_b200.h (mm_attn_fwd).  head_dim 96 (video-long self-attention,
+// reference modeling.py:1078) runs on the HD = 128 instantiation: the Q / K / V tensor maps carry the real head dim, so
+// the TMA boxes of the second 64-column block are zero-filled past column 96; S = Q K^T issues 6 of 8 k-steps and
+// O += P V uses an N = 96 instruction.  The mma.sync kernel in attn.cu is kept only as a second implementation for tests.
 #include "common.cuh"
 #include "ptx.cuh"
 #include "../../include/macaw_b200.h"
@@ -31,6 +33,8 @@ struct FaParams {
   const int* tk_dev;  // optional device-side number of valid keys (<= Tk)
   int causal;
   float scale_log2;
+  int hd;   // actual head dim (<= HD, multiple of 32): 96 runs on the HD = 128 instantiation — TMA zero-fills the
+            // out-of-range columns of the second 64-column block, S skips the all-zero k-steps, PV uses N = hd
   int qpc;  // query tiles per CTA (walked heaviest first)
   int rev;  // launch query-tile groups in descending order (heavier causal groups first)
 };
@@ -67,7 +71,7 @@ fa_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
   constexpr uint32_t PB = 128 * KT * 2;       // bytes of one P buffer
   constexpr int NCH = KT / 32;                // 32-key chunks per tile
   constexpr uint32_t IDESC_S = make_idesc_bf16(kFaMQ, KT, false, false);
-  constexpr uint32_t IDESC_O = make_idesc_bf16(kFaMQ, HD, false, true);
+  const uint32_t IDESC_O = make_idesc_bf16(kFaMQ, p.hd, false, true);
   constexpr uint32_t S_COL = 0, O_COL = 2 * KT;  // TMEM columns: S0 [0,KT), S1 [KT,2KT), O [2KT, 2KT+HD)
   constexpr uint32_t TMEM_COLS = (2 * KT + HD) <= 256 ? 256 : 512;
   static_assert(2 * KT + HD <= 512, "TMEM budget");
@@ -192,6 +196,7 @@ fa_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
           const uint32_t qa_ = smem_u32(sQ), ka = smem_u32(sK + st * QB);
 #pragma unroll
           for (int k = 0; k < HD / 16; ++k) {
+            if (k * 16 >= p.hd) break;  // columns >= hd are TMA zero fill
             const uint64_t ad = make_sdesc_sw128(qa_ + (k >> 2) * 16384 + (k & 3) * 32, 16, 1024);
             const uint64_t bd = make_sdesc_sw128(ka + (k >> 2) * (KT * 128) + (k & 3) * 32, 16, 1024);
             umma_bf16(tmem_base + S_COL + st * kFaKT, ad, bd, IDESC_S, k != 0 ? 1u : 0u);
@@ -346,7 +351,7 @@ fa_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
           }
           tc_fence_after();
 #pragma unroll 1
-          for (int c = 0; c < HD / 32; ++c) {
+          for (int c = 0; c < p.hd / 32; ++c) {
             uint32_t o[32];
             tmem_ld32(tmem_base + lane_base + O_COL + c * 32, o);
             tmem_ld_wait();
@@ -370,7 +375,7 @@ fa_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
       }
       bf16* orow = og + static_cast<long long>(qrow) * p.o_ts;
 #pragma unroll 1
-      for (int c = 0; c < HD / 32; ++c) {
+      for (int c = 0; c < p.hd / 32; ++c) {
         uint32_t o[32];
         if (n_tiles > 0) {
           tmem_ld32(tmem_base + lane_base + O_COL + c * 32, o);
@@ -454,10 +459,12 @@ static int launch_fa(const mm_attn_args* a, cudaStream_t st) {
   constexpr size_t smem = fa_smem_bytes<HD, KT, NPB>();
   if (int rc = ensure_smem_attr(fa_tcgen05_kernel<HD, KT, NPB>, smem, attr_set, "mm_attn_fwd")) return rc;
   CUtensorMap tq, tk, tv;
-  if (fa_make_map(&tq, a->q, HD, a->Tq, a->H, a->B, a->q_ts, a->q_hs, a->q_bs, kFaMQ)) return 1;
-  if (fa_make_map(&tk, a->k, HD, a->Tk, a->H, a->B, a->k_ts, a->k_hs, a->k_bs, KT)) return 1;
-  if (fa_make_map(&tv, a->v, HD, a->Tk, a->H, a->B, a->v_ts, a->v_hs, a->v_bs, KT)) return 1;
+  const int hd = a->head_dim;  // the maps carry the ACTUAL head dim: boxes reaching past it are zero-filled
+  if (fa_make_map(&tq, a->q, hd, a->Tq, a->H, a->B, a->q_ts, a->q_hs, a->q_bs, kFaMQ)) return 1;
+  if (fa_make_map(&tk, a->k, hd, a->Tk, a->H, a->B, a->k_ts, a->k_hs, a->k_bs, KT)) return 1;
+  if (fa_make_map(&tv, a->v, hd, a->Tk, a->H, a->B, a->v_ts, a->v_hs, a->v_bs, KT)) return 1;
   FaParams p;
+  p.hd = hd;
   p.out = reinterpret_cast<bf16*>(a->out);
   p.B = a->B; p.H = a->H; p.Tq = a->Tq; p.Tk = a->Tk;
   p.o_bs = a->o_bs; p.o_ts = a->o_ts; p.o_hs = a->o_hs;
@@ -484,7 +491,7 @@ static int launch_fa(const mm_attn_args* a, cudaStream_t st) {
   return check_launch("mm_attn_fwd(tcgen05)");
 }
 
-// called from mm_attn_fwd (attn.cu) for head_dim 64 / 128 when scale > 0
+// called from mm_attn_fwd (attn.cu) for head_dim 64 / 96 / 128 when scale > 0 (96 rides the 128 instantiation)
 int attn_tcgen05_dispatch(const mm_attn_args* a, cudaStream_t st) {
   return a->head_dim == 64 ? launch_fa<64, 64, 2>(a, st) : launch_fa<128, 64, 1>(a, st);
 }

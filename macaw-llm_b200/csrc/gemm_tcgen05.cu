@@ -46,6 +46,11 @@ struct GemmKParams {
   int rope_T, rope_cols;
   const int* rope_pos;
   int c_trans;
+  int c_fp16;
+  uint32_t idesc;  // tcgen05 instruction descriptor (operand formats are run-time properties)
+  const float* bias_rs;
+  const bf16* bias2;
+  const float* bias2_rs;
   int vec_ok;
   int group_m;  // rasterisation: M units per group
 };
@@ -136,15 +141,32 @@ __device__ __forceinline__ void store_row32(const GemmKParams& p, void* crow, in
   } else {
     bf16* c = reinterpret_cast<bf16*>(crow) + col0;
     if (p.vec_ok && col0 + 32 <= ncols_total) {
+      if (p.c_fp16) {
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        uint4 u;
-        u.x = pack_bf16x2(v[8 * i + 0], v[8 * i + 1]);
-        u.y = pack_bf16x2(v[8 * i + 2], v[8 * i + 3]);
-        u.z = pack_bf16x2(v[8 * i + 4], v[8 * i + 5]);
-        u.w = pack_bf16x2(v[8 * i + 6], v[8 * i + 7]);
-        reinterpret_cast<uint4*>(c)[i] = u;
+        for (int i = 0; i < 4; ++i) {
+          uint4 u;
+          u.x = pack_f16x2(v[8 * i + 0], v[8 * i + 1]);
+          u.y = pack_f16x2(v[8 * i + 2], v[8 * i + 3]);
+          u.z = pack_f16x2(v[8 * i + 4], v[8 * i + 5]);
+          u.w = pack_f16x2(v[8 * i + 6], v[8 * i + 7]);
+          reinterpret_cast<uint4*>(c)[i] = u;
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          uint4 u;
+          u.x = pack_bf16x2(v[8 * i + 0], v[8 * i + 1]);
+          u.y = pack_bf16x2(v[8 * i + 2], v[8 * i + 3]);
+          u.z = pack_bf16x2(v[8 * i + 4], v[8 * i + 5]);
+          u.w = pack_bf16x2(v[8 * i + 6], v[8 * i + 7]);
+          reinterpret_cast<uint4*>(c)[i] = u;
+        }
       }
+    } else if (p.c_fp16) {
+      __half* ch = reinterpret_cast<__half*>(c);
+#pragma unroll
+      for (int i = 0; i < 32; ++i)
+        if (col0 + i < ncols_total) ch[i] = __float2half_rn(v[i]);
     } else {
 #pragma unroll
       for (int i = 0; i < 32; ++i)
@@ -156,14 +178,15 @@ __device__ __forceinline__ void store_row32(const GemmKParams& p, void* crow, in
 // MC = true: clusters of 2 CTAs work on vertically adjacent tiles (m_blk = 2u, 2u+1; same n_blk) and share the B tile:
 // each CTA TMA-loads half of it and multicasts to both, cutting L2->SM operand traffic per CTA from 48 to 32 KiB per
 // k-block.  A smem slot is free only when BOTH CTAs' MMAs have retired (they both receive the peer's multicast).
-template <int BN, int EPI, bool B_MN, bool MC>
+// A_MN = true: A is given as [K][M] with M contiguous (the transpose of a row-major [tokens][features] activation): the
+// weight-gradient GEMM dW = dY^T X reads dY and X exactly as the forward pass wrote them, no transpose copies.
+template <int BN, int EPI, bool B_MN, bool MC, bool A_MN = false>
 __global__ void __launch_bounds__(320, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const GemmKParams p) {
   constexpr int STAGES = gemm_stages(BN);
   constexpr uint32_t B_BYTES = BN * kBlockK * 2;
   constexpr uint32_t TMEM_COLS = gemm_tmem_cols(BN);
-  constexpr uint32_t IDESC = make_idesc_bf16(kBlockM, BN, false, B_MN);
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -224,7 +247,14 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         for (int kb = 0; kb < p.num_k; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           mbar_arrive_expect_tx(&full_bar[stage], kABytes + B_BYTES);
-          tma_load_4d(&tmA, &full_bar[stage], sA + stage * kABytes, kb * kBlockK, t.m_blk * kBlockM, t.b_lo, t.b_hi);
+          if constexpr (A_MN) {
+#pragma unroll
+            for (int j = 0; j < kBlockM / 64; ++j)
+              tma_load_4d(&tmA, &full_bar[stage], sA + stage * kABytes + j * 8192, t.m_blk * kBlockM + j * 64,
+                          kb * kBlockK, t.b_lo, t.b_hi);
+          } else {
+            tma_load_4d(&tmA, &full_bar[stage], sA + stage * kABytes, kb * kBlockK, t.m_blk * kBlockM, t.b_lo, t.b_hi);
+          }
           if constexpr (MC) {
             // this CTA fetches its half of the B tile and multicasts it to both CTAs of the pair
             if constexpr (!B_MN) {
@@ -270,14 +300,14 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           const uint32_t a_addr = smem_u32(sA + stage * kABytes);
           const uint32_t b_addr = smem_u32(sB + stage * B_BYTES);
           // K-major operand: 8-row groups are 1024 B apart (SBO); LBO unused with 128B swizzle.
-          const uint64_t a_desc = make_sdesc_sw128(a_addr, 16, 1024);
+          const uint64_t a_desc = A_MN ? make_sdesc_sw128(a_addr, 8192, 1024) : make_sdesc_sw128(a_addr, 16, 1024);
           // MN-major operand: 64-column blocks are 8192 B apart (LBO); 8-k groups 1024 B apart (SBO).
           const uint64_t b_desc = B_MN ? make_sdesc_sw128(b_addr, 8192, 1024) : make_sdesc_sw128(b_addr, 16, 1024);
 #pragma unroll
           for (int kk = 0; kk < kBlockK / 16; ++kk) {
-            const uint64_t a_k = a_desc + static_cast<uint64_t>(kk * 2);                  // +32 B along K
+            const uint64_t a_k = a_desc + static_cast<uint64_t>(A_MN ? kk * 128 : kk * 2);  // +2048 B | +32 B along K
             const uint64_t b_k = b_desc + static_cast<uint64_t>(B_MN ? kk * 128 : kk * 2);  // +2048 B | +32 B
-            umma_bf16(d_tmem, a_k, b_k, IDESC, (kb | kk) != 0 ? 1u : 0u);
+            umma_bf16(d_tmem, a_k, b_k, p.idesc, (kb | kk) != 0 ? 1u : 0u);
           }
           // frees the smem slot once these MMAs retire (in both CTAs of a multicast pair)
           if constexpr (MC) umma_commit_mc(&empty_bar[stage], 3); else umma_commit(&empty_bar[stage]);
@@ -371,7 +401,19 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
           for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]) * rs;
           const bool full = p.vec_ok && (col0 + 32 <= p.N);
-          if (bias != nullptr) {
+          if (p.bias_rs != nullptr || p.bias2 != nullptr) {
+            // row-scaled bias terms (value-side biases of the absorbed alignment attention); narrow GEMMs only
+            const long long ri = static_cast<long long>(t.b) * p.M + row;
+            const float s1 = (p.bias_rs != nullptr && row_ok) ? p.bias_rs[ri] : 1.0f;
+            const float s2 = (p.bias2_rs != nullptr && row_ok) ? p.bias2_rs[ri] : 1.0f;
+            const bf16* b2 = p.bias2 ? p.bias2 + static_cast<long long>(t.b_lo) * p.bias_bs : nullptr;
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (col0 + i < p.N) {
+                if (bias != nullptr) v[i] = fmaf(s1, __bfloat162float(bias[col0 + i]), v[i]);
+                if (b2 != nullptr) v[i] = fmaf(s2, __bfloat162float(b2[col0 + i]), v[i]);
+              }
+          } else if (bias != nullptr) {
             if (full) {
 #pragma unroll
               for (int i = 0; i < 4; ++i) {
@@ -506,8 +548,8 @@ static EncodeTiledFn get_encode_fn() {
 }
 
 // bf16 4-D map {inner, rows, batch, batch2}; strides in elements; 128B swizzle; box {64, box_rows, 1, 1}.
-static int make_map(CUtensorMap* m, const void* ptr, uint64_t inner, uint64_t rows, uint64_t batch, uint64_t batch2,
-                    int64_t ld, int64_t bs, int64_t bs2, uint32_t box_rows) {
+int make_map(CUtensorMap* m, const void* ptr, uint64_t inner, uint64_t rows, uint64_t batch, uint64_t batch2,
+             int64_t ld, int64_t bs, int64_t bs2, uint32_t box_rows) {
   EncodeTiledFn fn = get_encode_fn();
   if (fn == nullptr) {
     set_error("cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)");
@@ -533,11 +575,11 @@ static int make_map(CUtensorMap* m, const void* ptr, uint64_t inner, uint64_t ro
   return 0;
 }
 
-template <int BN, int EPI, bool B_MN, bool MC>
+template <int BN, int EPI, bool B_MN, bool MC, bool A_MN = false>
 static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmKParams& p, cudaStream_t st) {
   static bool attr_set[kMaxDevices] = {};
   constexpr size_t smem = gemm_smem_bytes(BN);
-  auto kern = gemm_bf16_kernel<BN, EPI, B_MN, MC>;
+  auto kern = gemm_bf16_kernel<BN, EPI, B_MN, MC, A_MN>;
   if (int rc = ensure_smem_attr(kern, smem, attr_set, "mm_gemm_fwd")) return rc;
   const int m_units = MC ? (p.m_tiles + 1) / 2 : p.m_tiles;
   const int total = p.batch * p.batch2 * m_units * p.n_tiles;
@@ -589,6 +631,14 @@ extern "C" int32_t mm_gemm_fwd(const mm_gemm_args* a, void* stream) {
   p.rope_cos = a->rope_cos; p.rope_sin = a->rope_sin; p.rope_T = a->rope_T; p.rope_cols = a->rope_cols;
   p.rope_pos = a->rope_pos;
   p.c_trans = a->c_trans;
+  p.c_fp16 = a->c_fp16;
+  p.bias_rs = a->bias_rs; p.bias2 = reinterpret_cast<const bf16*>(a->bias2); p.bias2_rs = a->bias2_rs;
+  MM_REQUIRE(!(a->c_fp16 && a->c_fp32), "mm_gemm_fwd: c_fp16 and c_fp32 are exclusive");
+  MM_REQUIRE((a->a_fp16 != 0) == (a->b_fp16 != 0),
+             "mm_gemm_fwd: A and B must share one 16-bit format (sm_100a faults on mixed f16 x bf16 tcgen05.mma)");
+  MM_REQUIRE((!a->bias_rs && !a->bias2 && !a->bias2_rs) || (a->epi == MM_EPI_STD && !a->c_trans),
+             "mm_gemm_fwd: row-scaled bias terms need the standard, non-transposed epilogue");
+  MM_REQUIRE(!a->c_fp16 || (a->epi == MM_EPI_STD && !a->c_trans), "mm_gemm_fwd: fp16 output only with the standard epilogue");
   MM_REQUIRE(!a->c_trans || (a->epi == MM_EPI_STD && a->batch == 1 && batch2 == 1),
              "mm_gemm_fwd: c_trans needs the standard epilogue and no batching");
 
@@ -637,12 +687,13 @@ extern "C" int32_t mm_gemm_fwd(const mm_gemm_args* a, void* stream) {
     if (a->b_mn_major && BN < 64) BN = 64;
   }
   p.n_tiles = (a->N + BN - 1) / BN;
+  p.idesc = make_idesc_f16(kBlockM, BN, a->a_mn_major != 0, a->b_mn_major != 0, a->a_fp16 != 0, a->b_fp16 != 0);
   static const int gm_env = []() { const char* e = getenv("MACAW_B200_GEMM_GROUPM"); return e ? atoi(e) : 0; }();
   // multicast pairs: wide tiles, several waves of work, and at most ~3 % of rows lost to an odd number of M tiles
   static const int mc_env = []() { const char* e = getenv("MACAW_B200_GEMM_MC"); return e ? atoi(e) : 1; }();
   const long long tiles256 = (long long)a->batch * batch2 * p.m_tiles * p.n_tiles;
   // (measured A/B on one box, cfg4: LLaMA GEMMs 1282 -> 1325 TFLOP/s; short-K CLIP GEMMs do not gain, hence K >= 2048)
-  const bool use_mc = mc_env != 0 && BN == 256 && p.m_tiles >= 2 && p.num_k >= 32 && tiles256 >= 2LL * sms &&
+  const bool use_mc = mc_env != 0 && !a->a_mn_major && BN == 256 && p.m_tiles >= 2 && p.num_k >= 32 && tiles256 >= 2LL * sms &&
                       (((p.m_tiles + 1) / 2) * 2 - p.m_tiles) * 32 <= p.m_tiles;
   // rasterisation: keep one group's A rows (~32 MiB) resident in the 126 MB L2 while its B tiles stream
   // (measured on cfg4: 16 pairs at K=4096 is the optimum; 4 / 8 / 32 cost +5 % / +1 % / +9 % step time)
@@ -653,7 +704,13 @@ extern "C" int32_t mm_gemm_fwd(const mm_gemm_args* a, void* stream) {
     p.group_m = gm_env > 0 ? gm_env : static_cast<int>(g);
   }
   CUtensorMap ta, tb;
-  if (make_map(&ta, a->A, a->K, a->M, a->batch, batch2, a->lda, a->a_bs, a->a_bs2, kBlockM)) return 1;
+  if (a->a_mn_major) {
+    MM_REQUIRE(a->b_mn_major && a->epi == MM_EPI_STD && !a->c_trans,
+               "mm_gemm_fwd: MN-major A needs MN-major B and the standard epilogue");
+    if (make_map(&ta, a->A, a->M, a->K, a->batch, batch2, a->lda, a->a_bs, a->a_bs2, 64)) return 1;
+  } else if (make_map(&ta, a->A, a->K, a->M, a->batch, batch2, a->lda, a->a_bs, a->a_bs2, kBlockM)) {
+    return 1;
+  }
   const uint64_t b_batch = p.b_shared ? 1 : a->batch;
   const uint64_t b_batch2 = p.b2_shared ? 1 : batch2;
   if (!a->b_mn_major) {
@@ -680,6 +737,11 @@ extern "C" int32_t mm_gemm_fwd(const mm_gemm_args* a, void* stream) {
     if (BN == 256) MM_LAUNCH(256, MM_EPI_SWIGLU, false);
     MM_LAUNCH(128, MM_EPI_SWIGLU, false);
   }
+  if (a->a_mn_major) {
+    if (BN == 256) return launch_gemm<256, MM_EPI_STD, true, false, true>(ta, tb, p, st);
+    if (BN == 128) return launch_gemm<128, MM_EPI_STD, true, false, true>(ta, tb, p, st);
+    return launch_gemm<64, MM_EPI_STD, true, false, true>(ta, tb, p, st);
+  }
   if (a->b_mn_major) {
     if (BN == 256) MM_LAUNCH(256, MM_EPI_STD, true);
     if (BN == 128) MM_LAUNCH(128, MM_EPI_STD, true);
@@ -696,25 +758,28 @@ extern "C" int32_t mm_gemm_fwd(const mm_gemm_args* a, void* stream) {
 // ------------------------------------------------------------------------------------------------ split-K reduce
 namespace mm {
 __global__ void splitk_reduce_kernel(const float* __restrict__ part, int splits, int M, int N,
-                                     const bf16* __restrict__ bias, bf16* __restrict__ out, long long ldo) {
+                                     const bf16* __restrict__ bias, bf16* __restrict__ out, long long ldo, int out_fp16) {
   const long long total = static_cast<long long>(M) * N;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
     const int m = static_cast<int>(i / N), n = static_cast<int>(i % N);
     float acc = bias ? __bfloat162float(bias[n]) : 0.0f;
     for (int s = 0; s < splits; ++s) acc += part[static_cast<long long>(s) * total + i];
-    out[static_cast<long long>(m) * ldo + n] = __float2bfloat16(acc);
+    if (out_fp16)
+      reinterpret_cast<__half*>(out)[static_cast<long long>(m) * ldo + n] = __float2half_rn(acc);
+    else
+      out[static_cast<long long>(m) * ldo + n] = __float2bfloat16(acc);
   }
 }
 }  // namespace mm
 
 extern "C" int32_t mm_splitk_reduce(const float* partial, int32_t splits, int32_t M, int32_t N, const void* bias,
-                                    void* out, int64_t ldo, void* stream) {
+                                    void* out, int64_t ldo, int32_t out_fp16, void* stream) {
   MM_REQUIRE(partial && out && splits > 0 && M > 0 && N > 0, "mm_splitk_reduce: bad arguments");
   const long long total = static_cast<long long>(M) * N;
   int blocks = static_cast<int>((total + 255) / 256);
   if (blocks > 148 * 8) blocks = 148 * 8;
   splitk_reduce_kernel<<<blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      partial, splits, M, N, reinterpret_cast<const bf16*>(bias), reinterpret_cast<bf16*>(out), ldo);
+      partial, splits, M, N, reinterpret_cast<const bf16*>(bias), reinterpret_cast<bf16*>(out), ldo, out_fp16);
   return check_launch("mm_splitk_reduce");
 }

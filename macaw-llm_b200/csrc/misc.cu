@@ -2,6 +2,7 @@
 // All are one-pass-over-HBM designs with 128-bit accesses where the layout allows; reductions are fp32 with
 // warp-shuffle + one shared-memory stage.  Reference call sites: see include/macaw_b200.h.
 #include "common.cuh"
+#include <cuda_fp16.h>
 #include "ptx.cuh"
 #include "../../include/macaw_b200.h"
 
@@ -296,6 +297,24 @@ __global__ void add_rows_kernel(const bf16* __restrict__ x, long long ldx, const
       for (int k = 0; k < 8; ++k) f[k] += g[k];
     }
     *reinterpret_cast<uint4*>(y + r * ldy + c * 8) = pack8(f);
+  }
+}
+
+// bf16 rows -> fp16 rows (exact for |x| in fp16's normal range): the alignment chain computes in fp16
+__global__ void cast_bf16_f16_kernel(const bf16* __restrict__ x, long long ldx, __half* __restrict__ y, long long ldy,
+                                     int rows, int cols) {
+  const int nch = cols >> 3;
+  const long long total = static_cast<long long>(rows) * nch;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long r = i / nch;
+    const int c = static_cast<int>(i % nch);
+    float f[8];
+    unpack8(*reinterpret_cast<const uint4*>(x + r * ldx + c * 8), f);
+    __half2 h[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) h[k] = __floats2half2_rn(f[2 * k], f[2 * k + 1]);
+    *reinterpret_cast<uint4*>(y + r * ldy + c * 8) = *reinterpret_cast<const uint4*>(h);
   }
 }
 
@@ -623,6 +642,15 @@ extern "C" int32_t mm_add_rows(const void* x, int64_t ldx, const void* add, int6
 extern "C" int32_t mm_copy_rows(const void* x, int64_t ldx, void* y, int64_t ldy, int32_t rows, int32_t cols,
                                 void* stream) {
   return mm_add_rows(x, ldx, nullptr, 0, 1, y, ldy, rows, cols, stream);
+}
+
+extern "C" int32_t mm_cast_bf16_f16(const void* x, int64_t ldx, void* y, int64_t ldy, int32_t rows, int32_t cols,
+                                    void* stream) {
+  MM_REQUIRE(x && y && rows > 0 && cols > 0 && cols % 8 == 0 && ldx % 8 == 0 && ldy % 8 == 0 && AL16(x) && AL16(y),
+             "mm_cast_bf16_f16: bad arguments");
+  const long long total = static_cast<long long>(rows) * (cols / 8);
+  cast_bf16_f16_kernel<<<grid_for(total, 256), 256, 0, ST(stream)>>>((const bf16*)x, ldx, (__half*)y, ldy, rows, cols);
+  return check_launch("mm_cast_bf16_f16");
 }
 
 extern "C" int32_t mm_align_softmax(const float* scores, int64_t lds, const float* row_bias, const float* extra_score,

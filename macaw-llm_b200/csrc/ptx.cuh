@@ -4,6 +4,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda.h>
 #include <stdint.h>
 
@@ -211,6 +212,17 @@ __device__ __forceinline__ uint64_t make_sdesc_sw128(uint32_t smem_addr, uint32_
 }
 
 // Instruction descriptor for kind::f16 with bf16 A/B and fp32 accumulation.
+// a_fp16 / b_fp16: the operand is IEEE half instead of bf16 (the two formats are independent fields).
+__host__ __device__ constexpr uint32_t make_idesc_f16(int M, int N, bool a_mn_major, bool b_mn_major, bool a_fp16,
+                                                      bool b_fp16) {
+  return (1u << 4)                               // D format: f32
+         | ((a_fp16 ? 0u : 1u) << 7)             // A format: 0 = f16, 1 = bf16
+         | ((b_fp16 ? 0u : 1u) << 10)            // B format
+         | ((a_mn_major ? 1u : 0u) << 15)        // A major
+         | ((b_mn_major ? 1u : 0u) << 16)        // B major
+         | (static_cast<uint32_t>(N >> 3) << 17)  // N / 8
+         | (static_cast<uint32_t>(M >> 4) << 24); // M / 16
+}
 __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N, bool a_mn_major, bool b_mn_major) {
   return (1u << 4)                               // D format: f32
          | (1u << 7)                             // A format: bf16
@@ -224,6 +236,10 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N, bool a_mn_m
 // ----------------------------------------------------------------------------- misc
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+__device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
+  __half2 v = __floats2half2_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);
 }
 __device__ __forceinline__ float bf16lo(uint32_t v) { return __uint_as_float(v << 16); }

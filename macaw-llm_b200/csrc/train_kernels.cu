@@ -1,0 +1,365 @@
+// HBM-bound kernels of the training step: the backward halves of RMSNorm / SwiGLU / softmax /
+// cross-entropy, the embedding-gradient scatter and the fused AdamW update.  The contractions of the backward pass run on
+// the tcgen05 GEMM (dX = dY W with an MN-major B operand, dW = dY^T X with MN-major A and B operands).
+//
+// Reference: autograd of the vendored LLaMA in /root/reference/modeling.py (LlamaRMSNorm :302-319, LlamaMLP :126-140,
+// LlamaAttention :143-231, shifted CE :597-610) driven by llm_trainer.py:184-188 (compute_loss -> loss.backward()) and the
+// optimizer of train.sh / configs/deepspeed_config.json (AdamW, fp32 master weights).
+#include "common.cuh"
+#include "ptx.cuh"
+#include "../../include/macaw_b200.h"
+
+namespace mm {
+
+#define ST(s) reinterpret_cast<cudaStream_t>(s)
+
+__device__ __forceinline__ void unpack8f(const uint4& u, float (&f)[8]) {
+  f[0] = bf16lo(u.x); f[1] = bf16hi(u.x); f[2] = bf16lo(u.y); f[3] = bf16hi(u.y);
+  f[4] = bf16lo(u.z); f[5] = bf16hi(u.z); f[6] = bf16lo(u.w); f[7] = bf16hi(u.w);
+}
+__device__ __forceinline__ uint4 pack8f(const float (&f)[8]) {
+  return make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+// block-wide sum; `sh` holds >= 32 floats; every thread gets the result
+__device__ __forceinline__ float block_sum(float v, float* sh) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  v = warp_sum(v);
+  __syncthreads();
+  if (lane == 0) sh[w] = v;
+  __syncthreads();
+  float t = lane < nw ? sh[lane] : 0.f;
+  return warp_sum(t);
+}
+__device__ __forceinline__ float block_max(float v, float* sh) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  v = warp_max(v);
+  __syncthreads();
+  if (lane == 0) sh[w] = v;
+  __syncthreads();
+  float t = lane < nw ? sh[lane] : -INFINITY;
+  return warp_max(t);
+}
+
+// ------------------------------------------------------------------------------------------------ RMSNorm backward
+// y = x * rstd * g.   dx = rstd * (g*dy) - rstd^3/cols * x * sum(g*dy*x) (+ dres);   dg += sum_rows dy * x * rstd.
+// One CTA walks `rows_per_cta` rows; each thread owns a fixed set of 8-column chunks, so the dg partial sums stay in
+// registers across the CTA's rows and cost one fp32 atomicAdd per column per CTA.
+constexpr int kNormMaxChunks = 4;  // cols <= 256 threads * 8 * 4 = 8192
+__global__ void __launch_bounds__(256) rmsnorm_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x,
+                                                          const float* __restrict__ rstd, const bf16* __restrict__ g,
+                                                          const bf16* __restrict__ dres, bf16* __restrict__ dx,
+                                                          float* __restrict__ dg, int rows, int cols, int rows_per_cta) {
+  __shared__ float sh[32];
+  const int nch = cols >> 3;
+  float gacc[kNormMaxChunks][8];
+  float gv[kNormMaxChunks][8];
+#pragma unroll
+  for (int k = 0; k < kNormMaxChunks; ++k) {
+    const int c = threadIdx.x + k * blockDim.x;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) gacc[k][i] = 0.f;
+    if (c < nch) unpack8f(__ldg(reinterpret_cast<const uint4*>(g + c * 8)), gv[k]);
+  }
+  const int r0 = blockIdx.x * rows_per_cta, r1 = min(rows, r0 + rows_per_cta);
+  for (int r = r0; r < r1; ++r) {
+    const float rs = rstd[r];
+    float xv[kNormMaxChunks][8], tv[kNormMaxChunks][8];
+    float dot = 0.f;
+#pragma unroll
+    for (int k = 0; k < kNormMaxChunks; ++k) {
+      const int c = threadIdx.x + k * blockDim.x;
+      if (c < nch) {
+        float dv[8];
+        unpack8f(*reinterpret_cast<const uint4*>(dy + static_cast<long long>(r) * cols + c * 8), dv);
+        unpack8f(*reinterpret_cast<const uint4*>(x + static_cast<long long>(r) * cols + c * 8), xv[k]);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          tv[k][i] = dv[i] * gv[k][i];
+          dot += tv[k][i] * xv[k][i];
+          gacc[k][i] += dv[i] * xv[k][i] * rs;
+        }
+      }
+    }
+    dot = block_sum(dot, sh);
+    const float coef = rs * rs * rs * dot / static_cast<float>(cols);
+#pragma unroll
+    for (int k = 0; k < kNormMaxChunks; ++k) {
+      const int c = threadIdx.x + k * blockDim.x;
+      if (c < nch) {
+        float o[8];
+        if (dres != nullptr)
+          unpack8f(*reinterpret_cast<const uint4*>(dres + static_cast<long long>(r) * cols + c * 8), o);
+        else {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) o[i] = 0.f;
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o[i] += rs * tv[k][i] - coef * xv[k][i];
+        *reinterpret_cast<uint4*>(dx + static_cast<long long>(r) * cols + c * 8) = pack8f(o);
+      }
+    }
+  }
+  if (dg != nullptr) {
+#pragma unroll
+    for (int k = 0; k < kNormMaxChunks; ++k) {
+      const int c = threadIdx.x + k * blockDim.x;
+      if (c < nch) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) atomicAdd(&dg[c * 8 + i], gacc[k][i]);
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ SwiGLU
+__global__ void swiglu_fwd_kernel(const bf16* __restrict__ gate, const bf16* __restrict__ up, bf16* __restrict__ h,
+                                  long long n8) {
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n8;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    float a[8], b[8], o[8];
+    unpack8f(reinterpret_cast<const uint4*>(gate)[i], a);
+    unpack8f(reinterpret_cast<const uint4*>(up)[i], b);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) o[k] = a[k] / (1.f + __expf(-a[k])) * b[k];
+    reinterpret_cast<uint4*>(h)[i] = pack8f(o);
+  }
+}
+// dgate = dh * up * d silu(gate),  dup = dh * silu(gate);   d silu(a) = s (1 + a (1 - s)),  s = sigmoid(a)
+__global__ void swiglu_bwd_kernel(const bf16* __restrict__ dh, const bf16* __restrict__ gate, const bf16* __restrict__ up,
+                                  bf16* __restrict__ dgate, bf16* __restrict__ dup, long long n8) {
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n8;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    float d[8], a[8], b[8], og[8], ou[8];
+    unpack8f(reinterpret_cast<const uint4*>(dh)[i], d);
+    unpack8f(reinterpret_cast<const uint4*>(gate)[i], a);
+    unpack8f(reinterpret_cast<const uint4*>(up)[i], b);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const float s = 1.f / (1.f + __expf(-a[k]));
+      ou[k] = d[k] * a[k] * s;
+      og[k] = d[k] * b[k] * s * (1.f + a[k] * (1.f - s));
+    }
+    reinterpret_cast<uint4*>(dgate)[i] = pack8f(og);
+    reinterpret_cast<uint4*>(dup)[i] = pack8f(ou);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ attention softmax (backward)
+// One CTA per (b, h, query) row of the score matrices: S (pre-scale logits q.k) and dP = dO V^T, both fp32.
+//   P = softmax(scale * S + mask),  D = sum_j P_j dP_j,  dS = scale * P (dP - D).
+// P and dS are written as bf16 (A operands of dV = P^T dO, dK = dS^T Q, dQ = dS K).  Mask semantics match the forward
+// kernel: key j visible to query i iff j <= i + (Tk - Tq) (causal) and key_mask[b][j] != 0; fully masked rows give zeros.
+__global__ void __launch_bounds__(256) attn_softmax_bwd_kernel(const float* __restrict__ S, const float* __restrict__ dP,
+                                                               bf16* __restrict__ P, bf16* __restrict__ dS, int H, int Tq,
+                                                               int Tk, long long ld, float scale, int causal,
+                                                               const int* __restrict__ key_mask) {
+  __shared__ float sh[32];
+  const long long row = blockIdx.x;
+  const int i = static_cast<int>(row % Tq);
+  const int b = static_cast<int>(row / (static_cast<long long>(Tq) * H));
+  const float* s = S + row * ld;
+  const float* dp = dP + row * ld;
+  bf16* p = P + row * ld;
+  bf16* ds = dS + row * ld;
+  const int* km = key_mask ? key_mask + static_cast<long long>(b) * Tk : nullptr;
+  const int lim = causal ? i + (Tk - Tq) : Tk - 1;
+  float mx = -INFINITY;
+  for (int j = threadIdx.x; j < Tk; j += blockDim.x) {
+    const bool ok = j <= lim && (km == nullptr || km[j] != 0);
+    if (ok) mx = fmaxf(mx, s[j] * scale);
+  }
+  mx = block_max(mx, sh);
+  float sum = 0.f, dsum = 0.f;
+  for (int j = threadIdx.x; j < Tk; j += blockDim.x) {
+    const bool ok = j <= lim && (km == nullptr || km[j] != 0);
+    const float e = ok ? __expf(s[j] * scale - mx) : 0.f;
+    sum += e;
+    dsum += e * dp[j];
+  }
+  sum = block_sum(sum, sh);
+  dsum = block_sum(dsum, sh);
+  const float inv = sum > 0.f ? 1.f / sum : 0.f;
+  const float D = dsum * inv;
+  for (int j = threadIdx.x; j < Tk; j += blockDim.x) {
+    const bool ok = j <= lim && (km == nullptr || km[j] != 0);
+    const float pj = ok ? __expf(s[j] * scale - mx) * inv : 0.f;
+    p[j] = __float2bfloat16(pj);
+    ds[j] = __float2bfloat16(scale * pj * (dp[j] - D));
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ cross-entropy backward
+// Shifted CE of modeling.py:600-610: position t predicts labels[t+1].  dlogits[b,t,:] = (softmax(logits[b,t,:]) -
+// onehot(labels[b,t+1])) * gscale / n_valid  when t < T-1 and the label is not -100, else 0.  In place is allowed.
+__global__ void __launch_bounds__(512) ce_bwd_kernel(const bf16* __restrict__ logits, const long long* __restrict__ labels,
+                                                     bf16* __restrict__ dlogits, int T, int V,
+                                                     const int* __restrict__ n_valid, float gscale) {
+  __shared__ float sh[32];
+  const long long row = blockIdx.x;  // b * T + t
+  const int t = static_cast<int>(row % T);
+  const bf16* x = logits + row * V;
+  bf16* o = dlogits + row * V;
+  long long lab = -100;
+  if (t < T - 1) lab = labels[row + 1];
+  if (lab < 0 || lab >= V) {
+    for (int j = threadIdx.x; j < V; j += blockDim.x) o[j] = __float2bfloat16(0.f);
+    return;
+  }
+  float mx = -INFINITY;
+  for (int j = threadIdx.x; j < V; j += blockDim.x) mx = fmaxf(mx, __bfloat162float(x[j]));
+  mx = block_max(mx, sh);
+  float sum = 0.f;
+  for (int j = threadIdx.x; j < V; j += blockDim.x) sum += __expf(__bfloat162float(x[j]) - mx);
+  sum = block_sum(sum, sh);
+  const int nv = *n_valid;
+  const float sc = gscale / static_cast<float>(nv > 0 ? nv : 1);
+  const float inv = 1.f / sum;
+  for (int j = threadIdx.x; j < V; j += blockDim.x) {
+    float pj = __expf(__bfloat162float(x[j]) - mx) * inv;
+    if (j == lab) pj -= 1.f;
+    o[j] = __float2bfloat16(pj * sc);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ embedding gradient
+// dtable[ids[i], :] += dx[i, :]  (bf16x2 atomics; rows with ids outside [0, vocab) are skipped)
+__global__ void embed_scatter_add_kernel(const bf16* __restrict__ dx, long long ldx, const long long* __restrict__ ids,
+                                         long long n, int dim, int vocab, bf16* __restrict__ dtable) {
+  const int half_dim = dim >> 1;
+  const long long total = n * half_dim;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long r = i / half_dim;
+    const int c = static_cast<int>(i % half_dim);
+    const long long id = ids[r];
+    if (id < 0 || id >= vocab) continue;
+    const __nv_bfloat162 v = *reinterpret_cast<const __nv_bfloat162*>(dx + r * ldx + 2 * c);
+    atomicAdd(reinterpret_cast<__nv_bfloat162*>(dtable + id * dim + 2 * c), v);
+  }
+}
+
+// column sums of a bf16 (rows, cols) matrix into fp32 (bias gradients): out[c] += sum_r x[r, c]
+__global__ void colsum_kernel(const bf16* __restrict__ x, long long ldx, int rows, int cols, float* __restrict__ out,
+                              int rows_per_cta) {
+  const int c = blockIdx.y * blockDim.x + threadIdx.x;
+  if (c >= cols) return;
+  const int r0 = blockIdx.x * rows_per_cta, r1 = min(rows, r0 + rows_per_cta);
+  float acc = 0.f;
+  for (int r = r0; r < r1; ++r) acc += __bfloat162float(x[static_cast<long long>(r) * ldx + c]);
+  atomicAdd(&out[c], acc);
+}
+
+// ------------------------------------------------------------------------------------------------ AdamW
+// Decoupled weight decay (Loshchilov & Hutter), fp32 master weights + moments, bf16 working copy:
+//   m = b1 m + (1-b1) g;  v = b2 v + (1-b2) g^2;  w -= lr (m/bc1 / (sqrt(v/bc2) + eps) + wd w);  p = bf16(w)
+__global__ void adamw_kernel(bf16* __restrict__ p, const bf16* __restrict__ g, float* __restrict__ w, float* __restrict__ m,
+                             float* __restrict__ v, long long n, float lr, float b1, float b2, float eps, float wd,
+                             float inv_bc1, float inv_bc2, float gscale) {
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const float gi = __bfloat162float(g[i]) * gscale;
+    const float mi = b1 * m[i] + (1.f - b1) * gi;
+    const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+    float wi = w[i];
+    wi -= lr * (mi * inv_bc1 / (sqrtf(vi * inv_bc2) + eps) + wd * wi);
+    m[i] = mi;
+    v[i] = vi;
+    w[i] = wi;
+    p[i] = __float2bfloat16(wi);
+  }
+}
+
+static inline int grid_for(long long total, int block, int cap_mult = 16) {
+  long long g = (total + block - 1) / block;
+  const long long cap = static_cast<long long>(num_sms()) * cap_mult;
+  return static_cast<int>(g < 1 ? 1 : (g > cap ? cap : g));
+}
+
+}  // namespace mm
+
+using namespace mm;
+#define AL16(p) ((reinterpret_cast<uintptr_t>(p) & 15) == 0)
+
+extern "C" int32_t mm_rmsnorm_bwd(const void* dy, const void* x, const float* rstd, const void* g, const void* dres,
+                                  void* dx, float* dg, int32_t rows, int32_t cols, void* stream) {
+  MM_REQUIRE(dy && x && rstd && g && dx && rows > 0 && cols > 0 && cols % 8 == 0 && cols <= 256 * 8 * kNormMaxChunks,
+             "mm_rmsnorm_bwd: bad arguments (cols %% 8 == 0, cols <= %d)", 256 * 8 * kNormMaxChunks);
+  MM_REQUIRE(AL16(dy) && AL16(x) && AL16(g) && AL16(dx) && (dres == nullptr || AL16(dres)), "mm_rmsnorm_bwd: alignment");
+  int rpc = (rows + 4 * num_sms() - 1) / (4 * num_sms());
+  if (rpc < 1) rpc = 1;
+  const int grid = (rows + rpc - 1) / rpc;
+  rmsnorm_bwd_kernel<<<grid, 256, 0, ST(stream)>>>((const bf16*)dy, (const bf16*)x, rstd, (const bf16*)g, (const bf16*)dres,
+                                                   (bf16*)dx, dg, rows, cols, rpc);
+  return check_launch("mm_rmsnorm_bwd");
+}
+
+extern "C" int32_t mm_swiglu_fwd(const void* gate, const void* up, void* h, int64_t n, void* stream) {
+  MM_REQUIRE(gate && up && h && n > 0 && n % 8 == 0 && AL16(gate) && AL16(up) && AL16(h), "mm_swiglu_fwd: bad arguments");
+  swiglu_fwd_kernel<<<grid_for(n / 8, 256), 256, 0, ST(stream)>>>((const bf16*)gate, (const bf16*)up, (bf16*)h, n / 8);
+  return check_launch("mm_swiglu_fwd");
+}
+
+extern "C" int32_t mm_swiglu_bwd(const void* dh, const void* gate, const void* up, void* dgate, void* dup, int64_t n,
+                                 void* stream) {
+  MM_REQUIRE(dh && gate && up && dgate && dup && n > 0 && n % 8 == 0, "mm_swiglu_bwd: bad arguments");
+  MM_REQUIRE(AL16(dh) && AL16(gate) && AL16(up) && AL16(dgate) && AL16(dup), "mm_swiglu_bwd: alignment");
+  swiglu_bwd_kernel<<<grid_for(n / 8, 256), 256, 0, ST(stream)>>>((const bf16*)dh, (const bf16*)gate, (const bf16*)up,
+                                                                 (bf16*)dgate, (bf16*)dup, n / 8);
+  return check_launch("mm_swiglu_bwd");
+}
+
+extern "C" int32_t mm_attn_softmax_bwd(const float* S, const float* dP, void* P, void* dS, int32_t B, int32_t H, int32_t Tq,
+                                       int32_t Tk, int64_t ld, float scale, int32_t causal, const int32_t* key_mask,
+                                       void* stream) {
+  MM_REQUIRE(S && dP && P && dS && B > 0 && H > 0 && Tq > 0 && Tk > 0 && ld >= Tk, "mm_attn_softmax_bwd: bad arguments");
+  const long long rows = static_cast<long long>(B) * H * Tq;
+  MM_REQUIRE(rows < (1LL << 31), "mm_attn_softmax_bwd: too many rows");
+  attn_softmax_bwd_kernel<<<static_cast<unsigned>(rows), 256, 0, ST(stream)>>>(S, dP, (bf16*)P, (bf16*)dS, H, Tq, Tk, ld,
+                                                                               scale, causal, key_mask);
+  return check_launch("mm_attn_softmax_bwd");
+}
+
+extern "C" int32_t mm_ce_bwd(const void* logits, const int64_t* labels, void* dlogits, int32_t B, int32_t T, int32_t V,
+                             const int32_t* n_valid, float grad_scale, void* stream) {
+  MM_REQUIRE(logits && labels && dlogits && n_valid && B > 0 && T > 0 && V > 0, "mm_ce_bwd: bad arguments");
+  ce_bwd_kernel<<<B * T, 512, 0, ST(stream)>>>((const bf16*)logits, (const long long*)labels, (bf16*)dlogits, T, V, n_valid,
+                                               grad_scale);
+  return check_launch("mm_ce_bwd");
+}
+
+extern "C" int32_t mm_embed_scatter_add(const void* dx, int64_t ldx, const int64_t* ids, int64_t n, int32_t dim,
+                                        int32_t vocab, void* dtable, void* stream) {
+  MM_REQUIRE(dx && ids && dtable && n > 0 && dim > 0 && dim % 2 == 0 && ldx % 2 == 0 && vocab > 0,
+             "mm_embed_scatter_add: bad arguments");
+  embed_scatter_add_kernel<<<grid_for(n * (dim / 2), 256), 256, 0, ST(stream)>>>((const bf16*)dx, ldx, (const long long*)ids, n,
+                                                                                dim, vocab, (bf16*)dtable);
+  return check_launch("mm_embed_scatter_add");
+}
+
+extern "C" int32_t mm_colsum(const void* x, int64_t ldx, int32_t rows, int32_t cols, float* out, void* stream) {
+  MM_REQUIRE(x && out && rows > 0 && cols > 0, "mm_colsum: bad arguments");
+  int rpc = (rows + 63) / 64;
+  dim3 grid((rows + rpc - 1) / rpc, (cols + 255) / 256);
+  colsum_kernel<<<grid, 256, 0, ST(stream)>>>((const bf16*)x, ldx, rows, cols, out, rpc);
+  return check_launch("mm_colsum");
+}
+
+extern "C" int32_t mm_adamw(void* p, const void* g, float* master, float* m, float* v, int64_t n, float lr, float beta1,
+                            float beta2, float eps, float weight_decay, int32_t step, float grad_scale, void* stream) {
+  MM_REQUIRE(p && g && master && m && v && n > 0 && step > 0, "mm_adamw: bad arguments");
+  const float inv_bc1 = 1.f / (1.f - powf(beta1, static_cast<float>(step)));
+  const float inv_bc2 = 1.f / (1.f - powf(beta2, static_cast<float>(step)));
+  adamw_kernel<<<grid_for(n, 256), 256, 0, ST(stream)>>>((bf16*)p, (const bf16*)g, master, m, v, n, lr, beta1, beta2, eps,
+                                                        weight_decay, inv_bc1, inv_bc2, grad_scale);
+  return check_launch("mm_adamw");
+}

@@ -52,6 +52,12 @@ class Engine:
         self._cache[key] = (st, val)
         return val
 
+    def w16(self, p: torch.Tensor, key: str) -> torch.Tensor:
+        """fp16 copy of a parameter for the fp16 alignment chain: the bf16 value converted exactly (values below fp16's
+        normal range lose bits, values above 65504 saturate — neither occurs for weights / embeddings)."""
+        self.w(p, key)  # device / dtype checks
+        return self.derived("f16:" + key, [p], lambda: p.detach().to(BF16).to(torch.float16))
+
     def w(self, p: torch.Tensor, key: str) -> torch.Tensor:
         """bf16 CUDA view of a parameter (the parameter itself when it already is bf16)."""
         if not p.is_cuda:
@@ -258,20 +264,31 @@ class Engine:
         return out.view(B, N, P)
 
     # ------------------------------------------------------------------------------------------------ alignment
-    def align(self, feats: torch.Tensor, name: str, table: torch.Tensor, prefix: torch.Tensor, row_off: int) -> int:
+    def align(self, feats: torch.Tensor, name: str, table: torch.Tensor, prefix: torch.Tensor, row_off: int,
+              table16: Optional[torch.Tensor] = None) -> int:
         """One modality of reference modeling.py:982-987 / 999-1008 / 1022-1026 in ABSORBED form:
         the keys/values are never projected — q is pushed through W_k per head and both big contractions
-        (scores = q~ . table^T over E, ctx~ = P . table over V) stream tiles of the raw embedding table through TMA.
+        (scores = q~ . table^T over E, ctx~ = P . table over V) run inside ONE fused kernel (mm_align_fwd) that streams
+        tiles of the raw embedding table through TMA; neither the scores nor a softmax pass ever touch HBM in fp32.
+
+        Precision: the whole chain runs in fp16 x fp16 -> fp32 (11-bit significand; one stored stage costs 1.4e-4
+        norm-wise, bf16 1.1e-3) on exact fp16 copies of the bf16 weights / table, so the block's error is dominated by
+        the single bf16 rounding of its output.
 
         feats (B, N, C) bf16 with unit channel stride and row stride C (sample stride free); writes the Lq aligned
         rows into prefix[:, row_off : row_off + Lq] and returns Lq."""
         ops.TAG = "align.proj"
+        F16 = torch.float16
         m = self.m
         conv = getattr(m, f"project_{name}")
         lin = getattr(m, f"transform_{name}_to_hidden")
         mha = getattr(m, f"{name}_align_attention")
         B, N, C = feats.shape
         assert feats.stride(2) == 1 and feats.stride(1) == C
+        feats = ops.cast_f16(feats.contiguous())
+        if table16 is None:  # stand-alone use (tests / tools): exact fp16 copy of the given table
+            table16 = self.derived("align.table16", [table], lambda: table.detach().to(F16))
+        assert table16.shape == table.shape and table16.dtype == F16
         kk, ss = conv.kernel_size[0], conv.stride[0]
         Lq = (N - kk) // ss + 1
         Nq = B * Lq
@@ -281,9 +298,10 @@ class Engine:
         hd = E // H
         dev = feats.device
         pre = f"{name}_align."
+        f16 = dict(a_fp16=True, b_fp16=True)
         # ---- Conv1d over the token axis == GEMM on overlapping row windows (window = kk*C contiguous elements), split over K
         wc = self.derived(pre + "conv", [conv.weight],
-                          lambda: conv.weight.detach().to(BF16).permute(0, 2, 1).reshape(C, kk * C).contiguous())
+                          lambda: conv.weight.detach().to(BF16).to(F16).permute(0, 2, 1).reshape(C, kk * C).contiguous())
         K = kk * C
         S = 1
         for cand in (16, 12, 9, 8, 6, 4, 3, 2):
@@ -294,25 +312,25 @@ class Engine:
         part = torch.empty((S, Nq, C), device=dev, dtype=torch.float32)
         ops.gemm_raw(M=Lq, N=C, K=Kc, batch=S, batch2=B, A=feats.data_ptr(), lda=ss * C, a_bs=Kc, a_bs2=feats.stride(0),
                      B=wc.data_ptr(), ldb=K, b_bs=Kc, b_bs2=0, Cout=part.data_ptr(), ldc=C, c_bs=Nq * C, c_bs2=Lq * C,
-                     c_fp32=True)
-        y = torch.empty((Nq, C), device=dev, dtype=BF16)
+                     c_fp32=True, **f16)
+        y = torch.empty((Nq, C), device=dev, dtype=F16)
         ops.splitk_reduce(part, self.w(conv.bias, pre + "convb"), y)
         # ---- Linear C -> E, then the MHA query projection
-        z = ops.linear(y, self.w(lin.weight, pre + "lw"), self.w(lin.bias, pre + "lb"))
-        w_in = self.w(mha.in_proj_weight, pre + "win")
+        z = ops.linear(y, self.w16(lin.weight, pre + "lw"), self.w(lin.bias, pre + "lb"), out_dtype=F16)
+        w_in = self.w16(mha.in_proj_weight, pre + "win")
         b_in = self.w(mha.in_proj_bias, pre + "bin")
-        q = ops.linear(z, w_in[:E], b_in[:E])  # (Nq, E); the 1/sqrt(hd) scale is applied downstream (alpha)
+        q = ops.linear(z, w_in[:E], b_in[:E], out_dtype=F16)  # (Nq, E); the 1/sqrt(hd) scale is applied downstream (alpha)
         w_k, w_v = w_in[E:2 * E], w_in[2 * E:]
         bk2 = self.derived(pre + "bk2", [mha.in_proj_bias, mha.bias_k],
                            lambda: torch.stack([mha.in_proj_bias.detach()[E:2 * E].to(BF16),
-                                                mha.bias_k.detach().reshape(E).to(BF16)], 0).contiguous())
+                                                mha.bias_k.detach().reshape(E).to(BF16)], 0).to(F16).contiguous())
         b_v = b_in[2 * E:]
         bias_v = self.w(mha.bias_v, pre + "biasv").view(E)
         scale = 1.0 / math.sqrt(hd)
         Vp = _round_up(V, 8)
-        ctx = torch.empty((Nq, E), device=dev, dtype=BF16)
-        # bound the fp32 score buffer (R x V) to ~2 GiB by chunking query rows
-        max_nq = max(1, (1 << 31) // (H * Vp * 4))
+        ctx = torch.empty((Nq, E), device=dev, dtype=F16)
+        # bound the fp16 probability scratch (R x V) to ~2 GiB by chunking query rows
+        max_nq = max(1, (1 << 31) // (H * Vp * 2))
         if self.align_max_rows:
             max_nq = min(max_nq, int(self.align_max_rows))
         for n0 in range(0, Nq, max_nq):
@@ -323,37 +341,26 @@ class Engine:
             # per-row constants: q_h . b_k[h] (added to every real key) and q_h . bias_k[h] (the bias_k key's score)
             stats = torch.empty((H, nq, 2), device=dev, dtype=torch.float32)
             ops.gemm_raw(M=nq, N=2, K=hd, batch=H, A=qs.data_ptr(), lda=E, a_bs=hd, B=bk2.data_ptr(), ldb=E, b_bs=hd,
-                         Cout=stats.data_ptr(), ldc=2, c_bs=nq * 2, c_fp32=True, alpha=scale)
+                         Cout=stats.data_ptr(), ldc=2, c_bs=nq * 2, c_fp32=True, alpha=scale, **f16)
             # q~[h] = (q_h / sqrt(hd)) W_k[h]   (B operand = W_k rows of head h, N-contiguous -> MN-major UMMA descriptor)
-            qt = torch.empty((H, nq, E), device=dev, dtype=BF16)
+            qt = torch.empty((H, nq, E), device=dev, dtype=F16)
             ops.gemm_raw(M=nq, N=E, K=hd, batch=H, A=qs.data_ptr(), lda=E, a_bs=hd, B=w_k.data_ptr(), ldb=E, b_bs=hd * E,
-                         b_mn_major=True, Cout=qt.data_ptr(), ldc=E, c_bs=nq * E, alpha=scale)
-            # scores = q~ . table^T  (R x V, fp32)
-            scores = torch.empty((R, Vp), device=dev, dtype=torch.float32)
-            ops.TAG = "align.scores"
-            ops.gemm_raw(M=R, N=V, K=E, A=qt.data_ptr(), lda=E, B=table.data_ptr(), ldb=E, Cout=scores.data_ptr(), ldc=Vp,
-                         c_fp32=True)
-            P = torch.empty((R, Vp), device=dev, dtype=BF16)
-            psum, pext = ops.align_softmax(scores, stats.view(R, 2), P, V)
-            del scores
-            # ctx~ = P . table   (K = V runs down the table rows: MN-major B straight from the table, no transpose copy)
-            ctxt = torch.empty((H, nq, E), device=dev, dtype=BF16)
-            ops.TAG = "align.pv"
-            ops.gemm_raw(M=R, N=E, K=V, A=P.data_ptr(), lda=Vp, B=table.data_ptr(), ldb=E, b_mn_major=True,
-                         Cout=ctxt.data_ptr(), ldc=E)
-            del P
-            # ctx[:, h] = ctx~[h] W_v[h]^T, then the two value-bias terms
+                         b_mn_major=True, Cout=qt.data_ptr(), ldc=E, c_bs=nq * E, alpha=scale, c_fp16=True, **f16)
+            # ctx~ = softmax(q~ . table^T + bias terms)[:, :V] . table — the fused kernel (both table contractions)
+            ctxt, psum, pext = ops.align_fused(table16, qt.view(R, E), stats.view(R, 2))
+            # ctx[:, h] = ctx~[h] W_v[h]^T + (sum_real P) b_v[h] + P_bias bias_v[h]   (value-side bias terms in the epilogue)
             cs = ctx[n0:n1]
             ops.TAG = "align.proj"
             ops.gemm_raw(M=nq, N=hd, K=E, batch=H, A=ctxt.data_ptr(), lda=E, a_bs=nq * E, B=w_v.data_ptr(), ldb=E,
-                         b_bs=hd * E, Cout=cs.data_ptr(), ldc=E, c_bs=hd)
-            ops.align_ctx_fixup(cs, psum, pext, b_v, bias_v, hd)
+                         b_bs=hd * E, Cout=cs.data_ptr(), ldc=E, c_bs=hd, c_fp16=True, **f16,
+                         bias=b_v.data_ptr(), bias_bs=hd, bias_rs=psum.data_ptr(), bias2=bias_v.data_ptr(),
+                         bias2_rs=pext.data_ptr())
         # ---- out_proj straight into the prefix block of every sample
         Ptot = prefix.shape[1]
         ops.gemm_raw(M=Lq, N=E, K=E, batch=B, A=ctx.data_ptr(), lda=E, a_bs=Lq * E,
-                     B=self.w(mha.out_proj.weight, pre + "wo").data_ptr(), ldb=E, b_bs=0,
+                     B=self.w16(mha.out_proj.weight, pre + "wo").data_ptr(), ldb=E, b_bs=0,
                      Cout=prefix.data_ptr() + row_off * E * 2, ldc=E, c_bs=Ptot * E,
-                     bias=self.w(mha.out_proj.bias, pre + "bo").data_ptr())
+                     bias=self.w(mha.out_proj.bias, pre + "bo").data_ptr(), **f16)
         return Lq
 
     @staticmethod
@@ -411,7 +418,8 @@ class Engine:
                     continue
                 Lq = lens[name]
                 ops.embed_gather(table, inputs[f"{name}_starts"].to(dev), out=prefix[:, off, :])
-                got = self.align(feats[name], name, table, prefix, off + 1)
+                got = self.align(feats[name], name, table, prefix, off + 1,
+                                 self.w16(m.llm.model.embed_tokens.weight, "llm.embed"))
                 assert got == Lq
                 ops.embed_gather(table, inputs[f"{name}_ends"].to(dev), out=prefix[:, off + 1 + Lq, :])
                 off += Lq + 2

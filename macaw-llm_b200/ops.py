@@ -11,12 +11,14 @@ from typing import Optional
 import torch
 
 from . import _lib
-from ._lib import AttnArgs, GemmArgs
+from ._lib import AlignArgs, AttnArgs, GemmArgs
 
 ACT_NONE, ACT_GELU, ACT_QUICK_GELU, ACT_SILU = 0, 1, 2, 3
 EPI_STD, EPI_SWIGLU, EPI_ROPE = 0, 1, 2
 
 _BF16 = torch.bfloat16
+_F16 = torch.float16
+_16BIT = (torch.bfloat16, torch.float16)
 
 
 def _stream() -> int:
@@ -62,11 +64,13 @@ def launch_count_reset() -> None:
 def gemm_raw(*, M, N, K, A, lda, B, ldb, Cout, ldc, batch=1, a_bs=0, b_bs=0, c_bs=0, batch2=1, a_bs2=0, b_bs2=0,
              c_bs2=0, b_mn_major=False, c_fp32=False, epi=EPI_STD, act=ACT_NONE, alpha=1.0, bias=None, bias_bs=0,
              row_scale=None, residual=None, ldr=0, r_bs=0, r_bs2=0, res_row_mod=0, rope_cos=None, rope_sin=None,
-             rope_T=0, rope_cols=0, rope_pos=None, c_trans=False) -> None:
+             rope_T=0, rope_cols=0, rope_pos=None, c_trans=False, a_fp16=False, b_fp16=False, c_fp16=False,
+             bias_rs=None, bias2=None, bias2_rs=None, a_mn_major=False) -> None:
     """Direct binding of mm_gemm_fwd; pointers are ints (data_ptr() + byte offsets)."""
     a = GemmArgs(M, N, K, batch, batch2, A, lda, a_bs, a_bs2, B, ldb, b_bs, b_bs2, int(b_mn_major), Cout, ldc, c_bs,
                  c_bs2, int(c_fp32), epi, act, float(alpha), bias, bias_bs, row_scale, residual, ldr, r_bs, r_bs2,
-                 res_row_mod, rope_cos, rope_sin, rope_T, rope_cols, rope_pos, int(c_trans))
+                 res_row_mod, rope_cos, rope_sin, rope_T, rope_cols, rope_pos, int(c_trans), int(a_fp16), int(b_fp16), int(c_fp16),
+                 bias_rs, bias2, bias2_rs, int(a_mn_major))
     if PROFILE is None:
         _check(_lib.load().mm_gemm_fwd(C.byref(a), _stream()), "mm_gemm_fwd")
         return
@@ -80,16 +84,19 @@ def gemm_raw(*, M, N, K, A, lda, B, ldb, Cout, ldc, batch=1, a_bs=0, b_bs=0, c_b
 def linear(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, *, act: int = ACT_NONE,
            residual: Optional[torch.Tensor] = None, res_row_mod: int = 0, out: Optional[torch.Tensor] = None,
            out_fp32: bool = False, alpha: float = 1.0, row_scale: Optional[torch.Tensor] = None, epi: int = EPI_STD,
-           rope=None) -> torch.Tensor:
-    """out = epilogue(alpha * x @ w.T): x (M, K) bf16 with unit inner stride, w (N, K) bf16 (an nn.Linear weight)."""
-    _cuda(x, _BF16, "x"); _cuda(w, _BF16, "w")
+           rope=None, out_dtype=None) -> torch.Tensor:
+    """out = epilogue(alpha * x @ w.T): x (M, K) bf16 or fp16 with unit inner stride, w (N, K) bf16 or fp16 (an nn.Linear
+    weight); out bf16 (default), fp16 or fp32 (`out_dtype` / the dtype of `out`)."""
+    _cuda(x, None, "x"); _cuda(w, None, "w")
+    assert x.dtype in _16BIT and w.dtype in _16BIT, (x.dtype, w.dtype)
     assert x.dim() == 2 and w.dim() == 2 and x.shape[1] == w.shape[1], (x.shape, w.shape)
     assert x.stride(1) == 1 and w.stride(1) == 1
     M, K = x.shape
     N = w.shape[0]
     n_out = N // 2 if epi == EPI_SWIGLU else N
     if out is None:
-        out = torch.empty((M, n_out), device=x.device, dtype=torch.float32 if out_fp32 else _BF16)
+        out = torch.empty((M, n_out), device=x.device,
+                          dtype=out_dtype if out_dtype is not None else (torch.float32 if out_fp32 else _BF16))
     assert out.shape[0] == M and out.shape[1] == n_out and out.stride(1) == 1
     kw = {}
     if residual is not None:
@@ -102,8 +109,8 @@ def linear(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None
         if len(rope) > 4 and rope[4] is not None:  # device-side position offset (int32 tensor)
             kw.update(rope_pos=rope[4].data_ptr())
     gemm_raw(M=M, N=N, K=K, A=x.data_ptr(), lda=x.stride(0), B=w.data_ptr(), ldb=w.stride(0), Cout=out.data_ptr(),
-             ldc=out.stride(0), c_fp32=out.dtype == torch.float32, epi=epi, act=act, alpha=alpha, bias=_ptr(bias),
-             row_scale=_ptr(row_scale), **kw)
+             ldc=out.stride(0), c_fp32=out.dtype == torch.float32, c_fp16=out.dtype == _F16, a_fp16=x.dtype == _F16,
+             b_fp16=w.dtype == _F16, epi=epi, act=act, alpha=alpha, bias=_ptr(bias), row_scale=_ptr(row_scale), **kw)
     return out
 
 
@@ -132,10 +139,11 @@ def linear_thin(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] =
 
 
 def splitk_reduce(partial: torch.Tensor, bias: Optional[torch.Tensor], out: torch.Tensor) -> torch.Tensor:
-    _cuda(partial, torch.float32, "partial"); _cuda(out, _BF16, "out")
+    _cuda(partial, torch.float32, "partial"); _cuda(out, None, "out")
+    assert out.dtype in _16BIT
     S, M, N = partial.shape
     _check(_lib.load().mm_splitk_reduce(partial.data_ptr(), S, M, N, _ptr(bias), out.data_ptr(), out.stride(0),
-                                        _stream()), "mm_splitk_reduce")
+                                        int(out.dtype == _F16), _stream()), "mm_splitk_reduce")
     return out
 
 
@@ -254,6 +262,17 @@ def transpose_pad(x: torch.Tensor, pad: int) -> torch.Tensor:
     return out
 
 
+def cast_f16(x: torch.Tensor) -> torch.Tensor:
+    """bf16 (..., cols) contiguous -> fp16 copy (mm_cast_bf16_f16)."""
+    _cuda(x, _BF16, "x")
+    assert x.is_contiguous()
+    cols = x.shape[-1]
+    rows = x.numel() // cols
+    y = torch.empty(x.shape, device=x.device, dtype=_F16)
+    _check(_lib.load().mm_cast_bf16_f16(x.data_ptr(), cols, y.data_ptr(), cols, rows, cols, _stream()), "mm_cast_bf16_f16")
+    return y
+
+
 def add_rows(x: torch.Tensor, add: Optional[torch.Tensor], out: torch.Tensor) -> torch.Tensor:
     """out[r] = x[r] + add[r % add.shape[0]] over 2-D bf16 views with unit inner stride."""
     _cuda(x, _BF16, "x"); _cuda(out, _BF16, "out")
@@ -271,6 +290,41 @@ def add_rows(x: torch.Tensor, add: Optional[torch.Tensor], out: torch.Tensor) ->
 
 
 # ---------------------------------------------------------------------------------------------------- alignment
+ALIGN_MODE = 0  # 0: one cooperative launch with grid-wide barriers between the phases; 1: three stream-ordered launches
+
+
+def align_fused(table: torch.Tensor, qt: torch.Tensor, stats: torch.Tensor, out: Optional[torch.Tensor] = None,
+                mode: Optional[int] = None):
+    """Fused absorbed-form alignment attention (mm_align_fwd).  table (V, E) fp16; qt (R, E) fp16 absorbed queries;
+    stats (R, 2) fp32 = [row_bias, extra score] -> (ctx~ (R, E) fp16, p_sum_real (R,), p_extra (R,))."""
+    _cuda(table, _F16, "table"); _cuda(qt, _F16, "qt"); _cuda(stats, torch.float32, "stats")
+    R, E = qt.shape
+    V = table.shape[0]
+    assert table.shape[1] == E and table.stride(1) == 1 and qt.stride(1) == 1 and stats.shape == (R, 2) and stats.is_contiguous()
+    dev = qt.device
+    if out is None:
+        out = torch.empty((R, E), device=dev, dtype=_F16)
+    assert out.shape == (R, E) and out.stride(1) == 1 and out.dtype == _F16
+    Vp = (V + 7) // 8 * 8
+    P = torch.empty((R, Vp), device=dev, dtype=_F16)
+    lib = _lib.load()
+    ws = torch.empty((int(lib.mm_align_workspace_bytes(R, V)) + 15) // 16 * 4, device=dev, dtype=torch.int32)
+    psum = torch.empty((R,), device=dev, dtype=torch.float32)
+    pext = torch.empty((R,), device=dev, dtype=torch.float32)
+    a = AlignArgs(table.data_ptr(), V, E, table.stride(0), qt.data_ptr(), R, qt.stride(0), stats.data_ptr(),
+                  stats.data_ptr() + 4, 2, out.data_ptr(), out.stride(0), psum.data_ptr(), pext.data_ptr(), P.data_ptr(), Vp,
+                  ws.data_ptr(), ALIGN_MODE if mode is None else int(mode))
+    if PROFILE is None:
+        _check(lib.mm_align_fwd(C.byref(a), _stream()), "mm_align_fwd")
+    else:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        _check(lib.mm_align_fwd(C.byref(a), _stream()), "mm_align_fwd")
+        e1.record()
+        PROFILE.append(("align.fused", 4.0 * R * V * E, e0, e1))
+    return out, psum, pext
+
+
 def align_softmax(scores: torch.Tensor, stats: torch.Tensor, P: torch.Tensor, V: int):
     """scores fp32 (R, >=V); stats fp32 (R, 2) = [row_bias, extra_score]; P bf16 (R, ldp) -> (p_sum_real, p_extra)."""
     _cuda(scores, torch.float32, "scores"); _cuda(stats, torch.float32, "stats"); _cuda(P, _BF16, "P")

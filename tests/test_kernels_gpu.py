@@ -419,3 +419,89 @@ def test_rope_rows_and_swiglu_rows():
     gu = torch.stack([g.view(B, I // 32, 32), u.view(B, I // 32, 32)], dim=2).reshape(B, 2 * I).contiguous()
     out = ops.swiglu_rows(gu, I)
     assert rel_err(out, torch.nn.functional.silu(g.float()) * u.float()) < 3e-3
+
+
+# ------------------------------------------------------------------------------------------------ fp16 activation chain
+def test_gemm_fp16_operands():
+    """tcgen05 kind::f16 with fp16 A and B operands and fp16 output: the alignment chain's format.  One fp16 rounding is
+    ~1.4e-4 norm-wise (bf16: ~1.1e-3).  Mixed f16 x bf16 is rejected up front: sm_100a raises an illegal-instruction
+    fault for it even though the instruction descriptor has independent format fields (measured in round 2)."""
+    ops = _ops()
+    M, N, K = 200, 768, 1096
+    g = torch.Generator().manual_seed(5)
+    x = (torch.randn(M, K, generator=g)).to(DEV).to(torch.float16)
+    w = rnd(N, K, scale=K ** -0.5, seed=6).to(torch.float16)
+    b = rnd(N, seed=7)
+    y = ops.linear(x, w, b, out_dtype=torch.float16)
+    ref = x.float() @ w.float().t() + b.float()
+    assert y.dtype == torch.float16 and rel_err(y, ref) < 4e-4
+    y32 = ops.linear(x, w, b, out_fp32=True)
+    assert rel_err(y32, ref) < 2e-5
+    with pytest.raises(RuntimeError, match="share one 16-bit format"):
+        ops.linear(x, w.to(torch.bfloat16), b)
+    src = rnd(33, 64, seed=8)
+    c = ops.cast_f16(src)
+    assert c.dtype == torch.float16 and torch.equal(c, src.to(torch.float16))
+    big = src.float().abs() >= 2.0 ** -14  # fp16's normal range: the conversion is exact there
+    assert torch.equal(c.float()[big], src.float()[big])
+
+
+def test_gemm_row_scaled_bias_terms():
+    """out = A B^T + rs1[m] * bias[n] + rs2[m] * bias2[n] per batch (value-side bias terms of the absorbed alignment)."""
+    ops = _ops()
+    Hh, nq, hd, E = 4, 37, 64, 256
+    g = torch.Generator().manual_seed(8)
+    a = torch.randn(Hh, nq, E, generator=g).to(DEV).to(torch.float16)
+    w = rnd(Hh * hd, E, scale=E ** -0.5, seed=9).to(torch.float16)
+    b1, b2 = rnd(Hh * hd, seed=10), rnd(Hh * hd, seed=11)
+    r1 = torch.rand(Hh * nq, generator=g).to(DEV)
+    r2 = torch.rand(Hh * nq, generator=g).to(DEV)
+    out = torch.empty(nq, Hh * hd, device=DEV, dtype=torch.float16)
+    ops.gemm_raw(M=nq, N=hd, K=E, batch=Hh, A=a.data_ptr(), lda=E, a_bs=nq * E, B=w.data_ptr(), ldb=E, b_bs=hd * E,
+                 Cout=out.data_ptr(), ldc=Hh * hd, c_bs=hd, a_fp16=True, b_fp16=True, c_fp16=True, bias=b1.data_ptr(),
+                 bias_bs=hd,
+                 bias_rs=r1.data_ptr(), bias2=b2.data_ptr(), bias2_rs=r2.data_ptr())
+    ref = torch.empty(nq, Hh * hd, device=DEV)
+    for h in range(Hh):
+        sl = slice(h * hd, (h + 1) * hd)
+        ref[:, sl] = (a[h].float() @ w[sl].float().t() + r1[h * nq:(h + 1) * nq, None] * b1[sl].float()
+                      + r2[h * nq:(h + 1) * nq, None] * b2[sl].float())
+    assert rel_err(out, ref) < 4e-4
+
+
+def _align_ref(qt, table, stats):
+    V = table.shape[0]
+    s = qt.double() @ table.double().t() + stats[:, :1].double()
+    full = torch.cat([s, stats[:, 1:2].double(), torch.zeros_like(stats[:, :1]).double()], dim=1)
+    p = torch.softmax(full, dim=-1)
+    return (p[:, :V] @ table.double()).float(), p[:, :V].sum(-1).float(), p[:, V].float()
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+@pytest.mark.parametrize(
+    "R,V,E,qs,kind",
+    [
+        (37, 32000, 4096, 1.0, "real width, ragged rows"),
+        (300, 519, 256, 1.0, "odd vocab (resized table), several row blocks"),
+        (384, 1000, 512, 1.0, "vocab not a multiple of the 256-key tile"),
+        (130, 2048, 256, 40.0, "scores far above the synthetic keys: overflow flag -> exact-max second attempt"),
+        (64, 2048, 256, -1.0, "real keys far BELOW the zero key (all mass on the synthetic keys)"),
+    ],
+)
+def test_align_fused(R, V, E, qs, kind, mode):
+    """mm_align_fwd (one persistent kernel: scores + fp16 probabilities, then P . table) vs an fp64 softmax over the
+    V + 2 keys.  fp16 P' and fp16 output: ~2e-4 norm-wise each."""
+    ops = _ops()
+    g = torch.Generator().manual_seed(R + V)
+    table = (torch.randn(V, E, generator=g) * 0.5).to(DEV).to(torch.bfloat16).to(torch.float16)
+    qt = (torch.randn(R, E, generator=g) * (abs(qs) * 2.0 / math.sqrt(E))).to(DEV).to(torch.float16)
+    stats = torch.randn(R, 2, generator=g).to(DEV)
+    if qs < 0:  # push every real score ~60 nats below zero
+        stats[:, 0] = -60.0
+    out, psum, pext = ops.align_fused(table, qt, stats.contiguous(), mode=mode)
+    torch.cuda.synchronize()
+    ref, rsum, rext = _align_ref(qt, table, stats)
+    e = (rel_err(out, ref) if qs > 0 else float((out.float() - ref).abs().max()), rel_err(psum, rsum) if qs > 0 else float((psum - rsum).abs().max()),
+         rel_err(pext, rext))
+    print(f"\n[align_fused mode {mode}] {kind}: ctx~ {e[0]:.2e}  p_sum_real {e[1]:.2e}  p_extra {e[2]:.2e}")
+    assert e[0] < 6e-4 and e[1] < 2e-4 and e[2] < 2e-4

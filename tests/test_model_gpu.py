@@ -69,10 +69,18 @@ def test_forward_vs_golden_and_oracle(tiny, name):
     valid = torch.from_numpy(case["attention_mask"]).bool()
     e_log = H.rel_err(out.logits.cpu()[valid], o["logits"][valid])
     e_gold = H.rel_err(out.logits.cpu()[valid], torch.from_numpy(case["logits"])[valid])
-    print(f"\n[parity:{name}] prefix {e_pre:.3e}  embeds {e_emb:.3e}  logits {e_log:.3e}  logits-vs-golden {e_gold:.3e}")
-    assert e_pre < 1e-2 and e_emb < 1e-2
-    assert e_log < 3e-2
-    assert e_gold < 5e-2
+    # the reference algorithm's OWN bf16 arithmetic on the same inputs (oracle run in bf16 on the CPU) as the yardstick
+    ob = O.forward({k: (v.float() if isinstance(v, torch.Tensor) and v.is_floating_point() else v) for k, v in inp.items()},
+                   sd, hp, dtype=torch.bfloat16)
+    r_log = H.rel_err(ob["logits"][valid], o["logits"][valid])
+    r_pre = H.rel_err(ob["embeds"][:, 1:1 + n_prefix], o["embeds"][:, 1:1 + n_prefix]) if n_prefix else 0.0
+    print(f"\n[parity:{name}] prefix {e_pre:.3e}  embeds {e_emb:.3e}  logits {e_log:.3e}  logits-vs-golden {e_gold:.3e}"
+          f"  | reference algorithm in bf16: prefix {r_pre:.3e} logits {r_log:.3e}")
+    # prefix: the block output is rounded to bf16 once (1.1e-3 norm-wise); encoder features (bf16-stored CLIP / Whisper
+    # layers) feed it, so the bar is 2.5e-3 here and 1.5e-3 for the alignment block alone (test_real_width_alignment_block)
+    assert e_pre < 2.5e-3 and e_emb < 2.5e-3
+    assert e_log < 1e-2 and e_log < 2.0 * max(r_log, 2e-3)
+    assert e_gold < 2e-2
     if int(case["with_labels"]):
         assert abs(float(out.loss) - float(o["loss"])) < 2e-2 * abs(float(o["loss"]))
 
@@ -146,8 +154,12 @@ def test_real_width_alignment_block():
     ref = O.align_block(feats.float().cpu(), table.float().cpu(), sd.sub("project_image."),
                         sd.sub("transform_image_to_hidden."), sd.sub("image_align_attention."), 36, H)
     e = H_rel(prefix[:, 1:2], ref)
-    print(f"\n[parity:align 32000x4096] {e:.3e}")
-    assert e < 1e-2
+    # yardstick measured here: the EXACT fp32 result rounded once to bf16 (the block's output lands in the bf16
+    # inputs_embeds, so no implementation can do better than this)
+    e_round = H_rel(ref.to(torch.bfloat16), ref)
+    print(f"\n[parity:align 32000x4096] {e:.3e}   (one bf16 rounding of the exact result: {e_round:.3e})")
+    # fp16 activation chain inside the block: one bf16 rounding of the output + ~8 fp16-stored stages (1.9e-4 each)
+    assert e < 2e-3 and e < 1.35 * e_round
     assert float(prefix[:, 0].abs().max()) == 0 and float(prefix[:, 2].abs().max()) == 0
 
 
