@@ -235,6 +235,128 @@ def cpu_reference_sample(cfgs, hyper, L, steps, warmup, seed=1234, state_dict=No
                        f"reference cost is linear in B; {cores} threads (physical cores of one socket, capped by the cgroup)")
 
 
+# ---------------------------------------------------------------------------------------------------- secondary modes
+def run_train(args, cfgs, hyper, rank, local_rank, world):
+    """Secondary line: one TRAINING step = zero_grad + forward + backward + gradient all-reduce +
+    fused AdamW on the cfg4 shape at the reference's micro-batch (train.sh: 4 samples per GPU, fp32 master weights).
+    Weak scaling: per-GPU work is fixed, the data-parallel group grows."""
+    import torch.distributed as dist
+
+    from macaw_llm_b200 import ops
+    from macaw_llm_b200.modeling import MM_LLMs, MM_LLMs_Config
+    from macaw_llm_b200.training import FusedAdamW, freeze_like_reference, trainable_parameters
+
+    clip, whisper, llama = cfgs
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    L, V, Bl = args.seq_len, llama.vocab_size, args.micro_batch
+    cfg = MM_LLMs_Config(clip_config=clip, whisper_config=whisper, llm_config=llama, **hyper)
+    model = MM_LLMs.build_random(cfg, device=dev, dtype=torch.bfloat16, seed=0)
+    freeze_like_reference(model)
+    host = synth_inputs(Bl, L, V, clip.vision_config.image_size, 2 * whisper.max_source_positions, 1234 + rank)
+    host["labels"] = host["input_ids"].clone()
+    inp = {k: (v.to(dev) if isinstance(v, torch.Tensor) else v) for k, v in host.items()}
+    params = [p for _, p in trainable_parameters(model)]
+    opt = FusedAdamW(params, lr=2e-5, weight_decay=0.0)
+    model.train()
+    model.train_step.set_world(world, overlap=True)
+
+    def step():
+        opt.zero_grad()
+        out = model(inp)
+        out.loss.backward()
+        model.train_step.llama.finish_allreduce()
+        opt.step()
+        return out.loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    losses = []
+    for _ in range(max(args.warmup, 3)):
+        losses.append(float(step()))
+    barrier()
+    ops.launch_count_reset()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        loss = step()
+    e1.record()
+    barrier()
+    launches = ops.launch_count()
+    t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item()) / args.steps
+    losses.append(float(loss))
+    if rank == 0:
+        T = L + 16
+        n_train = sum(p.numel() for p in params)
+        # 6 FLOP per trainable parameter per token (fwd 2 + bwd 4) + the frozen encoders' / alignment forward
+        tf = (6.0 * n_train * Bl * T + Bl * (162.4e9 + 87.4e9)) / 1e12
+        print(json.dumps({
+            "mode": "train", "metric": "multimodal training tokens/sec (img+audio+text->LLaMA, fwd+bwd+all-reduce+AdamW)",
+            "value": world * Bl * T / (ms / 1e3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "dtype": "bf16",
+            "data": "synthetic",
+            "config": {"workload": f"cfg4 shape, micro-batch {Bl}/GPU (train.sh), L={L} -> T={T}, LLaMA-7B + CLIP-L + Whisper-base",
+                       "trainable_params": n_train, "optimizer": "fused AdamW, fp32 master + moments",
+                       "grad_sync": "flat bf16 buffer, one NCCL all-reduce per decoder layer overlapped with backward" if world > 1 else "none (1 rank)",
+                       "differentiable_set": "llm.* + the alignment modules of every modality (incl. the table as the alignment attention's keys/values); encoders frozen; video_long_self_attention and MHA dropout not differentiated"},
+            "approx_tflops": tf / (ms / 1e3), "gpu_launches": launches, "loss_first_last": [losses[0], losses[-1]],
+            "mem_gb": torch.cuda.max_memory_allocated() / 2 ** 30}), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_decode(args, cfgs, hyper, rank, local_rank, world):
+    """Secondary line: greedy decoding behind inputs['inference'] = True: image+text, B=8 per GPU,
+    prefill + 64 new tokens; reports ms per decode step against the 13.5 GB weight-streaming floor."""
+    from macaw_llm_b200.modeling import MM_LLMs, MM_LLMs_Config
+
+    clip, whisper, llama = cfgs
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    V, B, L, n_new = llama.vocab_size, 8, 256, 64
+    cfg = MM_LLMs_Config(clip_config=clip, whisper_config=whisper, llm_config=llama, **hyper)
+    model = MM_LLMs.build_random(cfg, device=dev, dtype=torch.bfloat16, seed=0)
+    host = synth_inputs(B, L, V, clip.vision_config.image_size, 2 * whisper.max_source_positions, 1234 + rank)
+    inp = {k: (v.to(dev) if isinstance(v, torch.Tensor) else v) for k, v in host.items()}
+    inp["audios"] = None
+    inp["inference"] = True
+
+    def run(n):
+        d = dict(inp, max_new_tokens=n)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        toks = model.engine.generate(d, max_new_tokens=n, eos_token_id=-1)  # eos -1: never stop early (timing)
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1), toks
+
+    for _ in range(max(1, min(args.warmup, 2))):
+        run(n_new)
+    t1 = min(run(1)[0] for _ in range(2))           # prefill + first token
+    tn = min(run(n_new)[0] for _ in range(max(1, min(args.steps, 3))))
+    ms_step = (tn - t1) / (n_new - 1)
+    hbm, _, _, src = load_peaks()
+    wbytes = sum(p.numel() * p.element_size() for n_, p in model.named_parameters() if n_.startswith("llm.model.layers") or n_ == "llm.lm_head.weight")
+    floor_ms = wbytes / (hbm * 1e9) * 1e3
+    if rank == 0:
+        print(json.dumps({
+            "mode": "decode", "metric": "greedy decode tokens/sec (image+text prefix, KV cache)", "value": B / (ms_step / 1e3),
+            "unit": UNIT, "n_gpus": 1, "higher_is_better": True, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": f"image+text, B={B}, L={L} -> T={L + 8}, {n_new} new tokens, LLaMA-7B", "submission": "cuda_graph_replay"},
+            "prefill_ms": t1, "ms_per_decode_step": ms_step,
+            "roofline": {"bound": "hbm", "achieved": wbytes / (ms_step / 1e3) / 1e9, "peak": hbm, "unit": "GB/s",
+                         "frac": floor_ms / ms_step, "peak_source": src, "algorithmic_bytes_per_step": wbytes}}), flush=True)
+
+
 # ---------------------------------------------------------------------------------------------------- main
 def main():
     ap = argparse.ArgumentParser()
@@ -248,6 +370,9 @@ def main():
     ap.add_argument("--small", action="store_true", help="tiny stand-in model (tests only; the result is not a bench value)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graphs", action="store_true", help="launch every kernel from the host instead of replaying a CUDA graph")
+    ap.add_argument("--mode", default="prefill", choices=["prefill", "train", "decode"],
+                    help="prefill = the benchmark of record; train / decode = secondary lines (SURVEY.md §8f ranks 1, 2)")
+    ap.add_argument("--micro-batch", type=int, default=4, help="--mode train: samples per GPU per step (train.sh: 4)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -284,6 +409,10 @@ def main():
     # ------------------------------------------------------------------ B200 arm
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device — the B200 path has no CPU fallback (use --impl reference for the CPU arm)")
+    if args.mode == "train":
+        return run_train(args, cfgs, hyper, rank, local_rank, world)
+    if args.mode == "decode":
+        return run_decode(args, cfgs, hyper, rank, local_rank, world)
     import torch.distributed as dist
 
     from macaw_llm_b200 import ops

@@ -205,6 +205,7 @@ typedef struct mm_align_args {
   int64_t ldp;
   void* workspace;
   int32_t mode;
+  float* inv_l; /* optional fp32 [R]: 1 / softmax denominator, so that P = P' * inv_l (kept for the backward pass) */
 } mm_align_args;
 int32_t mm_align_fwd(const mm_align_args* args, void* stream);
 int64_t mm_align_workspace_bytes(int32_t R, int32_t V);
@@ -273,6 +274,48 @@ int32_t mm_colsum(const void* x, int64_t ldx, int32_t rows, int32_t cols, float*
 /* Fused AdamW step on one parameter tensor: bf16 working copy p, bf16 gradient g (times grad_scale), fp32 master / m / v. */
 int32_t mm_adamw(void* p, const void* g, float* master, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
                  float eps, float weight_decay, int32_t step, float grad_scale, void* stream);
+
+/* Backward of the absorbed alignment attention through its (V + 2)-key softmax (reference: autograd of
+ * nn.MultiheadAttention, modeling.py:986-987 / 1007-1008 / 1025-1026).  See train_kernels.cu for the formulas. */
+int32_t mm_align_softmax_bwd(const float* G, int64_t ldg, const void* P_unnorm_f16, int64_t ldp, const float* inv_l,
+                             const float* d_p_sum_real, const float* p_extra, const float* d_p_extra, float gscale,
+                             void* P_bf16, void* dS_bf16, int64_t ldo, float* dstats, int32_t R, int32_t V, void* stream);
+/* out[h*hd + d] += sum_n w[(h*Nq + n) * w_stride] * x[n, h*hd + d]; x bf16 (x_fp16 == 0) or fp16. */
+int32_t mm_head_weighted_colsum(const void* x, int64_t ldx, int32_t x_fp16, const float* w, int64_t w_stride, int32_t Nq,
+                                int32_t E, int32_t head_dim, float* out, void* stream);
+int32_t mm_cast_f16_bf16(const void* x, int64_t ldx, void* y, int64_t ldy, int32_t rows, int32_t cols, void* stream);
+
+/* ------------------------------------------------------------------------------------------------ input pipeline
+ * Device-side replacement of the per-sample host work in LLMTrainer.get_self_inputs (llm_trainer.py:306-381).
+ *
+ * mm_image_preprocess: `_transform(224)` of llm_trainer.py:151-158 on ONE decoded 8-bit RGB image (HWC, row stride ld bytes):
+ * Pillow's two-pass antialiased bicubic resize with its 22-bit fixed-point coefficients (tables built by the host with
+ * Pillow's arithmetic, restricted to the centre-crop window), then ToTensor + Normalize.  row0 / n_rows: source rows the
+ * vertical taps of the cropped output need (tmp holds n_rows x out_w x 3 bytes).  out: (3, out_h, out_w) bf16 or fp32;
+ * out_u8 (optional, HWC) receives the 8-bit resized + cropped image (bit-exact with PIL). */
+typedef struct mm_image_args {
+  const void* src;
+  int64_t ld;
+  int32_t row0, n_rows;
+  int32_t out_h, out_w;
+  const int32_t* bounds_h; /* [out_w][2] = (xmin, count) */
+  const int32_t* kk_h;     /* [out_w][ksize_h] */
+  int32_t ksize_h;
+  const int32_t* bounds_v; /* [out_h][2] */
+  const int32_t* kk_v;     /* [out_h][ksize_v] */
+  int32_t ksize_v;
+  float mean[3], std[3];
+  void* tmp;
+  void* out;
+  int32_t out_fp32;
+  void* out_u8;
+} mm_image_args;
+int32_t mm_image_preprocess(const mm_image_args* args, void* stream);
+/* whisper.pad_or_trim + whisper.log_mel_spectrogram (llm_trainer.py:338-345) of ONE clip: pcm fp32 [n_samples] at 16 kHz ->
+ * (80, 3000) bf16 / fp32.  basisT: fp32 [400][2][208] windowed DFT basis (Hann folded in; cos, -sin; bin index
+ * contiguous); mel: fp32 [80][201] filter bank; logspec: scratch fp32 [80][3000]; max_scratch: 4 bytes. */
+int32_t mm_log_mel(const float* pcm, int32_t n_samples, const float* basisT, const float* mel, float* logspec,
+                   void* max_scratch, void* out, int32_t out_fp32, void* stream);
 
 #ifdef __cplusplus
 }

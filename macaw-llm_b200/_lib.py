@@ -54,7 +54,17 @@ class AlignArgs(C.Structure):
         ("qt", c_vp), ("R", c_i32), ("ldq", c_i64),
         ("row_bias", c_vp), ("extra", c_vp), ("stat_stride", c_i64),
         ("out", c_vp), ("ldo", c_i64), ("p_sum_real", c_vp), ("p_extra", c_vp),
-        ("P", c_vp), ("ldp", c_i64), ("workspace", c_vp), ("mode", c_i32),
+        ("P", c_vp), ("ldp", c_i64), ("workspace", c_vp), ("mode", c_i32), ("inv_l", c_vp),
+    ]
+
+
+class ImageArgs(C.Structure):
+    """Mirror of `mm_image_args` (include/macaw_b200.h)."""
+
+    _fields_ = [
+        ("src", c_vp), ("ld", c_i64), ("row0", c_i32), ("n_rows", c_i32), ("out_h", c_i32), ("out_w", c_i32),
+        ("bounds_h", c_vp), ("kk_h", c_vp), ("ksize_h", c_i32), ("bounds_v", c_vp), ("kk_v", c_vp), ("ksize_v", c_i32),
+        ("mean", c_f32 * 3), ("std", c_f32 * 3), ("tmp", c_vp), ("out", c_vp), ("out_fp32", c_i32), ("out_u8", c_vp),
     ]
 
 
@@ -95,6 +105,12 @@ SIGNATURES = {
     "mm_embed_scatter_add": (c_i32, [c_vp, c_i64, c_vp, c_i64, c_i32, c_i32, c_vp, c_vp]),
     "mm_colsum": (c_i32, [c_vp, c_i64, c_i32, c_i32, c_vp, c_vp]),
     "mm_adamw": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_f32, c_f32, c_f32, c_f32, c_f32, c_i32, c_f32, c_vp]),
+    "mm_image_preprocess": (c_i32, [C.POINTER(ImageArgs), c_vp]),
+    "mm_log_mel": (c_i32, [c_vp, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp, c_i32, c_vp]),
+    "mm_align_softmax_bwd": (c_i32, [c_vp, c_i64, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_f32, c_vp, c_vp, c_i64, c_vp, c_i32,
+                                     c_i32, c_vp]),
+    "mm_head_weighted_colsum": (c_i32, [c_vp, c_i64, c_i32, c_vp, c_i64, c_i32, c_i32, c_i32, c_vp, c_vp]),
+    "mm_cast_f16_bf16": (c_i32, [c_vp, c_i64, c_vp, c_i64, c_i32, c_i32, c_vp]),
     "mm_ce_loss": (c_i32, [c_vp, c_vp, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp]),
 }
 

@@ -43,6 +43,7 @@ struct AlignKParams {
   int* flag;           // overflow flag
   float* p_sum_real;
   float* p_extra;
+  float* inv_l_out;
   __half* out;
   long long ldo;
   int step_lo, step_hi;  // steps to run: 0 = phase 1, 1 = phase 1 again if flagged, 2 = phase 2
@@ -276,6 +277,7 @@ align_fused_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
             if (n_blk == 0 && half == 0 && row_ok) {
               p.p_sum_real[rs] = p_real * inv;
               p.p_extra[rs] = e_extra * inv;
+              if (p.inv_l_out != nullptr) p.inv_l_out[rs] = inv;
             }
             mbar_wait(&tfull_bar[acc], acc_phase);
             tc_fence_after();
@@ -370,7 +372,7 @@ extern "C" int32_t mm_align_fwd(const mm_align_args* a, void* stream) {
   p.flag = reinterpret_cast<int*>(ws + 4);
   p.rowmax_u = reinterpret_cast<unsigned*>(ws + 16);
   p.part = reinterpret_cast<float*>(ws + 16 + 4LL * a->R);
-  p.p_sum_real = a->p_sum_real; p.p_extra = a->p_extra;
+  p.p_sum_real = a->p_sum_real; p.p_extra = a->p_extra; p.inv_l_out = a->inv_l;
   p.out = reinterpret_cast<__half*>(a->out); p.ldo = a->ldo;
 
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);

@@ -6,6 +6,7 @@
 // LlamaAttention :143-231, shifted CE :597-610) driven by llm_trainer.py:184-188 (compute_loss -> loss.backward()) and the
 // optimizer of train.sh / configs/deepspeed_config.json (AdamW, fp32 master weights).
 #include "common.cuh"
+#include <cuda_fp16.h>
 #include "ptx.cuh"
 #include "../../include/macaw_b200.h"
 
@@ -279,6 +280,74 @@ __global__ void adamw_kernel(bf16* __restrict__ p, const bf16* __restrict__ g, f
   }
 }
 
+// ------------------------------------------------------------------------------------------------ alignment softmax backward
+// One CTA per query row r of the absorbed alignment attention.  Inputs: G[r, v] = dctx~[r] . table[v] (fp32), the
+// un-normalised fp16 probabilities P' of the forward pass and 1 / l, the gradients of the two per-row probability sums
+// (d p_sum_real, d p_extra) and p_extra itself.  With P = P' / l over the V real keys (+ the bias_k key with weight
+// p_extra; the zero key's dP is 0):
+//   dP_v = G_v + d p_sum_real,   D = sum_v P_v dP_v + p_extra * d p_extra,   dS_v = P_v (dP_v - D)
+// Outputs: P and dS as bf16 (operands of the table-gradient GEMMs dT += P^T dctx~ + dS^T q~ and of dq~ = dS . table),
+// dstats[0][r] = gscale * sum_v dS_v, dstats[1][r] = gscale * p_extra * (d p_extra - D) — the gradients of row_bias and of
+// the bias_k key's score (planar [2][R]).
+__global__ void __launch_bounds__(512) align_softmax_bwd_kernel(const float* __restrict__ G, long long ldg,
+                                                                const __half* __restrict__ Pp, long long ldp,
+                                                                const float* __restrict__ inv_l,
+                                                                const float* __restrict__ dpsr, const float* __restrict__ pe,
+                                                                const float* __restrict__ dpe, float gscale,
+                                                                bf16* __restrict__ P, bf16* __restrict__ dS, long long ldo,
+                                                                float* __restrict__ dstats, int V) {
+  __shared__ float sh[32];
+  const long long r = blockIdx.x;
+  const float* g = G + r * ldg;
+  const __half* pp = Pp + r * ldp;
+  bf16* po = P + r * ldo;
+  bf16* dso = dS + r * ldo;
+  const float il = inv_l[r], a = dpsr[r], pex = pe[r], dpex = dpe[r];
+  float acc = 0.f;
+  for (int v = threadIdx.x; v < V; v += blockDim.x) acc += __half2float(pp[v]) * il * (g[v] + a);
+  const float D = block_sum(acc, sh) + pex * dpex;
+  float srow = 0.f;
+  for (int v = threadIdx.x; v < V; v += blockDim.x) {
+    const float pv = __half2float(pp[v]) * il;
+    const float d = pv * (g[v] + a - D);
+    po[v] = __float2bfloat16(pv);
+    dso[v] = __float2bfloat16(d);
+    srow += d;
+  }
+  srow = block_sum(srow, sh);
+  if (threadIdx.x == 0) {  // planar [2][R]: each half is the per-row scale array of a row-scaled GEMM bias term
+    dstats[r] = gscale * srow;
+    dstats[gridDim.x + r] = gscale * pex * (dpex - D);
+  }
+}
+
+// out[h*hd + d] += sum_n w[h*Nq + n] * x[n, h*hd + d]   (x bf16 or fp16; bias gradients of the per-head bias terms)
+__global__ void head_weighted_colsum_kernel(const void* __restrict__ x, long long ldx, int x_fp16,
+                                            const float* __restrict__ w, long long w_stride, int Nq, int E, int hd,
+                                            float* __restrict__ out) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= E) return;
+  const int h = c / hd;
+  float acc = 0.f;
+  for (int n = 0; n < Nq; ++n) {
+    const float xv = x_fp16 ? __half2float(reinterpret_cast<const __half*>(x)[static_cast<long long>(n) * ldx + c])
+                            : __bfloat162float(reinterpret_cast<const bf16*>(x)[static_cast<long long>(n) * ldx + c]);
+    acc += w[(static_cast<long long>(h) * Nq + n) * w_stride] * xv;
+  }
+  atomicAdd(&out[c], acc);
+}
+
+__global__ void cast_f16_bf16_kernel(const __half* __restrict__ x, long long ldx, bf16* __restrict__ y, long long ldy,
+                                     int rows, int cols) {
+  const long long total = static_cast<long long>(rows) * cols;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long r = i / cols;
+    const int c = static_cast<int>(i % cols);
+    y[r * ldy + c] = __float2bfloat16(__half2float(x[r * ldx + c]));
+  }
+}
+
 static inline int grid_for(long long total, int block, int cap_mult = 16) {
   long long g = (total + block - 1) / block;
   const long long cap = static_cast<long long>(num_sms()) * cap_mult;
@@ -362,4 +431,30 @@ extern "C" int32_t mm_adamw(void* p, const void* g, float* master, float* m, flo
   adamw_kernel<<<grid_for(n, 256), 256, 0, ST(stream)>>>((bf16*)p, (const bf16*)g, master, m, v, n, lr, beta1, beta2, eps,
                                                         weight_decay, inv_bc1, inv_bc2, grad_scale);
   return check_launch("mm_adamw");
+}
+
+extern "C" int32_t mm_align_softmax_bwd(const float* G, int64_t ldg, const void* Pp, int64_t ldp, const float* inv_l,
+                                        const float* dpsr, const float* pe, const float* dpe, float gscale, void* P,
+                                        void* dS, int64_t ldo, float* dstats, int32_t R, int32_t V, void* stream) {
+  MM_REQUIRE(G && Pp && inv_l && dpsr && pe && dpe && P && dS && dstats && R > 0 && V > 0 && ldg >= V && ldp >= V && ldo >= V,
+             "mm_align_softmax_bwd: bad arguments");
+  align_softmax_bwd_kernel<<<R, 512, 0, ST(stream)>>>(G, ldg, (const __half*)Pp, ldp, inv_l, dpsr, pe, dpe, gscale, (bf16*)P,
+                                                      (bf16*)dS, ldo, dstats, V);
+  return check_launch("mm_align_softmax_bwd");
+}
+
+extern "C" int32_t mm_head_weighted_colsum(const void* x, int64_t ldx, int32_t x_fp16, const float* w, int64_t w_stride,
+                                           int32_t Nq, int32_t E, int32_t head_dim, float* out, void* stream) {
+  MM_REQUIRE(x && w && out && Nq > 0 && E > 0 && head_dim > 0 && E % head_dim == 0 && w_stride > 0,
+             "mm_head_weighted_colsum: bad arguments");
+  head_weighted_colsum_kernel<<<(E + 255) / 256, 256, 0, ST(stream)>>>(x, ldx, x_fp16, w, w_stride, Nq, E, head_dim, out);
+  return check_launch("mm_head_weighted_colsum");
+}
+
+extern "C" int32_t mm_cast_f16_bf16(const void* x, int64_t ldx, void* y, int64_t ldy, int32_t rows, int32_t cols,
+                                    void* stream) {
+  MM_REQUIRE(x && y && rows > 0 && cols > 0, "mm_cast_f16_bf16: bad arguments");
+  cast_f16_bf16_kernel<<<grid_for(static_cast<long long>(rows) * cols, 256), 256, 0, ST(stream)>>>(
+      (const __half*)x, ldx, (bf16*)y, ldy, rows, cols);
+  return check_launch("mm_cast_f16_bf16");
 }

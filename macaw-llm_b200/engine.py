@@ -265,7 +265,7 @@ class Engine:
 
     # ------------------------------------------------------------------------------------------------ alignment
     def align(self, feats: torch.Tensor, name: str, table: torch.Tensor, prefix: torch.Tensor, row_off: int,
-              table16: Optional[torch.Tensor] = None) -> int:
+              table16: Optional[torch.Tensor] = None, save: Optional[dict] = None) -> int:
         """One modality of reference modeling.py:982-987 / 999-1008 / 1022-1026 in ABSORBED form:
         the keys/values are never projected — q is pushed through W_k per head and both big contractions
         (scores = q~ . table^T over E, ctx~ = P . table over V) run inside ONE fused kernel (mm_align_fwd) that streams
@@ -285,7 +285,8 @@ class Engine:
         mha = getattr(m, f"{name}_align_attention")
         B, N, C = feats.shape
         assert feats.stride(2) == 1 and feats.stride(1) == C
-        feats = ops.cast_f16(feats.contiguous())
+        feats_bf = feats.contiguous()
+        feats = ops.cast_f16(feats_bf)
         if table16 is None:  # stand-alone use (tests / tools): exact fp16 copy of the given table
             table16 = self.derived("align.table16", [table], lambda: table.detach().to(F16))
         assert table16.shape == table.shape and table16.dtype == F16
@@ -347,7 +348,14 @@ class Engine:
             ops.gemm_raw(M=nq, N=E, K=hd, batch=H, A=qs.data_ptr(), lda=E, a_bs=hd, B=w_k.data_ptr(), ldb=E, b_bs=hd * E,
                          b_mn_major=True, Cout=qt.data_ptr(), ldc=E, c_bs=nq * E, alpha=scale, c_fp16=True, **f16)
             # ctx~ = softmax(q~ . table^T + bias terms)[:, :V] . table — the fused kernel (both table contractions)
-            ctxt, psum, pext = ops.align_fused(table16, qt.view(R, E), stats.view(R, 2))
+            keep = {} if save is not None else None
+            ctxt, psum, pext = ops.align_fused(table16, qt.view(R, E), stats.view(R, 2), keep=keep)
+            if save is not None:
+                if nq != Nq:
+                    raise NotImplementedError("macaw_b200 training: the alignment block must fit one row chunk")
+                save.update(keep)
+                save.update(feats=feats_bf, y=y, z=z, q=q, stats=stats, qt=qt, ctxt=ctxt, psum=psum, pext=pext, ctx=ctx,
+                            B=B, N=N, C=C, Lq=Lq, kk=kk, ss=ss, H=H, hd=hd, row_off=row_off)
             # ctx[:, h] = ctx~[h] W_v[h]^T + (sum_real P) b_v[h] + P_bias bias_v[h]   (value-side bias terms in the epilogue)
             cs = ctx[n0:n1]
             ops.TAG = "align.proj"
@@ -375,8 +383,9 @@ class Engine:
             t = t.to(BF16)
         return t.contiguous()
 
-    def prepare_inputs(self, inputs: dict):
-        """MM_LLMs.prepare_inputs_for_generation (reference modeling.py:965-1048)."""
+    def prepare_inputs(self, inputs: dict, save: Optional[dict] = None):
+        """MM_LLMs.prepare_inputs_for_generation (reference modeling.py:965-1048).  `save` (training step): receives the
+        alignment activations of every modality, keyed by modality name, for the backward pass."""
         m = self.m
         table = self.w(m.llm.model.embed_tokens.weight, "llm.embed")
         dev = table.device
@@ -409,6 +418,7 @@ class Engine:
                 conv = getattr(m, f"project_{name}")
                 lens[name] = self.align_len(feats[name].shape[1], conv.kernel_size[0], conv.stride[0])
         n_prefix = sum(v + 2 for v in lens.values())
+        self.last_lens = dict(lens)  # aligned rows per modality of the most recent call (the training step maps prefix rows to token ids)
         prefix = None
         if n_prefix > 0:
             prefix = torch.empty((B, n_prefix, E), device=dev, dtype=BF16)
@@ -418,8 +428,11 @@ class Engine:
                     continue
                 Lq = lens[name]
                 ops.embed_gather(table, inputs[f"{name}_starts"].to(dev), out=prefix[:, off, :])
+                sv = None
+                if save is not None:
+                    sv = save.setdefault(name, {})
                 got = self.align(feats[name], name, table, prefix, off + 1,
-                                 self.w16(m.llm.model.embed_tokens.weight, "llm.embed"))
+                                 self.w16(m.llm.model.embed_tokens.weight, "llm.embed"), save=sv)
                 assert got == Lq
                 ops.embed_gather(table, inputs[f"{name}_ends"].to(dev), out=prefix[:, off + 1 + Lq, :])
                 off += Lq + 2

@@ -290,7 +290,7 @@ class MM_LLMs(PreTrainedModel):
         new = cls.__new__(cls)
         memo[id(self)] = new
         for k, v in self.__dict__.items():
-            if k != "_engine":
+            if k not in ("_engine", "_train_step"):
                 new.__dict__[k] = copy.deepcopy(v, memo)
         new._attach_engine()
         return new
@@ -298,6 +298,7 @@ class MM_LLMs(PreTrainedModel):
     def __getstate__(self):
         st = dict(self.__dict__)
         st.pop("_engine", None)
+        st.pop("_train_step", None)
         return st
 
     def __setstate__(self, st):
@@ -331,10 +332,27 @@ class MM_LLMs(PreTrainedModel):
         return CausalLMOutputWithPast(loss=loss, logits=logits)
 
     def _forward_train(self, inputs):
-        raise NotImplementedError(
-            "macaw_b200: MM_LLMs.forward was called in train() mode with gradients enabled, but this build only "
-            "implements the inference forward (no autograd graph is recorded by the sm_100a kernels). Call model.eval() "
-            "/ torch.no_grad() for evaluation.")
+        """train() mode with gradients enabled (reference llm_trainer.py:184-188: `loss = model(**inputs)[0]`, then
+        `loss.backward()`): the loss is produced by the kernel-library training step (training.py) and carries a grad_fn
+        whose backward runs the hand-written backward pass.  Logits are not returned in this mode (they are consumed in
+        place by the cross-entropy backward)."""
+        from .training import TrainStep
+
+        if "_train_step" not in self.__dict__:
+            self.__dict__["_train_step"] = TrainStep(self)
+        if inputs.get("labels") is None:
+            raise ValueError("macaw_b200: a train()-mode forward needs `labels` (the differentiated quantity is the loss); "
+                             "call model.eval() / torch.no_grad() for logits")
+        loss = self.__dict__["_train_step"](inputs)
+        return CausalLMOutputWithPast(loss=loss, logits=None)
+
+    @property
+    def train_step(self):
+        from .training import TrainStep
+
+        if "_train_step" not in self.__dict__:
+            self.__dict__["_train_step"] = TrainStep(self)
+        return self.__dict__["_train_step"]
 
     def prepare_inputs_for_generation(self, inputs):
         return self._engine.prepare_inputs(inputs)

@@ -294,7 +294,7 @@ ALIGN_MODE = 0  # 0: one cooperative launch with grid-wide barriers between the 
 
 
 def align_fused(table: torch.Tensor, qt: torch.Tensor, stats: torch.Tensor, out: Optional[torch.Tensor] = None,
-                mode: Optional[int] = None):
+                mode: Optional[int] = None, keep: Optional[dict] = None):
     """Fused absorbed-form alignment attention (mm_align_fwd).  table (V, E) fp16; qt (R, E) fp16 absorbed queries;
     stats (R, 2) fp32 = [row_bias, extra score] -> (ctx~ (R, E) fp16, p_sum_real (R,), p_extra (R,))."""
     _cuda(table, _F16, "table"); _cuda(qt, _F16, "qt"); _cuda(stats, torch.float32, "stats")
@@ -311,9 +311,12 @@ def align_fused(table: torch.Tensor, qt: torch.Tensor, stats: torch.Tensor, out:
     ws = torch.empty((int(lib.mm_align_workspace_bytes(R, V)) + 15) // 16 * 4, device=dev, dtype=torch.int32)
     psum = torch.empty((R,), device=dev, dtype=torch.float32)
     pext = torch.empty((R,), device=dev, dtype=torch.float32)
+    inv_l = torch.empty((R,), device=dev, dtype=torch.float32) if keep is not None else None
     a = AlignArgs(table.data_ptr(), V, E, table.stride(0), qt.data_ptr(), R, qt.stride(0), stats.data_ptr(),
                   stats.data_ptr() + 4, 2, out.data_ptr(), out.stride(0), psum.data_ptr(), pext.data_ptr(), P.data_ptr(), Vp,
-                  ws.data_ptr(), ALIGN_MODE if mode is None else int(mode))
+                  ws.data_ptr(), ALIGN_MODE if mode is None else int(mode), _ptr(inv_l))
+    if keep is not None:  # the training step keeps the un-normalised probabilities and 1 / l for the backward pass
+        keep.update(P=P, inv_l=inv_l)
     if PROFILE is None:
         _check(lib.mm_align_fwd(C.byref(a), _stream()), "mm_align_fwd")
     else:
@@ -400,3 +403,197 @@ def ce_loss(logits: torch.Tensor, labels: torch.Tensor) -> torch.Tensor:
     _check(_lib.load().mm_ce_loss(logits.data_ptr(), labels.data_ptr(), B, T, V, acc.data_ptr(), cnt.data_ptr(),
                                   _stream()), "mm_ce_loss")
     return acc[0] / cnt[0].to(torch.float32)
+
+
+# ---------------------------------------------------------------------------------------------------- training step
+def gemm_dx(dy: torch.Tensor, w: torch.Tensor, out: Optional[torch.Tensor] = None, accumulate: bool = False) -> torch.Tensor:
+    """Input gradient of y = x @ w.T:  dx (M, K) = dy (M, N) @ w (N, K) — w is read as an MN-major B operand in place."""
+    _cuda(dy, _BF16, "dy"); _cuda(w, _BF16, "w")
+    M, N = dy.shape
+    K = w.shape[1]
+    assert w.shape[0] == N and dy.stride(1) == 1 and w.stride(1) == 1
+    if out is None:
+        assert not accumulate
+        out = torch.empty((M, K), device=dy.device, dtype=_BF16)
+    kw = dict(residual=out.data_ptr(), ldr=out.stride(0)) if accumulate else {}
+    gemm_raw(M=M, N=K, K=N, A=dy.data_ptr(), lda=dy.stride(0), B=w.data_ptr(), ldb=w.stride(0), b_mn_major=True,
+             Cout=out.data_ptr(), ldc=out.stride(0), **kw)
+    return out
+
+
+def gemm_dw(dy: torch.Tensor, x: torch.Tensor, out: torch.Tensor, accumulate: bool) -> torch.Tensor:
+    """Weight gradient of y = x @ w.T:  dw (N, K) (+)= dy (M, N).T @ x (M, K) — both activations are read as stored
+    (MN-major A and B operands), no transposes."""
+    _cuda(dy, _BF16, "dy"); _cuda(x, _BF16, "x"); _cuda(out, _BF16, "dw")
+    M, N = dy.shape
+    K = x.shape[1]
+    assert x.shape[0] == M and out.shape == (N, K) and dy.stride(1) == 1 and x.stride(1) == 1 and out.stride(1) == 1
+    kw = dict(residual=out.data_ptr(), ldr=out.stride(0)) if accumulate else {}
+    gemm_raw(M=N, N=K, K=M, A=dy.data_ptr(), lda=dy.stride(0), a_mn_major=True, B=x.data_ptr(), ldb=x.stride(0),
+             b_mn_major=True, Cout=out.data_ptr(), ldc=out.stride(0), **kw)
+    return out
+
+
+def rmsnorm_bwd(dy: torch.Tensor, x: torch.Tensor, rstd: torch.Tensor, g: torch.Tensor, dres: Optional[torch.Tensor],
+                dg: Optional[torch.Tensor]) -> torch.Tensor:
+    """dx of y = x * rstd * g (+ dres); dg (fp32, cols) is accumulated in place."""
+    _cuda(dy, _BF16, "dy"); _cuda(x, _BF16, "x"); _cuda(rstd, torch.float32, "rstd"); _cuda(g, _BF16, "g")
+    assert dy.is_contiguous() and x.is_contiguous() and (dres is None or dres.is_contiguous())
+    rows, cols = x.shape
+    dx = torch.empty_like(x)
+    _check(_lib.load().mm_rmsnorm_bwd(dy.data_ptr(), x.data_ptr(), rstd.data_ptr(), g.data_ptr(), _ptr(dres), dx.data_ptr(),
+                                      _ptr(dg), rows, cols, _stream()), "mm_rmsnorm_bwd")
+    return dx
+
+
+def swiglu_fwd(gate: torch.Tensor, up: torch.Tensor) -> torch.Tensor:
+    _cuda(gate, _BF16, "gate"); _cuda(up, _BF16, "up")
+    assert gate.is_contiguous() and up.is_contiguous() and gate.shape == up.shape
+    h = torch.empty_like(gate)
+    _check(_lib.load().mm_swiglu_fwd(gate.data_ptr(), up.data_ptr(), h.data_ptr(), gate.numel(), _stream()), "mm_swiglu_fwd")
+    return h
+
+
+def swiglu_bwd(dh: torch.Tensor, gate: torch.Tensor, up: torch.Tensor):
+    _cuda(dh, _BF16, "dh")
+    assert dh.is_contiguous() and gate.is_contiguous() and up.is_contiguous()
+    dg, du = torch.empty_like(gate), torch.empty_like(up)
+    _check(_lib.load().mm_swiglu_bwd(dh.data_ptr(), gate.data_ptr(), up.data_ptr(), dg.data_ptr(), du.data_ptr(), dh.numel(),
+                                     _stream()), "mm_swiglu_bwd")
+    return dg, du
+
+
+def attention_bwd(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, do: torch.Tensor, *, scale: float, causal: bool,
+                  key_mask: Optional[torch.Tensor] = None):
+    """Backward of mm_attn_fwd composed from tcgen05 GEMMs: S = q k^T and dP = dO v^T (fp32, batched over (b, h)), one
+    row-wise softmax-backward kernel (P, dS in bf16), then dV = P^T dO, dK = dS^T q (MN-major A), dQ = dS k.
+    q / do (B, Tq, H, hd), k / v (B, Tk, H, hd): bf16 views with unit head-dim stride.  Returns contiguous dq, dk, dv."""
+    for n, t in (("q", q), ("k", k), ("v", v), ("do", do)):
+        _cuda(t, _BF16, n)
+        assert t.dim() == 4 and t.stride(3) == 1
+    B, Tq, H, hd = q.shape
+    Tk = k.shape[1]
+    dev = q.device
+    Tp = (Tk + 7) // 8 * 8
+    S = torch.empty((B, H, Tq, Tp), device=dev, dtype=torch.float32)
+    dP = torch.empty((B, H, Tq, Tp), device=dev, dtype=torch.float32)
+
+    def bat(t):  # (lda, head stride, sample stride) of a (B, T, H, hd) view
+        return dict(ld=t.stride(1), bs=t.stride(2), bs2=t.stride(0))
+
+    def scores(a, b, out):
+        sa, sb = bat(a), bat(b)
+        gemm_raw(M=Tq, N=Tk, K=hd, batch=H, batch2=B, A=a.data_ptr(), lda=sa["ld"], a_bs=sa["bs"], a_bs2=sa["bs2"],
+                 B=b.data_ptr(), ldb=sb["ld"], b_bs=sb["bs"], b_bs2=sb["bs2"], Cout=out.data_ptr(), ldc=Tp, c_bs=Tq * Tp,
+                 c_bs2=H * Tq * Tp, c_fp32=True)
+
+    scores(q, k, S)
+    scores(do, v, dP)
+    P = torch.empty((B, H, Tq, Tp), device=dev, dtype=_BF16)
+    dS = torch.empty((B, H, Tq, Tp), device=dev, dtype=_BF16)
+    if key_mask is not None:
+        _cuda(key_mask, torch.int32, "key_mask")
+    _check(_lib.load().mm_attn_softmax_bwd(S.data_ptr(), dP.data_ptr(), P.data_ptr(), dS.data_ptr(), B, H, Tq, Tk, Tp,
+                                           float(scale), int(causal), _ptr(key_mask), _stream()), "mm_attn_softmax_bwd")
+    del S, dP
+    dq = torch.empty((B, Tq, H, hd), device=dev, dtype=_BF16)
+    dk = torch.empty((B, Tk, H, hd), device=dev, dtype=_BF16)
+    dv = torch.empty((B, Tk, H, hd), device=dev, dtype=_BF16)
+
+    def pt_x(p_, x_, out):  # out_bh (Tk, hd) = p_bh^T (Tk x Tq) @ x_bh (Tq, hd)
+        sx, so = bat(x_), bat(out)
+        gemm_raw(M=Tk, N=hd, K=Tq, batch=H, batch2=B, A=p_.data_ptr(), lda=Tp, a_bs=Tq * Tp, a_bs2=H * Tq * Tp,
+                 a_mn_major=True, B=x_.data_ptr(), ldb=sx["ld"], b_bs=sx["bs"], b_bs2=sx["bs2"], b_mn_major=True,
+                 Cout=out.data_ptr(), ldc=so["ld"], c_bs=so["bs"], c_bs2=so["bs2"])
+
+    pt_x(P, do, dv)
+    pt_x(dS, q, dk)
+    sk, so = bat(k), bat(dq)
+    gemm_raw(M=Tq, N=hd, K=Tk, batch=H, batch2=B, A=dS.data_ptr(), lda=Tp, a_bs=Tq * Tp, a_bs2=H * Tq * Tp,
+             B=k.data_ptr(), ldb=sk["ld"], b_bs=sk["bs"], b_bs2=sk["bs2"], b_mn_major=True, Cout=dq.data_ptr(),
+             ldc=so["ld"], c_bs=so["bs"], c_bs2=so["bs2"])
+    return dq, dk, dv
+
+
+def ce_loss_with_count(logits: torch.Tensor, labels: torch.Tensor):
+    """mm_ce_loss -> (loss fp32 scalar tensor, n_valid int32 1-element tensor)."""
+    _cuda(logits, _BF16, "logits"); _cuda(labels, torch.int64, "labels")
+    assert logits.is_contiguous() and labels.is_contiguous()
+    B, T, V = logits.shape
+    acc = torch.zeros((2,), device=logits.device, dtype=torch.float32)
+    cnt = acc[1:].view(torch.int32)
+    _check(_lib.load().mm_ce_loss(logits.data_ptr(), labels.data_ptr(), B, T, V, acc.data_ptr(), cnt.data_ptr(),
+                                  _stream()), "mm_ce_loss")
+    return acc[0] / cnt[0].to(torch.float32), cnt
+
+
+def ce_bwd(logits: torch.Tensor, labels: torch.Tensor, n_valid: torch.Tensor, grad_scale: float = 1.0) -> torch.Tensor:
+    """d loss / d logits, written IN PLACE over the bf16 logits."""
+    B, T, V = logits.shape
+    _check(_lib.load().mm_ce_bwd(logits.data_ptr(), labels.data_ptr(), logits.data_ptr(), B, T, V, n_valid.data_ptr(),
+                                 float(grad_scale), _stream()), "mm_ce_bwd")
+    return logits
+
+
+def embed_scatter_add(dx: torch.Tensor, ids: torch.Tensor, dtable: torch.Tensor) -> None:
+    """dtable[ids[i]] += dx[i] for bf16 rows dx (n, dim) with unit inner stride."""
+    _cuda(dx, _BF16, "dx"); _cuda(dtable, _BF16, "dtable")
+    ids64 = ids.reshape(-1).to(torch.int64)
+    assert dx.dim() == 2 and dx.stride(1) == 1 and dx.shape[0] == ids64.numel() and dtable.is_contiguous()
+    _check(_lib.load().mm_embed_scatter_add(dx.data_ptr(), dx.stride(0), ids64.data_ptr(), ids64.numel(), dx.shape[1],
+                                            dtable.shape[0], dtable.data_ptr(), _stream()), "mm_embed_scatter_add")
+
+
+def colsum(x: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
+    _cuda(x, _BF16, "x"); _cuda(out, torch.float32, "out")
+    assert x.dim() == 2 and x.stride(1) == 1 and out.numel() == x.shape[1]
+    _check(_lib.load().mm_colsum(x.data_ptr(), x.stride(0), x.shape[0], x.shape[1], out.data_ptr(), _stream()), "mm_colsum")
+    return out
+
+
+def adamw(p: torch.Tensor, g: torch.Tensor, master: torch.Tensor, m: torch.Tensor, v: torch.Tensor, *, lr: float,
+          beta1: float, beta2: float, eps: float, weight_decay: float, step: int, grad_scale: float = 1.0) -> None:
+    _cuda(p, _BF16, "p"); _cuda(g, _BF16, "g")
+    assert p.is_contiguous() and g.is_contiguous() and master.numel() == p.numel()
+    _check(_lib.load().mm_adamw(p.data_ptr(), g.data_ptr(), master.data_ptr(), m.data_ptr(), v.data_ptr(), p.numel(),
+                                float(lr), float(beta1), float(beta2), float(eps), float(weight_decay), int(step),
+                                float(grad_scale), _stream()), "mm_adamw")
+
+
+def cast_bf16(x: torch.Tensor) -> torch.Tensor:
+    """fp16 contiguous tensor -> bf16 copy (mm_cast_f16_bf16): the alignment backward runs in bf16 (gradient range)."""
+    _cuda(x, _F16, "x")
+    assert x.is_contiguous()
+    cols = x.shape[-1]
+    rows = x.numel() // cols
+    y = torch.empty(x.shape, device=x.device, dtype=_BF16)
+    _check(_lib.load().mm_cast_f16_bf16(x.data_ptr(), cols, y.data_ptr(), cols, rows, cols, _stream()), "mm_cast_f16_bf16")
+    return y
+
+
+def align_softmax_bwd(G: torch.Tensor, P_unnorm: torch.Tensor, inv_l: torch.Tensor, dpsr: torch.Tensor, pe: torch.Tensor,
+                      dpe: torch.Tensor, gscale: float, V: int):
+    """-> (P bf16 (R, ldp), dS bf16 (R, ldp), dstats fp32 (2, R)); see mm_align_softmax_bwd."""
+    _cuda(G, torch.float32, "G"); _cuda(P_unnorm, _F16, "P")
+    R, ldp = P_unnorm.shape
+    assert G.shape[0] == R and G.stride(1) == 1 and P_unnorm.stride(1) == 1
+    for t in (inv_l, dpsr, pe, dpe):
+        assert t.dtype == torch.float32 and t.is_contiguous() and t.numel() == R
+    P = torch.empty((R, ldp), device=G.device, dtype=_BF16)
+    dS = torch.empty((R, ldp), device=G.device, dtype=_BF16)
+    dstats = torch.empty((2, R), device=G.device, dtype=torch.float32)
+    _check(_lib.load().mm_align_softmax_bwd(G.data_ptr(), G.stride(0), P_unnorm.data_ptr(), ldp, inv_l.data_ptr(), dpsr.data_ptr(),
+                                            pe.data_ptr(), dpe.data_ptr(), float(gscale), P.data_ptr(), dS.data_ptr(), ldp,
+                                            dstats.data_ptr(), R, V, _stream()), "mm_align_softmax_bwd")
+    return P, dS, dstats
+
+
+def head_weighted_colsum(x: torch.Tensor, w: torch.Tensor, head_dim: int, out: torch.Tensor) -> torch.Tensor:
+    """out[h*hd + d] += sum_n w[h, n] * x[n, h*hd + d]; x (Nq, E) bf16 / fp16, w (H*Nq,) fp32 contiguous, out fp32 (E,)."""
+    _cuda(x, None, "x"); _cuda(w, torch.float32, "w"); _cuda(out, torch.float32, "out")
+    assert x.dtype in _16BIT and x.stride(1) == 1 and w.is_contiguous()
+    Nq, E = x.shape
+    assert w.numel() == (E // head_dim) * Nq and out.numel() == E
+    _check(_lib.load().mm_head_weighted_colsum(x.data_ptr(), x.stride(0), int(x.dtype == _F16), w.data_ptr(), 1, Nq, E,
+                                               head_dim, out.data_ptr(), _stream()), "mm_head_weighted_colsum")
+    return out

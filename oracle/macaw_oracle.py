@@ -63,17 +63,20 @@ def _act(name: str):
 class _SD:
     """state_dict view that upcasts on access (so bf16 checkpoints can be consumed layer by layer)."""
 
-    def __init__(self, sd: Dict[str, Tensor], dtype=torch.float32, prefix: str = ""):
-        self.sd, self.dtype, self.prefix = sd, dtype, prefix
+    def __init__(self, sd: Dict[str, Tensor], dtype=torch.float32, prefix: str = "", keep_graph: bool = False):
+        self.sd, self.dtype, self.prefix, self.keep_graph = sd, dtype, prefix, keep_graph
 
     def __call__(self, name: str) -> Tensor:
-        return self.sd[self.prefix + name].detach().to("cpu").to(self.dtype)
+        t = self.sd[self.prefix + name]
+        if self.keep_graph:  # gradient oracle: the tensors are autograd leaves (already on the CPU in the working dtype)
+            return t
+        return t.detach().to("cpu").to(self.dtype)
 
     def has(self, name: str) -> bool:
         return (self.prefix + name) in self.sd
 
     def sub(self, prefix: str) -> "_SD":
-        return _SD(self.sd, self.dtype, self.prefix + prefix)
+        return _SD(self.sd, self.dtype, self.prefix + prefix, self.keep_graph)
 
 
 # ------------------------------------------------------------------------------------------------ torch MHA restatement
@@ -263,9 +266,9 @@ def shifted_ce(logits: Tensor, labels: Tensor) -> Tensor:
 
 
 # ------------------------------------------------------------------------------------------------ whole forward
-def prepare_inputs(inputs: dict, sd_raw: Dict[str, Tensor], hp: dict, dtype=torch.float32):
+def prepare_inputs(inputs: dict, sd_raw: Dict[str, Tensor], hp: dict, dtype=torch.float32, keep_graph: bool = False):
     """MM_LLMs.prepare_inputs_for_generation (modeling.py:965-1048) -> (embeds, attention_mask | None, labels | None)."""
-    sd = _SD(sd_raw, dtype)
+    sd = _SD(sd_raw, dtype, keep_graph=keep_graph)
     table = sd("llm.model.embed_tokens.weight")
     H2 = hp["attention_heads"] * 2
     cast = lambda t: None if t is None else t.to("cpu").to(dtype)
@@ -329,3 +332,73 @@ def generate_greedy(inputs: dict, sd_raw: Dict[str, Tensor], hp: dict, max_new_t
                 break
             embeds = torch.cat([embeds, table[tok.clamp(max=table.shape[0] - 1)].unsqueeze(1)], dim=1)
     return torch.stack(out, dim=1), torch.stack(step_logits, dim=1)
+
+
+# ------------------------------------------------------------------------------------------------ gradient oracle
+def llama_loss_and_grads(inputs: dict, sd_raw: Dict[str, Tensor], hp: dict, dtype=torch.float32):
+    """Loss of MM_LLMs.forward (modeling.py:941-963, 597-610) and its autograd gradients w.r.t. every `llm.*` parameter,
+    as the HF Trainer obtains them (llm_trainer.py:184-188: `loss = model(**inputs)[0]`; `loss.backward()`), with the
+    ALIGNED rows of the multimodal prefix held constant (they are computed without a graph): the gradient then reaches
+    the embedding table through the gathered rows only (BOS / text tokens, start / end tokens), which is the
+    differentiable set of this repo's training step (macaw-llm_b200/training.py).  For text-only inputs this IS the
+    reference's full gradient.  -> (loss, {name: grad}, d loss / d inputs_embeds)."""
+    with torch.no_grad():
+        embeds_c, mask, labels = prepare_inputs(inputs, sd_raw, hp, dtype)
+    leaves = {k: v.detach().to("cpu").to(dtype).clone().requires_grad_(True) for k, v in sd_raw.items()
+              if k.startswith("llm.") and v.is_floating_point() and not k.endswith("inv_freq")}
+    table = leaves["llm.model.embed_tokens.weight"]
+    ids = inputs["input_ids"].to("cpu").long()
+    B, L = ids.shape
+    n_prefix = embeds_c.shape[1] - L
+    rows = [table[ids[:, :1]]]
+    off = 1
+    # final layout [BOS, <image> .. </image>, <audio> .. </audio>, <video> .. </video>, text[1:]]
+    for name, key in (("image", "images"), ("audio", "audios"), ("video", "videos")):
+        if inputs.get(key) is None:
+            continue
+        Lq = None
+        # block length: scan for the end token position is ambiguous; recompute from the conv geometry
+        kk, ss = hp[f"{name}_conv"]
+        n_tok = {"image": (hp["clip"]["image_size"] // hp["clip"]["patch"]) ** 2, "audio": hp["whisper"]["max_pos"],
+                 "video": hp["n_frames"] * (hp["clip"]["image_size"] // hp["clip"]["patch"]) ** 2}[name]
+        Lq = (n_tok - kk) // ss + 1
+        rows.append(table[inputs[f"{name}_starts"].to("cpu").long()].unsqueeze(1))
+        rows.append(embeds_c[:, off + 1: off + 1 + Lq])
+        rows.append(table[inputs[f"{name}_ends"].to("cpu").long()].unsqueeze(1))
+        off += Lq + 2
+    assert off == 1 + n_prefix, (off, n_prefix)
+    rows.append(table[ids[:, 1:]])
+    embeds = torch.cat(rows, dim=1)
+    embeds.retain_grad()
+    logits = llama_forward(embeds, mask, _SD(leaves, dtype, keep_graph=True), hp)
+    loss = shifted_ce(logits, labels)
+    loss.backward()
+    return loss.detach(), {k: v.grad for k, v in leaves.items()}, embeds.grad
+
+
+ALIGN_PREFIXES = tuple(f"project_{n}." for n in ("image", "audio", "video")) + \
+    tuple(f"transform_{n}_to_hidden." for n in ("image", "audio", "video")) + \
+    tuple(f"{n}_align_attention." for n in ("image", "audio", "video"))
+
+
+def full_loss_and_grads(inputs: dict, sd_raw: Dict[str, Tensor], hp: dict, dtype=torch.float32):
+    """Loss of MM_LLMs.forward and its autograd gradients w.r.t. every `llm.*` parameter AND the alignment modules
+    (project_*, transform_*_to_hidden, *_align_attention) — the gradient the HF Trainer obtains from the reference in eval-
+    mode arithmetic (dropout off), with the encoders frozen (run_clm_llms.py:390-393).  The embedding table is
+    differentiated through the gathered rows AND as the keys / values of the alignment attention (modeling.py:974-975).
+    `video_long_self_attention` is held constant (see macaw-llm_b200/training.py).  -> (loss, {name: grad})."""
+    merged, leaves = {}, {}
+    for k, v in sd_raw.items():
+        if not v.is_floating_point():
+            merged[k] = v
+            continue
+        t = v.detach().to("cpu").to(dtype)
+        if (k.startswith("llm.") and not k.endswith("inv_freq")) or k.startswith(ALIGN_PREFIXES):
+            t = t.clone().requires_grad_(True)
+            leaves[k] = t
+        merged[k] = t
+    embeds, mask, labels = prepare_inputs(inputs, merged, hp, dtype, keep_graph=True)
+    logits = llama_forward(embeds, mask, _SD(merged, dtype, keep_graph=True), hp)
+    loss = shifted_ce(logits, labels)
+    loss.backward()
+    return loss.detach(), {k: v.grad for k, v in leaves.items()}

@@ -128,3 +128,34 @@ def make_inputs(spec: dict, B: int, L: int, seed: int, modalities=("image", "aud
         d[f"{name}_starts"] = torch.full((B,), sp[2 * i], dtype=torch.int32)
         d[f"{name}_ends"] = torch.full((B,), sp[2 * i + 1], dtype=torch.int32)
     return d
+
+
+# ------------------------------------------------------------------------------------------------ input-pipeline fixtures
+PREPROCESS_IMAGE_SIZES = [(300, 400), (517, 389), (120, 200)]  # landscape down-scale, portrait down-scale, up-scale
+PREPROCESS_AUDIO_SECONDS = [5.0, 31.0]                          # padded clip, trimmed clip
+
+
+def synth_image(h: int, w: int, seed: int = 0):
+    """Deterministic 8-bit RGB test image (smooth gradients + a checker + seeded noise), numpy only."""
+    import numpy as np
+
+    rng = np.random.default_rng(1000 + seed)
+    y, x = np.mgrid[0:h, 0:w].astype(np.float64)
+    img = np.stack([127 + 120 * np.sin(x / 17.0 + seed) * np.cos(y / 23.0),
+                    255.0 * x / max(w - 1, 1),
+                    255.0 * ((x.astype(np.int64) // 16 + y.astype(np.int64) // 16) % 2)], axis=-1)
+    img += rng.normal(0.0, 12.0, size=img.shape)
+    return np.clip(np.rint(img), 0, 255).astype(np.uint8)
+
+
+def synth_audio(seconds: float, seed: int = 0, sr: int = 16000):
+    """Deterministic fp32 waveform in [-1, 1]: two chirps, an amplitude-modulated tone and low-level seeded noise."""
+    import numpy as np
+
+    rng = np.random.default_rng(2000 + seed)
+    n = int(seconds * sr)
+    t = np.arange(n, dtype=np.float64) / sr
+    x = 0.4 * np.sin(2 * np.pi * (200.0 + 300.0 * t) * t) + 0.2 * np.sin(2 * np.pi * (4000.0 - 100.0 * t) * t)
+    x += 0.15 * np.sin(2 * np.pi * 1000.0 * t) * (0.5 + 0.5 * np.sin(2 * np.pi * 3.0 * t))
+    x += rng.normal(0.0, 0.003, size=n)
+    return np.clip(x, -1.0, 1.0).astype(np.float32)

@@ -101,3 +101,59 @@ def test_sharding_and_reductions_world2_gloo():
     assert (res[0][2], res[0][3], res[1][2], res[1][3]) == (0, 3, 3, 5)      # contiguous cover of the global batch
     assert res[0][4] == res[1][4] == 11.0                                      # max over ranks
     assert abs(res[0][5] - (1 * 3 + 2 * 2) / 5) < 1e-12                        # token-weighted global mean
+
+
+def _gloo_grad_worker(rank, world, port, q):
+    """Each rank differentiates ITS shard with the CPU gradient oracle, deposits the gradients in the flat GradBuffer and
+    all-reduces it; rank 0 reports a few entries."""
+    import torch.distributed as dist
+
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    from macaw_llm_b200 import dist as D
+    from macaw_llm_b200.training import GradBuffer, allreduce_grads
+    from oracle import macaw_oracle as O
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    model, spec, hp, weights = H.build_tiny_model("cpu", torch.bfloat16)
+    inp = gen.make_inputs(spec, 4, 12, seed=11, modalities=(), with_labels=True)
+    sh = D.shard_inputs(inp, rank, world)
+    _, grads, _ = O.llama_loss_and_grads(sh, H.bf16_round(weights), hp)
+    gb = GradBuffer(model)
+    gb.attach()
+    named = dict(model.named_parameters())
+    for k, g in grads.items():
+        named[k].grad.copy_(g)
+    for i in range(len(gb.buckets)):  # bucket by bucket, as the backward pass issues them
+        allreduce_grads(gb, world, bucket=i)
+    # numpy arrays are pickled by value (torch tensors would travel as shared-memory handles that die with the worker)
+    q.put((rank, {k: named[k].grad.float().numpy().copy() for k in ("llm.lm_head.weight", "llm.model.layers.0.mlp.up_proj.weight",
+                                                                    "llm.model.norm.weight")}))
+    dist.destroy_process_group()
+
+
+def test_allreduced_gradient_equals_single_process_gradient_world2_gloo():
+    """the all-reduced (averaged) gradient of the per-rank mean losses equals the single-process
+    gradient of their mean — through the flat GradBuffer buckets the training step uses."""
+    import torch.multiprocessing as mp
+
+    from macaw_llm_b200 import dist as D
+    from oracle import macaw_oracle as O
+
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29700 + os.getpid() % 1000
+    ps = [ctx.Process(target=_gloo_grad_worker, args=(r, 2, port, q)) for r in range(2)]
+    [p.start() for p in ps]
+    res = dict(q.get(timeout=300) for _ in ps)
+    [p.join(60) for p in ps]
+    _, spec, hp, weights = H.build_tiny_model("cpu", torch.bfloat16)
+    inp = gen.make_inputs(spec, 4, 12, seed=11, modalities=(), with_labels=True)
+    sd = H.bf16_round(weights)
+    g0 = O.llama_loss_and_grads(D.shard_inputs(inp, 0, 2), sd, hp)[1]
+    g1 = O.llama_loss_and_grads(D.shard_inputs(inp, 1, 2), sd, hp)[1]
+    for k, got in res[0].items():
+        got = torch.from_numpy(got)
+        want = 0.5 * (g0[k] + g1[k])
+        assert H.rel_err(got, want) < 1e-2, k                       # bf16 storage of the gradient buffer
+        assert torch.equal(got, torch.from_numpy(res[1][k]))        # both ranks hold the same averaged gradient

@@ -61,14 +61,20 @@ def test_deepcopy_and_pickle_get_their_own_engine(tmp_path):
     assert r.engine.m is r and r.llm._engine_ref() is r.engine
 
 
-def test_train_mode_with_grad_is_loud():
-    """Until a caller opts into the training engine, a train()-mode forward must not hand back a graph-less loss."""
+def test_train_mode_is_loud_without_labels_or_cuda():
+    """train()-mode forward goes to the kernel-library training step: it refuses to run without labels (the loss is what
+    is differentiated) and — like every other path — without CUDA parameters; it never hands back a graph-less loss."""
     from macaw_llm_b200.modeling import MM_LLMs
 
     m = MM_LLMs(_tiny_cfg()).train()
     spec, _, _ = H.load_shapes()
-    with pytest.raises((NotImplementedError, RuntimeError)):
+    with pytest.raises(ValueError, match="needs `labels`"):
         m(H.case_inputs(spec, H.load_case("text")))
+    from tests.golden import gen as G
+
+    inp = G.make_inputs(spec, 2, 8, seed=1, modalities=(), with_labels=True)
+    with pytest.raises(RuntimeError, match="no CPU"):
+        m(inp)
 
 
 def test_loads_live_reference_state_dict_with_resized_table():
