@@ -28,6 +28,7 @@ sys.path.insert(0, ROOT)
 import torch  # noqa: E402
 
 METRIC = "multimodal prefill tokens/sec (img+audio+text->LLaMA)"
+DEFAULT_DTYPE = "bf16"
 UNIT = "tokens/s"
 
 
@@ -262,6 +263,11 @@ def run_train(args, cfgs, hyper, rank, local_rank, world):
     opt = FusedAdamW(params, lr=2e-5, weight_decay=0.0)
     model.train()
     model.train_step.set_world(world, overlap=True)
+    own_nccl = False
+    if world > 1:
+        from macaw_llm_b200 import dist as D
+
+        own_nccl = D.init_nccl(dev)  # the kernel library's own communicator (mm_nccl_allreduce)
 
     def step():
         opt.zero_grad()
@@ -281,13 +287,40 @@ def run_train(args, cfgs, hyper, rank, local_rank, world):
         losses.append(float(step()))
     barrier()
     ops.launch_count_reset()
+    step()
+    launches_per_step = ops.launch_count()
+    # ---- the whole step (forward, backward, optimizer: ~5000 launches issued from Python) replayed from ONE CUDA graph.
+    #      Every step-dependent scalar lives on the device (AdamW step counter, upstream loss gradient), buffers are static.
+    #      With a data-parallel group the eager launches are kept (the NCCL buckets are issued from the host).
+    use_graph = (world == 1) and not args.no_graphs
+    if use_graph:
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            step()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        static = {}
+        with torch.cuda.graph(graph, capture_error_mode="thread_local"):
+            static["loss"] = step()
+        eager_step = step
+
+        def step():  # noqa: F811
+            graph.replay()
+            return static["loss"]
+
+        for _ in range(2):
+            losses.append(float(step()))
+    barrier()
+    ops.launch_count_reset()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(args.steps):
         loss = step()
     e1.record()
     barrier()
-    launches = ops.launch_count()
+    launches = launches_per_step * args.steps
     t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -305,7 +338,9 @@ def run_train(args, cfgs, hyper, rank, local_rank, world):
             "data": "synthetic",
             "config": {"workload": f"cfg4 shape, micro-batch {Bl}/GPU (train.sh), L={L} -> T={T}, LLaMA-7B + CLIP-L + Whisper-base",
                        "trainable_params": n_train, "optimizer": "fused AdamW, fp32 master + moments",
-                       "grad_sync": "flat bf16 buffer, one NCCL all-reduce per decoder layer overlapped with backward" if world > 1 else "none (1 rank)",
+                       "submission": "cuda_graph_replay of the whole step" if use_graph else "host_launches",
+                       "grad_sync": ("flat bf16 buffer, one NCCL all-reduce per decoder layer on a side stream, overlapped with backward ("
+                                     + ("mm_nccl_allreduce" if own_nccl else "torch.distributed") + ")") if world > 1 else "none (1 rank)",
                        "differentiable_set": "llm.* + the alignment modules of every modality (incl. the table as the alignment attention's keys/values); encoders frozen; video_long_self_attention and MHA dropout not differentiated"},
             "approx_tflops": tf / (ms / 1e3), "gpu_launches": launches, "loss_first_last": [losses[0], losses[-1]],
             "mem_gb": torch.cuda.max_memory_allocated() / 2 ** 30}), flush=True)
@@ -373,6 +408,9 @@ def main():
     ap.add_argument("--mode", default="prefill", choices=["prefill", "train", "decode"],
                     help="prefill = the benchmark of record; train / decode = secondary lines (SURVEY.md §8f ranks 1, 2)")
     ap.add_argument("--micro-batch", type=int, default=4, help="--mode train: samples per GPU per step (train.sh: 4)")
+    ap.add_argument("--dtype", default=DEFAULT_DTYPE, choices=["bf16", "fp16"],
+                    help="storage / tensor-core operand format of the prefill arm (fp32 accumulation either way); the "
+                         "reference itself runs fp16 (train.sh --fp16 True)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -429,8 +467,9 @@ def main():
         B_local, B_global = args.global_batch, args.global_batch * world
 
     cfg = MM_LLMs_Config(clip_config=clip, whisper_config=whisper, llm_config=llama, **hyper)
-    model = MM_LLMs.build_random(cfg, device=dev, dtype=torch.bfloat16, seed=0)  # same seed -> identical replicas
-    host = synth_inputs(B_local, L, V, clip.vision_config.image_size, 2 * whisper.max_source_positions, 1234 + rank)
+    tdt = torch.float16 if args.dtype == "fp16" else torch.bfloat16
+    model = MM_LLMs.build_random(cfg, device=dev, dtype=tdt, seed=0)  # same seed -> identical replicas
+    host = synth_inputs(B_local, L, V, clip.vision_config.image_size, 2 * whisper.max_source_positions, 1234 + rank, dtype=tdt)
     dev_in = {k: (v.to(dev) if isinstance(v, torch.Tensor) else v) for k, v in host.items()}
 
     def step_resident():
@@ -488,7 +527,7 @@ def main():
 
     # ---- timed region 2: end to end through the public call with HOST (pinned) buffers: H2D of every input + forward
     #      + D2H of the step's result (next-token logits of every sample)
-    out_host = torch.empty((B_local, V), dtype=torch.bfloat16).pin_memory()
+    out_host = torch.empty((B_local, V), dtype=tdt).pin_memory()
 
     def step_e2e():
         d = {k: (v.to(dev, non_blocking=True) if isinstance(v, torch.Tensor) else v) for k, v in host.items()}
@@ -558,29 +597,39 @@ def main():
         cpu = {"value": cb["value"], "unit": UNIT, "cores": cb["cores"], "kind": cb["kind"], "sample": cb["sample"]}
         r_log, r_emb = cb["logits"].float(), cb["embeds"].float()
         n_prefix = r_emb.shape[1] - L
+        # aligned rows only: [BOS, <image>, img x Lq, </image>, <audio>, aud x Lq, </audio>, text...] — the start / end rows
+        # are exact table gathers and (with random-init scales) 100x larger than the aligned rows, so they are left out
+        lens = model.engine.last_lens
+        rows, off = [], 1
+        for name in ("image", "audio", "video"):
+            if name in lens:
+                rows += list(range(off + 1, off + 1 + lens[name]))
+                off += lens[name] + 2
+        rows = torch.tensor(rows, dtype=torch.long)
 
         def rel(a, b):
             return float((a - b).norm() / (b.norm() + 1e-30))
 
         parity = {
-            "vs": cb["kind"] + " fp32 on the GPU arm's bf16 weights, rank-0 sample 0, full depth",
-            "embeds_rel": rel(g_emb, r_emb), "prefix_rel": rel(g_emb[:, 1:1 + n_prefix], r_emb[:, 1:1 + n_prefix]),
+            "vs": cb["kind"] + f" fp32 on the GPU arm's {args.dtype} weights, rank-0 sample 0, full depth",
+            "embeds_rel": rel(g_emb, r_emb), "prefix_rel": rel(g_emb[:, rows], r_emb[:, rows]),
+            "prefix_rows": "the aligned rows of every modality block (start / end token rows are exact gathers)",
             "logits_rel": rel(g_log, r_log),
             "argmax_agree": float((g_log.argmax(-1) == r_log.argmax(-1)).float().mean()),
-            "layout_exact": bool(torch.equal(g_emb[:, 1 + n_prefix:], r_emb[:, 1 + n_prefix:].to(torch.bfloat16).float())),
+            "layout_exact": bool(torch.equal(g_emb[:, 1 + n_prefix:], r_emb[:, 1 + n_prefix:].to(tdt).float())),
             "metric": "norm-wise relative error ||gpu - ref|| / ||ref||",
         }
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
-        "dtype": "bf16", "data": "synthetic",
+        "dtype": args.dtype, "data": "synthetic",
         "config": {"workload": workload, "global_batch": B_global, "per_gpu_batch": B_local, "seq_len": L, "T": T,
                    "parallelism": f"dp{world}", "submission": ("cuda_graph_replay" if use_graphs else "host_launches"),
                    "l2": "per-step working set (16 GB of weights) >> 126 MB L2; no flush needed"},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "result": "next-token logits (B, V) bf16 read back to pinned host memory"},
+                "result": f"next-token logits (B, V) {args.dtype} read back to pinned host memory (an inference consumer's result)"},
         "gpu_launches": launches,  # kernels of libmacaw_b200.so per timed region (counted on the eager pass; the graph replays the same nodes)
         "roofline": roofline,
         "cpu_baseline": cpu,

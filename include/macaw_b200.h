@@ -32,6 +32,13 @@ const char* mm_build_hash(void);
 /* Number of kernel launches issued through this library by the calling process since the last reset. */
 int64_t mm_launch_count(void);
 void mm_launch_count_reset(void);
+/* 16-bit storage format of activations and parameters for the CALLING THREAD: 0 = bf16 (default), 1 = fp16 (IEEE half).
+ * Wherever this header says "bf16" for an activation / parameter tensor, the tensor is fp16 while the format is 1.  The
+ * reference itself trains and runs in fp16 (train.sh:36 `--fp16 True`, llm_trainer.py:366-368 `.half()`); an fp16 model is
+ * computed in fp16 (11-bit significands: storage rounding 8x smaller than bf16), a bf16 model in bf16.  mm_gemm_fwd and
+ * mm_align_fwd take their operand formats explicitly; they use this flag for the epilogue's bias / residual tensors. */
+void mm_set_act_format(int32_t f16);
+int32_t mm_get_act_format(void);
 
 /* ------------------------------------------------------------------------------------------------ GEMM
  * C[b] = epilogue( alpha * A[b] (M x K, K contiguous) * B[b]^T ) for b in [0, batch).
@@ -235,6 +242,11 @@ int32_t mm_argmax_rows(const void* logits, int64_t ld, int32_t rows, int32_t V, 
  * mm_rope_rows: in-place rotate-half RoPE (head_dim 128, apply_rotary_pos_emb modeling.py:83-91) on the first rot_cols
  * columns; position of row r = (*pos_dev if given) + r % rope_T.  mm_swiglu_rows: out[r, j] = silu(gate_j) * up_j from
  * the [32 gate | 32 up]-interleaved product (LlamaMLP modeling.py:139-140). */
+/* Split-K tail of a thin (decode) GEMM: part fp32 [splits][N][ldp] holds W_s x_s^T per K slice (mm_gemm_fwd with the
+ * operands swapped, batch = splits, fp32 out); out[m][n] = row_scale[m] * sum_s part[s][n][m] (+ residual[m][n]), bf16.
+ * Splitting K lets the 32-tile o_proj / down_proj grids of a decode step cover all 148 SMs (weight streaming). */
+int32_t mm_thin_reduce(const float* part, int32_t splits, int32_t N, int32_t M, int32_t ldp, const float* row_scale,
+                       const void* residual, int64_t ldr, void* out, int64_t ldo, void* stream);
 int32_t mm_rope_rows(void* x, int64_t ld, int32_t rows, int32_t rot_cols, const float* cos_t, const float* sin_t,
                      int32_t rope_T, const int32_t* pos_dev, void* stream);
 int32_t mm_swiglu_rows(const void* gu, int64_t ld, int32_t rows, int32_t I, void* out, int64_t ldo, void* stream);
@@ -263,17 +275,19 @@ int32_t mm_swiglu_bwd(const void* dh, const void* gate, const void* up, void* dg
  * bf16 with the same layout.  Masks as in mm_attn_fwd. */
 int32_t mm_attn_softmax_bwd(const float* S, const float* dP, void* P, void* dS, int32_t B, int32_t H, int32_t Tq,
                             int32_t Tk, int64_t ld, float scale, int32_t causal, const int32_t* key_mask, void* stream);
-/* Gradient of mm_ce_loss w.r.t. the logits (modeling.py:600-610), times grad_scale / n_valid; may run in place. */
+/* Gradient of mm_ce_loss w.r.t. the logits (modeling.py:600-610), times grad_scale (* *grad_scale_dev when given: the
+ * upstream gradient of the loss as a device scalar, so the launch is CUDA-graph capturable) / n_valid; may run in place. */
 int32_t mm_ce_bwd(const void* logits, const int64_t* labels, void* dlogits, int32_t B, int32_t T, int32_t V,
-                  const int32_t* n_valid, float grad_scale, void* stream);
+                  const int32_t* n_valid, float grad_scale, const float* grad_scale_dev, void* stream);
 /* Gradient of mm_embed_gather: dtable[ids[i], :] += dx[i, :] (bf16x2 atomics). */
 int32_t mm_embed_scatter_add(const void* dx, int64_t ldx, const int64_t* ids, int64_t n, int32_t dim, int32_t vocab,
                              void* dtable, void* stream);
 /* out[c] += sum_r x[r, c]  (bias gradients; fp32 atomics) */
 int32_t mm_colsum(const void* x, int64_t ldx, int32_t rows, int32_t cols, float* out, void* stream);
-/* Fused AdamW step on one parameter tensor: bf16 working copy p, bf16 gradient g (times grad_scale), fp32 master / m / v. */
+/* Fused AdamW step on one parameter tensor: bf16 working copy p, bf16 gradient g (times grad_scale), fp32 master / m / v.
+ * The bias corrections use `step`, or the device int *step_dev when given (graph-replayed training steps). */
 int32_t mm_adamw(void* p, const void* g, float* master, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
-                 float eps, float weight_decay, int32_t step, float grad_scale, void* stream);
+                 float eps, float weight_decay, int32_t step, const int32_t* step_dev, float grad_scale, void* stream);
 
 /* Backward of the absorbed alignment attention through its (V + 2)-key softmax (reference: autograd of
  * nn.MultiheadAttention, modeling.py:986-987 / 1007-1008 / 1025-1026).  See train_kernels.cu for the formulas. */
@@ -284,6 +298,18 @@ int32_t mm_align_softmax_bwd(const float* G, int64_t ldg, const void* P_unnorm_f
 int32_t mm_head_weighted_colsum(const void* x, int64_t ldx, int32_t x_fp16, const float* w, int64_t w_stride, int32_t Nq,
                                 int32_t E, int32_t head_dim, float* out, void* stream);
 int32_t mm_cast_f16_bf16(const void* x, int64_t ldx, void* y, int64_t ldy, int32_t rows, int32_t cols, void* stream);
+
+/* ------------------------------------------------------------------------------------------------ gradient all-reduce
+ * The one collective of the path: the data-parallel gradient all-reduce of the training step (reference: DeepSpeed ZeRO-3
+ * reduce-scatter / all-gather, configs/deepspeed_config.json:22-41; north_star: "a single NCCL all-reduce on gradients").
+ * NCCL is bound at run time (dlopen); one communicator per process (one process per GPU).  Bootstrap: rank 0 calls
+ * mm_nccl_unique_id, ships the 128 bytes to the other ranks (any channel: torch.distributed store, MPI, a file), every
+ * rank calls mm_nccl_init.  mm_nccl_allreduce is in place, asynchronous on `stream`; dtype 0 = bf16, 1 = fp32;
+ * average != 0 divides by the group size (ncclAvg). */
+int32_t mm_nccl_unique_id(void* out128);
+int32_t mm_nccl_init(const void* id128, int32_t world, int32_t rank);
+int32_t mm_nccl_allreduce(void* buf, int64_t count, int32_t dtype, int32_t average, void* stream);
+int32_t mm_nccl_destroy(void);
 
 /* ------------------------------------------------------------------------------------------------ input pipeline
  * Device-side replacement of the per-sample host work in LLMTrainer.get_self_inputs (llm_trainer.py:306-381).

@@ -107,7 +107,7 @@ def _build_locked(force: bool, verbose: bool) -> str:
         with concurrent.futures.ThreadPoolExecutor(max_workers=min(8, len(jobs))) as ex:
             list(ex.map(run, jobs))
     tmp = LIB + f".tmp{os.getpid()}"
-    run([nvcc, "-shared", "-o", tmp] + objs + ["-gencode", "arch=compute_100a,code=sm_100a"])
+    run([nvcc, "-shared", "-o", tmp] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-ldl"])
     os.replace(tmp, LIB)
     with open(LIB + ".hash.tmp", "w") as f:
         f.write(want + "\n")

@@ -7,6 +7,8 @@
 namespace mm {
 
 static thread_local char g_err[512] = "";
+static thread_local int g_act_f16 = 0;
+bool act_f16() { return g_act_f16 != 0; }
 static std::atomic<long long> g_launches{0};
 
 void set_error(const char* fmt, ...) {
@@ -46,4 +48,6 @@ int32_t mm_abi_version(void) { return 2; }
 const char* mm_build_hash(void) { return MM_SRC_HASH; }
 int64_t mm_launch_count(void) { return mm::g_launches.load(); }
 void mm_launch_count_reset(void) { mm::g_launches.store(0); }
+void mm_set_act_format(int32_t f16) { mm::g_act_f16 = f16 ? 1 : 0; }
+int32_t mm_get_act_format(void) { return mm::g_act_f16; }
 }

@@ -60,7 +60,7 @@ __host__ __device__ constexpr size_t fa_smem_bytes() {
   return (size_t)(HD / 64) * 16384 + 4 * (size_t)(HD / 64) * KT * 128 + (size_t)NPB * 128 * KT * 2 + 256;  // 21 barriers + TMEM slot
 }
 
-template <int HD, int KT, int NPB>
+template <int HD, int KT, int NPB, bool F16>
 __global__ void __launch_bounds__(192, 2)
 fa_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                   const __grid_constant__ CUtensorMap tmV, const FaParams p) {
@@ -70,8 +70,8 @@ fa_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
   constexpr uint32_t QB = KB * KT * 128;      // bytes of one K / V stage
   constexpr uint32_t PB = 128 * KT * 2;       // bytes of one P buffer
   constexpr int NCH = KT / 32;                // 32-key chunks per tile
-  constexpr uint32_t IDESC_S = make_idesc_bf16(kFaMQ, KT, false, false);
-  const uint32_t IDESC_O = make_idesc_bf16(kFaMQ, p.hd, false, true);
+  constexpr uint32_t IDESC_S = make_idesc_f16(kFaMQ, KT, false, false, F16, F16);
+  const uint32_t IDESC_O = make_idesc_f16(kFaMQ, p.hd, false, true, F16, F16);
   constexpr uint32_t S_COL = 0, O_COL = 2 * KT;  // TMEM columns: S0 [0,KT), S1 [KT,2KT), O [2KT, 2KT+HD)
   constexpr uint32_t TMEM_COLS = (2 * KT + HD) <= 256 ? 256 : 512;
   static_assert(2 * KT + HD <= 512, "TMEM budget");
@@ -337,7 +337,7 @@ fa_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
               e1 = (okb[c] & (1u << (2 * i + 1))) ? e1 : 0.f;
             }
             psum += e0 + e1;
-            pk[i] = pack_bf16x2(e0, e1);
+            pk[i] = pack2<F16>(e0, e1);
           }
           uint8_t* blk = prow + (c >> 1) * 16384;
 #pragma unroll
@@ -392,10 +392,10 @@ fa_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             uint4 u;
-            u.x = pack_bf16x2(__uint_as_float(o[8 * i + 0]) * inv, __uint_as_float(o[8 * i + 1]) * inv);
-            u.y = pack_bf16x2(__uint_as_float(o[8 * i + 2]) * inv, __uint_as_float(o[8 * i + 3]) * inv);
-            u.z = pack_bf16x2(__uint_as_float(o[8 * i + 4]) * inv, __uint_as_float(o[8 * i + 5]) * inv);
-            u.w = pack_bf16x2(__uint_as_float(o[8 * i + 6]) * inv, __uint_as_float(o[8 * i + 7]) * inv);
+            u.x = pack2<F16>(__uint_as_float(o[8 * i + 0]) * inv, __uint_as_float(o[8 * i + 1]) * inv);
+            u.y = pack2<F16>(__uint_as_float(o[8 * i + 2]) * inv, __uint_as_float(o[8 * i + 3]) * inv);
+            u.z = pack2<F16>(__uint_as_float(o[8 * i + 4]) * inv, __uint_as_float(o[8 * i + 5]) * inv);
+            u.w = pack2<F16>(__uint_as_float(o[8 * i + 6]) * inv, __uint_as_float(o[8 * i + 7]) * inv);
             *reinterpret_cast<uint4*>(orow + c * 32 + i * 8) = u;
           }
         }
@@ -457,11 +457,11 @@ static int fa_make_map(CUtensorMap* m, const void* ptr, int hd, int T, int H, in
   return 0;
 }
 
-template <int HD, int KT, int NPB>
+template <int HD, int KT, int NPB, bool F16>
 static int launch_fa(const mm_attn_args* a, cudaStream_t st) {
   static bool attr_set[kMaxDevices] = {};
   constexpr size_t smem = fa_smem_bytes<HD, KT, NPB>();
-  if (int rc = ensure_smem_attr(fa_tcgen05_kernel<HD, KT, NPB>, smem, attr_set, "mm_attn_fwd")) return rc;
+  if (int rc = ensure_smem_attr(fa_tcgen05_kernel<HD, KT, NPB, F16>, smem, attr_set, "mm_attn_fwd")) return rc;
   CUtensorMap tq, tk, tv;
   const int hd = a->head_dim;  // the maps carry the ACTUAL head dim: boxes reaching past it are zero-filled
   if (fa_make_map(&tq, a->q, hd, a->Tq, a->H, a->B, a->q_ts, a->q_hs, a->q_bs, kFaMQ)) return 1;
@@ -487,7 +487,7 @@ static int launch_fa(const mm_attn_args* a, cudaStream_t st) {
   p.qpc = static_cast<int>(qpc);
   p.rev = (a->causal && nq % p.qpc == 0) ? 1 : 0;  // a trailing partial group is the light one: launch it last
   dim3 grid((nq + p.qpc - 1) / p.qpc, a->H, a->B);
-  cudaError_t e = launch_kernel(fa_tcgen05_kernel<HD, KT, NPB>, grid, dim3(192), smem, st, 1, tq, tk, tv, p);
+  cudaError_t e = launch_kernel(fa_tcgen05_kernel<HD, KT, NPB, F16>, grid, dim3(192), smem, st, 1, tq, tk, tv, p);
   if (e != cudaSuccess) {
     set_error("mm_attn_fwd: launch failed: %s", cudaGetErrorString(e));
     return 2;
@@ -497,7 +497,8 @@ static int launch_fa(const mm_attn_args* a, cudaStream_t st) {
 
 // called from mm_attn_fwd (attn.cu) for head_dim 64 / 96 / 128 when scale > 0 (96 rides the 128 instantiation)
 int attn_tcgen05_dispatch(const mm_attn_args* a, cudaStream_t st) {
-  return a->head_dim == 64 ? launch_fa<64, 64, 2>(a, st) : launch_fa<128, 64, 1>(a, st);
+  if (act_f16()) return a->head_dim == 64 ? launch_fa<64, 64, 2, true>(a, st) : launch_fa<128, 64, 1, true>(a, st);
+  return a->head_dim == 64 ? launch_fa<64, 64, 2, false>(a, st) : launch_fa<128, 64, 1, false>(a, st);
 }
 
 }  // namespace mm

@@ -42,6 +42,13 @@ inline int current_device() {
 }
 int num_sms();  // SM count of the current device (cached per device)
 
+// 16-bit storage format of ACTIVATIONS and PARAMETERS for the calling host thread: 0 = bf16 (default), 1 = fp16.
+// Set through mm_set_act_format() by the host code that owns the model (an fp16 checkpoint — the reference trains and runs
+// in fp16, train.sh:36 — is computed in fp16: 11-bit significands, 8x smaller storage rounding than bf16).  The entry points
+// that read or write activations dispatch their kernels on it; mm_gemm_fwd / mm_align_fwd take their operand formats
+// explicitly and use this flag only for the bias / residual tensors of the epilogue.
+bool act_f16();
+
 // Opt a kernel into `smem` bytes of dynamic shared memory on the current device, once per (kernel instantiation, device).
 // `flags` is a zero-initialised static array owned by the calling template instantiation.
 template <typename K>

@@ -47,6 +47,7 @@ struct GemmKParams {
   const int* rope_pos;
   int c_trans;
   int c_fp16;
+  int aux_f16;     // bias / bias2 / residual tensors are fp16 (the calling thread's activation format), else bf16
   uint32_t idesc;  // tcgen05 instruction descriptor (operand formats are run-time properties)
   const float* bias_rs;
   const bf16* bias2;
@@ -108,6 +109,26 @@ __device__ __forceinline__ float gelu_erf(float x) {
   poly *= t;
   const float e = 1.0f - poly * exp2f(-1.4426950408889634f * z * z);  // erf(|x| / sqrt 2)
   return 0.5f * x + 0.5f * fabsf(x) * e;                                 // 0.5 x (1 + sign(x) erf(|x|/sqrt2))
+}
+
+// bias / residual elements in the run-time activation format
+__device__ __forceinline__ float aux_ld(const bf16* p, long long i, int f16) {
+  const uint16_t raw = reinterpret_cast<const uint16_t*>(p)[i];
+  return f16 ? __half2float(__ushort_as_half(raw)) : __uint_as_float(static_cast<uint32_t>(raw) << 16);
+}
+__device__ __forceinline__ void aux_add8(float* v, const uint4& u, int f16) {
+  if (f16) {
+    const __half2* h = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float2 f = __half22float2(h[k]);
+      v[2 * k] += f.x;
+      v[2 * k + 1] += f.y;
+    }
+  } else {
+    v[0] += bf16lo(u.x); v[1] += bf16hi(u.x); v[2] += bf16lo(u.y); v[3] += bf16hi(u.y);
+    v[4] += bf16lo(u.z); v[5] += bf16hi(u.z); v[6] += bf16lo(u.w); v[7] += bf16hi(u.w);
+  }
 }
 
 // Activation over a 32-wide chunk: the switch is hoisted so each case is a straight unrolled loop.
@@ -351,7 +372,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           // the 128-row A operand so every MMA row is useful) and its columns are the activation rows.  C / residual are
           // addressed transposed, bias is per tile row, row_scale per tile column.  Outputs are tiny: scalar stores.
           constexpr int CPH_T = BN >= 64 ? BN / 64 : 1;
-          const float bias_r = (p.bias != nullptr && row_ok) ? __bfloat162float(p.bias[row]) : 0.f;
+          const float bias_r = (p.bias != nullptr && row_ok) ? aux_ld(p.bias, row, p.aux_f16) : 0.f;
 #pragma unroll 1
           for (int c = half * CPH_T; c < (half + 1) * CPH_T && c < BN / 32; ++c) {
             uint32_t r[32];
@@ -373,9 +394,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               const int col = col0 + i;
               if (col < p.N) {
                 float o = v[i];
-                if (p.residual != nullptr) o += __bfloat162float(p.residual[static_cast<long long>(col) * p.ldr + row]);
+                if (p.residual != nullptr) o += aux_ld(p.residual, static_cast<long long>(col) * p.ldr + row, p.aux_f16);
                 if (p.c_fp32)
                   reinterpret_cast<float*>(p.C)[static_cast<long long>(col) * p.ldc + row] = o;
+                else if (p.c_fp16)
+                  reinterpret_cast<__half*>(p.C)[static_cast<long long>(col) * p.ldc + row] = __float2half_rn(o);
                 else
                   reinterpret_cast<bf16*>(p.C)[static_cast<long long>(col) * p.ldc + row] = __float2bfloat16(o);
               }
@@ -410,40 +433,29 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
             for (int i = 0; i < 32; ++i)
               if (col0 + i < p.N) {
-                if (bias != nullptr) v[i] = fmaf(s1, __bfloat162float(bias[col0 + i]), v[i]);
-                if (b2 != nullptr) v[i] = fmaf(s2, __bfloat162float(b2[col0 + i]), v[i]);
+                if (bias != nullptr) v[i] = fmaf(s1, aux_ld(bias, col0 + i, p.aux_f16), v[i]);
+                if (b2 != nullptr) v[i] = fmaf(s2, aux_ld(b2, col0 + i, p.aux_f16), v[i]);
               }
           } else if (bias != nullptr) {
             if (full) {
 #pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                const uint4 u = __ldg(reinterpret_cast<const uint4*>(bias + col0) + i);
-                v[8 * i + 0] += bf16lo(u.x); v[8 * i + 1] += bf16hi(u.x);
-                v[8 * i + 2] += bf16lo(u.y); v[8 * i + 3] += bf16hi(u.y);
-                v[8 * i + 4] += bf16lo(u.z); v[8 * i + 5] += bf16hi(u.z);
-                v[8 * i + 6] += bf16lo(u.w); v[8 * i + 7] += bf16hi(u.w);
-              }
+              for (int i = 0; i < 4; ++i)
+                aux_add8(v + 8 * i, __ldg(reinterpret_cast<const uint4*>(bias + col0) + i), p.aux_f16);
             } else {
 #pragma unroll
               for (int i = 0; i < 32; ++i)
-                if (col0 + i < p.N) v[i] += __bfloat162float(bias[col0 + i]);
+                if (col0 + i < p.N) v[i] += aux_ld(bias, col0 + i, p.aux_f16);
             }
           }
           if (p.act != MM_ACT_NONE) apply_act32(v, p.act);
           if (rrow != nullptr) {
             if (full) {
 #pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                const uint4 u = *(reinterpret_cast<const uint4*>(rrow + col0) + i);
-                v[8 * i + 0] += bf16lo(u.x); v[8 * i + 1] += bf16hi(u.x);
-                v[8 * i + 2] += bf16lo(u.y); v[8 * i + 3] += bf16hi(u.y);
-                v[8 * i + 4] += bf16lo(u.z); v[8 * i + 5] += bf16hi(u.z);
-                v[8 * i + 6] += bf16lo(u.w); v[8 * i + 7] += bf16hi(u.w);
-              }
+              for (int i = 0; i < 4; ++i) aux_add8(v + 8 * i, *(reinterpret_cast<const uint4*>(rrow + col0) + i), p.aux_f16);
             } else {
 #pragma unroll
               for (int i = 0; i < 32; ++i)
-                if (col0 + i < p.N) v[i] += __bfloat162float(rrow[col0 + i]);
+                if (col0 + i < p.N) v[i] += aux_ld(rrow, col0 + i, p.aux_f16);
             }
           }
           if (row_ok) store_row32(p, crow, col0, n_out_total, v);
@@ -632,13 +644,14 @@ extern "C" int32_t mm_gemm_fwd(const mm_gemm_args* a, void* stream) {
   p.rope_pos = a->rope_pos;
   p.c_trans = a->c_trans;
   p.c_fp16 = a->c_fp16;
+  p.aux_f16 = act_f16() ? 1 : 0;
   p.bias_rs = a->bias_rs; p.bias2 = reinterpret_cast<const bf16*>(a->bias2); p.bias2_rs = a->bias2_rs;
   MM_REQUIRE(!(a->c_fp16 && a->c_fp32), "mm_gemm_fwd: c_fp16 and c_fp32 are exclusive");
   MM_REQUIRE((a->a_fp16 != 0) == (a->b_fp16 != 0),
              "mm_gemm_fwd: A and B must share one 16-bit format (sm_100a faults on mixed f16 x bf16 tcgen05.mma)");
   MM_REQUIRE((!a->bias_rs && !a->bias2 && !a->bias2_rs) || (a->epi == MM_EPI_STD && !a->c_trans),
              "mm_gemm_fwd: row-scaled bias terms need the standard, non-transposed epilogue");
-  MM_REQUIRE(!a->c_fp16 || (a->epi == MM_EPI_STD && !a->c_trans), "mm_gemm_fwd: fp16 output only with the standard epilogue");
+  MM_REQUIRE(!(a->c_fp16 && a->c_fp32), "mm_gemm_fwd: c_fp16 and c_fp32 are exclusive");
   MM_REQUIRE(!a->c_trans || (a->epi == MM_EPI_STD && a->batch == 1 && batch2 == 1),
              "mm_gemm_fwd: c_trans needs the standard epilogue and no batching");
 
@@ -758,12 +771,13 @@ extern "C" int32_t mm_gemm_fwd(const mm_gemm_args* a, void* stream) {
 // ------------------------------------------------------------------------------------------------ split-K reduce
 namespace mm {
 __global__ void splitk_reduce_kernel(const float* __restrict__ part, int splits, int M, int N,
-                                     const bf16* __restrict__ bias, bf16* __restrict__ out, long long ldo, int out_fp16) {
+                                     const bf16* __restrict__ bias, bf16* __restrict__ out, long long ldo, int out_fp16,
+                                     int bias_f16) {
   const long long total = static_cast<long long>(M) * N;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
     const int m = static_cast<int>(i / N), n = static_cast<int>(i % N);
-    float acc = bias ? __bfloat162float(bias[n]) : 0.0f;
+    float acc = bias ? aux_ld(bias, n, bias_f16) : 0.0f;
     for (int s = 0; s < splits; ++s) acc += part[static_cast<long long>(s) * total + i];
     if (out_fp16)
       reinterpret_cast<__half*>(out)[static_cast<long long>(m) * ldo + n] = __float2half_rn(acc);
@@ -780,6 +794,7 @@ extern "C" int32_t mm_splitk_reduce(const float* partial, int32_t splits, int32_
   int blocks = static_cast<int>((total + 255) / 256);
   if (blocks > 148 * 8) blocks = 148 * 8;
   splitk_reduce_kernel<<<blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      partial, splits, M, N, reinterpret_cast<const bf16*>(bias), reinterpret_cast<bf16*>(out), ldo, out_fp16);
+      partial, splits, M, N, reinterpret_cast<const bf16*>(bias), reinterpret_cast<bf16*>(out), ldo, out_fp16,
+      act_f16() ? 1 : 0);
   return check_launch("mm_splitk_reduce");
 }

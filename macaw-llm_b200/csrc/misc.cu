@@ -42,6 +42,12 @@ __device__ __forceinline__ float block_max(float v, float* sh) {
   return r;
 }
 
+// value-level 16-bit conversions in the activation format F16 (the pointers keep the `bf16` spelling: 16-bit storage)
+template <bool F16>
+__device__ __forceinline__ float ldv(bf16 v) { return cvt_in<F16>(__bfloat16_as_ushort(v)); }
+template <bool F16>
+__device__ __forceinline__ bf16 stv(float v) { return __ushort_as_bfloat16(cvt_out<F16>(v)); }
+
 __device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
   f[0] = bf16lo(u.x); f[1] = bf16hi(u.x); f[2] = bf16lo(u.y); f[3] = bf16hi(u.y);
   f[4] = bf16lo(u.z); f[5] = bf16hi(u.z); f[6] = bf16lo(u.w); f[7] = bf16hi(u.w);
@@ -55,6 +61,7 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
 
 // ------------------------------------------------------------------------------------------------ RMSNorm
 // one CTA per row; cols % 8 == 0
+template <bool F16>
 __global__ void __launch_bounds__(256) rmsnorm_kernel(const bf16* __restrict__ x, const bf16* __restrict__ w,
                                                       bf16* __restrict__ y, int cols, float eps) {
   __shared__ float sh[32];
@@ -66,7 +73,7 @@ __global__ void __launch_bounds__(256) rmsnorm_kernel(const bf16* __restrict__ x
   float ss = 0.f;
   for (int c = threadIdx.x; c < nch; c += blockDim.x) {
     float f[8];
-    unpack8(xr[c], f);
+    unpack8t<F16>(xr[c], f);
 #pragma unroll
     for (int i = 0; i < 8; ++i) ss += f[i] * f[i];
   }
@@ -74,15 +81,16 @@ __global__ void __launch_bounds__(256) rmsnorm_kernel(const bf16* __restrict__ x
   const float rstd = rsqrtf(ss / static_cast<float>(cols) + eps);
   for (int c = threadIdx.x; c < nch; c += blockDim.x) {
     float f[8], g[8];
-    unpack8(xr[c], f);
-    unpack8(__ldg(wr + c), g);
+    unpack8t<F16>(xr[c], f);
+    unpack8t<F16>(__ldg(wr + c), g);
 #pragma unroll
     for (int i = 0; i < 8; ++i) f[i] = f[i] * rstd * g[i];
-    yr[c] = pack8(f);
+    yr[c] = pack8t<F16>(f);
   }
 }
 
 // rstd[row] = rsqrt(mean(x^2) + eps): the only part of RMSNorm that cannot ride a GEMM epilogue.  One warp per row.
+template <bool F16>
 __global__ void __launch_bounds__(256) rms_rstd_kernel(const bf16* __restrict__ x, float* __restrict__ rstd, int rows,
                                                        int cols, float eps) {
   griddep_launch();
@@ -94,7 +102,7 @@ __global__ void __launch_bounds__(256) rms_rstd_kernel(const bf16* __restrict__ 
   float ss = 0.f;
   for (int c = lane; c < (cols >> 3); c += 32) {
     float f[8];
-    unpack8(xr[c], f);
+    unpack8t<F16>(xr[c], f);
 #pragma unroll
     for (int i = 0; i < 8; ++i) ss += f[i] * f[i];
   }
@@ -103,6 +111,7 @@ __global__ void __launch_bounds__(256) rms_rstd_kernel(const bf16* __restrict__ 
 }
 
 // ------------------------------------------------------------------------------------------------ LayerNorm
+template <bool F16>
 __global__ void __launch_bounds__(256) layernorm_kernel(const bf16* __restrict__ x, long long ldx,
                                                         const bf16* __restrict__ w, const bf16* __restrict__ b,
                                                         bf16* __restrict__ y, long long ldy, int cols, float eps) {
@@ -114,7 +123,7 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const bf16* __restrict__
   float s = 0.f;
   for (int c = threadIdx.x; c < nch; c += blockDim.x) {
     float f[8];
-    unpack8(xr[c], f);
+    unpack8t<F16>(xr[c], f);
 #pragma unroll
     for (int i = 0; i < 8; ++i) s += f[i];
   }
@@ -122,7 +131,7 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const bf16* __restrict__
   float vs = 0.f;
   for (int c = threadIdx.x; c < nch; c += blockDim.x) {
     float f[8];
-    unpack8(xr[c], f);
+    unpack8t<F16>(xr[c], f);
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       const float d = f[i] - mean;
@@ -132,17 +141,17 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const bf16* __restrict__
   const float rstd = rsqrtf(block_sum(vs, sh) / static_cast<float>(cols) + eps);
   for (int c = threadIdx.x; c < nch; c += blockDim.x) {
     float f[8], g[8], h[8];
-    unpack8(xr[c], f);
-    unpack8(__ldg(reinterpret_cast<const uint4*>(w) + c), g);
-    unpack8(__ldg(reinterpret_cast<const uint4*>(b) + c), h);
+    unpack8t<F16>(xr[c], f);
+    unpack8t<F16>(__ldg(reinterpret_cast<const uint4*>(w) + c), g);
+    unpack8t<F16>(__ldg(reinterpret_cast<const uint4*>(b) + c), h);
 #pragma unroll
     for (int i = 0; i < 8; ++i) f[i] = (f[i] - mean) * rstd * g[i] + h[i];
-    yr[c] = pack8(f);
+    yr[c] = pack8t<F16>(f);
   }
 }
 
 // LayerNorm for narrow rows (cols <= 1024): one warp per row, the row lives in registers (single HBM read).
-template <int CH>  // 16-byte chunks per lane
+template <int CH, bool F16>  // 16-byte chunks per lane
 __global__ void __launch_bounds__(256) layernorm_warp_kernel(const bf16* __restrict__ x, long long ldx,
                                                              const bf16* __restrict__ w, const bf16* __restrict__ b,
                                                              bf16* __restrict__ y, long long ldy, int rows, int cols,
@@ -160,7 +169,7 @@ __global__ void __launch_bounds__(256) layernorm_warp_kernel(const bf16* __restr
   for (int i = 0; i < CH; ++i) {
     const int c = lane + 32 * i;
     if (c < nch) {
-      unpack8(xr[c], f[i]);
+      unpack8t<F16>(xr[c], f[i]);
 #pragma unroll
       for (int k = 0; k < 8; ++k) s += f[i][k];
     }
@@ -184,11 +193,11 @@ __global__ void __launch_bounds__(256) layernorm_warp_kernel(const bf16* __restr
     const int c = lane + 32 * i;
     if (c < nch) {
       float g[8], h[8];
-      unpack8(__ldg(reinterpret_cast<const uint4*>(w) + c), g);
-      unpack8(__ldg(reinterpret_cast<const uint4*>(b) + c), h);
+      unpack8t<F16>(__ldg(reinterpret_cast<const uint4*>(w) + c), g);
+      unpack8t<F16>(__ldg(reinterpret_cast<const uint4*>(b) + c), h);
 #pragma unroll
       for (int k = 0; k < 8; ++k) f[i][k] = (f[i][k] - mean) * rstd * g[k] + h[k];
-      yr[c] = pack8(f[i]);
+      yr[c] = pack8t<F16>(f[i]);
     }
   }
 }
@@ -281,6 +290,7 @@ __global__ void transpose_pad_kernel(const bf16* __restrict__ x, int C, int T, i
   }
 }
 
+template <bool F16>
 __global__ void add_rows_kernel(const bf16* __restrict__ x, long long ldx, const bf16* __restrict__ add, long long lda,
                                 int add_rows, bf16* __restrict__ y, long long ldy, int rows, int cols) {
   const int nch = cols >> 3;
@@ -290,13 +300,13 @@ __global__ void add_rows_kernel(const bf16* __restrict__ x, long long ldx, const
     const long long r = i / nch;
     const int c = static_cast<int>(i % nch);
     float f[8], g[8];
-    unpack8(*reinterpret_cast<const uint4*>(x + r * ldx + c * 8), f);
+    unpack8t<F16>(*reinterpret_cast<const uint4*>(x + r * ldx + c * 8), f);
     if (add != nullptr) {
-      unpack8(__ldg(reinterpret_cast<const uint4*>(add + (r % add_rows) * lda + c * 8)), g);
+      unpack8t<F16>(__ldg(reinterpret_cast<const uint4*>(add + (r % add_rows) * lda + c * 8)), g);
 #pragma unroll
       for (int k = 0; k < 8; ++k) f[k] += g[k];
     }
-    *reinterpret_cast<uint4*>(y + r * ldy + c * 8) = pack8(f);
+    *reinterpret_cast<uint4*>(y + r * ldy + c * 8) = pack8t<F16>(f);
   }
 }
 
@@ -430,6 +440,7 @@ __global__ void __launch_bounds__(128) kv_append_kernel(const bf16* __restrict__
 
 // rotate-half RoPE (head_dim 128) in place on the first `rot_cols` columns of thin rows (decode step): position of row r
 // = pos_base (+ *pos_dev) + r % rope_T.  Same arithmetic as the GEMM's RoPE epilogue (fp32, tables (T, 64)).
+template <bool F16>
 __global__ void rope_rows_kernel(bf16* __restrict__ x, long long ld, int rows, int rot_cols, const float* __restrict__ cs,
                                  const float* __restrict__ sn, int rope_T, const int* __restrict__ pos_dev) {
   const int pairs_per_row = rot_cols / 2;
@@ -441,14 +452,15 @@ __global__ void rope_rows_kernel(bf16* __restrict__ x, long long ld, int rows, i
     const int head = pi / 64, j = pi % 64;
     const int pos = pos0 + r % rope_T;
     bf16* p1 = x + r * ld + head * 128 + j;
-    const float a = __bfloat162float(p1[0]), b = __bfloat162float(p1[64]);
+    const float a = ldv<F16>(p1[0]), b = ldv<F16>(p1[64]);
     const float c = cs[static_cast<long long>(pos) * 64 + j], s = sn[static_cast<long long>(pos) * 64 + j];
-    p1[0] = __float2bfloat16(a * c - b * s);
-    p1[64] = __float2bfloat16(b * c + a * s);
+    p1[0] = stv<F16>(a * c - b * s);
+    p1[64] = stv<F16>(b * c + a * s);
   }
 }
 
 // out[r, 32 q + i] = silu(gu[r, 64 q + i]) * gu[r, 64 q + 32 + i]: the [32 gate | 32 up] interleave of the fused weight
+template <bool F16>
 __global__ void swiglu_rows_kernel(const bf16* __restrict__ gu, long long ld, int rows, int I, bf16* __restrict__ out,
                                    long long ldo) {
   const long long total = static_cast<long long>(rows) * I;
@@ -456,12 +468,31 @@ __global__ void swiglu_rows_kernel(const bf16* __restrict__ gu, long long ld, in
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
     const int r = static_cast<int>(i / I), c = static_cast<int>(i % I);
     const bf16* g = gu + r * ld + (c / 32) * 64 + (c % 32);
-    const float a = __bfloat162float(g[0]), b = __bfloat162float(g[32]);
-    out[r * ldo + c] = __float2bfloat16(a / (1.0f + __expf(-a)) * b);
+    const float a = ldv<F16>(g[0]), b = ldv<F16>(g[32]);
+    out[r * ldo + c] = stv<F16>(a / (1.0f + __expf(-a)) * b);
+  }
+}
+
+// Tail of the split-K thin GEMMs of a decode step: part[s][n][m] fp32 (the swapped-operand product W_s x_s^T per K slice)
+// -> out[m][n] = act_scale[m] * sum_s part[s][n][m] (+ residual[m][n]), bf16.
+template <bool F16>
+__global__ void thin_reduce_kernel(const float* __restrict__ part, int S, int N, int M, int ldp,
+                                   const float* __restrict__ row_scale, const bf16* __restrict__ residual, long long ldr,
+                                   bf16* __restrict__ out, long long ldo) {
+  const long long total = static_cast<long long>(N) * M;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int n = static_cast<int>(i / M), m = static_cast<int>(i % M);
+    float acc = 0.f;
+    for (int s = 0; s < S; ++s) acc += part[(static_cast<long long>(s) * N + n) * ldp + m];
+    if (row_scale != nullptr) acc *= row_scale[m];
+    if (residual != nullptr) acc += ldv<F16>(residual[static_cast<long long>(m) * ldr + n]);
+    out[static_cast<long long>(m) * ldo + n] = stv<F16>(acc);
   }
 }
 
 // greedy next token: index of the largest logit per row (lowest index on ties), bf16 logits with row stride ld
+template <bool F16>
 __global__ void __launch_bounds__(512) argmax_rows_kernel(const bf16* __restrict__ logits, long long ld, int V,
                                                           long long* __restrict__ out) {
   __shared__ float sv[16];
@@ -470,7 +501,7 @@ __global__ void __launch_bounds__(512) argmax_rows_kernel(const bf16* __restrict
   float best = -INFINITY;
   int bi = 0x7fffffff;
   for (int c = threadIdx.x; c < V; c += blockDim.x) {
-    const float v = __bfloat162float(row[c]);
+    const float v = ldv<F16>(row[c]);
     if (v > best || (v == best && c < bi)) {
       best = v;
       bi = c;
@@ -508,6 +539,7 @@ __global__ void __launch_bounds__(512) argmax_rows_kernel(const bf16* __restrict
 }
 
 // ------------------------------------------------------------------------------------------------ CE loss
+template <bool F16>
 __global__ void __launch_bounds__(512) ce_loss_kernel(const bf16* __restrict__ logits, const long long* __restrict__ labels,
                                                       int T, int V, float* __restrict__ loss_sum,
                                                       int* __restrict__ n_valid) {
@@ -518,7 +550,7 @@ __global__ void __launch_bounds__(512) ce_loss_kernel(const bf16* __restrict__ l
   const bf16* row = logits + (static_cast<long long>(b) * T + t) * V;
   float m = -INFINITY, l = 0.f;
   for (int c = threadIdx.x; c < V; c += blockDim.x) {
-    const float v = __bfloat162float(row[c]);
+    const float v = ldv<F16>(row[c]);
     if (v > m) {
       l *= __expf(m - v);
       m = v;
@@ -530,7 +562,7 @@ __global__ void __launch_bounds__(512) ce_loss_kernel(const bf16* __restrict__ l
   const float ll = block_sum(l, sh);
   if (threadIdx.x == 0) {
     const float lse = mm_ + logf(ll);
-    atomicAdd(loss_sum, lse - __bfloat162float(row[tgt]));
+    atomicAdd(loss_sum, lse - ldv<F16>(row[tgt]));
     atomicAdd(n_valid, 1);
   }
 }
@@ -551,13 +583,14 @@ extern "C" int32_t mm_rmsnorm_fwd(const void* x, const void* w, void* y, int32_t
                                   void* stream) {
   MM_REQUIRE(x && w && y && rows > 0 && cols > 0 && cols % 8 == 0, "mm_rmsnorm_fwd: bad arguments (cols %% 8 != 0?)");
   MM_REQUIRE(AL16(x) && AL16(w) && AL16(y), "mm_rmsnorm_fwd: pointers must be 16-byte aligned");
-  rmsnorm_kernel<<<rows, 256, 0, ST(stream)>>>((const bf16*)x, (const bf16*)w, (bf16*)y, cols, eps);
+  auto kern = act_f16() ? rmsnorm_kernel<true> : rmsnorm_kernel<false>;
+  kern<<<rows, 256, 0, ST(stream)>>>((const bf16*)x, (const bf16*)w, (bf16*)y, cols, eps);
   return check_launch("mm_rmsnorm_fwd");
 }
 
 extern "C" int32_t mm_rms_rstd(const void* x, float* rstd, int32_t rows, int32_t cols, float eps, void* stream) {
   MM_REQUIRE(x && rstd && rows > 0 && cols > 0 && cols % 8 == 0 && AL16(x), "mm_rms_rstd: bad arguments");
-  if (launch_kernel(rms_rstd_kernel, dim3((rows + 7) / 8), dim3(256), 0, ST(stream), 1, (const bf16*)x, rstd, rows, cols,
+  if (launch_kernel(act_f16() ? rms_rstd_kernel<true> : rms_rstd_kernel<false>, dim3((rows + 7) / 8), dim3(256), 0, ST(stream), 1, (const bf16*)x, rstd, rows, cols,
                     eps) != cudaSuccess) {
     set_error("mm_rms_rstd: launch failed");
     return 2;
@@ -571,13 +604,14 @@ extern "C" int32_t mm_layernorm_fwd(const void* x, int64_t ldx, const void* w, c
              "mm_layernorm_fwd: bad arguments");
   MM_REQUIRE(AL16(x) && AL16(w) && AL16(b) && AL16(y), "mm_layernorm_fwd: pointers must be 16-byte aligned");
   if (cols <= 512) {
-    launch_kernel(layernorm_warp_kernel<2>, dim3((rows + 7) / 8), dim3(256), 0, ST(stream), 1, (const bf16*)x,
+    launch_kernel(act_f16() ? layernorm_warp_kernel<2, true> : layernorm_warp_kernel<2, false>, dim3((rows + 7) / 8), dim3(256), 0, ST(stream), 1, (const bf16*)x,
                   (long long)ldx, (const bf16*)w, (const bf16*)b, (bf16*)y, (long long)ldy, rows, cols, eps);
   } else if (cols <= 1024) {
-    launch_kernel(layernorm_warp_kernel<4>, dim3((rows + 7) / 8), dim3(256), 0, ST(stream), 1, (const bf16*)x,
+    launch_kernel(act_f16() ? layernorm_warp_kernel<4, true> : layernorm_warp_kernel<4, false>, dim3((rows + 7) / 8), dim3(256), 0, ST(stream), 1, (const bf16*)x,
                   (long long)ldx, (const bf16*)w, (const bf16*)b, (bf16*)y, (long long)ldy, rows, cols, eps);
   } else {
-    layernorm_kernel<<<rows, 128, 0, ST(stream)>>>((const bf16*)x, ldx, (const bf16*)w, (const bf16*)b, (bf16*)y, ldy,
+    auto kern = act_f16() ? layernorm_kernel<true> : layernorm_kernel<false>;
+    kern<<<rows, 128, 0, ST(stream)>>>((const bf16*)x, ldx, (const bf16*)w, (const bf16*)b, (bf16*)y, ldy,
                                                    cols, eps);
   }
   return check_launch("mm_layernorm_fwd");
@@ -634,7 +668,8 @@ extern "C" int32_t mm_add_rows(const void* x, int64_t ldx, const void* add, int6
   MM_REQUIRE(add == nullptr || (add_rows > 0 && lda % 8 == 0 && AL16(add)), "mm_add_rows: bad addend");
   MM_REQUIRE(AL16(x) && AL16(y), "mm_add_rows: alignment");
   const long long total = static_cast<long long>(rows) * (cols / 8);
-  add_rows_kernel<<<grid_for(total, 256), 256, 0, ST(stream)>>>((const bf16*)x, ldx, (const bf16*)add, lda, add_rows,
+  auto kern = act_f16() ? add_rows_kernel<true> : add_rows_kernel<false>;
+  kern<<<grid_for(total, 256), 256, 0, ST(stream)>>>((const bf16*)x, ldx, (const bf16*)add, lda, add_rows,
                                                                 (bf16*)y, ldy, rows, cols);
   return check_launch("mm_add_rows");
 }
@@ -688,27 +723,42 @@ extern "C" int32_t mm_rope_rows(void* x, int64_t ld, int32_t rows, int32_t rot_c
                                 int32_t rope_T, const int32_t* pos_dev, void* stream) {
   MM_REQUIRE(x && cos_t && sin_t && rows > 0 && rot_cols > 0 && rot_cols % 128 == 0 && rope_T > 0, "mm_rope_rows: bad arguments");
   const long long total = static_cast<long long>(rows) * rot_cols / 2;
-  rope_rows_kernel<<<grid_for(total, 256), 256, 0, ST(stream)>>>((bf16*)x, ld, rows, rot_cols, cos_t, sin_t, rope_T, pos_dev);
+  auto kern = act_f16() ? rope_rows_kernel<true> : rope_rows_kernel<false>;
+  kern<<<grid_for(total, 256), 256, 0, ST(stream)>>>((bf16*)x, ld, rows, rot_cols, cos_t, sin_t, rope_T, pos_dev);
   return check_launch("mm_rope_rows");
 }
 
 extern "C" int32_t mm_swiglu_rows(const void* gu, int64_t ld, int32_t rows, int32_t I, void* out, int64_t ldo, void* stream) {
   MM_REQUIRE(gu && out && rows > 0 && I > 0 && I % 32 == 0, "mm_swiglu_rows: bad arguments");
   const long long total = static_cast<long long>(rows) * I;
-  swiglu_rows_kernel<<<grid_for(total, 256), 256, 0, ST(stream)>>>((const bf16*)gu, ld, rows, I, (bf16*)out, ldo);
+  auto kern = act_f16() ? swiglu_rows_kernel<true> : swiglu_rows_kernel<false>;
+  kern<<<grid_for(total, 256), 256, 0, ST(stream)>>>((const bf16*)gu, ld, rows, I, (bf16*)out, ldo);
   return check_launch("mm_swiglu_rows");
+}
+
+extern "C" int32_t mm_thin_reduce(const float* part, int32_t splits, int32_t N, int32_t M, int32_t ldp,
+                                  const float* row_scale, const void* residual, int64_t ldr, void* out, int64_t ldo,
+                                  void* stream) {
+  MM_REQUIRE(part && out && splits > 0 && N > 0 && M > 0 && ldp >= M, "mm_thin_reduce: bad arguments");
+  const long long total = static_cast<long long>(N) * M;
+  auto kern = act_f16() ? thin_reduce_kernel<true> : thin_reduce_kernel<false>;
+  kern<<<grid_for(total, 256), 256, 0, ST(stream)>>>(part, splits, N, M, ldp, row_scale,
+                                                                  (const bf16*)residual, ldr, (bf16*)out, ldo);
+  return check_launch("mm_thin_reduce");
 }
 
 extern "C" int32_t mm_argmax_rows(const void* logits, int64_t ld, int32_t rows, int32_t V, int64_t* out, void* stream) {
   MM_REQUIRE(logits && out && rows > 0 && V > 0 && ld >= V, "mm_argmax_rows: bad arguments");
-  argmax_rows_kernel<<<rows, 512, 0, ST(stream)>>>((const bf16*)logits, ld, V, (long long*)out);
+  auto kern = act_f16() ? argmax_rows_kernel<true> : argmax_rows_kernel<false>;
+  kern<<<rows, 512, 0, ST(stream)>>>((const bf16*)logits, ld, V, (long long*)out);
   return check_launch("mm_argmax_rows");
 }
 
 extern "C" int32_t mm_ce_loss(const void* logits, const int64_t* labels, int32_t B, int32_t T, int32_t V,
                               float* loss_sum, int32_t* n_valid, void* stream) {
   MM_REQUIRE(logits && labels && loss_sum && n_valid && B > 0 && T > 1 && V > 0, "mm_ce_loss: bad arguments");
-  ce_loss_kernel<<<B * (T - 1), 512, 0, ST(stream)>>>((const bf16*)logits, (const long long*)labels, T, V, loss_sum,
+  auto kern = act_f16() ? ce_loss_kernel<true> : ce_loss_kernel<false>;
+  kern<<<B * (T - 1), 512, 0, ST(stream)>>>((const bf16*)logits, (const long long*)labels, T, V, loss_sum,
                                                       n_valid);
   return check_launch("mm_ce_loss");
 }

@@ -245,4 +245,43 @@ __device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
 __device__ __forceinline__ float bf16lo(uint32_t v) { return __uint_as_float(v << 16); }
 __device__ __forceinline__ float bf16hi(uint32_t v) { return __uint_as_float(v & 0xFFFF0000u); }
 
+// ----------------------------------------------------------------------------- 16-bit storage, format chosen at compile time
+template <bool F16>
+__device__ __forceinline__ float cvt_in(uint16_t raw) {
+  if constexpr (F16) return __half2float(__ushort_as_half(raw));
+  return __uint_as_float(static_cast<uint32_t>(raw) << 16);
+}
+template <bool F16>
+__device__ __forceinline__ uint16_t cvt_out(float v) {
+  if constexpr (F16) return __half_as_ushort(__float2half_rn(v));
+  return __bfloat16_as_ushort(__float2bfloat16(v));
+}
+template <bool F16>
+__device__ __forceinline__ uint32_t pack2(float lo, float hi) {
+  if constexpr (F16) return pack_f16x2(lo, hi);
+  return pack_bf16x2(lo, hi);
+}
+template <bool F16>
+__device__ __forceinline__ void unpack2(uint32_t v, float& lo, float& hi) {
+  if constexpr (F16) {
+    const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&v));
+    lo = f.x;
+    hi = f.y;
+  } else {
+    lo = bf16lo(v);
+    hi = bf16hi(v);
+  }
+}
+template <bool F16>
+__device__ __forceinline__ void unpack8t(const uint4& u, float (&f)[8]) {
+  unpack2<F16>(u.x, f[0], f[1]);
+  unpack2<F16>(u.y, f[2], f[3]);
+  unpack2<F16>(u.z, f[4], f[5]);
+  unpack2<F16>(u.w, f[6], f[7]);
+}
+template <bool F16>
+__device__ __forceinline__ uint4 pack8t(const float (&f)[8]) {
+  return make_uint4(pack2<F16>(f[0], f[1]), pack2<F16>(f[2], f[3]), pack2<F16>(f[4], f[5]), pack2<F16>(f[6], f[7]));
+}
+
 }  // namespace mm

@@ -204,7 +204,8 @@ __global__ void __launch_bounds__(256) attn_softmax_bwd_kernel(const float* __re
 // onehot(labels[b,t+1])) * gscale / n_valid  when t < T-1 and the label is not -100, else 0.  In place is allowed.
 __global__ void __launch_bounds__(512) ce_bwd_kernel(const bf16* __restrict__ logits, const long long* __restrict__ labels,
                                                      bf16* __restrict__ dlogits, int T, int V,
-                                                     const int* __restrict__ n_valid, float gscale) {
+                                                     const int* __restrict__ n_valid, float gscale,
+                                                     const float* __restrict__ gscale_dev) {
   __shared__ float sh[32];
   const long long row = blockIdx.x;  // b * T + t
   const int t = static_cast<int>(row % T);
@@ -223,7 +224,7 @@ __global__ void __launch_bounds__(512) ce_bwd_kernel(const bf16* __restrict__ lo
   for (int j = threadIdx.x; j < V; j += blockDim.x) sum += __expf(__bfloat162float(x[j]) - mx);
   sum = block_sum(sum, sh);
   const int nv = *n_valid;
-  const float sc = gscale / static_cast<float>(nv > 0 ? nv : 1);
+  const float sc = gscale * (gscale_dev != nullptr ? *gscale_dev : 1.0f) / static_cast<float>(nv > 0 ? nv : 1);
   const float inv = 1.f / sum;
   for (int j = threadIdx.x; j < V; j += blockDim.x) {
     float pj = __expf(__bfloat162float(x[j]) - mx) * inv;
@@ -265,7 +266,12 @@ __global__ void colsum_kernel(const bf16* __restrict__ x, long long ldx, int row
 //   m = b1 m + (1-b1) g;  v = b2 v + (1-b2) g^2;  w -= lr (m/bc1 / (sqrt(v/bc2) + eps) + wd w);  p = bf16(w)
 __global__ void adamw_kernel(bf16* __restrict__ p, const bf16* __restrict__ g, float* __restrict__ w, float* __restrict__ m,
                              float* __restrict__ v, long long n, float lr, float b1, float b2, float eps, float wd,
-                             float inv_bc1, float inv_bc2, float gscale) {
+                             float inv_bc1, float inv_bc2, float gscale, const int* __restrict__ step_dev) {
+  if (step_dev != nullptr) {  // step count read on the device: the launch can be replayed from a CUDA graph
+    const float t = static_cast<float>(*step_dev);
+    inv_bc1 = 1.f / (1.f - powf(b1, t));
+    inv_bc2 = 1.f / (1.f - powf(b2, t));
+  }
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
     const float gi = __bfloat162float(g[i]) * gscale;
@@ -399,10 +405,10 @@ extern "C" int32_t mm_attn_softmax_bwd(const float* S, const float* dP, void* P,
 }
 
 extern "C" int32_t mm_ce_bwd(const void* logits, const int64_t* labels, void* dlogits, int32_t B, int32_t T, int32_t V,
-                             const int32_t* n_valid, float grad_scale, void* stream) {
+                             const int32_t* n_valid, float grad_scale, const float* grad_scale_dev, void* stream) {
   MM_REQUIRE(logits && labels && dlogits && n_valid && B > 0 && T > 0 && V > 0, "mm_ce_bwd: bad arguments");
   ce_bwd_kernel<<<B * T, 512, 0, ST(stream)>>>((const bf16*)logits, (const long long*)labels, (bf16*)dlogits, T, V, n_valid,
-                                               grad_scale);
+                                               grad_scale, grad_scale_dev);
   return check_launch("mm_ce_bwd");
 }
 
@@ -424,12 +430,14 @@ extern "C" int32_t mm_colsum(const void* x, int64_t ldx, int32_t rows, int32_t c
 }
 
 extern "C" int32_t mm_adamw(void* p, const void* g, float* master, float* m, float* v, int64_t n, float lr, float beta1,
-                            float beta2, float eps, float weight_decay, int32_t step, float grad_scale, void* stream) {
-  MM_REQUIRE(p && g && master && m && v && n > 0 && step > 0, "mm_adamw: bad arguments");
+                            float beta2, float eps, float weight_decay, int32_t step, const int32_t* step_dev,
+                            float grad_scale, void* stream) {
+  MM_REQUIRE(p && g && master && m && v && n > 0 && (step > 0 || step_dev != nullptr), "mm_adamw: bad arguments");
+  if (step <= 0) step = 1;
   const float inv_bc1 = 1.f / (1.f - powf(beta1, static_cast<float>(step)));
   const float inv_bc2 = 1.f / (1.f - powf(beta2, static_cast<float>(step)));
   adamw_kernel<<<grid_for(n, 256), 256, 0, ST(stream)>>>((bf16*)p, (const bf16*)g, master, m, v, n, lr, beta1, beta2, eps,
-                                                        weight_decay, inv_bc1, inv_bc2, grad_scale);
+                                                        weight_decay, inv_bc1, inv_bc2, grad_scale, step_dev);
   return check_launch("mm_adamw");
 }
 

@@ -48,3 +48,59 @@ def weighted_mean_loss(loss_sum: float, n_valid: int, device=None) -> float:
     t = torch.tensor([loss_sum, float(n_valid)], dtype=torch.float64, device=device or "cpu")
     dist.all_reduce(t, op=dist.ReduceOp.SUM)
     return float(t[0] / t[1].clamp_min(1.0))
+
+
+# ---------------------------------------------------------------------------------------------------- gradient all-reduce
+_NCCL_READY = False
+
+
+def init_nccl(device=None) -> bool:
+    """Create the kernel library's own NCCL communicator for the default torch.distributed group (one process per GPU):
+    rank 0 draws the unique id (mm_nccl_unique_id) and ships it through torch.distributed's broadcast (plumbing), every
+    rank calls mm_nccl_init.  Returns True when the communicator is up."""
+    global _NCCL_READY
+    if _NCCL_READY:
+        return True
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return False
+    import ctypes as C
+
+    from . import _lib
+
+    lib = _lib.load()
+    world, rank = dist.get_world_size(), dist.get_rank()
+    buf = (C.c_ubyte * 128)()
+    if rank == 0:
+        rc = lib.mm_nccl_unique_id(buf)
+        if rc != 0:
+            raise RuntimeError(f"mm_nccl_unique_id failed: {_lib.last_error()}")
+    dev = device if device is not None else torch.device("cuda", torch.cuda.current_device())
+    t = torch.tensor(list(buf), dtype=torch.uint8, device=dev)
+    dist.broadcast(t, src=0)
+    ids = (C.c_ubyte * 128)(*t.cpu().tolist())
+    with torch.cuda.device(dev):
+        rc = lib.mm_nccl_init(ids, world, rank)
+    if rc != 0:
+        raise RuntimeError(f"mm_nccl_init failed: {_lib.last_error()}")
+    _NCCL_READY = True
+    return True
+
+
+def nccl_allreduce_(t: torch.Tensor, average: bool = True) -> None:
+    """In-place all-reduce of a contiguous bf16 / fp32 CUDA tensor on torch's CURRENT stream through mm_nccl_allreduce."""
+    from . import _lib
+
+    assert _NCCL_READY and t.is_cuda and t.is_contiguous() and t.dtype in (torch.bfloat16, torch.float32)
+    rc = _lib.load().mm_nccl_allreduce(t.data_ptr(), t.numel(), int(t.dtype == torch.float32), int(average),
+                                       torch.cuda.current_stream().cuda_stream)
+    if rc != 0:
+        raise RuntimeError(f"mm_nccl_allreduce failed: {_lib.last_error()}")
+
+
+def destroy_nccl() -> None:
+    global _NCCL_READY
+    if _NCCL_READY:
+        from . import _lib
+
+        _lib.load().mm_nccl_destroy()
+        _NCCL_READY = False

@@ -22,6 +22,11 @@ from . import ops
 BF16 = torch.bfloat16
 
 
+def ADT():
+    """The 16-bit storage dtype of the model being run (set per call by Engine._set_format): bf16, or fp16 for an fp16 model."""
+    return ops.ACT()
+
+
 def _round_up(x: int, m: int) -> int:
     return (x + m - 1) // m * m
 
@@ -34,6 +39,7 @@ class Engine:
         self._pe: Dict[Tuple[int, int, str], torch.Tensor] = {}
         self._zeros: Dict[Tuple[int, str], torch.Tensor] = {}
         self._graphs: Dict[tuple, tuple] = {}
+        self._decode: Dict[tuple, dict] = {}  # KV buffers + captured decode step per (batch, capacity, device)
         self._graphs_on = False
         self.align_max_rows = None  # test hook: cap on query rows per alignment chunk (default: ~2 GiB of fp32 scores)
 
@@ -56,23 +62,33 @@ class Engine:
         """fp16 copy of a parameter for the fp16 alignment chain: the bf16 value converted exactly (values below fp16's
         normal range lose bits, values above 65504 saturate — neither occurs for weights / embeddings)."""
         self.w(p, key)  # device / dtype checks
-        return self.derived("f16:" + key, [p], lambda: p.detach().to(BF16).to(torch.float16))
+        if p.dtype == torch.float16:
+            return p.detach()  # an fp16 model already is in the chain's format
+        return self.derived("f16:" + key, [p], lambda: p.detach().to(torch.bfloat16).to(torch.float16))
+
+    def set_format(self) -> None:
+        """Choose the 16-bit storage format for this call from the model's dtype: an fp16 model (the reference's own
+        precision: train.sh `--fp16 True`, llm_trainer.py:366-368 `.half()`) is computed in fp16 — 11-bit significands, the
+        storage rounding of every activation is 8x smaller than bf16's; bf16 and fp32 models are computed in bf16 (fp32
+        parameters through bf16 shadows).  Sets both the Python-side dtype and the kernel library's thread-local format."""
+        dt = self.m.llm.model.embed_tokens.weight.dtype
+        ops.set_act_format(torch.float16 if dt == torch.float16 else torch.bfloat16)
 
     def w(self, p: torch.Tensor, key: str) -> torch.Tensor:
-        """bf16 CUDA view of a parameter (the parameter itself when it already is bf16)."""
+        """CUDA view of a parameter in the activation format (the parameter itself when it already has that dtype)."""
         if not p.is_cuda:
             raise RuntimeError(
                 "macaw_b200: model parameters live on the CPU; move the model to a CUDA device "
                 "(there is no CPU execution path)")
-        if p.dtype == BF16:
+        if p.dtype == ADT():
             return p.detach()
-        return self.derived("bf16:" + key, [p], lambda: p.detach().to(BF16))
+        return self.derived("shadow:" + key, [p], lambda: p.detach().to(ADT()))
 
     def zeros(self, n: int, dev) -> torch.Tensor:
         k = (n, str(dev))
         z = self._zeros.get(k)
         if z is None:
-            z = torch.zeros((1, n), device=dev, dtype=BF16)
+            z = torch.zeros((1, n), device=dev, dtype=ADT())
             self._zeros[k] = z
         return z
 
@@ -91,6 +107,10 @@ class Engine:
 
     # ------------------------------------------------------------------------------------------------ CLIP
     def clip_tokens(self, images: torch.Tensor, which: str) -> torch.Tensor:
+        self.set_format()
+        return self._clip_tokens(images, which)
+
+    def _clip_tokens(self, images: torch.Tensor, which: str) -> torch.Tensor:
         """visual_projection(vision_model(images)[0])[:, 1:, :] (reference modeling.py:1092 / :1073) -> (n_img, 256, P).
 
         CLS rows are skipped by the projection GEMM itself (A starts at row 1 of every image)."""
@@ -110,8 +130,8 @@ class Engine:
         emb = vm.embeddings
 
         def pack_patch():
-            wt = emb.patch_embedding.weight.detach().to(BF16).reshape(D, -1)
-            out = torch.zeros((D, kp), device=dev, dtype=BF16)
+            wt = emb.patch_embedding.weight.detach().to(ADT()).reshape(D, -1)
+            out = torch.zeros((D, kp), device=dev, dtype=ADT())
             out[:, : wt.shape[1]] = wt
             return out
 
@@ -123,7 +143,7 @@ class Engine:
         cls = self.w(emb.class_embedding, pre + "cls").view(1, D)
 
         cols = ops.patchify(images, p, kp)  # (n_img * G, kp)
-        x = torch.empty((n_img, T, D), device=dev, dtype=BF16)
+        x = torch.empty((n_img, T, D), device=dev, dtype=ADT())
         # patch embedding + position embedding, written to rows 1..G of every image
         ops.gemm_raw(M=G, N=D, K=kp, batch=n_img, A=cols.data_ptr(), lda=kp, a_bs=G * kp, B=w_patch.data_ptr(), ldb=kp,
                      b_bs=0, Cout=x.data_ptr() + D * 2, ldc=D, c_bs=T * D, residual=pos.data_ptr() + D * 2, ldr=D, r_bs=0)
@@ -136,9 +156,9 @@ class Engine:
             k = f"{pre}l{i}."
             sa = l.self_attn
             wqkv = self.derived(k + "wqkv", [sa.q_proj.weight, sa.k_proj.weight, sa.v_proj.weight],
-                                lambda sa=sa: torch.cat([sa.q_proj.weight, sa.k_proj.weight, sa.v_proj.weight], 0).detach().to(BF16).contiguous())
+                                lambda sa=sa: torch.cat([sa.q_proj.weight, sa.k_proj.weight, sa.v_proj.weight], 0).detach().to(ADT()).contiguous())
             bqkv = self.derived(k + "bqkv", [sa.q_proj.bias, sa.k_proj.bias, sa.v_proj.bias],
-                                lambda sa=sa: torch.cat([sa.q_proj.bias, sa.k_proj.bias, sa.v_proj.bias], 0).detach().to(BF16).contiguous())
+                                lambda sa=sa: torch.cat([sa.q_proj.bias, sa.k_proj.bias, sa.v_proj.bias], 0).detach().to(ADT()).contiguous())
             x2 = self._self_attn_block(
                 x2, n_img, T, D, H,
                 (self.w(l.layer_norm1.weight, k + "ln1w"), self.w(l.layer_norm1.bias, k + "ln1b")),
@@ -149,7 +169,7 @@ class Engine:
                 act, eps, (D // H) ** -0.5)
         wp = self.w(clip.visual_projection.weight, which + ".vproj")
         P = wp.shape[0]
-        tok = torch.empty((n_img, G, P), device=dev, dtype=BF16)
+        tok = torch.empty((n_img, G, P), device=dev, dtype=ADT())
         ops.gemm_raw(M=G, N=P, K=D, batch=n_img, A=x2.data_ptr() + D * 2, lda=D, a_bs=T * D, B=wp.data_ptr(), ldb=D, b_bs=0,
                      Cout=tok.data_ptr(), ldc=P, c_bs=G * P)
         return tok
@@ -161,6 +181,7 @@ class Engine:
         Both stem convolutions run as GEMMs over overlapping row windows of a time-major, zero-padded buffer
         (no im2col copy): conv1 k=3 s=1 p=1, conv2 k=3 s=2 p=1; GELU and the position embedding ride the epilogues."""
         ops.TAG = "whisper"
+        self.set_format()
         enc = self.m.audio_encoder.encoder
         cfg = self.m.audio_encoder.config
         D, H = cfg.d_model, cfg.encoder_attention_heads
@@ -169,11 +190,11 @@ class Engine:
         dev = mel.device
         pre = "audio_encoder.encoder."
         w1 = self.derived(pre + "conv1", [enc.conv1.weight],
-                          lambda: enc.conv1.weight.detach().to(BF16).permute(0, 2, 1).reshape(D, 3 * C).contiguous())
+                          lambda: enc.conv1.weight.detach().to(ADT()).permute(0, 2, 1).reshape(D, 3 * C).contiguous())
         w2 = self.derived(pre + "conv2", [enc.conv2.weight],
-                          lambda: enc.conv2.weight.detach().to(BF16).permute(0, 2, 1).reshape(D, 3 * D).contiguous())
+                          lambda: enc.conv2.weight.detach().to(ADT()).permute(0, 2, 1).reshape(D, 3 * D).contiguous())
         xt = ops.transpose_pad(mel, 1)  # (B, Tm + 2, C)
-        h1 = torch.empty((B, Tm + 2, D), device=dev, dtype=BF16)
+        h1 = torch.empty((B, Tm + 2, D), device=dev, dtype=ADT())
         z = self.zeros(D, dev)
         ops.add_rows(z.expand(B, D), None, h1[:, 0, :])
         ops.add_rows(z.expand(B, D), None, h1[:, Tm + 1, :])
@@ -185,7 +206,7 @@ class Engine:
         if T != pos.shape[0]:  # HF WhisperEncoder.forward raises on any other mel length; the GEMM reads pos by raw pointer
             raise ValueError(f"Whisper expects the mel input features to be of length {2 * pos.shape[0]}, but found {Tm}. "
                              f"Make sure to pad the input mel features to {2 * pos.shape[0]}.")
-        x = torch.empty((B, T, D), device=dev, dtype=BF16)
+        x = torch.empty((B, T, D), device=dev, dtype=ADT())
         ops.gemm_raw(M=T, N=D, K=3 * D, batch=B, A=h1.data_ptr(), lda=2 * D, a_bs=(Tm + 2) * D, B=w2.data_ptr(), ldb=3 * D,
                      b_bs=0, Cout=x.data_ptr(), ldc=D, c_bs=T * D, bias=self.w(enc.conv2.bias, pre + "b2").data_ptr(),
                      act=ops.ACT_GELU, residual=pos.data_ptr(), ldr=D, r_bs=0)
@@ -194,9 +215,9 @@ class Engine:
             k = f"{pre}l{i}."
             sa = l.self_attn
             wqkv = self.derived(k + "wqkv", [sa.q_proj.weight, sa.k_proj.weight, sa.v_proj.weight],
-                                lambda sa=sa: torch.cat([sa.q_proj.weight, sa.k_proj.weight, sa.v_proj.weight], 0).detach().to(BF16).contiguous())
+                                lambda sa=sa: torch.cat([sa.q_proj.weight, sa.k_proj.weight, sa.v_proj.weight], 0).detach().to(ADT()).contiguous())
             bqkv = self.derived(k + "bqkv", [sa.q_proj.bias, sa.v_proj.bias],
-                                lambda sa=sa: torch.cat([sa.q_proj.bias, torch.zeros_like(sa.q_proj.bias), sa.v_proj.bias], 0).detach().to(BF16).contiguous())
+                                lambda sa=sa: torch.cat([sa.q_proj.bias, torch.zeros_like(sa.q_proj.bias), sa.v_proj.bias], 0).detach().to(ADT()).contiguous())
             x2 = self._self_attn_block(
                 x2, B, T, D, H,
                 (self.w(l.self_attn_layer_norm.weight, k + "ln1w"), self.w(l.self_attn_layer_norm.bias, k + "ln1b")),
@@ -222,7 +243,7 @@ class Engine:
             t = torch.zeros(L, h, dtype=torch.float32)
             t[:, 0::2] = torch.sin(pos * div)
             t[:, 1::2] = torch.cos(pos * div)
-            pe = t.to(BF16).to(dev)
+            pe = t.to(ADT()).to(dev)
             self._pe[key] = pe
         return pe
 
@@ -247,7 +268,7 @@ class Engine:
         pre = "video_long_self_attention."
         w_in = self.w(mha.in_proj_weight, pre + "win")
         b_in = self.w(mha.in_proj_bias, pre + "bin")
-        qkv = torch.empty((B, N + 2, 3 * P), device=dev, dtype=BF16)
+        qkv = torch.empty((B, N + 2, 3 * P), device=dev, dtype=ADT())
         ops.gemm_raw(M=N, N=3 * P, K=P, batch=B, A=xp.data_ptr(), lda=P, a_bs=N * P, B=w_in.data_ptr(), ldb=P, b_bs=0,
                      Cout=qkv.data_ptr(), ldc=3 * P, c_bs=(N + 2) * 3 * P, bias=b_in.data_ptr())
         # synthetic keys: row N = (bias_k, bias_v) appended un-projected, row N+1 = zeros (functional.py:6531-6537, 6585-6602)
@@ -286,7 +307,7 @@ class Engine:
         B, N, C = feats.shape
         assert feats.stride(2) == 1 and feats.stride(1) == C
         feats_bf = feats.contiguous()
-        feats = ops.cast_f16(feats_bf)
+        feats = feats_bf if feats_bf.dtype == F16 else ops.cast_f16(feats_bf)
         if table16 is None:  # stand-alone use (tests / tools): exact fp16 copy of the given table
             table16 = self.derived("align.table16", [table], lambda: table.detach().to(F16))
         assert table16.shape == table.shape and table16.dtype == F16
@@ -302,7 +323,7 @@ class Engine:
         f16 = dict(a_fp16=True, b_fp16=True)
         # ---- Conv1d over the token axis == GEMM on overlapping row windows (window = kk*C contiguous elements), split over K
         wc = self.derived(pre + "conv", [conv.weight],
-                          lambda: conv.weight.detach().to(BF16).to(F16).permute(0, 2, 1).reshape(C, kk * C).contiguous())
+                          lambda: conv.weight.detach().to(ADT()).to(F16).permute(0, 2, 1).reshape(C, kk * C).contiguous())
         K = kk * C
         S = 1
         for cand in (16, 12, 9, 8, 6, 4, 3, 2):
@@ -323,8 +344,8 @@ class Engine:
         q = ops.linear(z, w_in[:E], b_in[:E], out_dtype=F16)  # (Nq, E); the 1/sqrt(hd) scale is applied downstream (alpha)
         w_k, w_v = w_in[E:2 * E], w_in[2 * E:]
         bk2 = self.derived(pre + "bk2", [mha.in_proj_bias, mha.bias_k],
-                           lambda: torch.stack([mha.in_proj_bias.detach()[E:2 * E].to(BF16),
-                                                mha.bias_k.detach().reshape(E).to(BF16)], 0).to(F16).contiguous())
+                           lambda: torch.stack([mha.in_proj_bias.detach()[E:2 * E].to(ADT()),
+                                                mha.bias_k.detach().reshape(E).to(ADT())], 0).to(F16).contiguous())
         b_v = b_in[2 * E:]
         bias_v = self.w(mha.bias_v, pre + "biasv").view(E)
         scale = 1.0 / math.sqrt(hd)
@@ -379,14 +400,15 @@ class Engine:
     def _to_dev_bf16(self, t: torch.Tensor, dev) -> torch.Tensor:
         if t.device != dev:
             t = t.to(dev, non_blocking=True)
-        if t.dtype != BF16:
-            t = t.to(BF16)
+        if t.dtype != ADT():
+            t = t.to(ADT())
         return t.contiguous()
 
     def prepare_inputs(self, inputs: dict, save: Optional[dict] = None):
         """MM_LLMs.prepare_inputs_for_generation (reference modeling.py:965-1048).  `save` (training step): receives the
         alignment activations of every modality, keyed by modality name, for the backward pass."""
         m = self.m
+        self.set_format()
         table = self.w(m.llm.model.embed_tokens.weight, "llm.embed")
         dev = table.device
         E = table.shape[1]
@@ -421,7 +443,7 @@ class Engine:
         self.last_lens = dict(lens)  # aligned rows per modality of the most recent call (the training step maps prefix rows to token ids)
         prefix = None
         if n_prefix > 0:
-            prefix = torch.empty((B, n_prefix, E), device=dev, dtype=BF16)
+            prefix = torch.empty((B, n_prefix, E), device=dev, dtype=ADT())
             off = 0
             for name in ("image", "audio", "video"):
                 if name not in feats:
@@ -463,11 +485,11 @@ class Engine:
         g1, g2 = l.input_layernorm.weight, l.post_attention_layernorm.weight
         wqkv = self.derived(k + "wqkv", [sa.q_proj.weight, sa.k_proj.weight, sa.v_proj.weight, g1],
                             lambda: (torch.cat([sa.q_proj.weight, sa.k_proj.weight, sa.v_proj.weight], 0).detach().float()
-                                     * g1.detach().float()[None, :]).to(BF16).contiguous())
+                                     * g1.detach().float()[None, :]).to(ADT()).contiguous())
         wgu = self.derived(k + "wgu", [mlp.gate_proj.weight, mlp.up_proj.weight, g2],
                            lambda: torch.stack(
-                               [(mlp.gate_proj.weight.detach().float() * g2.detach().float()[None, :]).to(BF16).view(I // 32, 32, E),
-                                (mlp.up_proj.weight.detach().float() * g2.detach().float()[None, :]).to(BF16).view(I // 32, 32, E)], 1)
+                               [(mlp.gate_proj.weight.detach().float() * g2.detach().float()[None, :]).to(ADT()).view(I // 32, 32, E),
+                                (mlp.up_proj.weight.detach().float() * g2.detach().float()[None, :]).to(ADT()).view(I // 32, 32, E)], 1)
                            .reshape(2 * I, E).contiguous())
         return wqkv, wgu, self.w(sa.o_proj.weight, k + "wo"), self.w(mlp.down_proj.weight, k + "wd")
 
@@ -506,7 +528,7 @@ class Engine:
             rstd = ops.rms_rstd(x, eps)
             thin = T == 1 and B * T <= 64  # decode step: swap operands so the weights fill the 128-row MMA tiles
             if thin:
-                qkv = ops.linear_thin(x, wqkv, row_scale=rstd)
+                qkv = ops.linear_thin_splitk(x, wqkv, row_scale=rstd)
                 ops.rope_rows(qkv, 2 * E, rope[0], rope[1], rope[2], rope[4] if len(rope) > 4 else None)
             else:
                 qkv = ops.linear(x, wqkv, epi=ops.EPI_ROPE, rope=rope, row_scale=rstd)
@@ -523,10 +545,10 @@ class Engine:
                 kv = cache[i][:, : pos0 + T].unflatten(-1, (H, hd))  # (B, Tk, 2, H, hd) view of the cache
                 a = ops.attention(q5[:, :, 0], kv[:, :, 0], kv[:, :, 1], scale=scale, causal=False, key_mask=kmask)
             if thin:
-                ops.linear_thin(a.view(B * T, E), wo, residual=x, out=x)
+                ops.linear_thin_splitk(a.view(B * T, E), wo, residual=x, out=x)
                 rstd = ops.rms_rstd(x, eps)
-                g = ops.swiglu_rows(ops.linear_thin(x, wgu, row_scale=rstd), I)
-                ops.linear_thin(g, wd, residual=x, out=x)
+                g = ops.swiglu_rows(ops.linear_thin_splitk(x, wgu, row_scale=rstd), I)
+                ops.linear_thin_splitk(g, wd, residual=x, out=x)
             else:
                 ops.linear(a.view(B * T, E), wo, residual=x, out=x)
                 rstd = ops.rms_rstd(x, eps)
@@ -539,7 +561,7 @@ class Engine:
         llm = self.m.llm
         gn = llm.model.norm.weight
         wl = self.derived("llm.lm_head_g", [llm.lm_head.weight, gn],
-                          lambda: (llm.lm_head.weight.detach().float() * gn.detach().float()[None, :]).to(BF16).contiguous())
+                          lambda: (llm.lm_head.weight.detach().float() * gn.detach().float()[None, :]).to(ADT()).contiguous())
         rstd = ops.rms_rstd(x, llm.config.rms_norm_eps)
         if rows is not None:  # strided row subset (last position of every sample)
             x, rstd = rows, rstd.view(rows.shape[0], -1)[:, -1].contiguous()
@@ -555,6 +577,7 @@ class Engine:
         GEMM epilogue, SwiGLU in the gate/up GEMM epilogue, both residual adds in the o_proj / down_proj epilogues
         (in place on the residual stream)."""
         ops.TAG = "llama"
+        self.set_format()
         B, T, E = embeds.shape
         dev = embeds.device
         x = embeds.reshape(B * T, E)
@@ -582,43 +605,58 @@ class Engine:
             dev = embeds.device
             table = self.w(self.m.llm.model.embed_tokens.weight, "llm.embed")
             n_layers = len(self.m.llm.model.layers)
-            t_max = T + max_new_tokens
-            # zero-filled: the graph-replayed decode attention addresses the cache at full capacity and masks keys beyond
-            # the current length by score, so never-written V rows must be finite (0 * NaN would poison the PV product)
-            cache = [torch.zeros((B, t_max, 2, E), device=dev, dtype=BF16) for _ in range(n_layers)]
+            # KV buffers, step state and the captured decode graph are kept ACROSS generate() calls (keyed by batch and
+            # capacity, dropped when any parameter changes): a call re-uses them instead of re-allocating 2*E*t_max*B bytes
+            # per layer and re-capturing ~350 launches.  Stale rows beyond the current length are finite and masked by the
+            # device-side key count, so the caches are not re-zeroed.
+            t_max = _round_up(T + max_new_tokens, 64)
+            stamp = self._stamp(*self.m.llm.parameters())
+            key = (B, t_max, str(dev))
+            st = self._decode.get(key)
+            if st is None or st["stamp"] != stamp:
+                st = dict(stamp=stamp, graph=None,
+                          cache=[torch.zeros((B, t_max, 2, E), device=dev, dtype=ADT()) for _ in range(n_layers)],
+                          finished=torch.zeros((B,), device=dev, dtype=torch.bool),
+                          pos_dev=torch.zeros((2,), device=dev, dtype=torch.int32),
+                          tok_in=torch.zeros((B,), device=dev, dtype=torch.int64))
+                self._decode[key] = st
+            cache, finished, pos_dev, tok_in = st["cache"], st["finished"], st["pos_dev"], st["tok_in"]
             x = embeds.reshape(B * T, E).contiguous()
             x = self._llama_layers(x, B, T, None, 0, cache, t_max)
             logits = self._lm_head(x, rows=x.view(B, T, E)[:, -1, :])
             out = torch.full((B, max_new_tokens), pad_token_id, device=dev, dtype=torch.int64)
-            finished = torch.zeros((B,), device=dev, dtype=torch.bool)
+            finished.zero_()
             pad = torch.full((B,), pad_token_id, device=dev, dtype=torch.int64)
             tok = ops.argmax_rows(logits)
             out[:, 0] = tok
             finished |= tok == eos_token_id
             n = 1
             if max_new_tokens > 1 and not bool(finished.all()):
-                # One decode step = ~8 launches per layer: host-bound when launched one by one, so the step is captured
+                # One decode step = ~10 launches per layer: host-bound when launched one by one, so the step is captured
                 # ONCE in a CUDA graph whose kernels read position / cache slot / key count from `pos_dev`.
-                pos_dev = torch.tensor([T, T + 1], device=dev, dtype=torch.int32)
-                tok_in = tok.clone()
+                pos_dev.copy_(torch.tensor([T, T + 1], dtype=torch.int32), non_blocking=True)
+                tok_in.copy_(tok)
+                eos_t, pad_t = int(eos_token_id), pad
 
                 def decode_step():
                     x1 = ops.embed_gather(table, tok_in)  # ids beyond the table (pad of finished rows) are clamped
                     x1 = self._llama_layers(x1, B, 1, None, 1, cache, t_max, pos_dev)
                     nxt = ops.argmax_rows(self._lm_head(x1))
-                    nxt = torch.where(finished, pad, nxt)  # HF: finished rows emit pad
-                    finished.logical_or_(nxt == eos_token_id)
+                    nxt = torch.where(finished, pad_t, nxt)  # HF: finished rows emit pad
+                    finished.logical_or_(nxt == eos_t)
                     tok_in.copy_(nxt)
                     pos_dev.add_(1)
 
-                decode_step()  # eager first step: fills caches / function attributes, and is a real step
-                out[:, 1] = tok_in
-                n = 2
-                graph = None
+                graph = st["graph"] if st.get("graph_key") == (eos_t, int(pad_token_id)) else None
+                if graph is None:
+                    decode_step()  # eager first step: fills weight caches / function attributes, and is a real step
+                    out[:, 1] = tok_in
+                    n = 2
                 while n < max_new_tokens:
                     if n % 8 == 2 and bool(finished.all()):  # host check every 8 steps (finished rows only emit pad)
                         break
                     if graph is None:
+                        st["pad"] = pad_t  # keep the captured pad tensor alive with the graph
                         graph = torch.cuda.CUDAGraph()
                         prof, ops.PROFILE = ops.PROFILE, None
                         try:
@@ -626,6 +664,7 @@ class Engine:
                                 decode_step()
                         finally:
                             ops.PROFILE = prof
+                        st["graph"], st["graph_key"] = graph, (eos_t, int(pad_token_id))
                     graph.replay()
                     out[:, n] = tok_in
                     n += 1
@@ -663,6 +702,7 @@ class Engine:
                     "audio_starts", "audio_ends", "video_starts", "video_ends")
 
     def _forward_graphed(self, inputs: dict):
+        self.set_format()
         dev = self.w(self.m.llm.model.embed_tokens.weight, "llm.embed").device
         # graphs bake parameter ADDRESSES in: any replaced Parameter (resize_token_embeddings), `.data` swap (model.to)
         # or in-place update (optimizer step) must drop them — same key the derived-weight cache uses
@@ -677,7 +717,7 @@ class Engine:
             static_in = {k: v for k, v in inputs.items() if not isinstance(v, torch.Tensor)}
             for k, _ in present:
                 v = inputs[k]
-                dt = BF16 if v.is_floating_point() else v.dtype
+                dt = ADT() if v.is_floating_point() else v.dtype
                 static_in[k] = torch.empty(v.shape, device=dev, dtype=dt)
                 static_in[k].copy_(v, non_blocking=True)
             cur = torch.cuda.current_stream()

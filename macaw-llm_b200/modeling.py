@@ -217,12 +217,13 @@ class LlamaForCausalLM(_LlamaPreTrained):
         if (input_ids is None) == (inputs_embeds is None):
             raise ValueError("You have to specify exactly one of input_ids or inputs_embeds")
         with torch.no_grad():
+            eng.set_format()
             if inputs_embeds is None:
                 table = eng.w(self.model.embed_tokens.weight, "llm.embed")
                 B, L = input_ids.shape
                 inputs_embeds = ops.embed_gather(table, input_ids.to(table.device)).view(B, L, -1)
-            elif inputs_embeds.dtype != torch.bfloat16:
-                inputs_embeds = inputs_embeds.to(torch.bfloat16)
+            elif inputs_embeds.dtype != ops.ACT():
+                inputs_embeds = inputs_embeds.to(ops.ACT())
             logits = eng.llama_forward(inputs_embeds, attention_mask)
             loss = None
             if labels is not None:

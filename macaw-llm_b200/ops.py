@@ -18,6 +18,23 @@ EPI_STD, EPI_SWIGLU, EPI_ROPE = 0, 1, 2
 
 _BF16 = torch.bfloat16
 _F16 = torch.float16
+_ACT_DTYPE = torch.bfloat16
+
+
+def ACT():
+    """16-bit storage dtype of activations / parameters of the model being run (see set_act_format)."""
+    return _ACT_DTYPE
+
+
+def set_act_format(dtype) -> None:
+    """Select the activation format (torch.bfloat16 | torch.float16) for this thread: the Python-side dtype checks and
+    the kernel library's thread-local format (mm_set_act_format) move together."""
+    global _ACT_DTYPE
+    if dtype not in _16BIT:
+        raise TypeError(f"macaw_b200: activation format must be bf16 or fp16, got {dtype}")
+    if dtype != _ACT_DTYPE or int(_lib.load().mm_get_act_format()) != int(dtype == _F16):
+        _lib.load().mm_set_act_format(int(dtype == _F16))
+        _ACT_DTYPE = dtype
 _16BIT = (torch.bfloat16, torch.float16)
 
 
@@ -64,9 +81,14 @@ def launch_count_reset() -> None:
 def gemm_raw(*, M, N, K, A, lda, B, ldb, Cout, ldc, batch=1, a_bs=0, b_bs=0, c_bs=0, batch2=1, a_bs2=0, b_bs2=0,
              c_bs2=0, b_mn_major=False, c_fp32=False, epi=EPI_STD, act=ACT_NONE, alpha=1.0, bias=None, bias_bs=0,
              row_scale=None, residual=None, ldr=0, r_bs=0, r_bs2=0, res_row_mod=0, rope_cos=None, rope_sin=None,
-             rope_T=0, rope_cols=0, rope_pos=None, c_trans=False, a_fp16=False, b_fp16=False, c_fp16=False,
+             rope_T=0, rope_cols=0, rope_pos=None, c_trans=False, a_fp16=None, b_fp16=None, c_fp16=None,
              bias_rs=None, bias2=None, bias2_rs=None, a_mn_major=False) -> None:
-    """Direct binding of mm_gemm_fwd; pointers are ints (data_ptr() + byte offsets)."""
+    """Direct binding of mm_gemm_fwd; pointers are ints (data_ptr() + byte offsets).  Operand / output formats default to
+    the current activation format (ACT()): fp16 for an fp16 model, bf16 otherwise."""
+    f16 = ACT() == _F16
+    a_fp16 = f16 if a_fp16 is None else a_fp16
+    b_fp16 = f16 if b_fp16 is None else b_fp16
+    c_fp16 = (f16 and not c_fp32) if c_fp16 is None else c_fp16
     a = GemmArgs(M, N, K, batch, batch2, A, lda, a_bs, a_bs2, B, ldb, b_bs, b_bs2, int(b_mn_major), Cout, ldc, c_bs,
                  c_bs2, int(c_fp32), epi, act, float(alpha), bias, bias_bs, row_scale, residual, ldr, r_bs, r_bs2,
                  res_row_mod, rope_cos, rope_sin, rope_T, rope_cols, rope_pos, int(c_trans), int(a_fp16), int(b_fp16), int(c_fp16),
@@ -96,11 +118,11 @@ def linear(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None
     n_out = N // 2 if epi == EPI_SWIGLU else N
     if out is None:
         out = torch.empty((M, n_out), device=x.device,
-                          dtype=out_dtype if out_dtype is not None else (torch.float32 if out_fp32 else _BF16))
+                          dtype=out_dtype if out_dtype is not None else (torch.float32 if out_fp32 else ACT()))
     assert out.shape[0] == M and out.shape[1] == n_out and out.stride(1) == 1
     kw = {}
     if residual is not None:
-        _cuda(residual, _BF16, "residual")
+        _cuda(residual, ACT(), "residual")
         assert residual.stride(-1) == 1
         kw.update(residual=residual.data_ptr(), ldr=residual.stride(0), res_row_mod=res_row_mod)
     if rope is not None:
@@ -120,12 +142,12 @@ def linear_thin(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] =
     """out = epilogue(x @ w.T) for a THIN x (a few rows, e.g. one decode step): operands are swapped so the weight rows
     fill the 128-row MMA tile (weight-streaming regime) and the epilogue stores transposed.  Same semantics as `linear`
     with the standard epilogue: row_scale scales rows of x, bias is per output feature, residual/out are (M, N)."""
-    _cuda(x, _BF16, "x"); _cuda(w, _BF16, "w")
+    _cuda(x, ACT(), "x"); _cuda(w, ACT(), "w")
     M, K = x.shape
     N = w.shape[0]
     assert x.stride(1) == 1 and w.stride(1) == 1 and w.shape[1] == K
     if out is None:
-        out = torch.empty((M, N), device=x.device, dtype=_BF16)
+        out = torch.empty((M, N), device=x.device, dtype=ACT())
     assert out.shape == (M, N) and out.stride(1) == 1
     kw = {}
     if residual is not None:
@@ -135,6 +157,35 @@ def linear_thin(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] =
     gemm_raw(M=N, N=M, K=K, A=w.data_ptr(), lda=w.stride(0), B=x.data_ptr(), ldb=x.stride(0), Cout=out.data_ptr(),
              ldc=out.stride(0), c_fp32=out.dtype == torch.float32, act=act, bias=_ptr(bias), row_scale=_ptr(row_scale),
              c_trans=True, **kw)
+    return out
+
+
+THIN_SPLITS = 4  # K slices of a thin (decode) GEMM: 32..172-tile grids become 128..688 units on 148 SMs
+
+
+def linear_thin_splitk(x: torch.Tensor, w: torch.Tensor, *, residual: Optional[torch.Tensor] = None,
+                       out: Optional[torch.Tensor] = None, row_scale: Optional[torch.Tensor] = None,
+                       splits: Optional[int] = None) -> torch.Tensor:
+    """`linear_thin` (no bias / activation) with the K dimension split over `splits` CTAs per weight tile: fp32 partials +
+    mm_thin_reduce.  Falls back to `linear_thin` when K does not split into 64-element multiples."""
+    _cuda(x, ACT(), "x"); _cuda(w, ACT(), "w")
+    M, K = x.shape
+    N = w.shape[0]
+    S = THIN_SPLITS if splits is None else int(splits)
+    if S <= 1 or K % (S * 64) != 0:
+        return linear_thin(x, w, residual=residual, out=out, row_scale=row_scale)
+    assert x.stride(1) == 1 and w.stride(1) == 1 and w.shape[1] == K
+    Kc = K // S
+    Mp = (M + 3) // 4 * 4
+    part = torch.empty((S, N, Mp), device=x.device, dtype=torch.float32)
+    gemm_raw(M=N, N=M, K=Kc, batch=S, A=w.data_ptr(), lda=w.stride(0), a_bs=Kc, B=x.data_ptr(), ldb=x.stride(0), b_bs=Kc,
+             Cout=part.data_ptr(), ldc=Mp, c_bs=N * Mp, c_fp32=True)
+    if out is None:
+        out = torch.empty((M, N), device=x.device, dtype=ACT())
+    assert out.shape == (M, N) and out.stride(1) == 1
+    _check(_lib.load().mm_thin_reduce(part.data_ptr(), S, N, M, Mp, _ptr(row_scale), _ptr(residual),
+                                      0 if residual is None else residual.stride(0), out.data_ptr(), out.stride(0),
+                                      _stream()), "mm_thin_reduce")
     return out
 
 
@@ -153,12 +204,12 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, *, scale: float
               tk_dev: Optional[torch.Tensor] = None) -> torch.Tensor:
     """q (B, Tq, H, hd), k/v (B, Tk, H, hd) bf16 views (hd contiguous, arbitrary other strides) -> (B, Tq, H, hd)."""
     for n, t in (("q", q), ("k", k), ("v", v)):
-        _cuda(t, _BF16, n)
+        _cuda(t, ACT(), n)
         assert t.dim() == 4 and t.stride(3) == 1
     B, Tq, H, hd = q.shape
     Tk = k.shape[1]
     if out is None:
-        out = torch.empty((B, Tq, H, hd), device=q.device, dtype=_BF16)
+        out = torch.empty((B, Tq, H, hd), device=q.device, dtype=ACT())
     if key_mask is not None:
         _cuda(key_mask, torch.int32, "key_mask")
         assert key_mask.shape == (B, Tk) and key_mask.is_contiguous()
@@ -172,7 +223,7 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, *, scale: float
 
 # ---------------------------------------------------------------------------------------------------- norms
 def rmsnorm(x: torch.Tensor, w: torch.Tensor, eps: float, out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    _cuda(x, _BF16, "x"); _cuda(w, _BF16, "w")
+    _cuda(x, ACT(), "x"); _cuda(w, ACT(), "w")
     assert x.is_contiguous()
     cols = x.shape[-1]
     rows = x.numel() // cols
@@ -185,7 +236,7 @@ def rmsnorm(x: torch.Tensor, w: torch.Tensor, eps: float, out: Optional[torch.Te
 
 def rms_rstd(x: torch.Tensor, eps: float) -> torch.Tensor:
     """fp32 rsqrt(mean(x^2) + eps) per row of a contiguous bf16 (rows, cols) tensor."""
-    _cuda(x, _BF16, "x")
+    _cuda(x, ACT(), "x")
     assert x.is_contiguous()
     cols = x.shape[-1]
     rows = x.numel() // cols
@@ -197,11 +248,11 @@ def rms_rstd(x: torch.Tensor, eps: float) -> torch.Tensor:
 def layernorm(x: torch.Tensor, w: torch.Tensor, b: torch.Tensor, eps: float,
               out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """x (rows, cols) bf16 with unit inner stride (row stride free)."""
-    _cuda(x, _BF16, "x"); _cuda(w, _BF16, "w"); _cuda(b, _BF16, "b")
+    _cuda(x, ACT(), "x"); _cuda(w, ACT(), "w"); _cuda(b, ACT(), "b")
     assert x.dim() == 2 and x.stride(1) == 1
     rows, cols = x.shape
     if out is None:
-        out = torch.empty((rows, cols), device=x.device, dtype=_BF16)
+        out = torch.empty((rows, cols), device=x.device, dtype=ACT())
     _check(_lib.load().mm_layernorm_fwd(x.data_ptr(), x.stride(0), w.data_ptr(), b.data_ptr(), out.data_ptr(),
                                         out.stride(0), rows, cols, float(eps), _stream()), "mm_layernorm_fwd")
     return out
@@ -210,11 +261,11 @@ def layernorm(x: torch.Tensor, w: torch.Tensor, b: torch.Tensor, eps: float,
 # ---------------------------------------------------------------------------------------------------- gathers / layout
 def embed_gather(table: torch.Tensor, ids: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """out[i] = table[ids[i]]; ids any integer dtype (converted to int64 on device), out (n, dim) row stride free."""
-    _cuda(table, _BF16, "table"); _cuda(ids, None, "ids")
+    _cuda(table, ACT(), "table"); _cuda(ids, None, "ids")
     ids64 = ids.reshape(-1).to(torch.int64)
     n, dim = ids64.numel(), table.shape[1]
     if out is None:
-        out = torch.empty((n, dim), device=table.device, dtype=_BF16)
+        out = torch.empty((n, dim), device=table.device, dtype=ACT())
     assert out.stride(-1) == 1
     _check(_lib.load().mm_embed_gather(table.data_ptr(), table.shape[0], dim, ids64.data_ptr(), n, out.data_ptr(),
                                        out.stride(0), _stream()), "mm_embed_gather")
@@ -224,11 +275,11 @@ def embed_gather(table: torch.Tensor, ids: torch.Tensor, out: Optional[torch.Ten
 def splice_prefix(text: torch.Tensor, prefix: Optional[torch.Tensor], mask_in: Optional[torch.Tensor],
                   labels_in: Optional[torch.Tensor]):
     """text (B, L, E), prefix (B, P, E) -> embeds (B, P + L, E), mask (B, P + L) | None, labels (B, P + L) | None."""
-    _cuda(text, _BF16, "text")
+    _cuda(text, ACT(), "text")
     B, L, E = text.shape
     P = 0 if prefix is None else prefix.shape[1]
     assert text.is_contiguous() and (prefix is None or prefix.is_contiguous())
-    dst = torch.empty((B, P + L, E), device=text.device, dtype=_BF16)
+    dst = torch.empty((B, P + L, E), device=text.device, dtype=ACT())
     mask_out = labels_out = None
     if mask_in is not None:
         mask_in = _cuda(mask_in, None, "attention_mask").to(torch.int64).contiguous()
@@ -243,10 +294,10 @@ def splice_prefix(text: torch.Tensor, prefix: Optional[torch.Tensor], mask_in: O
 
 
 def patchify(images: torch.Tensor, patch: int, ldo: int) -> torch.Tensor:
-    _cuda(images, _BF16, "images")
+    _cuda(images, ACT(), "images")
     assert images.is_contiguous()
     B, Cc, H, W = images.shape
-    out = torch.empty((B * (H // patch) * (W // patch), ldo), device=images.device, dtype=_BF16)
+    out = torch.empty((B * (H // patch) * (W // patch), ldo), device=images.device, dtype=ACT())
     _check(_lib.load().mm_patchify(images.data_ptr(), B, Cc, H, W, patch, out.data_ptr(), ldo, _stream()),
            "mm_patchify")
     return out
@@ -254,17 +305,17 @@ def patchify(images: torch.Tensor, patch: int, ldo: int) -> torch.Tensor:
 
 def transpose_pad(x: torch.Tensor, pad: int) -> torch.Tensor:
     """(B, C, T) -> (B, T + 2 pad, C) with zero pad rows."""
-    _cuda(x, _BF16, "x")
+    _cuda(x, ACT(), "x")
     assert x.is_contiguous()
     B, Cc, T = x.shape
-    out = torch.empty((B, T + 2 * pad, Cc), device=x.device, dtype=_BF16)
+    out = torch.empty((B, T + 2 * pad, Cc), device=x.device, dtype=ACT())
     _check(_lib.load().mm_transpose_pad(x.data_ptr(), B, Cc, T, pad, out.data_ptr(), _stream()), "mm_transpose_pad")
     return out
 
 
 def cast_f16(x: torch.Tensor) -> torch.Tensor:
     """bf16 (..., cols) contiguous -> fp16 copy (mm_cast_bf16_f16)."""
-    _cuda(x, _BF16, "x")
+    _cuda(x, torch.bfloat16, "x")
     assert x.is_contiguous()
     cols = x.shape[-1]
     rows = x.numel() // cols
@@ -275,14 +326,14 @@ def cast_f16(x: torch.Tensor) -> torch.Tensor:
 
 def add_rows(x: torch.Tensor, add: Optional[torch.Tensor], out: torch.Tensor) -> torch.Tensor:
     """out[r] = x[r] + add[r % add.shape[0]] over 2-D bf16 views with unit inner stride."""
-    _cuda(x, _BF16, "x"); _cuda(out, _BF16, "out")
+    _cuda(x, ACT(), "x"); _cuda(out, ACT(), "out")
     rows, cols = x.shape
     assert x.stride(1) == 1 and out.stride(1) == 1 and out.shape == x.shape
     if add is None:
         _check(_lib.load().mm_copy_rows(x.data_ptr(), x.stride(0), out.data_ptr(), out.stride(0), rows, cols,
                                         _stream()), "mm_copy_rows")
     else:
-        _cuda(add, _BF16, "add")
+        _cuda(add, ACT(), "add")
         assert add.stride(1) == 1 and add.shape[1] == cols
         _check(_lib.load().mm_add_rows(x.data_ptr(), x.stride(0), add.data_ptr(), add.stride(0), add.shape[0],
                                        out.data_ptr(), out.stride(0), rows, cols, _stream()), "mm_add_rows")
@@ -330,7 +381,7 @@ def align_fused(table: torch.Tensor, qt: torch.Tensor, stats: torch.Tensor, out:
 
 def align_softmax(scores: torch.Tensor, stats: torch.Tensor, P: torch.Tensor, V: int):
     """scores fp32 (R, >=V); stats fp32 (R, 2) = [row_bias, extra_score]; P bf16 (R, ldp) -> (p_sum_real, p_extra)."""
-    _cuda(scores, torch.float32, "scores"); _cuda(stats, torch.float32, "stats"); _cuda(P, _BF16, "P")
+    _cuda(scores, torch.float32, "scores"); _cuda(stats, torch.float32, "stats"); _cuda(P, ACT(), "P")
     R = scores.shape[0]
     assert stats.shape == (R, 2) and stats.is_contiguous() and P.shape[0] == R
     psum = torch.empty((R,), device=scores.device, dtype=torch.float32)
@@ -343,7 +394,7 @@ def align_softmax(scores: torch.Tensor, stats: torch.Tensor, P: torch.Tensor, V:
 
 def align_ctx_fixup(ctx: torch.Tensor, psum: torch.Tensor, pext: torch.Tensor, b_v: torch.Tensor,
                     bias_v: torch.Tensor, head_dim: int) -> torch.Tensor:
-    _cuda(ctx, _BF16, "ctx")
+    _cuda(ctx, ACT(), "ctx")
     Nq, E = ctx.shape
     _check(_lib.load().mm_align_ctx_fixup(ctx.data_ptr(), ctx.stride(0), psum.data_ptr(), pext.data_ptr(),
                                           b_v.data_ptr(), bias_v.data_ptr(), Nq, E, head_dim, _stream()),
@@ -355,7 +406,7 @@ def align_ctx_fixup(ctx: torch.Tensor, psum: torch.Tensor, pext: torch.Tensor, b
 def kv_append(qkv: torch.Tensor, B: int, T_new: int, cache: torch.Tensor, t0: int,
               t0_dev: Optional[torch.Tensor] = None) -> None:
     """qkv (B*T_new, 3E) fused activation -> cache (B, Tmax, 2, E) at positions t0 .. t0+T_new-1 (K and V thirds)."""
-    _cuda(qkv, _BF16, "qkv"); _cuda(cache, _BF16, "cache")
+    _cuda(qkv, ACT(), "qkv"); _cuda(cache, ACT(), "cache")
     E = cache.shape[-1]
     assert qkv.shape == (B * T_new, 3 * E) and qkv.stride(1) == 1 and cache.is_contiguous() and cache.shape[2] == 2
     _check(_lib.load().mm_kv_append(qkv.data_ptr(), qkv.stride(0), B, T_new, E, cache.data_ptr(), cache.shape[1], t0,
@@ -365,7 +416,7 @@ def kv_append(qkv: torch.Tensor, B: int, T_new: int, cache: torch.Tensor, t0: in
 def rope_rows(x: torch.Tensor, rot_cols: int, cos: torch.Tensor, sin: torch.Tensor, rope_T: int,
               pos_dev: Optional[torch.Tensor] = None) -> torch.Tensor:
     """In-place rotate-half RoPE (head_dim 128) on the first rot_cols columns of thin bf16 rows."""
-    _cuda(x, _BF16, "x")
+    _cuda(x, ACT(), "x")
     assert x.dim() == 2 and x.stride(1) == 1
     _check(_lib.load().mm_rope_rows(x.data_ptr(), x.stride(0), x.shape[0], rot_cols, cos.data_ptr(), sin.data_ptr(), rope_T,
                                     _ptr(pos_dev), _stream()), "mm_rope_rows")
@@ -374,9 +425,9 @@ def rope_rows(x: torch.Tensor, rot_cols: int, cos: torch.Tensor, sin: torch.Tens
 
 def swiglu_rows(gu: torch.Tensor, I: int) -> torch.Tensor:
     """(rows, 2I) [32 gate | 32 up]-interleaved product -> (rows, I) silu(gate) * up."""
-    _cuda(gu, _BF16, "gu")
+    _cuda(gu, ACT(), "gu")
     assert gu.dim() == 2 and gu.stride(1) == 1 and gu.shape[1] == 2 * I
-    out = torch.empty((gu.shape[0], I), device=gu.device, dtype=_BF16)
+    out = torch.empty((gu.shape[0], I), device=gu.device, dtype=ACT())
     _check(_lib.load().mm_swiglu_rows(gu.data_ptr(), gu.stride(0), gu.shape[0], I, out.data_ptr(), out.stride(0),
                                       _stream()), "mm_swiglu_rows")
     return out
@@ -384,7 +435,7 @@ def swiglu_rows(gu: torch.Tensor, I: int) -> torch.Tensor:
 
 def argmax_rows(logits: torch.Tensor) -> torch.Tensor:
     """Greedy token per row of bf16 logits (rows, V) with unit inner stride -> int64 (rows,)."""
-    _cuda(logits, _BF16, "logits")
+    _cuda(logits, ACT(), "logits")
     assert logits.dim() == 2 and logits.stride(1) == 1
     out = torch.empty((logits.shape[0],), device=logits.device, dtype=torch.int64)
     _check(_lib.load().mm_argmax_rows(logits.data_ptr(), logits.stride(0), logits.shape[0], logits.shape[1],
@@ -395,7 +446,7 @@ def argmax_rows(logits: torch.Tensor) -> torch.Tensor:
 # ---------------------------------------------------------------------------------------------------- loss
 def ce_loss(logits: torch.Tensor, labels: torch.Tensor) -> torch.Tensor:
     """Shifted CE (mean over labels != -100) of bf16 logits (B, T, V) against int64 labels (B, T); returns fp32 scalar."""
-    _cuda(logits, _BF16, "logits"); _cuda(labels, torch.int64, "labels")
+    _cuda(logits, ACT(), "logits"); _cuda(labels, torch.int64, "labels")
     assert logits.is_contiguous() and labels.is_contiguous()
     B, T, V = logits.shape
     acc = torch.zeros((2,), device=logits.device, dtype=torch.float32)
@@ -408,13 +459,13 @@ def ce_loss(logits: torch.Tensor, labels: torch.Tensor) -> torch.Tensor:
 # ---------------------------------------------------------------------------------------------------- training step
 def gemm_dx(dy: torch.Tensor, w: torch.Tensor, out: Optional[torch.Tensor] = None, accumulate: bool = False) -> torch.Tensor:
     """Input gradient of y = x @ w.T:  dx (M, K) = dy (M, N) @ w (N, K) — w is read as an MN-major B operand in place."""
-    _cuda(dy, _BF16, "dy"); _cuda(w, _BF16, "w")
+    _cuda(dy, ACT(), "dy"); _cuda(w, ACT(), "w")
     M, N = dy.shape
     K = w.shape[1]
     assert w.shape[0] == N and dy.stride(1) == 1 and w.stride(1) == 1
     if out is None:
         assert not accumulate
-        out = torch.empty((M, K), device=dy.device, dtype=_BF16)
+        out = torch.empty((M, K), device=dy.device, dtype=ACT())
     kw = dict(residual=out.data_ptr(), ldr=out.stride(0)) if accumulate else {}
     gemm_raw(M=M, N=K, K=N, A=dy.data_ptr(), lda=dy.stride(0), B=w.data_ptr(), ldb=w.stride(0), b_mn_major=True,
              Cout=out.data_ptr(), ldc=out.stride(0), **kw)
@@ -424,7 +475,7 @@ def gemm_dx(dy: torch.Tensor, w: torch.Tensor, out: Optional[torch.Tensor] = Non
 def gemm_dw(dy: torch.Tensor, x: torch.Tensor, out: torch.Tensor, accumulate: bool) -> torch.Tensor:
     """Weight gradient of y = x @ w.T:  dw (N, K) (+)= dy (M, N).T @ x (M, K) — both activations are read as stored
     (MN-major A and B operands), no transposes."""
-    _cuda(dy, _BF16, "dy"); _cuda(x, _BF16, "x"); _cuda(out, _BF16, "dw")
+    _cuda(dy, ACT(), "dy"); _cuda(x, ACT(), "x"); _cuda(out, ACT(), "dw")
     M, N = dy.shape
     K = x.shape[1]
     assert x.shape[0] == M and out.shape == (N, K) and dy.stride(1) == 1 and x.stride(1) == 1 and out.stride(1) == 1
@@ -437,7 +488,7 @@ def gemm_dw(dy: torch.Tensor, x: torch.Tensor, out: torch.Tensor, accumulate: bo
 def rmsnorm_bwd(dy: torch.Tensor, x: torch.Tensor, rstd: torch.Tensor, g: torch.Tensor, dres: Optional[torch.Tensor],
                 dg: Optional[torch.Tensor]) -> torch.Tensor:
     """dx of y = x * rstd * g (+ dres); dg (fp32, cols) is accumulated in place."""
-    _cuda(dy, _BF16, "dy"); _cuda(x, _BF16, "x"); _cuda(rstd, torch.float32, "rstd"); _cuda(g, _BF16, "g")
+    _cuda(dy, ACT(), "dy"); _cuda(x, ACT(), "x"); _cuda(rstd, torch.float32, "rstd"); _cuda(g, ACT(), "g")
     assert dy.is_contiguous() and x.is_contiguous() and (dres is None or dres.is_contiguous())
     rows, cols = x.shape
     dx = torch.empty_like(x)
@@ -447,7 +498,7 @@ def rmsnorm_bwd(dy: torch.Tensor, x: torch.Tensor, rstd: torch.Tensor, g: torch.
 
 
 def swiglu_fwd(gate: torch.Tensor, up: torch.Tensor) -> torch.Tensor:
-    _cuda(gate, _BF16, "gate"); _cuda(up, _BF16, "up")
+    _cuda(gate, ACT(), "gate"); _cuda(up, ACT(), "up")
     assert gate.is_contiguous() and up.is_contiguous() and gate.shape == up.shape
     h = torch.empty_like(gate)
     _check(_lib.load().mm_swiglu_fwd(gate.data_ptr(), up.data_ptr(), h.data_ptr(), gate.numel(), _stream()), "mm_swiglu_fwd")
@@ -455,7 +506,7 @@ def swiglu_fwd(gate: torch.Tensor, up: torch.Tensor) -> torch.Tensor:
 
 
 def swiglu_bwd(dh: torch.Tensor, gate: torch.Tensor, up: torch.Tensor):
-    _cuda(dh, _BF16, "dh")
+    _cuda(dh, ACT(), "dh")
     assert dh.is_contiguous() and gate.is_contiguous() and up.is_contiguous()
     dg, du = torch.empty_like(gate), torch.empty_like(up)
     _check(_lib.load().mm_swiglu_bwd(dh.data_ptr(), gate.data_ptr(), up.data_ptr(), dg.data_ptr(), du.data_ptr(), dh.numel(),
@@ -469,7 +520,7 @@ def attention_bwd(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, do: torch.T
     row-wise softmax-backward kernel (P, dS in bf16), then dV = P^T dO, dK = dS^T q (MN-major A), dQ = dS k.
     q / do (B, Tq, H, hd), k / v (B, Tk, H, hd): bf16 views with unit head-dim stride.  Returns contiguous dq, dk, dv."""
     for n, t in (("q", q), ("k", k), ("v", v), ("do", do)):
-        _cuda(t, _BF16, n)
+        _cuda(t, ACT(), n)
         assert t.dim() == 4 and t.stride(3) == 1
     B, Tq, H, hd = q.shape
     Tk = k.shape[1]
@@ -489,16 +540,16 @@ def attention_bwd(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, do: torch.T
 
     scores(q, k, S)
     scores(do, v, dP)
-    P = torch.empty((B, H, Tq, Tp), device=dev, dtype=_BF16)
-    dS = torch.empty((B, H, Tq, Tp), device=dev, dtype=_BF16)
+    P = torch.empty((B, H, Tq, Tp), device=dev, dtype=ACT())
+    dS = torch.empty((B, H, Tq, Tp), device=dev, dtype=ACT())
     if key_mask is not None:
         _cuda(key_mask, torch.int32, "key_mask")
     _check(_lib.load().mm_attn_softmax_bwd(S.data_ptr(), dP.data_ptr(), P.data_ptr(), dS.data_ptr(), B, H, Tq, Tk, Tp,
                                            float(scale), int(causal), _ptr(key_mask), _stream()), "mm_attn_softmax_bwd")
     del S, dP
-    dq = torch.empty((B, Tq, H, hd), device=dev, dtype=_BF16)
-    dk = torch.empty((B, Tk, H, hd), device=dev, dtype=_BF16)
-    dv = torch.empty((B, Tk, H, hd), device=dev, dtype=_BF16)
+    dq = torch.empty((B, Tq, H, hd), device=dev, dtype=ACT())
+    dk = torch.empty((B, Tk, H, hd), device=dev, dtype=ACT())
+    dv = torch.empty((B, Tk, H, hd), device=dev, dtype=ACT())
 
     def pt_x(p_, x_, out):  # out_bh (Tk, hd) = p_bh^T (Tk x Tq) @ x_bh (Tq, hd)
         sx, so = bat(x_), bat(out)
@@ -517,7 +568,7 @@ def attention_bwd(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, do: torch.T
 
 def ce_loss_with_count(logits: torch.Tensor, labels: torch.Tensor):
     """mm_ce_loss -> (loss fp32 scalar tensor, n_valid int32 1-element tensor)."""
-    _cuda(logits, _BF16, "logits"); _cuda(labels, torch.int64, "labels")
+    _cuda(logits, ACT(), "logits"); _cuda(labels, torch.int64, "labels")
     assert logits.is_contiguous() and labels.is_contiguous()
     B, T, V = logits.shape
     acc = torch.zeros((2,), device=logits.device, dtype=torch.float32)
@@ -527,17 +578,22 @@ def ce_loss_with_count(logits: torch.Tensor, labels: torch.Tensor):
     return acc[0] / cnt[0].to(torch.float32), cnt
 
 
-def ce_bwd(logits: torch.Tensor, labels: torch.Tensor, n_valid: torch.Tensor, grad_scale: float = 1.0) -> torch.Tensor:
-    """d loss / d logits, written IN PLACE over the bf16 logits."""
+def ce_bwd(logits: torch.Tensor, labels: torch.Tensor, n_valid: torch.Tensor, grad_scale=1.0) -> torch.Tensor:
+    """d loss / d logits, written IN PLACE over the bf16 logits.  grad_scale: python float or a device fp32 scalar tensor
+    (the upstream gradient of the loss, read by the kernel — no host sync, CUDA-graph capturable)."""
     B, T, V = logits.shape
+    gs_dev = None
+    if isinstance(grad_scale, torch.Tensor):
+        gs_dev = _cuda(grad_scale.reshape(1).to(torch.float32), torch.float32, "grad_scale")
+        grad_scale = 1.0
     _check(_lib.load().mm_ce_bwd(logits.data_ptr(), labels.data_ptr(), logits.data_ptr(), B, T, V, n_valid.data_ptr(),
-                                 float(grad_scale), _stream()), "mm_ce_bwd")
+                                 float(grad_scale), _ptr(gs_dev), _stream()), "mm_ce_bwd")
     return logits
 
 
 def embed_scatter_add(dx: torch.Tensor, ids: torch.Tensor, dtable: torch.Tensor) -> None:
     """dtable[ids[i]] += dx[i] for bf16 rows dx (n, dim) with unit inner stride."""
-    _cuda(dx, _BF16, "dx"); _cuda(dtable, _BF16, "dtable")
+    _cuda(dx, ACT(), "dx"); _cuda(dtable, ACT(), "dtable")
     ids64 = ids.reshape(-1).to(torch.int64)
     assert dx.dim() == 2 and dx.stride(1) == 1 and dx.shape[0] == ids64.numel() and dtable.is_contiguous()
     _check(_lib.load().mm_embed_scatter_add(dx.data_ptr(), dx.stride(0), ids64.data_ptr(), ids64.numel(), dx.shape[1],
@@ -545,19 +601,20 @@ def embed_scatter_add(dx: torch.Tensor, ids: torch.Tensor, dtable: torch.Tensor)
 
 
 def colsum(x: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
-    _cuda(x, _BF16, "x"); _cuda(out, torch.float32, "out")
+    _cuda(x, ACT(), "x"); _cuda(out, torch.float32, "out")
     assert x.dim() == 2 and x.stride(1) == 1 and out.numel() == x.shape[1]
     _check(_lib.load().mm_colsum(x.data_ptr(), x.stride(0), x.shape[0], x.shape[1], out.data_ptr(), _stream()), "mm_colsum")
     return out
 
 
 def adamw(p: torch.Tensor, g: torch.Tensor, master: torch.Tensor, m: torch.Tensor, v: torch.Tensor, *, lr: float,
-          beta1: float, beta2: float, eps: float, weight_decay: float, step: int, grad_scale: float = 1.0) -> None:
-    _cuda(p, _BF16, "p"); _cuda(g, _BF16, "g")
+          beta1: float, beta2: float, eps: float, weight_decay: float, step: int, grad_scale: float = 1.0,
+          step_dev: Optional[torch.Tensor] = None) -> None:
+    _cuda(p, ACT(), "p"); _cuda(g, ACT(), "g")
     assert p.is_contiguous() and g.is_contiguous() and master.numel() == p.numel()
     _check(_lib.load().mm_adamw(p.data_ptr(), g.data_ptr(), master.data_ptr(), m.data_ptr(), v.data_ptr(), p.numel(),
                                 float(lr), float(beta1), float(beta2), float(eps), float(weight_decay), int(step),
-                                float(grad_scale), _stream()), "mm_adamw")
+                                _ptr(step_dev), float(grad_scale), _stream()), "mm_adamw")
 
 
 def cast_bf16(x: torch.Tensor) -> torch.Tensor:
@@ -566,7 +623,7 @@ def cast_bf16(x: torch.Tensor) -> torch.Tensor:
     assert x.is_contiguous()
     cols = x.shape[-1]
     rows = x.numel() // cols
-    y = torch.empty(x.shape, device=x.device, dtype=_BF16)
+    y = torch.empty(x.shape, device=x.device, dtype=torch.bfloat16)
     _check(_lib.load().mm_cast_f16_bf16(x.data_ptr(), cols, y.data_ptr(), cols, rows, cols, _stream()), "mm_cast_f16_bf16")
     return y
 
@@ -579,8 +636,8 @@ def align_softmax_bwd(G: torch.Tensor, P_unnorm: torch.Tensor, inv_l: torch.Tens
     assert G.shape[0] == R and G.stride(1) == 1 and P_unnorm.stride(1) == 1
     for t in (inv_l, dpsr, pe, dpe):
         assert t.dtype == torch.float32 and t.is_contiguous() and t.numel() == R
-    P = torch.empty((R, ldp), device=G.device, dtype=_BF16)
-    dS = torch.empty((R, ldp), device=G.device, dtype=_BF16)
+    P = torch.empty((R, ldp), device=G.device, dtype=ACT())
+    dS = torch.empty((R, ldp), device=G.device, dtype=ACT())
     dstats = torch.empty((2, R), device=G.device, dtype=torch.float32)
     _check(_lib.load().mm_align_softmax_bwd(G.data_ptr(), G.stride(0), P_unnorm.data_ptr(), ldp, inv_l.data_ptr(), dpsr.data_ptr(),
                                             pe.data_ptr(), dpe.data_ptr(), float(gscale), P.data_ptr(), dS.data_ptr(), ldp,

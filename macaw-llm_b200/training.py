@@ -132,7 +132,13 @@ def allreduce_grads(buf: GradBuffer, world: int, bucket: Optional[int] = None, a
     else:
         s, e = buf.buckets[bucket]
         t = buf.flat[s:e]
-    if t.is_cuda:  # NCCL: native average, bf16 on the wire, asynchronous w.r.t. the compute stream
+    if t.is_cuda:
+        from . import dist as D
+
+        if D._NCCL_READY:  # the kernel library's own communicator (mm_nccl_allreduce), on the caller's current stream
+            D.nccl_allreduce_(t, average=True)
+            return None
+        # torch.distributed's NCCL group: native average, bf16 on the wire, asynchronous w.r.t. the compute stream
         return dist.all_reduce(t, op=dist.ReduceOp.AVG, async_op=async_op)
     tmp = t.float()  # gloo (CPU test tier): sum in fp32, then average
     dist.all_reduce(tmp, op=dist.ReduceOp.SUM)
@@ -150,6 +156,7 @@ class FusedAdamW:
         self.lr, self.betas, self.eps, self.weight_decay = lr, betas, eps, weight_decay
         self.state: Dict[int, tuple] = {}
         self.t = 0
+        self.t_dev: Optional[torch.Tensor] = None  # device-side step counter (the kernels read it: graph-replayable)
 
     def zero_grad(self, set_to_none: bool = True) -> None:
         for p in self.params:
@@ -161,6 +168,10 @@ class FusedAdamW:
     def step(self, grad_scale: float = 1.0) -> None:
         self.t += 1
         with torch.no_grad():
+            if self.t_dev is None:
+                dev = next(p for p in self.params).device
+                self.t_dev = torch.zeros((1,), device=dev, dtype=torch.int32)
+            self.t_dev.add_(1)
             for p in self.params:
                 if p.grad is None:
                     continue
@@ -171,7 +182,8 @@ class FusedAdamW:
                     self.state[id(p)] = st
                 g = p.grad if p.grad.is_contiguous() else p.grad.contiguous()
                 ops.adamw(p.data, g, st[0], st[1], st[2], lr=self.lr, beta1=self.betas[0], beta2=self.betas[1],
-                          eps=self.eps, weight_decay=self.weight_decay, step=self.t, grad_scale=grad_scale)
+                          eps=self.eps, weight_decay=self.weight_decay, step=self.t, grad_scale=grad_scale,
+                          step_dev=self.t_dev)
                 # the kernel's in-place write is invisible to autograd's version counter, which the engine's
                 # derived-weight / CUDA-graph caches key on: bump it
                 torch.autograd.graph.increment_version(p)
@@ -206,6 +218,9 @@ class LlamaTrainer:
     def forward(self, embeds: torch.Tensor, attention_mask: Optional[torch.Tensor], labels: torch.Tensor):
         """embeds (B, T, E) bf16 (the spliced inputs_embeds), mask (B, T) | None, labels (B, T) int64 -> (loss, ctx)."""
         ops.TAG = "train.fwd"
+        if ops.ACT() != BF16:
+            raise RuntimeError("macaw_b200 training: the training step computes in bf16 (fp16 gradients of 1e-7 would "
+                               "underflow without loss scaling); use a bf16 model")
         E, H, hd, I, eps = self._dims()
         B, T, _ = embeds.shape
         dev = embeds.device
@@ -246,7 +261,7 @@ class LlamaTrainer:
                    B=B, T=T, neg_sin=None)
         return loss, ctx
 
-    def backward(self, ctx: dict, grad_loss: float = 1.0, skip=()) -> torch.Tensor:
+    def backward(self, ctx: dict, grad_loss=1.0, skip=()) -> torch.Tensor:
         """Fills `p.grad` of every LLaMA parameter (accumulating into existing gradients) and returns d loss / d embeds."""
         ops.TAG = "train.bwd"
         E, H, hd, I, eps = self._dims()
@@ -349,7 +364,21 @@ class LlamaTrainer:
 
     # ---- gradient all-reduce overlapped with the backward pass
     def _sync_bucket(self, i: int) -> None:
+        """All-reduce bucket i (complete on the compute stream as of now) on a side stream, so the collective overlaps the
+        backward pass of the layers still to be differentiated."""
         if self.world > 1 and self.overlap_allreduce:
+            from . import dist as D
+
+            if D._NCCL_READY and self.grads.flat.is_cuda:
+                if getattr(self, "_comm_stream", None) is None:
+                    self._comm_stream = torch.cuda.Stream(device=self.grads.flat.device)
+                ev = torch.cuda.Event()
+                ev.record()
+                self._comm_stream.wait_event(ev)
+                with torch.cuda.stream(self._comm_stream):
+                    allreduce_grads(self.grads, self.world, bucket=i)
+                self._comm_used = True
+                return
             w = allreduce_grads(self.grads, self.world, bucket=i, async_op=True)
             if w is not None:
                 self._pending.append(w)
@@ -357,6 +386,9 @@ class LlamaTrainer:
     def finish_allreduce(self) -> None:
         if self.world > 1 and not self.overlap_allreduce:
             allreduce_grads(self.grads, self.world)
+        if getattr(self, "_comm_used", False):
+            torch.cuda.current_stream().wait_stream(self._comm_stream)
+            self._comm_used = False
         for w in self._pending:
             w.wait()
         self._pending.clear()
@@ -490,7 +522,8 @@ class _TrainFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, grad_out):
-        ctx.trainer._backward_full(ctx.st, float(grad_out))
+        # the upstream gradient stays on the device (read by the CE-backward kernel): no host sync, graph-capturable
+        ctx.trainer._backward_full(ctx.st, grad_out.detach())
         ctx.st = None
         return None, None, None
 
@@ -524,21 +557,22 @@ class TrainStep:
             prefix_ids = None
             if n_prefix > 0:
                 B = embeds.shape[0]
-                prefix_ids = torch.full((B, n_prefix), -1, dtype=torch.int64)
+                dev = embeds.device
+                prefix_ids = torch.full((B, n_prefix), -1, dtype=torch.int64, device=dev)
                 off = 0
                 for name in ("image", "audio", "video"):
                     key = {"image": "images", "audio": "audios", "video": "videos"}[name]
                     if inputs.get(key) is None:
                         continue
                     Lq = m.engine.last_lens[name]
-                    prefix_ids[:, off] = inputs[f"{name}_starts"].to("cpu").long()
-                    prefix_ids[:, off + 1 + Lq] = inputs[f"{name}_ends"].to("cpu").long()
+                    prefix_ids[:, off] = inputs[f"{name}_starts"].to(dev).long()
+                    prefix_ids[:, off + 1 + Lq] = inputs[f"{name}_ends"].to(dev).long()
                     off += Lq + 2
             ctx["inputs_ids"] = dict(input_ids=inputs["input_ids"])
             ctx["n_prefix"], ctx["prefix_ids"], ctx["align"] = n_prefix, prefix_ids, saved_align
         return loss, ctx
 
-    def _backward_full(self, ctx: dict, grad_loss: float) -> None:
+    def _backward_full(self, ctx: dict, grad_loss) -> None:
         with torch.no_grad():
             if self.llama.grads is None:
                 self.llama.grads = GradBuffer(self.m)

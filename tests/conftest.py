@@ -25,3 +25,17 @@ def pytest_collection_modifyitems(config, items):
     for item in items:
         if "gpu" in item.keywords:
             item.add_marker(skip)
+
+
+@pytest.fixture(autouse=True)
+def _default_activation_format():
+    """Every test starts in the default (bf16) activation format; fp16-model tests switch it through the engine."""
+    try:
+        import torch
+
+        from macaw_llm_b200 import ops
+
+        ops.set_act_format(torch.bfloat16)
+    except Exception:
+        pass
+    yield

@@ -397,6 +397,22 @@ def test_linear_thin_swapped_operands(M):
     assert rel_err(h, x.float() @ w.float().t() + res.float()) < 4e-3
 
 
+@pytest.mark.parametrize("M,K,N", [(8, 4096, 4096), (8, 11008, 512), (3, 1024, 640), (8, 1000, 256)])
+def test_linear_thin_splitk(M, K, N):
+    """Decode GEMMs with K split over 4 CTAs per weight tile (fp32 partials + mm_thin_reduce); K that does not split into
+    64-element multiples takes the unsplit path."""
+    ops = _ops()
+    x, w = rnd(M, K, seed=94), rnd(N, K, scale=K ** -0.5, seed=95)
+    res = rnd(M, N, seed=96)
+    rs = torch.rand(M, device=DEV) + 0.5
+    ref = (x.float() @ w.float().t()) * rs[:, None] + res.float()
+    out = ops.linear_thin_splitk(x, w, residual=res, row_scale=rs)
+    assert rel_err(out, ref) < 4e-3
+    h = res.clone()
+    ops.linear_thin_splitk(x, w, residual=h, out=h, row_scale=rs)  # in-place residual stream update
+    assert rel_err(h, ref) < 4e-3
+
+
 def test_rope_rows_and_swiglu_rows():
     ops = _ops()
     B, E, I = 8, 512, 1376

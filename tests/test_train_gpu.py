@@ -186,6 +186,9 @@ def test_gradients_vs_oracle_autograd(tiny_train, name):
     named = dict(model.named_parameters())
     present = {"text_labels": (), "image_audio": ("image", "audio"), "all3": ("image", "audio", "video")}[name]
     worst, worst_align = ("", 0.0), ("", 0.0)
+    errs = {k: rel(named[k].grad, gr) for k, gr in grads_ref.items() if named[k].grad is not None}
+    top = sorted(errs.items(), key=lambda kv: -kv[1])[:8]
+    print(f"\n[train:{name}] largest gradient errors: " + ", ".join(f"{k}={e:.2e}" for k, e in top))
     for k, gr in grads_ref.items():
         is_align = not k.startswith("llm.")
         if is_align and not any(k.startswith((f"project_{m}.", f"transform_{m}_to_hidden.", f"{m}_align_attention.")) for m in present):
