@@ -28,7 +28,7 @@ sys.path.insert(0, ROOT)
 import torch  # noqa: E402
 
 METRIC = "multimodal prefill tokens/sec (img+audio+text->LLaMA)"
-DEFAULT_DTYPE = "bf16"
+DEFAULT_DTYPE = "fp16"
 UNIT = "tokens/s"
 
 

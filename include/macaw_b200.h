@@ -109,6 +109,15 @@ typedef struct mm_gemm_args {
    * b_mn_major this is the weight-gradient product dW[n][k] = sum_m dY[m][n] X[m][k] on the tensors as stored
    * (reference: autograd of every nn.Linear on the path; llm_trainer.py:184-188 -> loss.backward()). */
   int32_t a_mn_major;
+  /* RMSNorm statistics without a separate pass over the residual stream (LlamaRMSNorm modeling.py:311-319):
+   * sumsq_out (MM_EPI_STD, 16-bit C): fp32 [M][ceil(N/32)] — the epilogue that WRITES the new residual stream also writes,
+   * per row and 32-column chunk, the sum of squares of the values as stored.  rs_sumsq (any epilogue): fp32 [M][rs_parts] —
+   * the GEMM that CONSUMES the stream derives its per-row scale rsqrt(sum / K + rs_eps) from those partials (fixed
+   * summation order: deterministic) instead of reading `row_scale`. */
+  float* sumsq_out;
+  const float* rs_sumsq;
+  int32_t rs_parts;
+  float rs_eps;
 } mm_gemm_args;
 
 int32_t mm_gemm_fwd(const mm_gemm_args* args, void* stream);
@@ -297,6 +306,10 @@ int32_t mm_align_softmax_bwd(const float* G, int64_t ldg, const void* P_unnorm_f
 /* out[h*hd + d] += sum_n w[(h*Nq + n) * w_stride] * x[n, h*hd + d]; x bf16 (x_fp16 == 0) or fp16. */
 int32_t mm_head_weighted_colsum(const void* x, int64_t ldx, int32_t x_fp16, const float* w, int64_t w_stride, int32_t Nq,
                                 int32_t E, int32_t head_dim, float* out, void* stream);
+/* Data gradient of the Conv1d down-sampler (col2im over overlapping token windows): dfeats[b,t,c] = sum over windows l
+ * containing t of dwin[b*Lq + l][(t - l*ss)*C + c]; bf16 in / out. */
+int32_t mm_window_gather_add(const void* dwin, int32_t B, int32_t N, int32_t C, int32_t Lq, int32_t kk, int32_t ss,
+                             void* dfeats, void* stream);
 int32_t mm_cast_f16_bf16(const void* x, int64_t ldx, void* y, int64_t ldy, int32_t rows, int32_t cols, void* stream);
 
 /* ------------------------------------------------------------------------------------------------ gradient all-reduce

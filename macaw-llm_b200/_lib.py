@@ -29,6 +29,7 @@ class GemmArgs(C.Structure):
         ("rope_cos", c_vp), ("rope_sin", c_vp), ("rope_T", c_i32), ("rope_cols", c_i32), ("rope_pos", c_vp), ("c_trans", c_i32),
         ("a_fp16", c_i32), ("b_fp16", c_i32), ("c_fp16", c_i32),
         ("bias_rs", c_vp), ("bias2", c_vp), ("bias2_rs", c_vp), ("a_mn_major", c_i32),
+        ("sumsq_out", c_vp), ("rs_sumsq", c_vp), ("rs_parts", c_i32), ("rs_eps", c_f32),
     ]
 
 
@@ -113,6 +114,7 @@ SIGNATURES = {
     "mm_align_softmax_bwd": (c_i32, [c_vp, c_i64, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_f32, c_vp, c_vp, c_i64, c_vp, c_i32,
                                      c_i32, c_vp]),
     "mm_head_weighted_colsum": (c_i32, [c_vp, c_i64, c_i32, c_vp, c_i64, c_i32, c_i32, c_i32, c_vp, c_vp]),
+    "mm_window_gather_add": (c_i32, [c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp]),
     "mm_cast_f16_bf16": (c_i32, [c_vp, c_i64, c_vp, c_i64, c_i32, c_i32, c_vp]),
     "mm_nccl_unique_id": (c_i32, [c_vp]),
     "mm_nccl_init": (c_i32, [c_vp, c_i32, c_i32]),

@@ -52,6 +52,10 @@ struct GemmKParams {
   const float* bias_rs;
   const bf16* bias2;
   const float* bias2_rs;
+  float* sumsq_out;        // [M][sumsq_parts]: per-(row, 32-column chunk) sums of squares of the STORED outputs
+  const float* rs_sumsq;   // [M][rs_parts]: row_scale = rsqrt(sum_j rs_sumsq[row][j] / K + rs_eps) (RMSNorm of the A rows)
+  int sumsq_parts, rs_parts;
+  float rs_eps;
   int vec_ok;
   int group_m;  // rasterisation: M units per group
 };
@@ -354,8 +358,6 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     for (int tile = worker; tile < total_tiles; tile += n_workers) {
       TileCoord t = tile_coord(tile, p, m_units);
       if constexpr (MC) t.m_blk = 2 * t.m_blk + cta_rank;
-      mbar_wait(&tfull_bar[acc], acc_phase);
-      tc_fence_after();
       const int row = t.m_blk * kBlockM + q * 32 + lane;
       const bool row_ok = row < p.M;
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN;
@@ -364,7 +366,20 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     static_cast<long long>(row) * p.ldc) * (p.c_fp32 ? 4 : 2);
       float rs = 1.0f;
       if (p.row_scale != nullptr && row_ok && !p.c_trans) rs = p.row_scale[static_cast<long long>(t.b) * p.M + row];
+      if (p.rs_sumsq != nullptr && row_ok) {
+        // RMSNorm statistic of this A row from the partial sums the PRODUCING GEMM's epilogue left behind (fixed summation
+        // order: deterministic); done while this tile's MMAs are still running
+        const float4* sp = reinterpret_cast<const float4*>(p.rs_sumsq + static_cast<long long>(row) * p.rs_parts);
+        float ssum = 0.f;
+        for (int j = 0; j < p.rs_parts / 4; ++j) {
+          const float4 f = __ldg(sp + j);
+          ssum += (f.x + f.y) + (f.z + f.w);
+        }
+        rs = rsqrtf(ssum / static_cast<float>(p.K) + p.rs_eps);
+      }
       rs *= p.alpha;
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after();
 
       if constexpr (EPI == MM_EPI_STD) {
         if (p.c_trans) {
@@ -459,6 +474,16 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             }
           }
           if (row_ok) store_row32(p, crow, col0, n_out_total, v);
+          if (p.sumsq_out != nullptr && row_ok) {
+            // sum of squares of the values AS STORED (rounded to the output format), for the next RMSNorm
+            float ss = 0.f;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              const float r = p.c_fp16 ? __half2float(__float2half_rn(v[i])) : __bfloat162float(__float2bfloat16(v[i]));
+              ss = fmaf(r, r, ss);
+            }
+            p.sumsq_out[static_cast<long long>(row) * p.sumsq_parts + (col0 >> 5)] = ss;
+          }
         }
         }  // !c_trans
       } else if constexpr (EPI == MM_EPI_SWIGLU) {
@@ -646,6 +671,14 @@ extern "C" int32_t mm_gemm_fwd(const mm_gemm_args* a, void* stream) {
   p.c_fp16 = a->c_fp16;
   p.aux_f16 = act_f16() ? 1 : 0;
   p.bias_rs = a->bias_rs; p.bias2 = reinterpret_cast<const bf16*>(a->bias2); p.bias2_rs = a->bias2_rs;
+  p.sumsq_out = a->sumsq_out; p.sumsq_parts = (a->N + 31) / 32;
+  p.rs_sumsq = a->rs_sumsq; p.rs_parts = a->rs_parts; p.rs_eps = a->rs_eps;
+  MM_REQUIRE(a->sumsq_out == nullptr || (a->epi == MM_EPI_STD && !a->c_trans && !a->c_fp32 && a->batch == 1 && batch2 == 1 &&
+                                         a->N % 32 == 0),
+             "mm_gemm_fwd: sumsq_out needs the standard epilogue, 16-bit output, no batching and N %% 32 == 0");
+  MM_REQUIRE(a->rs_sumsq == nullptr || (a->rs_parts > 0 && a->rs_parts % 4 == 0 && !a->c_trans && a->batch == 1 && batch2 == 1 &&
+                                        (reinterpret_cast<uintptr_t>(a->rs_sumsq) & 15) == 0),
+             "mm_gemm_fwd: rs_sumsq needs rs_parts %% 4 == 0, a 16-byte aligned buffer and no batching");
   MM_REQUIRE(!(a->c_fp16 && a->c_fp32), "mm_gemm_fwd: c_fp16 and c_fp32 are exclusive");
   MM_REQUIRE((a->a_fp16 != 0) == (a->b_fp16 != 0),
              "mm_gemm_fwd: A and B must share one 16-bit format (sm_100a faults on mixed f16 x bf16 tcgen05.mma)");

@@ -354,6 +354,31 @@ __global__ void cast_f16_bf16_kernel(const __half* __restrict__ x, long long ldx
   }
 }
 
+// Data gradient of a strided Conv1d over the token axis (col2im): dwin[(b*Lq + l), k*C + c] holds d(window l)[k, c];
+// dfeats[b, t, c] = sum over the windows l that contain token t (l*ss <= t < l*ss + kk) of dwin[b*Lq + l, (t - l*ss)*C + c].
+__global__ void window_gather_add_kernel(const bf16* __restrict__ dwin, int B, int N, int C, int Lq, int kk, int ss,
+                                         bf16* __restrict__ dfeats) {
+  const long long total = static_cast<long long>(B) * N * C;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(i % C);
+    const int t = static_cast<int>((i / C) % N);
+    const int b = static_cast<int>(i / (static_cast<long long>(C) * N));
+    int l_hi = t / ss;
+    if (l_hi > Lq - 1) l_hi = Lq - 1;
+    int l_lo = (t - kk + ss) / ss;  // ceil((t - kk + 1) / ss)
+    if (t - kk + 1 <= 0) l_lo = 0;
+    float acc = 0.f;
+    for (int l = l_lo; l <= l_hi; ++l) {
+      const int k = t - l * ss;
+      if (k >= 0 && k < kk)
+        acc += __bfloat162float(dwin[(static_cast<long long>(b) * Lq + l) * (static_cast<long long>(kk) * C) +
+                                     static_cast<long long>(k) * C + c]);
+    }
+    dfeats[i] = __float2bfloat16(acc);
+  }
+}
+
 static inline int grid_for(long long total, int block, int cap_mult = 16) {
   long long g = (total + block - 1) / block;
   const long long cap = static_cast<long long>(num_sms()) * cap_mult;
@@ -465,4 +490,12 @@ extern "C" int32_t mm_cast_f16_bf16(const void* x, int64_t ldx, void* y, int64_t
   cast_f16_bf16_kernel<<<grid_for(static_cast<long long>(rows) * cols, 256), 256, 0, ST(stream)>>>(
       (const __half*)x, ldx, (bf16*)y, ldy, rows, cols);
   return check_launch("mm_cast_f16_bf16");
+}
+
+extern "C" int32_t mm_window_gather_add(const void* dwin, int32_t B, int32_t N, int32_t C, int32_t Lq, int32_t kk, int32_t ss,
+                                        void* dfeats, void* stream) {
+  MM_REQUIRE(dwin && dfeats && B > 0 && N > 0 && C > 0 && Lq > 0 && kk > 0 && ss > 0, "mm_window_gather_add: bad arguments");
+  window_gather_add_kernel<<<grid_for(static_cast<long long>(B) * N * C, 256), 256, 0, ST(stream)>>>(
+      (const bf16*)dwin, B, N, C, Lq, kk, ss, (bf16*)dfeats);
+  return check_launch("mm_window_gather_add");
 }

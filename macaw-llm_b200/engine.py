@@ -247,8 +247,10 @@ class Engine:
             self._pe[key] = pe
         return pe
 
-    def encode_video_long(self, videos: torch.Tensor) -> torch.Tensor:
-        """reference modeling.py:1070-1079 -> (B, F*256, P)."""
+    def encode_video_long(self, videos: torch.Tensor, save: Optional[dict] = None) -> torch.Tensor:
+        """reference modeling.py:1070-1079 -> (B, F*256, P).  `save` (training step) receives the activations of the
+        video_long_self_attention block (its input xp, the fused qkv buffer with the two synthetic key rows, the attention
+        output) for the backward pass."""
         m = self.m
         F_ = m.config.n_frames
         frames = videos.reshape(-1, *videos.shape[-3:])
@@ -282,6 +284,8 @@ class Engine:
         q5 = qkv.view(B, N + 2, 3, H, hd)
         a = ops.attention(q5[:, :N, 0], q5[:, :, 1], q5[:, :, 2], scale=hd ** -0.5)
         out = ops.linear(a.view(B * N, P), self.w(mha.out_proj.weight, pre + "wo"), self.w(mha.out_proj.bias, pre + "bo"))
+        if save is not None:
+            save.update(xp=xp, qkv=qkv, a=a, B=B, N=N, P=P, H=H, hd=hd)
         return out.view(B, N, P)
 
     # ------------------------------------------------------------------------------------------------ alignment
@@ -431,7 +435,8 @@ class Engine:
         if inputs.get("audios") is not None:
             feats["audio"] = self.whisper_encode(self._to_dev_bf16(inputs["audios"], dev))
         if inputs.get("videos") is not None:
-            feats["video"] = self.encode_video_long(self._to_dev_bf16(inputs["videos"], dev))
+            feats["video"] = self.encode_video_long(self._to_dev_bf16(inputs["videos"], dev),
+                                                    save=None if save is None else save.setdefault("video_long", {}))
         # final layout [BOS, <image> img </image>, <audio> aud </audio>, <video> vid </video>, text[1:]]: each block is
         # spliced right after BOS in the order video, audio, image (reference modeling.py:978-1034), so image ends up first
         lens = {}
@@ -523,15 +528,25 @@ class Engine:
         else:
             rope = (cos, sin, T, 2 * E) if pos0 == 0 else (cos[pos0:], sin[pos0:], 1, 2 * E)
         assert (pos0 == 0 and not dyn) or T == 1
+        # RMSNorm statistics ride the GEMM epilogues: the GEMM that WRITES the residual stream (o_proj / down_proj) leaves
+        # per-(row, 32-column) sums of squares of the stored values, the GEMM that CONSUMES it (QKV / gate-up / lm_head)
+        # derives rsqrt(mean(x^2) + eps) from them — no separate pass over the stream after the first layer's input.
+        M = x.shape[0]
+        fused_stats = not (T == 1 and B * T <= 64) and E % 128 == 0
+        ss_attn = torch.empty((M, E // 32), device=dev, dtype=torch.float32) if fused_stats else None
+        ss_mlp = torch.empty((M, E // 32), device=dev, dtype=torch.float32) if fused_stats else None
+        have_ss = False
         for i, l in enumerate(self.m.llm.model.layers):
             wqkv, wgu, wo, wd = self._llama_weights(i, l, E, I)
-            rstd = ops.rms_rstd(x, eps)
             thin = T == 1 and B * T <= 64  # decode step: swap operands so the weights fill the 128-row MMA tiles
             if thin:
+                rstd = ops.rms_rstd(x, eps)
                 qkv = ops.linear_thin_splitk(x, wqkv, row_scale=rstd)
                 ops.rope_rows(qkv, 2 * E, rope[0], rope[1], rope[2], rope[4] if len(rope) > 4 else None)
+            elif have_ss:
+                qkv = ops.linear(x, wqkv, epi=ops.EPI_ROPE, rope=rope, rms_from=(ss_mlp, eps))
             else:
-                qkv = ops.linear(x, wqkv, epi=ops.EPI_ROPE, rope=rope, row_scale=rstd)
+                qkv = ops.linear(x, wqkv, epi=ops.EPI_ROPE, rope=rope, row_scale=ops.rms_rstd(x, eps))
             q5 = qkv.view(B, T, 3, H, hd)
             if cache is not None:
                 ops.kv_append(qkv, B, T, cache[i], pos0, pos_dev[0:1] if dyn else None)
@@ -549,11 +564,16 @@ class Engine:
                 rstd = ops.rms_rstd(x, eps)
                 g = ops.swiglu_rows(ops.linear_thin_splitk(x, wgu, row_scale=rstd), I)
                 ops.linear_thin_splitk(g, wd, residual=x, out=x)
+            elif fused_stats:
+                ops.linear(a.view(B * T, E), wo, residual=x, out=x, sumsq_out=ss_attn)
+                g = ops.linear(x, wgu, epi=ops.EPI_SWIGLU, rms_from=(ss_attn, eps))
+                ops.linear(g, wd, residual=x, out=x, sumsq_out=ss_mlp)
+                have_ss = True
             else:
                 ops.linear(a.view(B * T, E), wo, residual=x, out=x)
-                rstd = ops.rms_rstd(x, eps)
-                g = ops.linear(x, wgu, epi=ops.EPI_SWIGLU, row_scale=rstd)
+                g = ops.linear(x, wgu, epi=ops.EPI_SWIGLU, row_scale=ops.rms_rstd(x, eps))
                 ops.linear(g, wd, residual=x, out=x)
+        self._last_ss = ss_mlp if have_ss else None  # statistics of the final residual stream (consumed by _lm_head)
         return x
 
     def _lm_head(self, x: torch.Tensor, rows: Optional[torch.Tensor] = None) -> torch.Tensor:
@@ -562,10 +582,13 @@ class Engine:
         gn = llm.model.norm.weight
         wl = self.derived("llm.lm_head_g", [llm.lm_head.weight, gn],
                           lambda: (llm.lm_head.weight.detach().float() * gn.detach().float()[None, :]).to(ADT()).contiguous())
+        ops.TAG = "lm_head"
+        ss, self._last_ss = getattr(self, "_last_ss", None), None
+        if rows is None and x.shape[0] > 64 and ss is not None and ss.shape[0] == x.shape[0]:
+            return ops.linear(x, wl, rms_from=(ss, llm.config.rms_norm_eps))  # statistics left by the last down_proj
         rstd = ops.rms_rstd(x, llm.config.rms_norm_eps)
         if rows is not None:  # strided row subset (last position of every sample)
             x, rstd = rows, rstd.view(rows.shape[0], -1)[:, -1].contiguous()
-        ops.TAG = "lm_head"
         if x.shape[0] <= 64:
             return ops.linear_thin(x, wl, row_scale=rstd)
         return ops.linear(x, wl, row_scale=rstd)

@@ -82,7 +82,8 @@ def gemm_raw(*, M, N, K, A, lda, B, ldb, Cout, ldc, batch=1, a_bs=0, b_bs=0, c_b
              c_bs2=0, b_mn_major=False, c_fp32=False, epi=EPI_STD, act=ACT_NONE, alpha=1.0, bias=None, bias_bs=0,
              row_scale=None, residual=None, ldr=0, r_bs=0, r_bs2=0, res_row_mod=0, rope_cos=None, rope_sin=None,
              rope_T=0, rope_cols=0, rope_pos=None, c_trans=False, a_fp16=None, b_fp16=None, c_fp16=None,
-             bias_rs=None, bias2=None, bias2_rs=None, a_mn_major=False) -> None:
+             bias_rs=None, bias2=None, bias2_rs=None, a_mn_major=False, sumsq_out=None, rs_sumsq=None, rs_parts=0,
+             rs_eps=0.0) -> None:
     """Direct binding of mm_gemm_fwd; pointers are ints (data_ptr() + byte offsets).  Operand / output formats default to
     the current activation format (ACT()): fp16 for an fp16 model, bf16 otherwise."""
     f16 = ACT() == _F16
@@ -92,7 +93,7 @@ def gemm_raw(*, M, N, K, A, lda, B, ldb, Cout, ldc, batch=1, a_bs=0, b_bs=0, c_b
     a = GemmArgs(M, N, K, batch, batch2, A, lda, a_bs, a_bs2, B, ldb, b_bs, b_bs2, int(b_mn_major), Cout, ldc, c_bs,
                  c_bs2, int(c_fp32), epi, act, float(alpha), bias, bias_bs, row_scale, residual, ldr, r_bs, r_bs2,
                  res_row_mod, rope_cos, rope_sin, rope_T, rope_cols, rope_pos, int(c_trans), int(a_fp16), int(b_fp16), int(c_fp16),
-                 bias_rs, bias2, bias2_rs, int(a_mn_major))
+                 bias_rs, bias2, bias2_rs, int(a_mn_major), sumsq_out, rs_sumsq, int(rs_parts), float(rs_eps))
     if PROFILE is None:
         _check(_lib.load().mm_gemm_fwd(C.byref(a), _stream()), "mm_gemm_fwd")
         return
@@ -106,7 +107,7 @@ def gemm_raw(*, M, N, K, A, lda, B, ldb, Cout, ldc, batch=1, a_bs=0, b_bs=0, c_b
 def linear(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, *, act: int = ACT_NONE,
            residual: Optional[torch.Tensor] = None, res_row_mod: int = 0, out: Optional[torch.Tensor] = None,
            out_fp32: bool = False, alpha: float = 1.0, row_scale: Optional[torch.Tensor] = None, epi: int = EPI_STD,
-           rope=None, out_dtype=None) -> torch.Tensor:
+           rope=None, out_dtype=None, sumsq_out: Optional[torch.Tensor] = None, rms_from=None) -> torch.Tensor:
     """out = epilogue(alpha * x @ w.T): x (M, K) bf16 or fp16 with unit inner stride, w (N, K) bf16 or fp16 (an nn.Linear
     weight); out bf16 (default), fp16 or fp32 (`out_dtype` / the dtype of `out`)."""
     _cuda(x, None, "x"); _cuda(w, None, "w")
@@ -130,6 +131,13 @@ def linear(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None
         kw.update(rope_cos=cos.data_ptr(), rope_sin=sin.data_ptr(), rope_T=T, rope_cols=cols)
         if len(rope) > 4 and rope[4] is not None:  # device-side position offset (int32 tensor)
             kw.update(rope_pos=rope[4].data_ptr())
+    if sumsq_out is not None:  # (M, N/32) fp32: per-chunk sums of squares of the stored outputs (next RMSNorm's statistic)
+        assert sumsq_out.dtype == torch.float32 and sumsq_out.is_contiguous() and sumsq_out.shape == (M, (N + 31) // 32)
+        kw.update(sumsq_out=sumsq_out.data_ptr())
+    if rms_from is not None:   # (partials (M, parts) fp32, eps): RMSNorm row scale derived in this GEMM's epilogue
+        parts, eps = rms_from
+        assert parts.dtype == torch.float32 and parts.is_contiguous() and parts.shape[0] == M and row_scale is None
+        kw.update(rs_sumsq=parts.data_ptr(), rs_parts=parts.shape[1], rs_eps=eps)
     gemm_raw(M=M, N=N, K=K, A=x.data_ptr(), lda=x.stride(0), B=w.data_ptr(), ldb=w.stride(0), Cout=out.data_ptr(),
              ldc=out.stride(0), c_fp32=out.dtype == torch.float32, c_fp16=out.dtype == _F16, a_fp16=x.dtype == _F16,
              b_fp16=w.dtype == _F16, epi=epi, act=act, alpha=alpha, bias=_ptr(bias), row_scale=_ptr(row_scale), **kw)
@@ -262,7 +270,7 @@ def layernorm(x: torch.Tensor, w: torch.Tensor, b: torch.Tensor, eps: float,
 def embed_gather(table: torch.Tensor, ids: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """out[i] = table[ids[i]]; ids any integer dtype (converted to int64 on device), out (n, dim) row stride free."""
     _cuda(table, ACT(), "table"); _cuda(ids, None, "ids")
-    ids64 = ids.reshape(-1).to(torch.int64)
+    ids64 = ids.reshape(-1).to(torch.int64).contiguous()  # (a strided 1-D view survives reshape(-1))
     n, dim = ids64.numel(), table.shape[1]
     if out is None:
         out = torch.empty((n, dim), device=table.device, dtype=ACT())
@@ -594,7 +602,7 @@ def ce_bwd(logits: torch.Tensor, labels: torch.Tensor, n_valid: torch.Tensor, gr
 def embed_scatter_add(dx: torch.Tensor, ids: torch.Tensor, dtable: torch.Tensor) -> None:
     """dtable[ids[i]] += dx[i] for bf16 rows dx (n, dim) with unit inner stride."""
     _cuda(dx, ACT(), "dx"); _cuda(dtable, ACT(), "dtable")
-    ids64 = ids.reshape(-1).to(torch.int64)
+    ids64 = ids.reshape(-1).to(torch.int64).contiguous()  # (a strided 1-D view survives reshape(-1))
     assert dx.dim() == 2 and dx.stride(1) == 1 and dx.shape[0] == ids64.numel() and dtable.is_contiguous()
     _check(_lib.load().mm_embed_scatter_add(dx.data_ptr(), dx.stride(0), ids64.data_ptr(), ids64.numel(), dx.shape[1],
                                             dtable.shape[0], dtable.data_ptr(), _stream()), "mm_embed_scatter_add")
@@ -653,4 +661,14 @@ def head_weighted_colsum(x: torch.Tensor, w: torch.Tensor, head_dim: int, out: t
     assert w.numel() == (E // head_dim) * Nq and out.numel() == E
     _check(_lib.load().mm_head_weighted_colsum(x.data_ptr(), x.stride(0), int(x.dtype == _F16), w.data_ptr(), 1, Nq, E,
                                                head_dim, out.data_ptr(), _stream()), "mm_head_weighted_colsum")
+    return out
+
+
+def window_gather_add(dwin: torch.Tensor, B: int, N: int, C: int, Lq: int, kk: int, ss: int) -> torch.Tensor:
+    """Conv1d data gradient: dwin (B*Lq, kk*C) bf16 -> dfeats (B, N, C) bf16 (mm_window_gather_add)."""
+    _cuda(dwin, torch.bfloat16, "dwin")
+    assert dwin.is_contiguous() and dwin.shape == (B * Lq, kk * C)
+    out = torch.empty((B, N, C), device=dwin.device, dtype=torch.bfloat16)
+    _check(_lib.load().mm_window_gather_add(dwin.data_ptr(), B, N, C, Lq, kk, ss, out.data_ptr(), _stream()),
+           "mm_window_gather_add")
     return out

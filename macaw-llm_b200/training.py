@@ -19,11 +19,11 @@ What runs here (all on hand-written kernels; torch only owns memory and the auto
 Differentiable set: every LLaMA parameter (decoder layers, norms, lm_head, embed_tokens) AND the alignment modules of
 every modality (project_* Conv1d, transform_*_to_hidden Linear, *_align_attention in/out projections and bias_k / bias_v)
 — their backward runs through the (V + 2)-key softmax of the absorbed alignment attention, including the embedding
-table's gradient as the attention's keys and values (`AlignTrainer`).  The encoders are frozen as in the reference
-(names containing 'encoder').  Not differentiated in this round: `video_long_self_attention` (its input, the frozen CLIP
-frame features, needs the Conv1d data gradient first) and the attention-probability dropout of the five MHAs
-(p = 0.1, modeling.py:879) — the training step runs them without dropout; `trainable_parameters` lists what gets a
-gradient.
+table's gradient as the attention's keys and values (`AlignTrainer`) — AND `video_long_self_attention` (through the
+Conv1d data gradient of the video down-sampler).  That is every parameter the reference trains: the encoders are frozen
+as there (names containing 'encoder').  One documented omission: the attention-probability dropout of the MHAs
+(p = 0.1, modeling.py:879) — the training step runs them without dropout (SURVEY.md §7 allows "implements Philox
+dropout or documents the omission").  `trainable_parameters` lists what gets a gradient.
 """
 from __future__ import annotations
 
@@ -40,6 +40,11 @@ BF16 = torch.bfloat16
 ALIGN_MODALITIES = ("image", "audio", "video")
 
 
+def _video_long_params(model) -> List[torch.Tensor]:
+    mha = model.video_long_self_attention
+    return [mha.in_proj_weight, mha.in_proj_bias, mha.bias_k, mha.bias_v, mha.out_proj.weight, mha.out_proj.bias]
+
+
 def _align_params(model, name: str) -> List[torch.Tensor]:
     conv = getattr(model, f"project_{name}")
     lin = getattr(model, f"transform_{name}_to_hidden")
@@ -51,7 +56,7 @@ def _align_params(model, name: str) -> List[torch.Tensor]:
 def trainable_parameters(model) -> List[tuple]:
     """(name, parameter) pairs this training step produces gradients for."""
     pre = tuple(f"project_{n}." for n in ALIGN_MODALITIES) + tuple(f"transform_{n}_to_hidden." for n in ALIGN_MODALITIES) + \
-        tuple(f"{n}_align_attention." for n in ALIGN_MODALITIES)
+        tuple(f"{n}_align_attention." for n in ALIGN_MODALITIES) + ("video_long_self_attention.",)
     return [(n, p) for n, p in model.named_parameters() if n.startswith("llm.") or n.startswith(pre)]
 
 
@@ -80,6 +85,7 @@ class GradBuffer:
             groups.append(ps)
         # last bucket: the embedding table (gathered rows + keys / values of the alignment attention) and the alignment modules
         self.align_params = {n: _align_params(model, n) for n in ALIGN_MODALITIES}
+        self.align_params["video"] = self.align_params["video"] + _video_long_params(model)
         groups.append([llm.model.embed_tokens.weight] + [p for n in ALIGN_MODALITIES for p in self.align_params[n]])
         dev = llm.lm_head.weight.device
         total = sum(p.numel() for g in groups for p in g)
@@ -412,7 +418,39 @@ class AlignTrainer:
     def __init__(self, model, grads: GradBuffer):
         self.m, self.gb = model, grads
 
-    def backward(self, name: str, sv: dict, d_embeds: torch.Tensor) -> None:
+    def video_long_backward(self, sv: dict, d_feats: torch.Tensor) -> None:
+        """Backward of `video_long_self_attention(x, x, x)` (modeling.py:1078; nn.MultiheadAttention with 8 heads of 96,
+        add_bias_kv, add_zero_attn) given d(out) (B, N, P): out_proj, attention backward over the N + 2 keys (batched
+        tcgen05 GEMMs + the row-wise softmax-backward kernel), the in-projection; its input (frozen CLIP frame features +
+        the sinusoid PE) is a constant, so the chain stops at the in-projection's weight / bias and at bias_k / bias_v."""
+        ops.TAG = "train.video_long_bwd"
+        m, gb = self.m, self.gb
+        mha = m.video_long_self_attention
+        g = lambda p: gb.views[id(p)]  # noqa: E731
+        B, N, P, H, hd = (sv[k] for k in ("B", "N", "P", "H", "hd"))
+        dev = d_feats.device
+        d_out = d_feats.reshape(B * N, P).contiguous()
+        a2 = sv["a"].reshape(B * N, P)
+        da = ops.gemm_dx(d_out, mha.out_proj.weight.detach())
+        ops.gemm_dw(d_out, a2, g(mha.out_proj.weight), accumulate=True)
+        acc_bo = ops.colsum(d_out, torch.zeros((P,), device=dev, dtype=torch.float32))
+        q5 = sv["qkv"].view(B, N + 2, 3, H, hd)
+        dq, dk, dv = ops.attention_bwd(q5[:, :N, 0], q5[:, :, 1], q5[:, :, 2], da.view(B, N, H, hd), scale=hd ** -0.5,
+                                       causal=False)
+        dqkv = torch.empty((B * N, 3 * P), device=dev, dtype=BF16)
+        ops.add_rows(dq.view(B * N, P), None, dqkv[:, :P])
+        for b in range(B):
+            ops.add_rows(dk.view(B, N + 2, P)[b, :N], None, dqkv[b * N:(b + 1) * N, P:2 * P])
+            ops.add_rows(dv.view(B, N + 2, P)[b, :N], None, dqkv[b * N:(b + 1) * N, 2 * P:])
+        ops.gemm_dw(dqkv, sv["xp"], g(mha.in_proj_weight), accumulate=True)
+        acc_bin = ops.colsum(dqkv, torch.zeros((3 * P,), device=dev, dtype=torch.float32))
+        g(mha.in_proj_bias).add_(acc_bin.to(BF16))
+        g(mha.out_proj.bias).add_(acc_bo.to(BF16))
+        # the appended (un-projected) bias_k / bias_v rows are key / value N of every sample
+        g(mha.bias_k).add_(dk.view(B, N + 2, P)[:, N].float().sum(0).to(BF16).view(1, 1, P))
+        g(mha.bias_v).add_(dv.view(B, N + 2, P)[:, N].float().sum(0).to(BF16).view(1, 1, P))
+
+    def backward(self, name: str, sv: dict, d_embeds: torch.Tensor, video_long: Optional[dict] = None) -> None:
         ops.TAG = "train.align_bwd"
         m, gb = self.m, self.gb
         conv = getattr(m, f"project_{name}")
@@ -497,6 +535,12 @@ class AlignTrainer:
                          B=feats.data_ptr() + b * feats.stride(0) * 2, ldb=ss * C, b_mn_major=True, Cout=dwc.data_ptr(),
                          ldc=kk * C, residual=dwc.data_ptr(), ldr=kk * C)
         acc_bc = ops.colsum(dy, f32(C))
+        # ---- video only: the modal features are the output of the trainable video_long_self_attention -> Conv1d data
+        #      gradient (col2im over the overlapping windows), then that block's backward
+        if video_long is not None:
+            wc = conv.weight.detach().permute(0, 2, 1).reshape(C, kk * C).contiguous()
+            dwin = ops.gemm_dx(dy, wc)
+            self.video_long_backward(video_long, ops.window_gather_add(dwin, B, N, C, Lq, kk, ss))
         # ---- deposit (torch glue on small tensors: layout permutation of the conv gradient, fp32 -> bf16 bias gradients)
         g(conv.weight).add_(dwc.view(C, kk, C).permute(0, 2, 1))
         g(conv.bias).add_(acc_bc.to(BF16))
@@ -587,6 +631,6 @@ class TrainStep:
                 for p in gb.align_params[n]:
                     if fresh[id(p)]:
                         gb.views[id(p)].zero_()
-                at.backward(n, ctx["align"][n], d_embeds)
+                at.backward(n, ctx["align"][n], d_embeds, video_long=ctx["align"].get("video_long") if n == "video" else None)
             ctx["align"] = None
             self.llama.sync_last_bucket()

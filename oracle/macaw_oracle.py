@@ -378,7 +378,7 @@ def llama_loss_and_grads(inputs: dict, sd_raw: Dict[str, Tensor], hp: dict, dtyp
 
 ALIGN_PREFIXES = tuple(f"project_{n}." for n in ("image", "audio", "video")) + \
     tuple(f"transform_{n}_to_hidden." for n in ("image", "audio", "video")) + \
-    tuple(f"{n}_align_attention." for n in ("image", "audio", "video"))
+    tuple(f"{n}_align_attention." for n in ("image", "audio", "video")) + ("video_long_self_attention.",)
 
 
 def full_loss_and_grads(inputs: dict, sd_raw: Dict[str, Tensor], hp: dict, dtype=torch.float32):
@@ -386,7 +386,8 @@ def full_loss_and_grads(inputs: dict, sd_raw: Dict[str, Tensor], hp: dict, dtype
     (project_*, transform_*_to_hidden, *_align_attention) — the gradient the HF Trainer obtains from the reference in eval-
     mode arithmetic (dropout off), with the encoders frozen (run_clm_llms.py:390-393).  The embedding table is
     differentiated through the gathered rows AND as the keys / values of the alignment attention (modeling.py:974-975).
-    `video_long_self_attention` is held constant (see macaw-llm_b200/training.py).  -> (loss, {name: grad})."""
+    `video_long_self_attention` is differentiated too (its input, frozen CLIP features + PE, is a constant).
+    -> (loss, {name: grad})."""
     merged, leaves = {}, {}
     for k, v in sd_raw.items():
         if not v.is_floating_point():
