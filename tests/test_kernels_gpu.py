@@ -413,6 +413,27 @@ def test_linear_thin_splitk(M, K, N):
     assert rel_err(h, ref) < 4e-3
 
 
+def test_rms_statistics_carried_by_gemm_epilogues():
+    """The GEMM that writes the residual stream leaves per-(row, 32-column) sums of squares of the STORED values; the
+    consuming GEMM derives the RMSNorm row scale from them (no separate pass).  Must equal the rms_rstd kernel's result."""
+    ops = _ops()
+    M, E, N2 = 300, 512, 384
+    h, wo, res = rnd(M, 256, seed=70), rnd(E, 256, scale=1 / 16, seed=71), rnd(M, E, seed=72)
+    ss = torch.empty(M, E // 32, device=DEV, dtype=torch.float32)
+    x = ops.linear(h, wo, residual=res, sumsq_out=ss)                       # new residual stream + its statistics
+    assert rel_err(ss.sum(-1), x.float().pow(2).sum(-1)) < 1e-6             # of the values as stored (bf16-rounded)
+    w2 = rnd(N2, E, scale=E ** -0.5, seed=73)
+    y_fused = ops.linear(x, w2, rms_from=(ss, 1e-6))
+    y_two = ops.linear(x, w2, row_scale=ops.rms_rstd(x, 1e-6))
+    assert rel_err(y_fused, y_two) < 1e-5
+    ref = (x.float() * torch.rsqrt(x.float().pow(2).mean(-1, keepdim=True) + 1e-6)) @ w2.float().t()
+    assert rel_err(y_fused, ref) < 4e-3
+    # SwiGLU and RoPE epilogues take the same statistics
+    wg = rnd(2 * 256, E, scale=E ** -0.5, seed=74)
+    assert rel_err(ops.linear(x, wg, epi=ops.EPI_SWIGLU, rms_from=(ss, 1e-6)),
+                   ops.linear(x, wg, epi=ops.EPI_SWIGLU, row_scale=ops.rms_rstd(x, 1e-6))) < 1e-5
+
+
 def test_rope_rows_and_swiglu_rows():
     ops = _ops()
     B, E, I = 8, 512, 1376
