@@ -55,11 +55,16 @@ def real_configs(small: bool = False):
     return (clip, whisper, llama), dict(n_frames=6, attention_heads=8)
 
 
-def synth_inputs(B, L, V, img, mel_T, seed, dtype=torch.bfloat16, pin=True):
-    """Seeded synthetic host inputs of the reference's `inputs` dict."""
+def synth_inputs(B, L, V, img, mel_T, seed, dtype=torch.bfloat16, pin=True, video_frames=0):
+    """Seeded synthetic host inputs of the reference's `inputs` dict.  video_frames > 0: BASELINE config 5
+    (a video of that many frames + audio, no image)."""
     g = torch.Generator().manual_seed(seed)
     d = dict(videos=None)
-    d["images"] = torch.randn(B, 3, img, img, generator=g).to(dtype)
+    if video_frames:
+        d["images"] = None
+        d["videos"] = torch.randn(B, video_frames, 3, img, img, generator=g).to(dtype)
+    else:
+        d["images"] = torch.randn(B, 3, img, img, generator=g).to(dtype)
     d["audios"] = torch.randn(B, 80, mel_T, generator=g).to(dtype)
     ids = torch.randint(3, V - 6, (B, L), generator=g)
     ids[:, 0] = 1
@@ -341,7 +346,7 @@ def run_train(args, cfgs, hyper, rank, local_rank, world):
                        "submission": "cuda_graph_replay of the whole step" if use_graph else "host_launches",
                        "grad_sync": ("flat bf16 buffer, one NCCL all-reduce per decoder layer on a side stream, overlapped with backward ("
                                      + ("mm_nccl_allreduce" if own_nccl else "torch.distributed") + ")") if world > 1 else "none (1 rank)",
-                       "differentiable_set": "llm.* + the alignment modules of every modality (incl. the table as the alignment attention's keys/values); encoders frozen; video_long_self_attention and MHA dropout not differentiated"},
+                       "differentiable_set": "llm.* + the alignment modules of every modality (incl. the table as the alignment attention's keys/values); video_long_self_attention; encoders frozen; MHA dropout omitted"},
             "approx_tflops": tf / (ms / 1e3), "gpu_launches": launches, "loss_first_last": [losses[0], losses[-1]],
             "mem_gb": torch.cuda.max_memory_allocated() / 2 ** 30}), flush=True)
     if world > 1:
@@ -408,6 +413,9 @@ def main():
     ap.add_argument("--mode", default="prefill", choices=["prefill", "train", "decode"],
                     help="prefill = the benchmark of record; train / decode = secondary lines (SURVEY.md §8f ranks 1, 2)")
     ap.add_argument("--micro-batch", type=int, default=4, help="--mode train: samples per GPU per step (train.sh: 4)")
+    ap.add_argument("--config", default="cfg4", choices=["cfg4", "cfg5"],
+                    help="cfg4 = the benchmark of record (image+audio+text, global batch 32); cfg5 = secondary line: video "
+                         "(16 CLIP frames -> 4096 tokens, head_dim-96 self-attention) + audio + text, global batch 16")
     ap.add_argument("--dtype", default=DEFAULT_DTYPE, choices=["bf16", "fp16"],
                     help="storage / tensor-core operand format of the prefill arm (fp32 accumulation either way); the "
                          "reference itself runs fp16 (train.sh --fp16 True)")
@@ -418,9 +426,18 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     cfgs, hyper = real_configs(args.small)
     clip, whisper, llama = cfgs
+    vframes = 0
+    if args.config == "cfg5":
+        vframes = 16
+        hyper = dict(hyper, n_frames=16)
+        if args.global_batch == 32:
+            args.global_batch = 16
     L, V = args.seq_len, llama.vocab_size
     workload = (f"cfg4 image+audio+text: CLIP ViT-L/14-224 + Whisper-base + alignment(V={V},E={llama.hidden_size},"
                 f"{hyper['attention_heads'] * 2} heads) + LLaMA-7B, global_batch={args.global_batch}, L={L}")
+    if args.config == "cfg5":
+        workload = (f"cfg5 video(16 frames)+audio+text: CLIP ViT-L/14-224 x16 frames + video-long self-attention (N=4096, 8x96) + "
+                    f"Whisper-base + alignment(V={V},E={llama.hidden_size}) + LLaMA-7B, global_batch={args.global_batch}, L={L}")
     if args.small:
         workload = "SMALL stand-in (tests only) " + workload
 
@@ -469,7 +486,18 @@ def main():
     cfg = MM_LLMs_Config(clip_config=clip, whisper_config=whisper, llm_config=llama, **hyper)
     tdt = torch.float16 if args.dtype == "fp16" else torch.bfloat16
     model = MM_LLMs.build_random(cfg, device=dev, dtype=tdt, seed=0)  # same seed -> identical replicas
-    host = synth_inputs(B_local, L, V, clip.vision_config.image_size, 2 * whisper.max_source_positions, 1234 + rank, dtype=tdt)
+    if args.scaling == "strong":
+        # ONE seeded global batch, sharded by sample with the product's own helper: every N runs the same 32 samples
+        from macaw_llm_b200 import dist as D
+
+        glob = synth_inputs(B_global, L, V, clip.vision_config.image_size, 2 * whisper.max_source_positions, 1234, dtype=tdt,
+                            pin=False, video_frames=vframes)
+        host = D.shard_inputs(glob, rank, world)
+        host = {k: (v.contiguous().pin_memory() if isinstance(v, torch.Tensor) else v) for k, v in host.items()}
+        del glob
+    else:
+        host = synth_inputs(B_local, L, V, clip.vision_config.image_size, 2 * whisper.max_source_positions, 1234 + rank, dtype=tdt,
+                            video_frames=vframes)
     dev_in = {k: (v.to(dev) if isinstance(v, torch.Tensor) else v) for k, v in host.items()}
 
     def step_resident():
@@ -584,7 +612,7 @@ def main():
     # ---- CPU arm on the SAME weights and the same sample 0 as the GPU arm: a timing baseline AND a full-depth parity
     #      check of the benchmarked configuration (the GPU side re-runs sample 0 alone, eager launches)
     cpu = parity = None
-    if not args.no_cpu_baseline and world == 1:
+    if not args.no_cpu_baseline and world == 1 and args.config == "cfg4":
         one = {k: (v[:1].clone() if isinstance(v, torch.Tensor) else v) for k, v in host.items()}
         model.engine.enable_cuda_graphs(False)
         with torch.no_grad():

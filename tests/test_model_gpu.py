@@ -370,3 +370,26 @@ def test_fp32_and_fp16_parameter_models_use_bf16_shadows():
     c = model_f32(dev_inp).logits
     torch.cuda.synchronize()
     assert H.rel_err(c, 2.0 * a.float()) < 1e-2
+
+
+def test_left_padding_does_not_leak_into_valid_positions(tiny):
+    """DESIGN.md "unspecified rows": a query position whose own key is padding has every key masked; the reference then
+    attends uniformly (additive finfo.min clamp), this implementation emits zeros for that row.  Those rows are never
+    read by valid positions (padded keys are masked for everyone), so with LEFT padding — where such rows exist — the
+    logits at all valid positions must still match the oracle."""
+    from oracle import macaw_oracle as O
+    from tests.golden import gen
+
+    model, spec, hp, weights = tiny
+    inp = gen.make_inputs(spec, 2, 14, seed=91, modalities=(), with_labels=False)
+    mask = torch.ones(2, 14, dtype=torch.int64)
+    mask[0, :5] = 0        # left padding in sample 0 (text-only: no prefix in front of it)
+    inp["attention_mask"] = mask
+    dev_inp = {k: (v.cuda() if isinstance(v, torch.Tensor) else v) for k, v in inp.items()}
+    out = model(dev_inp)
+    o = O.forward(inp, H.bf16_round(weights), hp, dtype=torch.float32)
+    valid = mask.bool()
+    e = H.rel_err(out.logits.cpu()[valid], o["logits"][valid])
+    print(f"\n[parity:left padding] logits at valid positions {e:.3e}")
+    assert e < 1e-2
+    assert torch.isfinite(out.logits.float()).all()   # the masked rows are zeros / finite, never NaN
