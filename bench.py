@@ -515,6 +515,8 @@ def main():
         logits = step_resident()
     T = logits.shape[1]
     barrier()
+    overlap = model.engine.overlap_encoders
+    model.engine.overlap_encoders = False  # per-launch events need the launches serialised on one stream
     ops.PROFILE = []
     ops.launch_count_reset()
     p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -526,6 +528,7 @@ def main():
     launches = ops.launch_count()
     prof_ms = p0.elapsed_time(p1)
     prof, ops.PROFILE = ops.PROFILE, None
+    model.engine.overlap_encoders = overlap
 
     use_graphs = not args.no_graphs
     if use_graphs:

@@ -283,7 +283,25 @@ int32_t mm_swiglu_bwd(const void* dh, const void* gate, const void* up, void* dg
  * and dP = dO.v^T, fp32 [B][H][Tq][ld]; writes P = softmax(scale*S + mask) and dS = scale * P * (dP - sum_j P_j dP_j) as
  * bf16 with the same layout.  Masks as in mm_attn_fwd. */
 int32_t mm_attn_softmax_bwd(const float* S, const float* dP, void* P, void* dS, int32_t B, int32_t H, int32_t Tq,
-                            int32_t Tk, int64_t ld, float scale, int32_t causal, const int32_t* key_mask, void* stream);
+                            int32_t Tk, int64_t ld, float scale, int32_t causal, const int32_t* key_mask, float p_drop,
+                            const uint64_t* seed_dev, uint32_t sid, void* stream);
+/* Training-mode attention dropout (reference: nn.MultiheadAttention(dropout=0.1), modeling.py:879-909; torch drops the
+ * softmax probabilities, functional.py:6640-6645).  The mask is a pure function of (*seed_dev, sid, row, column) through
+ * Philox4x32-10 (csrc/philox.cuh): forward and backward kernels regenerate it, nothing is stored; `seed_dev` is a DEVICE
+ * 64-bit seed so a captured CUDA graph draws a fresh mask per replay, `sid` separates the dropout sites.  p_drop == 0
+ * switches dropout off (seed_dev may be null).  With p_drop > 0, mm_attn_softmax_bwd uses dP <- m . dP and writes Pd = m . P.
+ * mm_attn_softmax_fwd: S fp32 [B][H][Tq][ld] -> Pd = dropout(softmax(scale * S + mask)) bf16, same layout. */
+int32_t mm_attn_softmax_fwd(const float* S, void* P, int32_t B, int32_t H, int32_t Tq, int32_t Tk, int64_t ld, float scale,
+                            int32_t causal, const int32_t* key_mask, float p_drop, const uint64_t* seed_dev, uint32_t sid,
+                            void* stream);
+/* Dropout of the alignment attention's probabilities (forward): P' (un-normalised fp16, R x ldp) -> Pm (kept entries,
+ * unscaled), rs = (1/l)/(1-p), p_sum_real_d = rs * sum_v Pm_v, p_extra_d = m_V * p_extra (column V = the bias_k key). */
+int32_t mm_align_dropout_fwd(const void* P_unnorm_f16, void* Pm_f16, int64_t ldp, const float* inv_l, const float* p_extra,
+                             float* rs, float* p_sum_real_d, float* p_extra_d, int32_t R, int32_t V, float p_drop,
+                             const uint64_t* seed_dev, uint32_t sid, void* stream);
+/* The multipliers themselves (fp32: 0 or 1/(1-p)) of a rows x cols block of stream `sid` — for tests / debugging. */
+int32_t mm_dropout_mask(float* out, int64_t ld, int32_t rows, int32_t cols, float p_drop, const uint64_t* seed_dev,
+                        uint32_t sid, void* stream);
 /* Gradient of mm_ce_loss w.r.t. the logits (modeling.py:600-610), times grad_scale (* *grad_scale_dev when given: the
  * upstream gradient of the loss as a device scalar, so the launch is CUDA-graph capturable) / n_valid; may run in place. */
 int32_t mm_ce_bwd(const void* logits, const int64_t* labels, void* dlogits, int32_t B, int32_t T, int32_t V,
@@ -302,7 +320,8 @@ int32_t mm_adamw(void* p, const void* g, float* master, float* m, float* v, int6
  * nn.MultiheadAttention, modeling.py:986-987 / 1007-1008 / 1025-1026).  See train_kernels.cu for the formulas. */
 int32_t mm_align_softmax_bwd(const float* G, int64_t ldg, const void* P_unnorm_f16, int64_t ldp, const float* inv_l,
                              const float* d_p_sum_real, const float* p_extra, const float* d_p_extra, float gscale,
-                             void* P_bf16, void* dS_bf16, int64_t ldo, float* dstats, int32_t R, int32_t V, void* stream);
+                             void* P_bf16, void* dS_bf16, int64_t ldo, float* dstats, int32_t R, int32_t V, float p_drop,
+                             const uint64_t* seed_dev, uint32_t sid, void* stream);
 /* out[h*hd + d] += sum_n w[(h*Nq + n) * w_stride] * x[n, h*hd + d]; x bf16 (x_fp16 == 0) or fp16. */
 int32_t mm_head_weighted_colsum(const void* x, int64_t ldx, int32_t x_fp16, const float* w, int64_t w_stride, int32_t Nq,
                                 int32_t E, int32_t head_dim, float* out, void* stream);

@@ -11,7 +11,7 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libmacaw_b200.so")
 
-c_i32, c_i64, c_f32, c_vp = C.c_int32, C.c_int64, C.c_float, C.c_void_p
+c_i32, c_i64, c_f32, c_vp, c_u32 = C.c_int32, C.c_int64, C.c_float, C.c_void_p, C.c_uint32
 
 
 class GemmArgs(C.Structure):
@@ -104,7 +104,11 @@ SIGNATURES = {
     "mm_rmsnorm_bwd": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_vp]),
     "mm_swiglu_fwd": (c_i32, [c_vp, c_vp, c_vp, c_i64, c_vp]),
     "mm_swiglu_bwd": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp]),
-    "mm_attn_softmax_bwd": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_i64, c_f32, c_i32, c_vp, c_vp]),
+    "mm_attn_softmax_bwd": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_i64, c_f32, c_i32, c_vp, c_f32, c_vp,
+                                    c_u32, c_vp]),
+    "mm_attn_softmax_fwd": (c_i32, [c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_i64, c_f32, c_i32, c_vp, c_f32, c_vp, c_u32, c_vp]),
+    "mm_align_dropout_fwd": (c_i32, [c_vp, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_f32, c_vp, c_u32, c_vp]),
+    "mm_dropout_mask": (c_i32, [c_vp, c_i64, c_i32, c_i32, c_f32, c_vp, c_u32, c_vp]),
     "mm_ce_bwd": (c_i32, [c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_vp, c_f32, c_vp, c_vp]),
     "mm_embed_scatter_add": (c_i32, [c_vp, c_i64, c_vp, c_i64, c_i32, c_i32, c_vp, c_vp]),
     "mm_colsum": (c_i32, [c_vp, c_i64, c_i32, c_i32, c_vp, c_vp]),
@@ -112,7 +116,7 @@ SIGNATURES = {
     "mm_image_preprocess": (c_i32, [C.POINTER(ImageArgs), c_vp]),
     "mm_log_mel": (c_i32, [c_vp, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp, c_i32, c_vp]),
     "mm_align_softmax_bwd": (c_i32, [c_vp, c_i64, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_f32, c_vp, c_vp, c_i64, c_vp, c_i32,
-                                     c_i32, c_vp]),
+                                     c_i32, c_f32, c_vp, c_u32, c_vp]),
     "mm_head_weighted_colsum": (c_i32, [c_vp, c_i64, c_i32, c_vp, c_i64, c_i32, c_i32, c_i32, c_vp, c_vp]),
     "mm_window_gather_add": (c_i32, [c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp]),
     "mm_cast_f16_bf16": (c_i32, [c_vp, c_i64, c_vp, c_i64, c_i32, c_i32, c_vp]),

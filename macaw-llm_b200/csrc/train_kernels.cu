@@ -8,6 +8,7 @@
 #include "common.cuh"
 #include <cuda_fp16.h>
 #include "ptx.cuh"
+#include "philox.cuh"
 #include "../../include/macaw_b200.h"
 
 namespace mm {
@@ -155,15 +156,18 @@ __global__ void swiglu_bwd_kernel(const bf16* __restrict__ dh, const bf16* __res
   }
 }
 
-// ------------------------------------------------------------------------------------------------ attention softmax (backward)
+// ------------------------------------------------------------------------------------------------ attention softmax (training)
 // One CTA per (b, h, query) row of the score matrices: S (pre-scale logits q.k) and dP = dO V^T, both fp32.
-//   P = softmax(scale * S + mask),  D = sum_j P_j dP_j,  dS = scale * P (dP - D).
-// P and dS are written as bf16 (A operands of dV = P^T dO, dK = dS^T Q, dQ = dS K).  Mask semantics match the forward
+//   P = softmax(scale * S + mask),  Pd = m . P  (m: dropout multipliers, 0 or 1/(1-p); all ones when dropout is off),
+//   dP <- m . dP,  D = sum_j P_j dP_j,  dS = scale * P (dP - D).
+// Pd and dS are written as bf16 (A operands of dV = Pd^T dO, dK = dS^T Q, dQ = dS K).  Mask semantics match the forward
 // kernel: key j visible to query i iff j <= i + (Tk - Tq) (causal) and key_mask[b][j] != 0; fully masked rows give zeros.
+// Dropout element index: (row = blockIdx.x, col = j) of stream `sid` (philox.cuh).
 __global__ void __launch_bounds__(256) attn_softmax_bwd_kernel(const float* __restrict__ S, const float* __restrict__ dP,
                                                                bf16* __restrict__ P, bf16* __restrict__ dS, int H, int Tq,
                                                                int Tk, long long ld, float scale, int causal,
-                                                               const int* __restrict__ key_mask) {
+                                                               const int* __restrict__ key_mask, float p_drop,
+                                                               const unsigned long long* __restrict__ seed_dev, uint32_t sid) {
   __shared__ float sh[32];
   const long long row = blockIdx.x;
   const int i = static_cast<int>(row % Tq);
@@ -174,6 +178,8 @@ __global__ void __launch_bounds__(256) attn_softmax_bwd_kernel(const float* __re
   bf16* ds = dS + row * ld;
   const int* km = key_mask ? key_mask + static_cast<long long>(b) * Tk : nullptr;
   const int lim = causal ? i + (Tk - Tq) : Tk - 1;
+  const DropCfg dc = drop_cfg(p_drop, seed_dev, sid);
+  const int n4 = (Tk + 3) >> 2;
   float mx = -INFINITY;
   for (int j = threadIdx.x; j < Tk; j += blockDim.x) {
     const bool ok = j <= lim && (km == nullptr || km[j] != 0);
@@ -181,21 +187,96 @@ __global__ void __launch_bounds__(256) attn_softmax_bwd_kernel(const float* __re
   }
   mx = block_max(mx, sh);
   float sum = 0.f, dsum = 0.f;
-  for (int j = threadIdx.x; j < Tk; j += blockDim.x) {
-    const bool ok = j <= lim && (km == nullptr || km[j] != 0);
-    const float e = ok ? __expf(s[j] * scale - mx) : 0.f;
-    sum += e;
-    dsum += e * dp[j];
+  for (int j4 = threadIdx.x; j4 < n4; j4 += blockDim.x) {
+    float m[4];
+    drop_mult4(dc, static_cast<uint32_t>(row), static_cast<uint32_t>(j4), m);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int j = 4 * j4 + u;
+      if (j >= Tk) break;
+      const bool ok = j <= lim && (km == nullptr || km[j] != 0);
+      const float e = ok ? __expf(s[j] * scale - mx) : 0.f;
+      sum += e;
+      dsum += e * m[u] * dp[j];
+    }
   }
   sum = block_sum(sum, sh);
   dsum = block_sum(dsum, sh);
   const float inv = sum > 0.f ? 1.f / sum : 0.f;
   const float D = dsum * inv;
+  for (int j4 = threadIdx.x; j4 < n4; j4 += blockDim.x) {
+    float m[4];
+    drop_mult4(dc, static_cast<uint32_t>(row), static_cast<uint32_t>(j4), m);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int j = 4 * j4 + u;
+      if (j >= Tk) break;
+      const bool ok = j <= lim && (km == nullptr || km[j] != 0);
+      const float pj = ok ? __expf(s[j] * scale - mx) * inv : 0.f;
+      p[j] = __float2bfloat16(pj * m[u]);
+      ds[j] = __float2bfloat16(scale * pj * (m[u] * dp[j] - D));
+    }
+  }
+}
+
+// Forward half for the training step of a dropout attention (video_long_self_attention in train() mode): S fp32 ->
+// Pd = dropout(softmax(scale * S + mask)) in bf16 (the A operand of O = Pd V); same row / mask / dropout conventions.
+__global__ void __launch_bounds__(256) attn_softmax_fwd_kernel(const float* __restrict__ S, bf16* __restrict__ P, int H, int Tq,
+                                                               int Tk, long long ld, float scale, int causal,
+                                                               const int* __restrict__ key_mask, float p_drop,
+                                                               const unsigned long long* __restrict__ seed_dev, uint32_t sid) {
+  __shared__ float sh[32];
+  const long long row = blockIdx.x;
+  const int i = static_cast<int>(row % Tq);
+  const int b = static_cast<int>(row / (static_cast<long long>(Tq) * H));
+  const float* s = S + row * ld;
+  bf16* p = P + row * ld;
+  const int* km = key_mask ? key_mask + static_cast<long long>(b) * Tk : nullptr;
+  const int lim = causal ? i + (Tk - Tq) : Tk - 1;
+  const DropCfg dc = drop_cfg(p_drop, seed_dev, sid);
+  float mx = -INFINITY;
   for (int j = threadIdx.x; j < Tk; j += blockDim.x) {
     const bool ok = j <= lim && (km == nullptr || km[j] != 0);
-    const float pj = ok ? __expf(s[j] * scale - mx) * inv : 0.f;
-    p[j] = __float2bfloat16(pj);
-    ds[j] = __float2bfloat16(scale * pj * (dp[j] - D));
+    if (ok) mx = fmaxf(mx, s[j] * scale);
+  }
+  mx = block_max(mx, sh);
+  float sum = 0.f;
+  for (int j = threadIdx.x; j < Tk; j += blockDim.x) {
+    const bool ok = j <= lim && (km == nullptr || km[j] != 0);
+    sum += ok ? __expf(s[j] * scale - mx) : 0.f;
+  }
+  sum = block_sum(sum, sh);
+  const float inv = sum > 0.f ? 1.f / sum : 0.f;
+  const int n4 = (Tk + 3) >> 2;
+  for (int j4 = threadIdx.x; j4 < n4; j4 += blockDim.x) {
+    float m[4];
+    drop_mult4(dc, static_cast<uint32_t>(row), static_cast<uint32_t>(j4), m);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int j = 4 * j4 + u;
+      if (j >= Tk) break;
+      const bool ok = j <= lim && (km == nullptr || km[j] != 0);
+      p[j] = __float2bfloat16(ok ? __expf(s[j] * scale - mx) * inv * m[u] : 0.f);
+    }
+    // padding columns Tk .. ld-1 are never read (the consuming GEMM's K extent is Tk)
+  }
+}
+
+// The dropout multipliers themselves (fp32, 0 or 1/(1-p)) for rows x cols of stream `sid`: test / debugging utility (the
+// parity tests hand this mask to the autograd oracle).
+__global__ void dropout_mask_kernel(float* __restrict__ out, long long ld, int rows, int cols, float p_drop,
+                                    const unsigned long long* __restrict__ seed_dev, uint32_t sid) {
+  const DropCfg dc = drop_cfg(p_drop, seed_dev, sid);
+  const int n4 = (cols + 3) >> 2;
+  const long long total = static_cast<long long>(rows) * n4;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int r = static_cast<int>(i / n4), c4 = static_cast<int>(i % n4);
+    float m[4];
+    drop_mult4(dc, static_cast<uint32_t>(r), static_cast<uint32_t>(c4), m);
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      if (4 * c4 + u < cols) out[r * ld + 4 * c4 + u] = m[u];
   }
 }
 
@@ -289,19 +370,21 @@ __global__ void adamw_kernel(bf16* __restrict__ p, const bf16* __restrict__ g, f
 // ------------------------------------------------------------------------------------------------ alignment softmax backward
 // One CTA per query row r of the absorbed alignment attention.  Inputs: G[r, v] = dctx~[r] . table[v] (fp32), the
 // un-normalised fp16 probabilities P' of the forward pass and 1 / l, the gradients of the two per-row probability sums
-// (d p_sum_real, d p_extra) and p_extra itself.  With P = P' / l over the V real keys (+ the bias_k key with weight
-// p_extra; the zero key's dP is 0):
-//   dP_v = G_v + d p_sum_real,   D = sum_v P_v dP_v + p_extra * d p_extra,   dS_v = P_v (dP_v - D)
-// Outputs: P and dS as bf16 (operands of the table-gradient GEMMs dT += P^T dctx~ + dS^T q~ and of dq~ = dS . table),
-// dstats[0][r] = gscale * sum_v dS_v, dstats[1][r] = gscale * p_extra * (d p_extra - D) — the gradients of row_bias and of
-// the bias_k key's score (planar [2][R]).
+// (d p_sum_real, d p_extra) and the UN-dropped p_extra.  With P = P' / l over the V real keys (+ the bias_k key, column V,
+// with weight p_extra; the zero key's value is 0 so its dP is 0) and m the dropout multipliers (ones when off):
+//   dP_v = m_v (G_v + d p_sum_real),   D = sum_v P_v dP_v + p_extra m_V d p_extra,   dS_v = P_v (dP_v - D)
+// Outputs: Pd = m . P and dS as bf16 (operands of the table-gradient GEMMs dT += Pd^T dctx~ + dS^T q~ and of dq~ = dS . table),
+// dstats[0][r] = gscale * sum_v dS_v, dstats[1][r] = gscale * p_extra * (m_V d p_extra - D) — the gradients of row_bias and
+// of the bias_k key's score (planar [2][R]).
 __global__ void __launch_bounds__(512) align_softmax_bwd_kernel(const float* __restrict__ G, long long ldg,
                                                                 const __half* __restrict__ Pp, long long ldp,
                                                                 const float* __restrict__ inv_l,
                                                                 const float* __restrict__ dpsr, const float* __restrict__ pe,
                                                                 const float* __restrict__ dpe, float gscale,
                                                                 bf16* __restrict__ P, bf16* __restrict__ dS, long long ldo,
-                                                                float* __restrict__ dstats, int V) {
+                                                                float* __restrict__ dstats, int V, float p_drop,
+                                                                const unsigned long long* __restrict__ seed_dev,
+                                                                uint32_t sid) {
   __shared__ float sh[32];
   const long long r = blockIdx.x;
   const float* g = G + r * ldg;
@@ -309,21 +392,79 @@ __global__ void __launch_bounds__(512) align_softmax_bwd_kernel(const float* __r
   bf16* po = P + r * ldo;
   bf16* dso = dS + r * ldo;
   const float il = inv_l[r], a = dpsr[r], pex = pe[r], dpex = dpe[r];
+  const DropCfg dc = drop_cfg(p_drop, seed_dev, sid);
+  const int n4 = (V + 3) >> 2;
   float acc = 0.f;
-  for (int v = threadIdx.x; v < V; v += blockDim.x) acc += __half2float(pp[v]) * il * (g[v] + a);
-  const float D = block_sum(acc, sh) + pex * dpex;
+  for (int v4 = threadIdx.x; v4 < n4; v4 += blockDim.x) {
+    float m[4];
+    drop_mult4(dc, static_cast<uint32_t>(r), static_cast<uint32_t>(v4), m);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int v = 4 * v4 + u;
+      if (v < V) acc += __half2float(pp[v]) * il * m[u] * (g[v] + a);
+    }
+  }
+  const float me = drop_mult1(dc, static_cast<uint32_t>(r), static_cast<uint32_t>(V));
+  const float D = block_sum(acc, sh) + pex * me * dpex;
   float srow = 0.f;
-  for (int v = threadIdx.x; v < V; v += blockDim.x) {
-    const float pv = __half2float(pp[v]) * il;
-    const float d = pv * (g[v] + a - D);
-    po[v] = __float2bfloat16(pv);
-    dso[v] = __float2bfloat16(d);
-    srow += d;
+  for (int v4 = threadIdx.x; v4 < n4; v4 += blockDim.x) {
+    float m[4];
+    drop_mult4(dc, static_cast<uint32_t>(r), static_cast<uint32_t>(v4), m);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int v = 4 * v4 + u;
+      if (v >= V) break;
+      const float pv = __half2float(pp[v]) * il;
+      const float d = pv * (m[u] * (g[v] + a) - D);
+      po[v] = __float2bfloat16(pv * m[u]);
+      dso[v] = __float2bfloat16(d);
+      srow += d;
+    }
   }
   srow = block_sum(srow, sh);
   if (threadIdx.x == 0) {  // planar [2][R]: each half is the per-row scale array of a row-scaled GEMM bias term
     dstats[r] = gscale * srow;
-    dstats[gridDim.x + r] = gscale * pex * (dpex - D);
+    dstats[gridDim.x + r] = gscale * pex * (me * dpex - D);
+  }
+}
+
+// Training-mode dropout of the alignment probabilities (forward): from the fused kernel's un-normalised fp16 P' makes
+// Pm = P' where kept, 0 where dropped (UNSCALED: P' may sit near the top of the fp16 range), the per-row scale
+// rs = (1 / l) / (1 - p) of the following ctx~ = rs . (Pm . table) GEMM, and the dropped probability sums
+// p_sum_real_d = rs * sum_v Pm_v,  p_extra_d = m_V * p_extra (column V = the bias_k key; the zero key has no effect).
+__global__ void __launch_bounds__(512) align_dropout_fwd_kernel(const __half* __restrict__ Pp, __half* __restrict__ Pm,
+                                                                long long ldp, const float* __restrict__ inv_l,
+                                                                const float* __restrict__ pe, float* __restrict__ rs,
+                                                                float* __restrict__ psum_d, float* __restrict__ pext_d,
+                                                                int V, float p_drop,
+                                                                const unsigned long long* __restrict__ seed_dev,
+                                                                uint32_t sid) {
+  __shared__ float sh[32];
+  const long long r = blockIdx.x;
+  const __half* pp = Pp + r * ldp;
+  __half* po = Pm + r * ldp;
+  const DropCfg dc = drop_cfg(p_drop, seed_dev, sid);
+  const int n4 = (V + 3) >> 2;
+  float acc = 0.f;
+  for (int v4 = threadIdx.x; v4 < n4; v4 += blockDim.x) {
+    float m[4];
+    drop_mult4(dc, static_cast<uint32_t>(r), static_cast<uint32_t>(v4), m);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int v = 4 * v4 + u;
+      if (v >= V) break;
+      const __half h = pp[v];
+      const bool keep = m[u] != 0.f;
+      po[v] = keep ? h : __float2half_rn(0.f);
+      if (keep) acc += __half2float(h);
+    }
+  }
+  acc = block_sum(acc, sh);
+  if (threadIdx.x == 0) {
+    const float s = inv_l[r] * dc.scale;
+    rs[r] = s;
+    psum_d[r] = s * acc;
+    pext_d[r] = pe[r] * drop_mult1(dc, static_cast<uint32_t>(r), static_cast<uint32_t>(V));
   }
 }
 
@@ -420,13 +561,47 @@ extern "C" int32_t mm_swiglu_bwd(const void* dh, const void* gate, const void* u
 
 extern "C" int32_t mm_attn_softmax_bwd(const float* S, const float* dP, void* P, void* dS, int32_t B, int32_t H, int32_t Tq,
                                        int32_t Tk, int64_t ld, float scale, int32_t causal, const int32_t* key_mask,
-                                       void* stream) {
+                                       float p_drop, const uint64_t* seed_dev, uint32_t sid, void* stream) {
   MM_REQUIRE(S && dP && P && dS && B > 0 && H > 0 && Tq > 0 && Tk > 0 && ld >= Tk, "mm_attn_softmax_bwd: bad arguments");
+  MM_REQUIRE(p_drop >= 0.f && p_drop < 1.f && (p_drop == 0.f || seed_dev != nullptr), "mm_attn_softmax_bwd: dropout arguments");
   const long long rows = static_cast<long long>(B) * H * Tq;
   MM_REQUIRE(rows < (1LL << 31), "mm_attn_softmax_bwd: too many rows");
   attn_softmax_bwd_kernel<<<static_cast<unsigned>(rows), 256, 0, ST(stream)>>>(S, dP, (bf16*)P, (bf16*)dS, H, Tq, Tk, ld,
-                                                                               scale, causal, key_mask);
+                                                                               scale, causal, key_mask, p_drop,
+                                                                               (const unsigned long long*)seed_dev, sid);
   return check_launch("mm_attn_softmax_bwd");
+}
+
+extern "C" int32_t mm_attn_softmax_fwd(const float* S, void* P, int32_t B, int32_t H, int32_t Tq, int32_t Tk, int64_t ld,
+                                       float scale, int32_t causal, const int32_t* key_mask, float p_drop,
+                                       const uint64_t* seed_dev, uint32_t sid, void* stream) {
+  MM_REQUIRE(S && P && B > 0 && H > 0 && Tq > 0 && Tk > 0 && ld >= Tk, "mm_attn_softmax_fwd: bad arguments");
+  MM_REQUIRE(p_drop >= 0.f && p_drop < 1.f && (p_drop == 0.f || seed_dev != nullptr), "mm_attn_softmax_fwd: dropout arguments");
+  const long long rows = static_cast<long long>(B) * H * Tq;
+  MM_REQUIRE(rows < (1LL << 31), "mm_attn_softmax_fwd: too many rows");
+  attn_softmax_fwd_kernel<<<static_cast<unsigned>(rows), 256, 0, ST(stream)>>>(S, (bf16*)P, H, Tq, Tk, ld, scale, causal,
+                                                                               key_mask, p_drop,
+                                                                               (const unsigned long long*)seed_dev, sid);
+  return check_launch("mm_attn_softmax_fwd");
+}
+
+extern "C" int32_t mm_dropout_mask(float* out, int64_t ld, int32_t rows, int32_t cols, float p_drop, const uint64_t* seed_dev,
+                                   uint32_t sid, void* stream) {
+  MM_REQUIRE(out && rows > 0 && cols > 0 && ld >= cols && p_drop >= 0.f && p_drop < 1.f && seed_dev, "mm_dropout_mask: bad arguments");
+  const long long total = static_cast<long long>(rows) * ((cols + 3) / 4);
+  dropout_mask_kernel<<<grid_for(total, 256), 256, 0, ST(stream)>>>(out, ld, rows, cols, p_drop,
+                                                                   (const unsigned long long*)seed_dev, sid);
+  return check_launch("mm_dropout_mask");
+}
+
+extern "C" int32_t mm_align_dropout_fwd(const void* Pp, void* Pm, int64_t ldp, const float* inv_l, const float* pe, float* rs,
+                                        float* psum_d, float* pext_d, int32_t R, int32_t V, float p_drop,
+                                        const uint64_t* seed_dev, uint32_t sid, void* stream) {
+  MM_REQUIRE(Pp && Pm && inv_l && pe && rs && psum_d && pext_d && R > 0 && V > 0 && ldp >= V, "mm_align_dropout_fwd: bad arguments");
+  MM_REQUIRE(p_drop >= 0.f && p_drop < 1.f && (p_drop == 0.f || seed_dev != nullptr), "mm_align_dropout_fwd: dropout arguments");
+  align_dropout_fwd_kernel<<<R, 512, 0, ST(stream)>>>((const __half*)Pp, (__half*)Pm, ldp, inv_l, pe, rs, psum_d, pext_d, V,
+                                                      p_drop, (const unsigned long long*)seed_dev, sid);
+  return check_launch("mm_align_dropout_fwd");
 }
 
 extern "C" int32_t mm_ce_bwd(const void* logits, const int64_t* labels, void* dlogits, int32_t B, int32_t T, int32_t V,
@@ -468,11 +643,14 @@ extern "C" int32_t mm_adamw(void* p, const void* g, float* master, float* m, flo
 
 extern "C" int32_t mm_align_softmax_bwd(const float* G, int64_t ldg, const void* Pp, int64_t ldp, const float* inv_l,
                                         const float* dpsr, const float* pe, const float* dpe, float gscale, void* P,
-                                        void* dS, int64_t ldo, float* dstats, int32_t R, int32_t V, void* stream) {
+                                        void* dS, int64_t ldo, float* dstats, int32_t R, int32_t V, float p_drop,
+                                        const uint64_t* seed_dev, uint32_t sid, void* stream) {
   MM_REQUIRE(G && Pp && inv_l && dpsr && pe && dpe && P && dS && dstats && R > 0 && V > 0 && ldg >= V && ldp >= V && ldo >= V,
              "mm_align_softmax_bwd: bad arguments");
+  MM_REQUIRE(p_drop >= 0.f && p_drop < 1.f && (p_drop == 0.f || seed_dev != nullptr), "mm_align_softmax_bwd: dropout arguments");
   align_softmax_bwd_kernel<<<R, 512, 0, ST(stream)>>>(G, ldg, (const __half*)Pp, ldp, inv_l, dpsr, pe, dpe, gscale, (bf16*)P,
-                                                      (bf16*)dS, ldo, dstats, V);
+                                                      (bf16*)dS, ldo, dstats, V, p_drop,
+                                                      (const unsigned long long*)seed_dev, sid);
   return check_launch("mm_align_softmax_bwd");
 }
 

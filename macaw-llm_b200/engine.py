@@ -40,6 +40,12 @@ class Engine:
         self._zeros: Dict[Tuple[int, str], torch.Tensor] = {}
         self._graphs: Dict[tuple, tuple] = {}
         self._decode: Dict[tuple, dict] = {}  # KV buffers + captured decode step per (batch, capacity, device)
+        self._side: Dict[str, torch.cuda.Stream] = {}
+        # Whisper tower on a side stream next to the CLIP tower(s).  Measured on B200 (profiles/r2_bench_lines.txt, run 12):
+        # neutral to slightly negative at global batch 32 (+2 ms of 36 ms outside LLaMA: both towers' GEMMs are persistent
+        # one-CTA-per-SM kernels, two of them cannot co-reside, so only launch tails overlap while the late-starting CTAs
+        # stretch the static tile schedule), -0.3 ms at batch 4.  Off by default; kept as a tested option.
+        self.overlap_encoders = False
         self._graphs_on = False
         self.align_max_rows = None  # test hook: cap on query rows per alignment chunk (default: ~2 GiB of fp32 scores)
 
@@ -247,10 +253,11 @@ class Engine:
             self._pe[key] = pe
         return pe
 
-    def encode_video_long(self, videos: torch.Tensor, save: Optional[dict] = None) -> torch.Tensor:
+    def encode_video_long(self, videos: torch.Tensor, save: Optional[dict] = None, dropout=None) -> torch.Tensor:
         """reference modeling.py:1070-1079 -> (B, F*256, P).  `save` (training step) receives the activations of the
         video_long_self_attention block (its input xp, the fused qkv buffer with the two synthetic key rows, the attention
-        output) for the backward pass."""
+        output) for the backward pass; `dropout` = (p, seed_dev, sid): its attention dropout (train() mode) — the
+        probabilities are then materialised (GEMM -> softmax + Philox mask -> GEMM) instead of the flash kernel."""
         m = self.m
         F_ = m.config.n_frames
         frames = videos.reshape(-1, *videos.shape[-3:])
@@ -282,15 +289,19 @@ class Engine:
         ops.add_rows(z.expand(B, P), None, qkv[:, N + 1, P:2 * P])
         ops.add_rows(z.expand(B, P), None, qkv[:, N + 1, 2 * P:])
         q5 = qkv.view(B, N + 2, 3, H, hd)
-        a = ops.attention(q5[:, :N, 0], q5[:, :, 1], q5[:, :, 2], scale=hd ** -0.5)
+        if dropout is not None and save is not None and float(dropout[0]) > 0.0:
+            a = ops.attention_train_fwd(q5[:, :N, 0], q5[:, :, 1], q5[:, :, 2], scale=hd ** -0.5, dropout=dropout)
+        else:
+            dropout = None
+            a = ops.attention(q5[:, :N, 0], q5[:, :, 1], q5[:, :, 2], scale=hd ** -0.5)
         out = ops.linear(a.view(B * N, P), self.w(mha.out_proj.weight, pre + "wo"), self.w(mha.out_proj.bias, pre + "bo"))
         if save is not None:
-            save.update(xp=xp, qkv=qkv, a=a, B=B, N=N, P=P, H=H, hd=hd)
+            save.update(xp=xp, qkv=qkv, a=a, B=B, N=N, P=P, H=H, hd=hd, dropout=dropout)
         return out.view(B, N, P)
 
     # ------------------------------------------------------------------------------------------------ alignment
     def align(self, feats: torch.Tensor, name: str, table: torch.Tensor, prefix: torch.Tensor, row_off: int,
-              table16: Optional[torch.Tensor] = None, save: Optional[dict] = None) -> int:
+              table16: Optional[torch.Tensor] = None, save: Optional[dict] = None, dropout=None) -> int:
         """One modality of reference modeling.py:982-987 / 999-1008 / 1022-1026 in ABSORBED form:
         the keys/values are never projected — q is pushed through W_k per head and both big contractions
         (scores = q~ . table^T over E, ctx~ = P . table over V) run inside ONE fused kernel (mm_align_fwd) that streams
@@ -301,7 +312,11 @@ class Engine:
         the single bf16 rounding of its output.
 
         feats (B, N, C) bf16 with unit channel stride and row stride C (sample stride free); writes the Lq aligned
-        rows into prefix[:, row_off : row_off + Lq] and returns Lq."""
+        rows into prefix[:, row_off : row_off + Lq] and returns Lq.
+
+        dropout = (p, seed_dev, sid) (training step only, with `save`): the MHA's attention dropout (modeling.py:879) on the
+        (V + 2)-key probabilities — the fused kernel's fp16 P' is masked (Philox, regenerated in the backward pass) and the
+        P . table contraction is redone on the masked probabilities."""
         ops.TAG = "align.proj"
         F16 = torch.float16
         m = self.m
@@ -379,6 +394,14 @@ class Engine:
                 if nq != Nq:
                     raise NotImplementedError("macaw_b200 training: the alignment block must fit one row chunk")
                 save.update(keep)
+                save.update(pext_raw=pext, dropout=None)
+                if dropout is not None and float(dropout[0]) > 0.0:
+                    ops.TAG = "align.dropout"
+                    Pm, rs, psum, pext = ops.align_dropout_fwd(keep["P"], keep["inv_l"], pext, V, dropout)
+                    ops.gemm_raw(M=R, N=E, K=V, A=Pm.data_ptr(), lda=Vp, B=table16.data_ptr(), ldb=table16.stride(0),
+                                 b_mn_major=True, Cout=ctxt.data_ptr(), ldc=E, row_scale=rs.data_ptr(), c_fp16=True, **f16)
+                    del Pm
+                    save.update(dropout=dropout)
                 save.update(feats=feats_bf, y=y, z=z, q=q, stats=stats, qt=qt, ctxt=ctxt, psum=psum, pext=pext, ctx=ctx,
                             B=B, N=N, C=C, Lq=Lq, kk=kk, ss=ss, H=H, hd=hd, row_off=row_off)
             # ctx[:, h] = ctx~[h] W_v[h]^T + (sum_real P) b_v[h] + P_bias bias_v[h]   (value-side bias terms in the epilogue)
@@ -408,9 +431,12 @@ class Engine:
             t = t.to(ADT())
         return t.contiguous()
 
-    def prepare_inputs(self, inputs: dict, save: Optional[dict] = None):
+    DROPOUT_SID = {"image": 1, "audio": 2, "video": 3, "video_long": 4}  # Philox stream id of each dropout site
+
+    def prepare_inputs(self, inputs: dict, save: Optional[dict] = None, dropout_seed: Optional[torch.Tensor] = None):
         """MM_LLMs.prepare_inputs_for_generation (reference modeling.py:965-1048).  `save` (training step): receives the
-        alignment activations of every modality, keyed by modality name, for the backward pass."""
+        alignment activations of every modality, keyed by modality name, for the backward pass.  `dropout_seed` (training
+        step, train() mode): device int64 seed -> the attention dropout of the MHAs (modeling.py:879) is applied."""
         m = self.m
         self.set_format()
         table = self.w(m.llm.model.embed_tokens.weight, "llm.embed")
@@ -430,13 +456,33 @@ class Engine:
         ids = ids.to(dev)
         B, L = ids.shape
         feats = {}
+        mel = self._to_dev_bf16(inputs["audios"], dev) if inputs.get("audios") is not None else None
+        side = None
+        if mel is not None and self.overlap_encoders and (inputs.get("images") is not None or inputs.get("videos") is not None):
+            # The Whisper tower is independent of the CLIP tower(s): run it on a side stream so its short-K GEMMs fill the
+            # SMs the other tower's 108..144-tile launches leave idle (the two towers' kernels interleave; under CUDA-graph
+            # capture the fork / join becomes graph edges).  Joined before the alignment blocks.
+            main = torch.cuda.current_stream(dev)
+            side = self._side.get(str(dev))
+            if side is None:
+                side = self._side[str(dev)] = torch.cuda.Stream(device=dev)
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                feats["audio"] = self.whisper_encode(mel)
+            mel.record_stream(side)
         if inputs.get("images") is not None:
             feats["image"] = self.clip_tokens(self._to_dev_bf16(inputs["images"], dev), "image_encoder")
-        if inputs.get("audios") is not None:
-            feats["audio"] = self.whisper_encode(self._to_dev_bf16(inputs["audios"], dev))
+        if mel is not None and side is None:
+            feats["audio"] = self.whisper_encode(mel)
         if inputs.get("videos") is not None:
-            feats["video"] = self.encode_video_long(self._to_dev_bf16(inputs["videos"], dev),
-                                                    save=None if save is None else save.setdefault("video_long", {}))
+            mha_v = m.video_long_self_attention
+            feats["video"] = self.encode_video_long(
+                self._to_dev_bf16(inputs["videos"], dev), save=None if save is None else save.setdefault("video_long", {}),
+                dropout=None if dropout_seed is None else (float(mha_v.dropout), dropout_seed, self.DROPOUT_SID["video_long"]))
+        if side is not None:
+            torch.cuda.current_stream(dev).wait_stream(side)
+            feats["audio"].record_stream(torch.cuda.current_stream(dev))
+            self.set_format()
         # final layout [BOS, <image> img </image>, <audio> aud </audio>, <video> vid </video>, text[1:]]: each block is
         # spliced right after BOS in the order video, audio, image (reference modeling.py:978-1034), so image ends up first
         lens = {}
@@ -445,6 +491,8 @@ class Engine:
                 conv = getattr(m, f"project_{name}")
                 lens[name] = self.align_len(feats[name].shape[1], conv.kernel_size[0], conv.stride[0])
         n_prefix = sum(v + 2 for v in lens.values())
+        if "video" in feats:
+            self._video_long_len = feats["video"].shape[1]  # tokens of video_long_self_attention (frames x patches)
         self.last_lens = dict(lens)  # aligned rows per modality of the most recent call (the training step maps prefix rows to token ids)
         prefix = None
         if n_prefix > 0:
@@ -458,8 +506,11 @@ class Engine:
                 sv = None
                 if save is not None:
                     sv = save.setdefault(name, {})
+                drop = None
+                if dropout_seed is not None and sv is not None:
+                    drop = (float(getattr(m, f"{name}_align_attention").dropout), dropout_seed, self.DROPOUT_SID[name])
                 got = self.align(feats[name], name, table, prefix, off + 1,
-                                 self.w16(m.llm.model.embed_tokens.weight, "llm.embed"), save=sv)
+                                 self.w16(m.llm.model.embed_tokens.weight, "llm.embed"), save=sv, dropout=drop)
                 assert got == Lq
                 ops.embed_gather(table, inputs[f"{name}_ends"].to(dev), out=prefix[:, off + 1 + Lq, :])
                 off += Lq + 2

@@ -522,11 +522,62 @@ def swiglu_bwd(dh: torch.Tensor, gate: torch.Tensor, up: torch.Tensor):
     return dg, du
 
 
+def _drop_args(dropout):
+    """dropout = None | (p, seed_dev int64 1-element CUDA tensor, stream id) -> (p, seed pointer, sid) for the C ABI."""
+    if dropout is None:
+        return 0.0, None, 0
+    p, seed, sid = dropout
+    if float(p) <= 0.0:
+        return 0.0, None, 0
+    assert seed.is_cuda and seed.dtype == torch.int64 and seed.numel() == 1
+    return float(p), seed.data_ptr(), int(sid)
+
+
+def dropout_mask(rows: int, cols: int, dropout, device) -> torch.Tensor:
+    """fp32 (rows, cols) multipliers (0 or 1/(1-p)) the dropout kernels apply for this (seed, stream id): tests only."""
+    p, seed, sid = _drop_args(dropout)
+    out = torch.empty((rows, cols), device=device, dtype=torch.float32)
+    _check(_lib.load().mm_dropout_mask(out.data_ptr(), cols, rows, cols, p, seed, sid, _stream()), "mm_dropout_mask")
+    return out
+
+
+def attention_train_fwd(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, *, scale: float, causal: bool = False,
+                        key_mask: Optional[torch.Tensor] = None, dropout=None) -> torch.Tensor:
+    """Training-mode forward of a DROPOUT attention (the flash kernel has no dropout): S = q k^T (fp32, batched tcgen05
+    GEMM), Pd = dropout(softmax(scale S)) (one row-wise kernel, Philox mask), O = Pd v.  Same operand conventions as
+    attention_bwd; returns O (B, Tq, H, hd) contiguous."""
+    for n, t in (("q", q), ("k", k), ("v", v)):
+        _cuda(t, ACT(), n)
+        assert t.dim() == 4 and t.stride(3) == 1
+    assert ACT() == torch.bfloat16, "the training step computes in bf16"
+    B, Tq, H, hd = q.shape
+    Tk = k.shape[1]
+    dev = q.device
+    Tp = (Tk + 7) // 8 * 8
+    S = torch.empty((B, H, Tq, Tp), device=dev, dtype=torch.float32)
+    gemm_raw(M=Tq, N=Tk, K=hd, batch=H, batch2=B, A=q.data_ptr(), lda=q.stride(1), a_bs=q.stride(2), a_bs2=q.stride(0),
+             B=k.data_ptr(), ldb=k.stride(1), b_bs=k.stride(2), b_bs2=k.stride(0), Cout=S.data_ptr(), ldc=Tp, c_bs=Tq * Tp,
+             c_bs2=H * Tq * Tp, c_fp32=True)
+    P = torch.empty((B, H, Tq, Tp), device=dev, dtype=ACT())
+    if key_mask is not None:
+        _cuda(key_mask, torch.int32, "key_mask")
+    pd, seed, sid = _drop_args(dropout)
+    _check(_lib.load().mm_attn_softmax_fwd(S.data_ptr(), P.data_ptr(), B, H, Tq, Tk, Tp, float(scale), int(causal),
+                                           _ptr(key_mask), pd, seed, sid, _stream()), "mm_attn_softmax_fwd")
+    del S
+    o = torch.empty((B, Tq, H, hd), device=dev, dtype=ACT())
+    gemm_raw(M=Tq, N=hd, K=Tk, batch=H, batch2=B, A=P.data_ptr(), lda=Tp, a_bs=Tq * Tp, a_bs2=H * Tq * Tp,
+             B=v.data_ptr(), ldb=v.stride(1), b_bs=v.stride(2), b_bs2=v.stride(0), b_mn_major=True, Cout=o.data_ptr(),
+             ldc=o.stride(1), c_bs=o.stride(2), c_bs2=o.stride(0))
+    return o
+
+
 def attention_bwd(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, do: torch.Tensor, *, scale: float, causal: bool,
-                  key_mask: Optional[torch.Tensor] = None):
+                  key_mask: Optional[torch.Tensor] = None, dropout=None):
     """Backward of mm_attn_fwd composed from tcgen05 GEMMs: S = q k^T and dP = dO v^T (fp32, batched over (b, h)), one
     row-wise softmax-backward kernel (P, dS in bf16), then dV = P^T dO, dK = dS^T q (MN-major A), dQ = dS k.
-    q / do (B, Tq, H, hd), k / v (B, Tk, H, hd): bf16 views with unit head-dim stride.  Returns contiguous dq, dk, dv."""
+    q / do (B, Tq, H, hd), k / v (B, Tk, H, hd): bf16 views with unit head-dim stride.  Returns contiguous dq, dk, dv.
+    dropout = (p, seed_dev, sid): backward of attention_train_fwd with the same mask (regenerated, not stored)."""
     for n, t in (("q", q), ("k", k), ("v", v), ("do", do)):
         _cuda(t, ACT(), n)
         assert t.dim() == 4 and t.stride(3) == 1
@@ -552,8 +603,10 @@ def attention_bwd(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, do: torch.T
     dS = torch.empty((B, H, Tq, Tp), device=dev, dtype=ACT())
     if key_mask is not None:
         _cuda(key_mask, torch.int32, "key_mask")
+    pd, seed, sid = _drop_args(dropout)
     _check(_lib.load().mm_attn_softmax_bwd(S.data_ptr(), dP.data_ptr(), P.data_ptr(), dS.data_ptr(), B, H, Tq, Tk, Tp,
-                                           float(scale), int(causal), _ptr(key_mask), _stream()), "mm_attn_softmax_bwd")
+                                           float(scale), int(causal), _ptr(key_mask), pd, seed, sid, _stream()),
+           "mm_attn_softmax_bwd")
     del S, dP
     dq = torch.empty((B, Tq, H, hd), device=dev, dtype=ACT())
     dk = torch.empty((B, Tk, H, hd), device=dev, dtype=ACT())
@@ -636,9 +689,24 @@ def cast_bf16(x: torch.Tensor) -> torch.Tensor:
     return y
 
 
+def align_dropout_fwd(P_unnorm: torch.Tensor, inv_l: torch.Tensor, pe: torch.Tensor, V: int, dropout):
+    """Training-mode dropout of the alignment probabilities -> (Pm fp16 (R, ldp) kept entries, rs (R,) = (1/l)/(1-p),
+    p_sum_real_d (R,), p_extra_d (R,)); see mm_align_dropout_fwd."""
+    _cuda(P_unnorm, _F16, "P")
+    R, ldp = P_unnorm.shape
+    dev = P_unnorm.device
+    Pm = torch.empty_like(P_unnorm)
+    rs, psum_d, pext_d = (torch.empty((R,), device=dev, dtype=torch.float32) for _ in range(3))
+    pd, seed, sid = _drop_args(dropout)
+    _check(_lib.load().mm_align_dropout_fwd(P_unnorm.data_ptr(), Pm.data_ptr(), ldp, inv_l.data_ptr(), pe.data_ptr(),
+                                            rs.data_ptr(), psum_d.data_ptr(), pext_d.data_ptr(), R, V, pd, seed, sid,
+                                            _stream()), "mm_align_dropout_fwd")
+    return Pm, rs, psum_d, pext_d
+
+
 def align_softmax_bwd(G: torch.Tensor, P_unnorm: torch.Tensor, inv_l: torch.Tensor, dpsr: torch.Tensor, pe: torch.Tensor,
-                      dpe: torch.Tensor, gscale: float, V: int):
-    """-> (P bf16 (R, ldp), dS bf16 (R, ldp), dstats fp32 (2, R)); see mm_align_softmax_bwd."""
+                      dpe: torch.Tensor, gscale: float, V: int, dropout=None):
+    """-> (Pd bf16 (R, ldp), dS bf16 (R, ldp), dstats fp32 (2, R)); see mm_align_softmax_bwd."""
     _cuda(G, torch.float32, "G"); _cuda(P_unnorm, _F16, "P")
     R, ldp = P_unnorm.shape
     assert G.shape[0] == R and G.stride(1) == 1 and P_unnorm.stride(1) == 1
@@ -647,9 +715,10 @@ def align_softmax_bwd(G: torch.Tensor, P_unnorm: torch.Tensor, inv_l: torch.Tens
     P = torch.empty((R, ldp), device=G.device, dtype=ACT())
     dS = torch.empty((R, ldp), device=G.device, dtype=ACT())
     dstats = torch.empty((2, R), device=G.device, dtype=torch.float32)
+    pd, seed, sid = _drop_args(dropout)
     _check(_lib.load().mm_align_softmax_bwd(G.data_ptr(), G.stride(0), P_unnorm.data_ptr(), ldp, inv_l.data_ptr(), dpsr.data_ptr(),
                                             pe.data_ptr(), dpe.data_ptr(), float(gscale), P.data_ptr(), dS.data_ptr(), ldp,
-                                            dstats.data_ptr(), R, V, _stream()), "mm_align_softmax_bwd")
+                                            dstats.data_ptr(), R, V, pd, seed, sid, _stream()), "mm_align_softmax_bwd")
     return P, dS, dstats
 
 

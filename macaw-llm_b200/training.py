@@ -436,7 +436,7 @@ class AlignTrainer:
         acc_bo = ops.colsum(d_out, torch.zeros((P,), device=dev, dtype=torch.float32))
         q5 = sv["qkv"].view(B, N + 2, 3, H, hd)
         dq, dk, dv = ops.attention_bwd(q5[:, :N, 0], q5[:, :, 1], q5[:, :, 2], da.view(B, N, H, hd), scale=hd ** -0.5,
-                                       causal=False)
+                                       causal=False, dropout=sv.get("dropout"))
         dqkv = torch.empty((B * N, 3 * P), device=dev, dtype=BF16)
         ops.add_rows(dq.view(B * N, P), None, dqkv[:, :P])
         for b in range(B):
@@ -497,7 +497,10 @@ class AlignTrainer:
         Vp = sv["P"].shape[1]
         G = torch.empty((R, Vp), device=dev, dtype=torch.float32)
         ops.gemm_raw(M=R, N=V, K=E, A=dctxt.data_ptr(), lda=E, B=table.data_ptr(), ldb=E, Cout=G.data_ptr(), ldc=Vp, c_fp32=True)
-        P, dS, dstats = ops.align_softmax_bwd(G, sv["P"], sv["inv_l"], dpsr, sv["pext"], dpe, 1.0, V)
+        # (with attention dropout: psum / pext above are the DROPPED sums the forward used; the softmax itself needs the
+        #  un-dropped p_extra, and the mask is regenerated from the same Philox stream)
+        P, dS, dstats = ops.align_softmax_bwd(G, sv["P"], sv["inv_l"], dpsr, sv["pext_raw"], dpe, 1.0, V,
+                                              dropout=sv.get("dropout"))
         del G
         dqt = torch.empty((H, Nq, E), device=dev, dtype=BF16)
         ops.gemm_raw(M=R, N=E, K=V, A=dS.data_ptr(), lda=Vp, B=table.data_ptr(), ldb=E, b_mn_major=True, Cout=dqt.data_ptr(), ldc=E)
@@ -579,6 +582,13 @@ class TrainStep:
         self.m = model
         self.llama = LlamaTrainer(model)
         self._anchor = None
+        # Attention dropout of the five MHAs (nn.MultiheadAttention(dropout=0.1), modeling.py:879) is live in train() mode,
+        # as in the reference.  The Philox seed lives on the device and advances by one per forward, so a captured
+        # CUDA graph of the step draws a fresh mask on every replay; `last_seed` is the seed the latest forward used.
+        self.attention_dropout = True
+        self.dropout_base_seed = 0x5EED
+        self._seed = None
+        self.last_seed = None
 
     def set_world(self, world: int, overlap: bool = True) -> None:
         self.llama.world, self.llama.overlap_allreduce = int(world), bool(overlap)
@@ -595,7 +605,14 @@ class TrainStep:
         with torch.no_grad():
             # multimodal prefix: frozen encoders -> alignment block, keeping the block's activations for its backward
             saved_align = {}
-            embeds, mask, labels = m.engine.prepare_inputs(inputs, save=saved_align)
+            seed = None
+            if self.attention_dropout:
+                dev = m.llm.lm_head.weight.device
+                if self._seed is None or self._seed.device != dev:
+                    self._seed = torch.tensor([int(self.dropout_base_seed)], dtype=torch.int64, device=dev)
+                self._seed.add_(1)
+                seed = self.last_seed = self._seed.clone()  # this step's own copy: its backward regenerates the masks from it
+            embeds, mask, labels = m.engine.prepare_inputs(inputs, save=saved_align, dropout_seed=seed)
             loss, ctx = self.llama.forward(embeds, mask, labels)
             n_prefix = embeds.shape[1] - inputs["input_ids"].shape[1]
             prefix_ids = None

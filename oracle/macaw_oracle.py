@@ -80,8 +80,12 @@ class _SD:
 
 
 # ------------------------------------------------------------------------------------------------ torch MHA restatement
-def mha_forward(query: Tensor, key: Tensor, value: Tensor, w: _SD, num_heads: int) -> Tensor:
-    """nn.MultiheadAttention(E, H, add_bias_kv=True, add_zero_attn=True), eval mode, seq-first layout.
+def mha_forward(query: Tensor, key: Tensor, value: Tensor, w: _SD, num_heads: int,
+                dropout_mult: Optional[Tensor] = None) -> Tensor:
+    """nn.MultiheadAttention(E, H, add_bias_kv=True, add_zero_attn=True), seq-first layout; eval mode unless
+    `dropout_mult` is given: the (B*H, Lq, S+2) multipliers (0 or 1/(1-p)) F.dropout would apply to the softmax
+    probabilities in train() mode (functional.py:6640-6645, dropout_p = 0.1 from modeling.py:879) — passed explicitly so
+    the gradient oracle and the device kernels use the SAME mask.
 
     Follows torch/nn/functional.py multi_head_attention_forward:
       in-projection (functional.py:5798-5868), bias_k/bias_v appended AFTER projection (:6531-6537), head split,
@@ -106,11 +110,14 @@ def mha_forward(query: Tensor, key: Tensor, value: Tensor, w: _SD, num_heads: in
     v = torch.cat([v, zeros], dim=1)
     q = q * (1.0 / math.sqrt(hd))
     p = torch.softmax(torch.bmm(q, k.transpose(1, 2)), dim=-1)
+    if dropout_mult is not None:
+        p = p * dropout_mult.to(p.dtype)
     ctx = torch.bmm(p, v).transpose(0, 1).reshape(Lq, B, E)
     return F.linear(ctx, w("out_proj.weight"), w("out_proj.bias"))
 
 
-def align_block(feats: Tensor, table: Tensor, conv: _SD, lin: _SD, mha: _SD, stride: int, num_heads: int) -> Tensor:
+def align_block(feats: Tensor, table: Tensor, conv: _SD, lin: _SD, mha: _SD, stride: int, num_heads: int,
+                dropout_mult: Optional[Tensor] = None) -> Tensor:
     """One modality of modeling.py:982-987 / 999-1008 / 1022-1026: Conv1d over tokens -> Linear C->E -> MHA(Q=feats,
     K=V=the whole embedding table).  The reference repeats the table per batch element (modeling.py:974-975); K/V
     are batch-invariant, so this restatement projects them once and broadcasts — numerically the same function.
@@ -119,7 +126,7 @@ def align_block(feats: Tensor, table: Tensor, conv: _SD, lin: _SD, mha: _SD, str
     z = F.linear(y, lin("weight"), lin("bias"))
     B = z.shape[0]
     kv = table.unsqueeze(1).expand(-1, B, -1)
-    return mha_forward(z.transpose(0, 1), kv, kv, mha, num_heads).transpose(0, 1)
+    return mha_forward(z.transpose(0, 1), kv, kv, mha, num_heads, dropout_mult).transpose(0, 1)
 
 
 # ------------------------------------------------------------------------------------------------ CLIP vision tower
@@ -195,7 +202,7 @@ def video_positional_encoding(L: int, h: int, dtype=torch.float32) -> Tensor:
     return pe.to(dtype)
 
 
-def encode_video_long(videos: Tensor, sd: _SD, hp: dict) -> Tensor:
+def encode_video_long(videos: Tensor, sd: _SD, hp: dict, dropout_mult: Optional[Tensor] = None) -> Tensor:
     """modeling.py:1070-1079: CLIP per frame -> (B, F*256, D) -> + sinusoid PE -> video_long_self_attention(x, x, x)."""
     F_ = hp["n_frames"]
     frames = videos.reshape(-1, *videos.shape[-3:])
@@ -204,7 +211,7 @@ def encode_video_long(videos: Tensor, sd: _SD, hp: dict) -> Tensor:
     x = tok.reshape(B, F_ * tok.shape[1], -1)
     x = x + video_positional_encoding(x.shape[1], x.shape[2], x.dtype)[None]
     xs = x.transpose(0, 1)
-    return mha_forward(xs, xs, xs, sd.sub("video_long_self_attention."), hp["attention_heads"]).transpose(0, 1)
+    return mha_forward(xs, xs, xs, sd.sub("video_long_self_attention."), hp["attention_heads"], dropout_mult).transpose(0, 1)
 
 
 # ------------------------------------------------------------------------------------------------ LLaMA
@@ -266,15 +273,19 @@ def shifted_ce(logits: Tensor, labels: Tensor) -> Tensor:
 
 
 # ------------------------------------------------------------------------------------------------ whole forward
-def prepare_inputs(inputs: dict, sd_raw: Dict[str, Tensor], hp: dict, dtype=torch.float32, keep_graph: bool = False):
-    """MM_LLMs.prepare_inputs_for_generation (modeling.py:965-1048) -> (embeds, attention_mask | None, labels | None)."""
+def prepare_inputs(inputs: dict, sd_raw: Dict[str, Tensor], hp: dict, dtype=torch.float32, keep_graph: bool = False,
+                   dropout: Optional[Dict[str, Tensor]] = None):
+    """MM_LLMs.prepare_inputs_for_generation (modeling.py:965-1048) -> (embeds, attention_mask | None, labels | None).
+    dropout: train()-mode attention-dropout multipliers per MHA, keys "image" / "audio" / "video" / "video_long"."""
+    dropout = dropout or {}
     sd = _SD(sd_raw, dtype, keep_graph=keep_graph)
     table = sd("llm.model.embed_tokens.weight")
     H2 = hp["attention_heads"] * 2
     cast = lambda t: None if t is None else t.to("cpu").to(dtype)
     image_feats = clip_tokens(cast(inputs["images"]), sd.sub("image_encoder."), hp) if inputs.get("images") is not None else None
     audio_feats = whisper_encode(cast(inputs["audios"]), sd.sub("audio_encoder.encoder."), hp) if inputs.get("audios") is not None else None
-    video_feats = encode_video_long(cast(inputs["videos"]), sd, hp) if inputs.get("videos") is not None else None
+    video_feats = (encode_video_long(cast(inputs["videos"]), sd, hp, dropout.get("video_long"))
+                   if inputs.get("videos") is not None else None)
     ids = inputs["input_ids"].to("cpu").long()
     text = table[ids]
     n_ignore = 0
@@ -285,7 +296,7 @@ def prepare_inputs(inputs: dict, sd_raw: Dict[str, Tensor], hp: dict, dtype=torc
         starts = table[inputs[f"{name}_starts"].to("cpu").long()].unsqueeze(1)
         ends = table[inputs[f"{name}_ends"].to("cpu").long()].unsqueeze(1)
         out = align_block(feats, table, sd.sub(f"project_{name}."), sd.sub(f"transform_{name}_to_hidden."),
-                          sd.sub(f"{name}_align_attention."), hp[f"{name}_conv"][1], H2)
+                          sd.sub(f"{name}_align_attention."), hp[f"{name}_conv"][1], H2, dropout.get(name))
         block = torch.cat([starts, out, ends], dim=1)
         text = torch.cat([text[:, :1], block, text[:, 1:]], dim=1)
         n_ignore += block.shape[1]
@@ -381,12 +392,14 @@ ALIGN_PREFIXES = tuple(f"project_{n}." for n in ("image", "audio", "video")) + \
     tuple(f"{n}_align_attention." for n in ("image", "audio", "video")) + ("video_long_self_attention.",)
 
 
-def full_loss_and_grads(inputs: dict, sd_raw: Dict[str, Tensor], hp: dict, dtype=torch.float32):
+def full_loss_and_grads(inputs: dict, sd_raw: Dict[str, Tensor], hp: dict, dtype=torch.float32,
+                        dropout: Optional[Dict[str, Tensor]] = None):
     """Loss of MM_LLMs.forward and its autograd gradients w.r.t. every `llm.*` parameter AND the alignment modules
     (project_*, transform_*_to_hidden, *_align_attention) — the gradient the HF Trainer obtains from the reference in eval-
     mode arithmetic (dropout off), with the encoders frozen (run_clm_llms.py:390-393).  The embedding table is
     differentiated through the gathered rows AND as the keys / values of the alignment attention (modeling.py:974-975).
     `video_long_self_attention` is differentiated too (its input, frozen CLIP features + PE, is a constant).
+    `dropout`: explicit train()-mode attention-dropout multipliers per MHA (see mha_forward); None = dropout off.
     -> (loss, {name: grad})."""
     merged, leaves = {}, {}
     for k, v in sd_raw.items():
@@ -398,7 +411,7 @@ def full_loss_and_grads(inputs: dict, sd_raw: Dict[str, Tensor], hp: dict, dtype
             t = t.clone().requires_grad_(True)
             leaves[k] = t
         merged[k] = t
-    embeds, mask, labels = prepare_inputs(inputs, merged, hp, dtype, keep_graph=True)
+    embeds, mask, labels = prepare_inputs(inputs, merged, hp, dtype, keep_graph=True, dropout=dropout)
     logits = llama_forward(embeds, mask, _SD(merged, dtype, keep_graph=True), hp)
     loss = shifted_ce(logits, labels)
     loss.backward()

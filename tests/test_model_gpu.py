@@ -234,6 +234,26 @@ def test_cuda_graph_replay_matches_eager(tiny):
     assert torch.equal(eager2.logits, out2.logits), float((eager2.logits.float() - out2.logits.float()).abs().max())
 
 
+def test_encoder_side_stream_option_is_bit_identical(tiny):
+    """`engine.overlap_encoders = True` (Whisper tower on a side stream, joined before the alignment blocks) changes only
+    the schedule: logits are bit-identical to the single-stream run, eagerly and under CUDA-graph capture."""
+    model, spec, hp, weights = tiny
+    inp = _to_bf16_inputs(H.case_inputs(spec, H.load_case("all3")))
+    dev_inp = {k: (v.cuda() if isinstance(v, torch.Tensor) else v) for k, v in inp.items()}
+    ref = model(dev_inp).logits.clone()
+    model.engine.overlap_encoders = True
+    try:
+        assert torch.equal(model(dev_inp).logits, ref)
+        model.engine.enable_cuda_graphs(True)
+        for _ in range(2):
+            out = model(inp)
+            torch.cuda.synchronize()
+            assert torch.equal(out.logits, ref)
+    finally:
+        model.engine.enable_cuda_graphs(False)
+        model.engine.overlap_encoders = False
+
+
 def test_resized_vocab_not_multiple_of_8():
     """The real pipeline resizes the table to 32007 rows (run_clm_llms.py:495): V % 8 != 0 exercises the padded score
     buffer, the ragged-K P.table GEMM and the unaligned (scalar-store) lm_head epilogue.  Tiny model, V = 512 + 7."""

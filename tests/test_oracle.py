@@ -98,6 +98,63 @@ def test_mha_restatement_vs_torch_module():
     assert float((ref - got).abs().max()) < 1e-12
 
 
+def test_mha_dropout_restatement_vs_torch_module(monkeypatch):
+    """train() mode: torch drops the SOFTMAX PROBABILITIES (all S + 2 keys, bias_k / zero keys included) before P.V
+    (functional.py:6640-6645).  nn.MultiheadAttention with F.dropout replaced by an explicit mask vs the restatement with
+    the same multipliers: outputs and gradients, fp64."""
+    import torch.nn.functional as Fn
+
+    torch.manual_seed(1)
+    E, Hh, V, B, Lq, pd = 32, 4, 50, 3, 5, 0.1
+    mha = torch.nn.MultiheadAttention(E, Hh, dropout=pd, add_bias_kv=True, add_zero_attn=True).double().train()
+    with torch.no_grad():
+        mha.in_proj_bias.normal_()
+        mha.out_proj.bias.normal_()
+    mult = (torch.rand(B * Hh, Lq, V + 2, dtype=torch.float64) >= pd).double() / (1 - pd)
+    seen = []
+
+    def fake_dropout(x, p=0.5, training=True, inplace=False):
+        assert training and abs(p - pd) < 1e-12 and x.shape == mult.shape
+        seen.append(1)
+        return x * mult
+
+    monkeypatch.setattr(Fn, "dropout", fake_dropout)
+    table = torch.randn(V, E, dtype=torch.float64, requires_grad=True)
+    q = torch.randn(Lq, B, E, dtype=torch.float64)
+    kv = table.unsqueeze(1).repeat(1, B, 1)
+    ref = mha(q, kv, kv)[0]
+    assert len(seen) == 1
+    w = torch.randn_like(ref)
+    (ref * w).sum().backward()
+    g_ref = {k: v.grad.clone() for k, v in mha.named_parameters()}
+    gt_ref = table.grad.clone()
+    leaves = {k: v.detach().clone().requires_grad_(True) for k, v in mha.state_dict().items()}
+    t2 = table.detach().clone().requires_grad_(True)
+    kv2 = t2.unsqueeze(1).expand(-1, B, -1)
+    got = O.mha_forward(q, kv2, kv2, O._SD(leaves, torch.float64, keep_graph=True), Hh, dropout_mult=mult)
+    assert float((ref - got).detach().abs().max()) < 1e-12
+    (got * w).sum().backward()
+    assert float((t2.grad - gt_ref).abs().max()) < 1e-10
+    for k, g in g_ref.items():
+        assert float((leaves[k].grad - g).abs().max()) < 1e-10, k
+
+
+def test_philox_known_answers():
+    """Philox4x32-10 restated in numpy (tests/helpers.py) against the published known-answer vectors of the Random123
+    distribution (Salmon et al., SC'11) — the generator csrc/philox.cuh implements; the GPU tier compares the device mask
+    with this restatement element by element."""
+    kat = [((0, 0, 0, 0), (0, 0), (0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8)),
+           ((0xffffffff,) * 4, (0xffffffff,) * 2, (0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd)),
+           ((0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344), (0xa4093822, 0x299f31d0),
+            (0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1))]
+    for ctr, key, want in kat:
+        got = H.philox4x32_10(np.array([ctr], dtype=np.uint32), key)
+        assert tuple(int(x) for x in got[0]) == want
+    m = H.dropout_multipliers(64, 37, 0.1, seed=(7 << 32) | 5, sid=3)
+    assert m.shape == (64, 37) and set(np.unique(m)).issubset({0.0, np.float32(1 / 0.9)})
+    assert abs(float((m != 0).mean()) - 0.9) < 0.03
+
+
 @pytest.mark.skipif(not os.path.isdir("/root/reference"), reason="reference tree only exists in the build container")
 def test_oracle_vs_live_reference():
     from tests.golden import make_golden as MG

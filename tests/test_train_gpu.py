@@ -145,15 +145,69 @@ def test_fused_adamw_matches_torch():
     assert rel(opt.state[id(p)][0], ref) < 1e-6 and rel(p, ref) < 3e-3
 
 
+def test_dropout_mask_matches_philox_restatement():
+    """mm_dropout_mask (the multipliers every dropout kernel regenerates) vs the numpy Philox4x32-10 restatement pinned to
+    the published known-answer vectors (tests/test_oracle.py): bit-exact; a different seed / stream id gives a different
+    mask; the forward and backward softmax kernels of a dropout attention apply exactly this mask."""
+    ops = _ops()
+    seed = torch.tensor([(9 << 32) | 1234567], dtype=torch.int64, device=DEV)
+    m = ops.dropout_mask(67, 131, (0.1, seed, 3), DEV).cpu().numpy()
+    want = H.dropout_multipliers(67, 131, 0.1, seed=(9 << 32) | 1234567, sid=3)
+    assert (m == want).all()
+    assert (ops.dropout_mask(67, 131, (0.1, seed, 4), DEV).cpu().numpy() != want).any()
+    assert (ops.dropout_mask(67, 131, (0.1, seed + 1, 3), DEV).cpu().numpy() != want).any()
+    # attention_train_fwd / attention_bwd against autograd with this mask
+    B, Hh, T, hd, pd = 2, 3, 37, 96, 0.1
+    q, k, v, do = (rnd(B, T, Hh, hd, scale=0.7, seed=s) for s in (1, 2, 3, 4))
+    drop = (pd, seed, 7)
+    o = ops.attention_train_fwd(q, k, v, scale=hd ** -0.5, dropout=drop)
+    dq, dk, dv = ops.attention_bwd(q, k, v, do, scale=hd ** -0.5, causal=False, dropout=drop)
+    mult = ops.dropout_mask(B * Hh * T, T, drop, DEV).view(B, Hh, T, T).double().cpu()
+    qf, kf, vf = (t.double().cpu().permute(0, 2, 1, 3).requires_grad_(True) for t in (q, k, v))
+    p = torch.softmax(qf @ kf.transpose(-1, -2) * hd ** -0.5, dim=-1) * mult
+    of = p @ vf
+    of.backward(do.double().cpu().permute(0, 2, 1, 3))
+    assert rel(o.permute(0, 2, 1, 3), of.detach()) < 6e-3
+    for got, ref in ((dq, qf.grad), (dk, kf.grad), (dv, vf.grad)):
+        assert rel(got.permute(0, 2, 1, 3), ref) < 8e-3
+
+
 @pytest.fixture(scope="module")
 def tiny_train():
     model, spec, hp, weights = H.build_tiny_model("cuda", torch.bfloat16)
     return model, spec, hp, weights
 
 
+def _oracle_dropout_masks(model, spec, present, B):
+    """The attention-dropout multipliers the device kernels applied in the latest training forward (regenerated from its
+    Philox seed through mm_dropout_mask), in the oracle's layout: (B*H, Lq, S+2) with batch-head index b*H + h."""
+    ops = _ops()
+    eng, ts = model.engine, model.train_step
+    masks = {}
+    V = model.llm.model.embed_tokens.weight.shape[0]
+    for n in present:
+        mha = getattr(model, f"{n}_align_attention")
+        Hh, Lq = mha.num_heads, eng.last_lens[n]
+        m = ops.dropout_mask(Hh * B * Lq, V + 2, (mha.dropout, ts.last_seed, eng.DROPOUT_SID[n]), DEV)
+        masks[n] = m.view(Hh, B, Lq, V + 2).permute(1, 0, 2, 3).reshape(B * Hh, Lq, V + 2).cpu()
+        keep = float((m != 0).float().mean())
+        assert abs(keep - (1 - mha.dropout)) < 0.01, (n, keep)
+        assert torch.all((m == 0) | ((m - 1 / (1 - mha.dropout)).abs() < 1e-6))
+    if "video" in present:
+        mha = model.video_long_self_attention
+        Hh = mha.num_heads
+        N = eng._video_long_len
+        m = ops.dropout_mask(B * Hh * N, N + 2, (mha.dropout, ts.last_seed, eng.DROPOUT_SID["video_long"]), DEV)
+        masks["video_long"] = m.view(B * Hh, N, N + 2).cpu()
+    return masks
+
+
+@pytest.mark.parametrize("dropout", [False, True])
 @pytest.mark.parametrize("name", ["text_labels", "image_audio", "all3"])
-def test_gradients_vs_oracle_autograd(tiny_train, name):
-    """`model.train(); model(inputs).loss.backward()` vs autograd of the fp32 CPU oracle on the same bf16-rounded weights:
+def test_gradients_vs_oracle_autograd(tiny_train, name, dropout):
+    """`model.train(); model(inputs).loss.backward()` vs autograd of the fp32 CPU oracle on the same bf16-rounded weights
+    (dropout=True: with the MHAs' attention dropout live, as in the reference's train() mode — the oracle applies the SAME
+    Philox mask, exported from the device; dropout=False: `train_step.attention_dropout = False`):
     every LLaMA parameter AND the alignment modules (Conv1d, Linear, MHA in/out projections, bias_k / bias_v), the embedding
     table through the gathered rows and as the alignment attention's keys / values.  text_labels / image_audio: the oracle
     gradient is the reference's FULL gradient (encoders frozen, dropout off); all3 adds the video path incl.
@@ -170,7 +224,11 @@ def test_gradients_vs_oracle_autograd(tiny_train, name):
         inp = gen.make_inputs(spec, 3, 24, seed=77, modalities=(), pad_tail=4, with_labels=True)
     inp = {k: (v.to(torch.bfloat16) if isinstance(v, torch.Tensor) and v.is_floating_point() else v) for k, v in inp.items()}
     dev_inp = {k: (v.cuda() if isinstance(v, torch.Tensor) else v) for k, v in inp.items()}
+    if dropout and name == "text_labels":
+        pytest.skip("no MHA on the text-only path")
+    present = {"text_labels": (), "image_audio": ("image", "audio"), "all3": ("image", "audio", "video")}[name]
     model.train()
+    model.train_step.attention_dropout = bool(dropout)
     try:
         for p in model.parameters():
             p.grad = None
@@ -178,14 +236,16 @@ def test_gradients_vs_oracle_autograd(tiny_train, name):
         assert out.loss.requires_grad and out.logits is None
         out.loss.backward()
         torch.cuda.synchronize()
+        masks = _oracle_dropout_masks(model, spec, present, inp["input_ids"].shape[0]) if dropout else None
     finally:
+        model.train_step.attention_dropout = True
         model.eval()
     sd = H.bf16_round(weights)
     loss_ref, grads_ref = O.full_loss_and_grads(
-        {k: (v.float() if isinstance(v, torch.Tensor) and v.is_floating_point() else v) for k, v in inp.items()}, sd, hp)
+        {k: (v.float() if isinstance(v, torch.Tensor) and v.is_floating_point() else v) for k, v in inp.items()}, sd, hp,
+        dropout=masks)
     assert abs(float(out.loss) - float(loss_ref)) < 2e-2 * abs(float(loss_ref))
     named = dict(model.named_parameters())
-    present = {"text_labels": (), "image_audio": ("image", "audio"), "all3": ("image", "audio", "video")}[name]
     worst, worst_align = ("", 0.0), ("", 0.0)
     errs = {k: rel(named[k].grad, gr) for k, gr in grads_ref.items() if named[k].grad is not None}
     top = sorted(errs.items(), key=lambda kv: -kv[1])[:8]
@@ -213,7 +273,7 @@ def test_gradients_vs_oracle_autograd(tiny_train, name):
     assert (named["video_long_self_attention.in_proj_weight"].grad is not None) == ("video" in present)
     assert named["temporal_self_attention.in_proj_weight"].grad is None    # never reached by forward (dead in the reference too)
     assert named["image_encoder.visual_projection.weight"].grad is None    # encoders are frozen (run_clm_llms.py:390-393)
-    print(f"\n[train:{name}] loss {float(out.loss):.5f} vs oracle {float(loss_ref):.5f}; worst gradient rel err: llm "
+    print(f"\n[train:{name}{'+dropout' if dropout else ''}] loss {float(out.loss):.5f} vs oracle {float(loss_ref):.5f}; worst gradient rel err: llm "
           f"{worst[1]:.3e} ({worst[0]}), alignment {worst_align[1]:.3e} ({worst_align[0]})")
 
 
@@ -233,10 +293,13 @@ def test_gradient_accumulation_and_optimizer_steps(tiny_train):
     opt = FusedAdamW(params, lr=3e-3, weight_decay=0.0)
     model.train()
     opt.zero_grad()
+    model.train_step.attention_dropout = False  # identical passes: the accumulated gradient is exactly twice the first
     model(inp).loss.backward()
     g1 = model.llm.lm_head.weight.grad.float().clone()
     model(inp).loss.backward()
     assert rel(model.llm.lm_head.weight.grad, 2 * g1) < 1e-2
+    model.train_step.attention_dropout = True
+    s0 = int(model.train_step._seed) if model.train_step._seed is not None else None
     losses = []
     for _ in range(6):
         opt.zero_grad()
@@ -244,6 +307,7 @@ def test_gradient_accumulation_and_optimizer_steps(tiny_train):
         out.loss.backward()
         opt.step()
         losses.append(float(out.loss))
+    assert int(model.train_step._seed) == (s0 + 6 if s0 is not None else model.train_step.dropout_base_seed + 6)  # one seed per step
     model.eval()
     with torch.no_grad():
         ev = float(model(inp).loss)
