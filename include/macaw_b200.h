@@ -118,9 +118,18 @@ typedef struct mm_gemm_args {
   const float* rs_sumsq;
   int32_t rs_parts;
   float rs_eps;
+  /* Stream-K tail (optional; null = plain data-parallel tiles).  When the tile count leaves a partial last wave
+   * (e.g. 272 tiles on 148 SMs), the tail's k-blocks are divided evenly over ALL CTAs; partial fp32 accumulators pass
+   * through this workspace: 8192 bytes of flags (zero before the first use, self-resetting afterwards) followed by one
+   * 128 x 256 fp32 slot per SM — mm_gemm_streamk_workspace_bytes().  One workspace must not be used by GEMMs running
+   * CONCURRENTLY on different streams.  Ignored for multicast-pair launches, c_trans and tiles narrower than 64. */
+  void* sk_workspace;
+  int64_t sk_workspace_bytes;
 } mm_gemm_args;
 
 int32_t mm_gemm_fwd(const mm_gemm_args* args, void* stream);
+/* bytes of mm_gemm_args.sk_workspace on the current device */
+int64_t mm_gemm_streamk_workspace_bytes(void);
 
 /* Sum fp32 partials [splits][M][N] (+ bf16 bias[N]) -> bf16 (or fp16 when out_fp16 != 0) [M][N] (row stride ldo).
  * Split-K tail of the Conv1d down-samplers (modeling.py:982, 999, 1022). */
@@ -256,6 +265,36 @@ int32_t mm_argmax_rows(const void* logits, int64_t ld, int32_t rows, int32_t V, 
  * Splitting K lets the 32-tile o_proj / down_proj grids of a decode step cover all 148 SMs (weight streaming). */
 int32_t mm_thin_reduce(const float* part, int32_t splits, int32_t N, int32_t M, int32_t ldp, const float* row_scale,
                        const void* residual, int64_t ldr, void* out, int64_t ldo, void* stream);
+/* Fused tail of a split-K thin GEMM — one launch instead of mm_thin_reduce + mm_rope_rows + mm_kv_append /
+ * mm_swiglu_rows / mm_rms_rstd (a decode step is launch-bound: 14 -> 9 kernels per LLaMA layer):
+ *   MM_THIN_RES     out = rs * sum_s part + residual; sumsq_out (optional, [M][N/32]) = per-(row, 32-column) sums of squares
+ *                   of the stored values, the next RMSNorm's statistic (LlamaRMSNorm modeling.py:311-319)
+ *   MM_THIN_SWIGLU  out[m][32q+i] = silu(gate) * up from the [32 gate | 32 up]-interleaved product (modeling.py:139-140)
+ *   MM_THIN_QKV     N = 3E: rotate-half RoPE (modeling.py:83-91) on q and k in fp32, q -> out[m][0..E), k / v -> the
+ *                   layer's KV cache (B, Tmax, 2, E) at slot t0 (*t0_dev if given), row m = sample m (modeling.py:190-195)
+ * rs = row_scale[m] | rsqrt(sum_j rs_sumsq[m][j] / rs_K + rs_eps) | 1. */
+enum { MM_THIN_RES = 0, MM_THIN_SWIGLU = 1, MM_THIN_QKV = 2 };
+typedef struct mm_thin_args {
+  const float* part;       /* [splits][N][ldp] fp32 */
+  int32_t splits, N, M, ldp, mode;
+  const float* row_scale;  /* [M] or null */
+  const float* rs_sumsq;   /* [M][rs_parts] or null */
+  int32_t rs_parts, rs_K;
+  float rs_eps;
+  const void* residual;    /* [M][ldr] 16-bit or null (MM_THIN_RES) */
+  int64_t ldr;
+  void* out;
+  int64_t ldo;
+  float* sumsq_out;
+  const float* rope_cos;   /* MM_THIN_QKV: (T, 64) fp32 tables; row = *pos_dev (0 if null) */
+  const float* rope_sin;
+  const int32_t* pos_dev;
+  int32_t E;
+  void* cache;
+  int32_t Tmax, t0;
+  const int32_t* t0_dev;
+} mm_thin_args;
+int32_t mm_thin_fused(const mm_thin_args* args, void* stream);
 int32_t mm_rope_rows(void* x, int64_t ld, int32_t rows, int32_t rot_cols, const float* cos_t, const float* sin_t,
                      int32_t rope_T, const int32_t* pos_dev, void* stream);
 int32_t mm_swiglu_rows(const void* gu, int64_t ld, int32_t rows, int32_t I, void* out, int64_t ldo, void* stream);

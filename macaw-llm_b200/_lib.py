@@ -30,7 +30,17 @@ class GemmArgs(C.Structure):
         ("a_fp16", c_i32), ("b_fp16", c_i32), ("c_fp16", c_i32),
         ("bias_rs", c_vp), ("bias2", c_vp), ("bias2_rs", c_vp), ("a_mn_major", c_i32),
         ("sumsq_out", c_vp), ("rs_sumsq", c_vp), ("rs_parts", c_i32), ("rs_eps", c_f32),
+        ("sk_workspace", c_vp), ("sk_workspace_bytes", c_i64),
     ]
+
+
+class ThinArgs(C.Structure):
+    """mirror of mm_thin_args"""
+    _fields_ = [("part", c_vp), ("splits", c_i32), ("N", c_i32), ("M", c_i32), ("ldp", c_i32), ("mode", c_i32),
+                ("row_scale", c_vp), ("rs_sumsq", c_vp), ("rs_parts", c_i32), ("rs_K", c_i32), ("rs_eps", c_f32),
+                ("residual", c_vp), ("ldr", c_i64), ("out", c_vp), ("ldo", c_i64), ("sumsq_out", c_vp),
+                ("rope_cos", c_vp), ("rope_sin", c_vp), ("pos_dev", c_vp), ("E", c_i32), ("cache", c_vp),
+                ("Tmax", c_i32), ("t0", c_i32), ("t0_dev", c_vp)]
 
 
 class AttnArgs(C.Structure):
@@ -97,6 +107,8 @@ SIGNATURES = {
     "mm_align_softmax": (c_i32, [c_vp, c_i64, c_vp, c_vp, c_i64, c_vp, c_i64, c_vp, c_vp, c_i32, c_i32, c_vp]),
     "mm_align_ctx_fixup": (c_i32, [c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_vp]),
     "mm_kv_append": (c_i32, [c_vp, c_i64, c_i32, c_i32, c_i32, c_vp, c_i32, c_i32, c_vp, c_vp]),
+    "mm_gemm_streamk_workspace_bytes": (c_i64, []),
+    "mm_thin_fused": (c_i32, [C.POINTER(ThinArgs), c_vp]),
     "mm_thin_reduce": (c_i32, [c_vp, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp, c_i64, c_vp, c_i64, c_vp]),
     "mm_argmax_rows": (c_i32, [c_vp, c_i64, c_i32, c_i32, c_vp, c_vp]),
     "mm_rope_rows": (c_i32, [c_vp, c_i64, c_i32, c_i32, c_vp, c_vp, c_i32, c_vp, c_vp]),

@@ -58,6 +58,11 @@ struct GemmKParams {
   float rs_eps;
   int vec_ok;
   int group_m;  // rasterisation: M units per group
+  // stream-K tail (0 tiles = off): the last sk_tiles tiles (indices >= sk_first) are split along K into equal shares,
+  // one per CTA; partial accumulators travel through sk_ws (fp32, one 128 x BN slot per CTA), sk_flags signals them
+  int sk_tiles, sk_first;
+  float* sk_ws;
+  int* sk_flags;
 };
 
 constexpr int kBlockM = 128;
@@ -93,6 +98,70 @@ __device__ __forceinline__ TileCoord tile_coord(int idx, const GemmKParams& p, i
   t.m_blk = first_m + rr % gsz;
   t.n_blk = rr / gsz;
   return t;
+}
+
+// One unit of a CTA's schedule: a whole tile (role 0), or — in the stream-K tail — a K-range of a tile whose partial
+// accumulator is handed over (role 1, "contributor") or which ends the tile and folds the others' partials in before
+// the epilogue (role 2, "finisher"; contributors are the CTAs c0 .. c0 + nc - 1, each with exactly one slot).
+//
+// Tail schedule: the sk_tiles * num_k k-blocks of the tail are cut into n_workers equal contiguous shares (share w =
+// [w U / W, (w + 1) U / W)).  A share is shorter than one tile's K extent (sk_tiles < n_workers), so it touches at most
+// two tiles: it may END one tile (finisher piece) and BEGIN the next (contributor piece), or sit inside one tile
+// (contributor).  Every CTA runs its contributor piece FIRST and never waits in it; finishers wait only for
+// contributors, so there is no cycle — and all CTAs are co-resident (grid <= SM count, one CTA per SM).
+struct GemmWork {
+  int tile, kb0, kb1, role, c0, nc;
+};
+__device__ __forceinline__ bool gemm_work(const GemmKParams& p, int worker, int n_workers, int total_tiles, int it,
+                                          GemmWork& w) {
+  const int first = p.sk_tiles > 0 ? p.sk_first : total_tiles;
+  const int n_full = first > worker ? (first - worker + n_workers - 1) / n_workers : 0;
+  w.c0 = 0;
+  w.nc = 0;
+  if (it < n_full) {
+    w.tile = worker + it * n_workers;
+    w.kb0 = 0;
+    w.kb1 = p.num_k;
+    w.role = 0;
+    return true;
+  }
+  if (p.sk_tiles == 0) return false;
+  const int j = it - n_full;
+  const long long nk = p.num_k;
+  const long long U = static_cast<long long>(p.sk_tiles) * nk;
+  const long long u0 = worker * U / n_workers, u1 = (worker + 1) * U / n_workers;
+  if (u0 >= u1) return false;
+  const long long ta = u0 / nk;
+  const long long end_a = u1 < (ta + 1) * nk ? u1 : (ta + 1) * nk;
+  const bool has_b = u1 > end_a;  // the share runs on into tile ta + 1 (then piece A ends tile ta)
+  if (has_b ? j > 1 : j > 0) return false;
+  if (has_b && j == 0) {  // contributor piece first
+    w.tile = first + static_cast<int>(ta) + 1;
+    w.kb0 = 0;
+    w.kb1 = static_cast<int>(u1 - end_a);
+    w.role = 1;
+    return true;
+  }
+  w.tile = first + static_cast<int>(ta);
+  w.kb0 = static_cast<int>(u0 - ta * nk);
+  w.kb1 = static_cast<int>(end_a - ta * nk);
+  w.role = (w.kb1 == p.num_k) ? 2 : 1;
+  if (w.role == 2) {  // contributors: the CTAs below this one whose shares reach into tile ta
+    int c0 = worker;
+    while (c0 > 0 && static_cast<long long>(c0) * U / n_workers > ta * nk) --c0;
+    w.c0 = c0;
+    w.nc = worker - c0;
+  }
+  return true;
+}
+
+__device__ __forceinline__ void st_release_gpu(int* p, int v) {
+  asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ int ld_acquire_gpu(const int* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
 }
 
 __device__ __forceinline__ float tanh_approx(float x) {
@@ -264,12 +333,13 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = worker; tile < total_tiles; tile += n_workers) {
-        TileCoord t = tile_coord(tile, p, m_units);
+      GemmWork wk;
+      for (int it = 0; gemm_work(p, worker, n_workers, total_tiles, it, wk); ++it) {
+        TileCoord t = tile_coord(wk.tile, p, m_units);
         if constexpr (MC) t.m_blk = 2 * t.m_blk + cta_rank;
         const int bb = p.b_shared ? 0 : t.b_lo;
         const int bh = p.b2_shared ? 0 : t.b_hi;
-        for (int kb = 0; kb < p.num_k; ++kb) {
+        for (int kb = wk.kb0; kb < wk.kb1; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           mbar_arrive_expect_tx(&full_bar[stage], kABytes + B_BYTES);
           if constexpr (A_MN) {
@@ -315,11 +385,12 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int tile = worker; tile < total_tiles; tile += n_workers) {
+      GemmWork wk;
+      for (int it = 0; gemm_work(p, worker, n_workers, total_tiles, it, wk); ++it) {
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
-        for (int kb = 0; kb < p.num_k; ++kb) {
+        for (int kb = wk.kb0; kb < wk.kb1; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           const uint32_t a_addr = smem_u32(sA + stage * kABytes);
@@ -332,7 +403,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           for (int kk = 0; kk < kBlockK / 16; ++kk) {
             const uint64_t a_k = a_desc + static_cast<uint64_t>(A_MN ? kk * 128 : kk * 2);  // +2048 B | +32 B along K
             const uint64_t b_k = b_desc + static_cast<uint64_t>(B_MN ? kk * 128 : kk * 2);  // +2048 B | +32 B
-            umma_bf16(d_tmem, a_k, b_k, p.idesc, (kb | kk) != 0 ? 1u : 0u);
+            umma_bf16(d_tmem, a_k, b_k, p.idesc, (kb != wk.kb0 || kk != 0) ? 1u : 0u);
           }
           // frees the smem slot once these MMAs retire (in both CTAs of a multicast pair)
           if constexpr (MC) umma_commit_mc(&empty_bar[stage], 3); else umma_commit(&empty_bar[stage]);
@@ -355,12 +426,79 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     int acc = 0;
     uint32_t acc_phase = 0;
     const int n_out_total = (EPI == MM_EPI_SWIGLU) ? p.N / 2 : p.N;
-    for (int tile = worker; tile < total_tiles; tile += n_workers) {
-      TileCoord t = tile_coord(tile, p, m_units);
+    const int wi = warp - 2;  // 0..7: this warp's private flag / workspace lane of the stream-K hand-over
+    GemmWork wk;
+    for (int it = 0; gemm_work(p, worker, n_workers, total_tiles, it, wk); ++it) {
+      TileCoord t = tile_coord(wk.tile, p, m_units);
       if constexpr (MC) t.m_blk = 2 * t.m_blk + cta_rank;
       const int row = t.m_blk * kBlockM + q * 32 + lane;
       const bool row_ok = row < p.M;
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN;
+      if (wk.role == 1) {
+        // ---- stream-K contributor: hand the raw fp32 partial accumulator of this K-range to the tile's finisher.
+        // Slot layout [32-col chunk][row 0..127][32 floats]: each thread writes 128 contiguous bytes per chunk; warp
+        // (q, half) writes exactly the part the finisher's warp (q, half) reads, so the hand-over is per warp.
+        mbar_wait(&tfull_bar[acc], acc_phase);
+        tc_fence_after();
+        constexpr int CPH_S = BN >= 64 ? BN / 64 : 1;
+        float* slot = p.sk_ws + static_cast<long long>(worker) * (kBlockM * BN);
+#pragma unroll 1
+        for (int c = half * CPH_S; c < (half + 1) * CPH_S && c < BN / 32; ++c) {
+          uint32_t r[32];
+          tmem_ld32(taddr + c * 32, r);
+          tmem_ld_wait();
+          float4* dst = reinterpret_cast<float4*>(slot + (static_cast<long long>(c) * kBlockM + q * 32 + lane) * 32);
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            dst[i] = make_float4(__uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1]), __uint_as_float(r[4 * i + 2]),
+                                 __uint_as_float(r[4 * i + 3]));
+        }
+        __threadfence();
+        __syncwarp();
+        if (lane == 0) st_release_gpu(p.sk_flags + worker * 8 + wi, 1);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+        if (++acc == 2) {
+          acc = 0;
+          acc_phase ^= 1;
+        }
+        continue;
+      }
+      // stream-K finisher: r[] += the contributors' partials of accumulator columns col_off .. col_off + 31 (fixed
+      // order: deterministic); a no-op for ordinary tiles (warp-uniform branch)
+      // (a CTA whose share of the tail is empty — more CTAs than tail k-blocks — has no piece and is skipped)
+      const long long sk_units = static_cast<long long>(p.sk_tiles) * p.num_k;
+      auto sk_has = [&](int sidx) { return sidx * sk_units / n_workers < (sidx + 1) * sk_units / n_workers; };
+      auto sk_add = [&](uint32_t (&r)[32], int col_off) {
+        if (wk.nc == 0) return;
+        const int c = col_off >> 5;
+        for (int sidx = wk.c0; sidx < wk.c0 + wk.nc; ++sidx) {
+          if (!sk_has(sidx)) continue;
+          const float4* src = reinterpret_cast<const float4*>(
+              p.sk_ws + static_cast<long long>(sidx) * (kBlockM * BN) + (static_cast<long long>(c) * kBlockM + q * 32 + lane) * 32);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float4 f = __ldcg(src + i);
+            r[4 * i] = __float_as_uint(__uint_as_float(r[4 * i]) + f.x);
+            r[4 * i + 1] = __float_as_uint(__uint_as_float(r[4 * i + 1]) + f.y);
+            r[4 * i + 2] = __float_as_uint(__uint_as_float(r[4 * i + 2]) + f.z);
+            r[4 * i + 3] = __float_as_uint(__uint_as_float(r[4 * i + 3]) + f.w);
+          }
+        }
+      };
+      if (wk.nc > 0) {  // wait for this warp's share of every contributor's partial
+        if (lane == 0)
+          for (int sidx = wk.c0; sidx < wk.c0 + wk.nc; ++sidx)
+            if (sk_has(sidx)) {
+              unsigned spins = 0;
+              while (ld_acquire_gpu(p.sk_flags + sidx * 8 + wi) == 0) {
+                __nanosleep(64);
+                if (++spins > (1u << 25)) asm volatile("trap;");  // seconds: a scheduling bug must fail, never hang
+              }
+            }
+        __syncwarp();
+      }
       char* crow = reinterpret_cast<char*>(p.C) +
                    (static_cast<long long>(t.b_lo) * p.c_bs + static_cast<long long>(t.b_hi) * p.c_bs2 +
                     static_cast<long long>(row) * p.ldc) * (p.c_fp32 ? 4 : 2);
@@ -433,6 +571,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           uint32_t r[32];
           tmem_ld32(taddr + c * 32, r);
           tmem_ld_wait();
+          sk_add(r, c * 32);
           const int col0 = t.n_blk * BN + c * 32;
           if (col0 >= p.N) continue;  // warp-uniform
           float v[32];
@@ -493,6 +632,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           tmem_ld32(taddr + c * 64, g);
           tmem_ld32(taddr + c * 64 + 32, u);
           tmem_ld_wait();
+          sk_add(g, c * 64);
+          sk_add(u, c * 64 + 32);
           const int col_in = t.n_blk * BN + c * 64;
           if (col_in >= p.N) continue;
           float v[32];
@@ -516,6 +657,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             tmem_ld32(taddr + h * 128 + hc * 32, x1);
             tmem_ld32(taddr + h * 128 + 64 + hc * 32, x2);
             tmem_ld_wait();
+            sk_add(x1, h * 128 + hc * 32);
+            sk_add(x2, h * 128 + 64 + hc * 32);
             const int col1 = t.n_blk * BN + h * 128 + hc * 32;
             if (col1 >= p.N) continue;
             float o1[32], o2[32];
@@ -547,6 +690,12 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             }
           }
         }
+      }
+      if (wk.nc > 0) {  // partials consumed: re-arm this warp's flags for the next launch (stream order separates launches)
+        __syncwarp();
+        if (lane == 0)
+          for (int sidx = wk.c0; sidx < wk.c0 + wk.nc; ++sidx)
+            if (sk_has(sidx)) p.sk_flags[sidx * 8 + wi] = 0;
       }
       // release this accumulator buffer back to the MMA warp
       tc_fence_before();
@@ -749,6 +898,20 @@ extern "C" int32_t mm_gemm_fwd(const mm_gemm_args* a, void* stream) {
     g = g < 2 ? 2 : (g > 32 ? 32 : g);
     p.group_m = gm_env > 0 ? gm_env : static_cast<int>(g);
   }
+  // ---- stream-K tail: only when the last wave is clearly partial (<= 85 % full) and K is long enough to split
+  p.sk_tiles = 0; p.sk_first = 0; p.sk_ws = nullptr; p.sk_flags = nullptr;
+  static const int sk_env = []() { const char* e = getenv("MACAW_B200_GEMM_STREAMK"); return e ? atoi(e) : 1; }();
+  if (sk_env != 0 && a->sk_workspace != nullptr && !use_mc && !a->c_trans && BN >= 64 && p.num_k >= 8 && tiles256 > sms) {
+    const int rem = static_cast<int>(tiles256 % sms);
+    const long long need = 8192 + static_cast<long long>(sms) * kBlockM * BN * 4;
+    if (rem > 0 && rem * 100 <= 85 * sms && a->sk_workspace_bytes >= need &&
+        (reinterpret_cast<uintptr_t>(a->sk_workspace) & 15) == 0) {
+      p.sk_tiles = rem;
+      p.sk_first = static_cast<int>(tiles256 - rem);
+      p.sk_flags = reinterpret_cast<int*>(a->sk_workspace);
+      p.sk_ws = reinterpret_cast<float*>(reinterpret_cast<char*>(a->sk_workspace) + 8192);
+    }
+  }
   CUtensorMap ta, tb;
   if (a->a_mn_major) {
     MM_REQUIRE(a->b_mn_major && a->epi == MM_EPI_STD && !a->c_trans,
@@ -799,6 +962,10 @@ extern "C" int32_t mm_gemm_fwd(const mm_gemm_args* a, void* stream) {
   MM_LAUNCH(32, MM_EPI_STD, false);
 #undef MM_LAUNCH
 #undef MM_LAUNCH_MC
+}
+
+extern "C" int64_t mm_gemm_streamk_workspace_bytes(void) {
+  return 8192 + static_cast<int64_t>(num_sms()) * kBlockM * 256 * 4;
 }
 
 // ------------------------------------------------------------------------------------------------ split-K reduce

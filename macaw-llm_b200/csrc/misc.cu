@@ -491,6 +491,125 @@ __global__ void thin_reduce_kernel(const float* __restrict__ part, int S, int N,
   }
 }
 
+// Fused tail of a split-K thin GEMM (decode step): one warp per unit of 32 (or 2 x 32) output features, all M rows.
+//   MM_THIN_RES    out[m][n] = rs_m * sum_s part[s][n][m] + residual[m][n];  optionally the per-(row, 32-column) sums of
+//                  squares of the STORED values (the next RMSNorm's statistic — replaces a pass over the stream)
+//   MM_THIN_SWIGLU out[m][32q + i] = silu(rs_m * gate) * (rs_m * up) from the [32 gate | 32 up]-interleaved product
+//   MM_THIN_QKV    rotate-half RoPE (head_dim 128, pairs (i, i + 64)) on the q and k features in fp32 — exactly what the
+//                  prefill GEMM's RoPE epilogue does —, q -> out[m][n], k / v -> straight into the layer's KV cache slot
+//                  (B, Tmax, 2, E) at position t0 (row m = sample m: one new token per sample)
+// rs_m = row_scale[m], or rsqrt(sum_j rs_sumsq[m][j] / rs_K + rs_eps) from the statistics a MM_THIN_RES pass left (fixed
+// summation order: deterministic), or 1.  Replaces thin_reduce + rope_rows + kv_append / swiglu_rows / rms_rstd launches.
+struct ThinFusedParams {
+  const float* part;
+  int S, N, M, ldp;
+  const float* row_scale;
+  const float* rs_sumsq;
+  int rs_parts, rs_K;
+  float rs_eps;
+  const bf16* residual;
+  long long ldr;
+  bf16* out;
+  long long ldo;
+  float* sumsq_out;
+  const float* rope_cos;
+  const float* rope_sin;
+  const int* pos_dev;
+  int E;
+  bf16* cache;
+  int Tmax, t0;
+  const int* t0_dev;
+};
+
+template <bool F16, int MODE>
+__global__ void __launch_bounds__(64) thin_fused_kernel(const ThinFusedParams p) {
+  griddep_launch();
+  griddep_wait();
+  const int lane = threadIdx.x & 31;
+  const int unit = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int n_units = MODE == MM_THIN_RES ? p.N / 32 : p.N / 64;
+  if (unit >= n_units) return;
+  // feature indices of this lane: n1 (and n2 for the paired modes)
+  int n1, n2 = 0;
+  if (MODE == MM_THIN_RES) {
+    n1 = unit * 32 + lane;
+  } else if (MODE == MM_THIN_SWIGLU) {
+    n1 = unit * 64 + lane;
+    n2 = n1 + 32;
+  } else {
+    n1 = (unit >> 1) * 128 + (unit & 1) * 32 + lane;
+    n2 = n1 + 64;
+  }
+  for (int m0 = 0; m0 < p.M; m0 += 8) {
+    float a1[8], a2[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) a1[j] = a2[j] = 0.f;
+    for (int s = 0; s < p.S; ++s) {
+      const float* p1 = p.part + (static_cast<long long>(s) * p.N + n1) * p.ldp + m0;
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if (m0 + j < p.M) a1[j] += p1[j];
+      if (MODE != MM_THIN_RES) {
+        const float* p2 = p.part + (static_cast<long long>(s) * p.N + n2) * p.ldp + m0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          if (m0 + j < p.M) a2[j] += p2[j];
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int m = m0 + j;
+      if (m >= p.M) break;  // warp-uniform
+      float rs = 1.0f;
+      if (p.row_scale != nullptr) {
+        rs = p.row_scale[m];
+      } else if (p.rs_sumsq != nullptr) {
+        float t = 0.f;
+        for (int k = lane; k < p.rs_parts; k += 32) t += p.rs_sumsq[static_cast<long long>(m) * p.rs_parts + k];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+        rs = rsqrtf(t / static_cast<float>(p.rs_K) + p.rs_eps);
+      }
+      if (MODE == MM_THIN_RES) {
+        float v = a1[j] * rs;
+        if (p.residual != nullptr) v += ldv<F16>(p.residual[static_cast<long long>(m) * p.ldr + n1]);
+        const bf16 st = stv<F16>(v);
+        p.out[static_cast<long long>(m) * p.ldo + n1] = st;
+        if (p.sumsq_out != nullptr) {
+          const float r = ldv<F16>(st);
+          float ss = r * r;
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+          if (lane == 0) p.sumsq_out[static_cast<long long>(m) * (p.N / 32) + unit] = ss;
+        }
+      } else if (MODE == MM_THIN_SWIGLU) {
+        const float g = a1[j] * rs, u = a2[j] * rs;
+        p.out[static_cast<long long>(m) * p.ldo + unit * 32 + lane] = stv<F16>(g / (1.0f + __expf(-g)) * u);
+      } else {
+        float x1 = a1[j] * rs, x2 = a2[j] * rs;
+        if (n1 < 2 * p.E) {  // q and k rotate; v passes through
+          const int pos = p.pos_dev != nullptr ? *p.pos_dev : 0;
+          const int jj = (unit & 1) * 32 + lane;
+          const float c = p.rope_cos[static_cast<long long>(pos) * 64 + jj], sn = p.rope_sin[static_cast<long long>(pos) * 64 + jj];
+          const float r1 = x1 * c - x2 * sn, r2 = x2 * c + x1 * sn;
+          x1 = r1;
+          x2 = r2;
+        }
+        if (n1 < p.E) {
+          p.out[static_cast<long long>(m) * p.ldo + n1] = stv<F16>(x1);
+          p.out[static_cast<long long>(m) * p.ldo + n2] = stv<F16>(x2);
+        } else {
+          const int t0 = p.t0_dev != nullptr ? *p.t0_dev : p.t0;
+          const int which = n1 < 2 * p.E ? 0 : 1;
+          bf16* dst = p.cache + ((static_cast<long long>(m) * p.Tmax + t0) * 2 + which) * p.E + (n1 - (which + 1) * p.E);
+          dst[0] = stv<F16>(x1);
+          dst[64] = stv<F16>(x2);
+        }
+      }
+    }
+  }
+}
+
 // greedy next token: index of the largest logit per row (lowest index on ties), bf16 logits with row stride ld
 template <bool F16>
 __global__ void __launch_bounds__(512) argmax_rows_kernel(const bf16* __restrict__ logits, long long ld, int V,
@@ -745,6 +864,42 @@ extern "C" int32_t mm_thin_reduce(const float* part, int32_t splits, int32_t N, 
   kern<<<grid_for(total, 256), 256, 0, ST(stream)>>>(part, splits, N, M, ldp, row_scale,
                                                                   (const bf16*)residual, ldr, (bf16*)out, ldo);
   return check_launch("mm_thin_reduce");
+}
+
+extern "C" int32_t mm_thin_fused(const mm_thin_args* a, void* stream) {
+  MM_REQUIRE(a != nullptr && a->part && a->out && a->splits > 0 && a->N > 0 && a->M > 0 && a->ldp >= a->M,
+             "mm_thin_fused: bad arguments");
+  MM_REQUIRE(a->mode >= MM_THIN_RES && a->mode <= MM_THIN_QKV, "mm_thin_fused: bad mode %d", a->mode);
+  MM_REQUIRE(a->mode == MM_THIN_RES ? a->N % 32 == 0 : a->N % 64 == 0, "mm_thin_fused: N must be a multiple of 32 (RES) / 64");
+  MM_REQUIRE(!(a->row_scale && a->rs_sumsq) && (a->rs_sumsq == nullptr || (a->rs_parts > 0 && a->rs_K > 0)),
+             "mm_thin_fused: one row-scale source (row_scale, or rs_sumsq with rs_parts / rs_K)");
+  MM_REQUIRE(a->sumsq_out == nullptr || a->mode == MM_THIN_RES, "mm_thin_fused: sumsq_out only in MM_THIN_RES");
+  if (a->mode == MM_THIN_QKV)
+    MM_REQUIRE(a->E > 0 && a->E % 128 == 0 && a->N == 3 * a->E && a->rope_cos && a->rope_sin && a->cache && a->Tmax > 0 &&
+                   a->t0 >= 0 && a->t0 < a->Tmax,
+               "mm_thin_fused: QKV mode needs N == 3 E, E %% 128 == 0, the RoPE tables and the KV cache");
+  ThinFusedParams p;
+  p.part = a->part; p.S = a->splits; p.N = a->N; p.M = a->M; p.ldp = a->ldp;
+  p.row_scale = a->row_scale; p.rs_sumsq = a->rs_sumsq; p.rs_parts = a->rs_parts; p.rs_K = a->rs_K; p.rs_eps = a->rs_eps;
+  p.residual = (const bf16*)a->residual; p.ldr = a->ldr; p.out = (bf16*)a->out; p.ldo = a->ldo; p.sumsq_out = a->sumsq_out;
+  p.rope_cos = a->rope_cos; p.rope_sin = a->rope_sin; p.pos_dev = a->pos_dev; p.E = a->E;
+  p.cache = (bf16*)a->cache; p.Tmax = a->Tmax; p.t0 = a->t0; p.t0_dev = a->t0_dev;
+  const int units = a->mode == MM_THIN_RES ? a->N / 32 : a->N / 64;
+  const dim3 grid((units + 1) / 2), block(64);
+  const bool f16 = act_f16();
+  cudaError_t e;
+#define MM_TF(MODE_) \
+  e = f16 ? launch_kernel(thin_fused_kernel<true, MODE_>, grid, block, 0, ST(stream), 1, p) \
+          : launch_kernel(thin_fused_kernel<false, MODE_>, grid, block, 0, ST(stream), 1, p)
+  if (a->mode == MM_THIN_RES) MM_TF(MM_THIN_RES);
+  else if (a->mode == MM_THIN_SWIGLU) MM_TF(MM_THIN_SWIGLU);
+  else MM_TF(MM_THIN_QKV);
+#undef MM_TF
+  if (e != cudaSuccess) {
+    set_error("mm_thin_fused: launch failed: %s", cudaGetErrorString(e));
+    return 2;
+  }
+  return check_launch("mm_thin_fused");
 }
 
 extern "C" int32_t mm_argmax_rows(const void* logits, int64_t ld, int32_t rows, int32_t V, int64_t* out, void* stream) {

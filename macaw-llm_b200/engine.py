@@ -46,6 +46,11 @@ class Engine:
         # one-CTA-per-SM kernels, two of them cannot co-reside, so only launch tails overlap while the late-starting CTAs
         # stretch the static tile schedule), -0.3 ms at batch 4.  Off by default; kept as a tested option.
         self.overlap_encoders = False
+        # Stream-K tail in the LLaMA GEMMs (a partial last wave of tiles is split along K over all SMs): matters at small
+        # per-GPU batch (272 tiles on 148 SMs -> 1.84 waves), a no-op when the tile count fills the waves.
+        self.streamk = True
+        self.fused_decode_tails = True  # decode step: one tail kernel per thin GEMM (mm_thin_fused) instead of 2-3 row-wise kernels
+        self._sk_ws: Dict[str, torch.Tensor] = {}
         self._graphs_on = False
         self.align_max_rows = None  # test hook: cap on query rows per alignment chunk (default: ~2 GiB of fp32 scores)
 
@@ -560,8 +565,24 @@ class Engine:
             raise NotImplementedError("macaw_b200: intermediate_size must be a multiple of 32")
         return E, H, hd, I, cfg.rms_norm_eps
 
-    def _llama_layers(self, x: torch.Tensor, B: int, T: int, kmask, pos0: int = 0, cache=None, t_max: int = 0,
-                      pos_dev: Optional[torch.Tensor] = None):
+    def _streamk_ws(self, dev) -> Optional[torch.Tensor]:
+        """Stream-K workspace of the LLaMA section on `dev` (its GEMMs run back to back on one stream)."""
+        if not self.streamk:
+            return None
+        ws = self._sk_ws.get(str(dev))
+        if ws is None:
+            ws = self._sk_ws[str(dev)] = ops.streamk_workspace(dev)
+        return ws
+
+    def _llama_layers(self, x: torch.Tensor, *args, **kw):
+        ops.STREAMK = self._streamk_ws(x.device)
+        try:
+            return self._llama_layers_impl(x, *args, **kw)
+        finally:
+            ops.STREAMK = None
+
+    def _llama_layers_impl(self, x: torch.Tensor, B: int, T: int, kmask, pos0: int = 0, cache=None, t_max: int = 0,
+                           pos_dev: Optional[torch.Tensor] = None):
         """The decoder stack on the residual stream x (B*T, E), updated in place.
 
         pos0 = position of the first row of every sample (0 for prefill, the current length for a decode step).
@@ -590,7 +611,19 @@ class Engine:
         for i, l in enumerate(self.m.llm.model.layers):
             wqkv, wgu, wo, wd = self._llama_weights(i, l, E, I)
             thin = T == 1 and B * T <= 64  # decode step: swap operands so the weights fill the 128-row MMA tiles
-            if thin:
+            fused_thin = thin and cache is not None and self.fused_decode_tails and E % 128 == 0
+            if fused_thin:
+                # decode step, 9 launches per layer: each split-K thin GEMM is followed by ONE tail kernel that also does
+                # the neighbouring row-wise work (RoPE + KV-cache write / SwiGLU / residual + next RMSNorm statistic)
+                if i == 0:
+                    thin_ss = (torch.empty((M, E // 32), device=dev, dtype=torch.float32),
+                               torch.empty((M, E // 32), device=dev, dtype=torch.float32))
+                    rs_kw = dict(row_scale=ops.rms_rstd(x, eps))
+                else:
+                    rs_kw = dict(rms_from=(thin_ss[1], eps))
+                qkv = ops.linear_thin_fused(x, wqkv, ops.THIN_QKV, rope=(rope[0], rope[1], rope[4] if len(rope) > 4 else None),
+                                            cache=cache[i], t0=pos0, t0_dev=pos_dev[0:1] if dyn else None, **rs_kw)
+            elif thin:
                 rstd = ops.rms_rstd(x, eps)
                 qkv = ops.linear_thin_splitk(x, wqkv, row_scale=rstd)
                 ops.rope_rows(qkv, 2 * E, rope[0], rope[1], rope[2], rope[4] if len(rope) > 4 else None)
@@ -599,7 +632,7 @@ class Engine:
             else:
                 qkv = ops.linear(x, wqkv, epi=ops.EPI_ROPE, rope=rope, row_scale=ops.rms_rstd(x, eps))
             q5 = qkv.view(B, T, 3, H, hd)
-            if cache is not None:
+            if cache is not None and not fused_thin:
                 ops.kv_append(qkv, B, T, cache[i], pos0, pos_dev[0:1] if dyn else None)
             if dyn:
                 kv = cache[i].unflatten(-1, (H, hd))  # whole capacity; the kernel reads the valid length from pos_dev[1]
@@ -610,7 +643,11 @@ class Engine:
             else:
                 kv = cache[i][:, : pos0 + T].unflatten(-1, (H, hd))  # (B, Tk, 2, H, hd) view of the cache
                 a = ops.attention(q5[:, :, 0], kv[:, :, 0], kv[:, :, 1], scale=scale, causal=False, key_mask=kmask)
-            if thin:
+            if fused_thin:
+                ops.linear_thin_fused(a.view(B * T, E), wo, ops.THIN_RES, residual=x, out=x, sumsq_out=thin_ss[0])
+                g = ops.linear_thin_fused(x, wgu, ops.THIN_SWIGLU, rms_from=(thin_ss[0], eps))
+                ops.linear_thin_fused(g, wd, ops.THIN_RES, residual=x, out=x, sumsq_out=thin_ss[1])
+            elif thin:
                 ops.linear_thin_splitk(a.view(B * T, E), wo, residual=x, out=x)
                 rstd = ops.rms_rstd(x, eps)
                 g = ops.swiglu_rows(ops.linear_thin_splitk(x, wgu, row_scale=rstd), I)

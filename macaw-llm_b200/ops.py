@@ -83,7 +83,7 @@ def gemm_raw(*, M, N, K, A, lda, B, ldb, Cout, ldc, batch=1, a_bs=0, b_bs=0, c_b
              row_scale=None, residual=None, ldr=0, r_bs=0, r_bs2=0, res_row_mod=0, rope_cos=None, rope_sin=None,
              rope_T=0, rope_cols=0, rope_pos=None, c_trans=False, a_fp16=None, b_fp16=None, c_fp16=None,
              bias_rs=None, bias2=None, bias2_rs=None, a_mn_major=False, sumsq_out=None, rs_sumsq=None, rs_parts=0,
-             rs_eps=0.0) -> None:
+             rs_eps=0.0, streamk: Optional[torch.Tensor] = None) -> None:
     """Direct binding of mm_gemm_fwd; pointers are ints (data_ptr() + byte offsets).  Operand / output formats default to
     the current activation format (ACT()): fp16 for an fp16 model, bf16 otherwise."""
     f16 = ACT() == _F16
@@ -93,7 +93,8 @@ def gemm_raw(*, M, N, K, A, lda, B, ldb, Cout, ldc, batch=1, a_bs=0, b_bs=0, c_b
     a = GemmArgs(M, N, K, batch, batch2, A, lda, a_bs, a_bs2, B, ldb, b_bs, b_bs2, int(b_mn_major), Cout, ldc, c_bs,
                  c_bs2, int(c_fp32), epi, act, float(alpha), bias, bias_bs, row_scale, residual, ldr, r_bs, r_bs2,
                  res_row_mod, rope_cos, rope_sin, rope_T, rope_cols, rope_pos, int(c_trans), int(a_fp16), int(b_fp16), int(c_fp16),
-                 bias_rs, bias2, bias2_rs, int(a_mn_major), sumsq_out, rs_sumsq, int(rs_parts), float(rs_eps))
+                 bias_rs, bias2, bias2_rs, int(a_mn_major), sumsq_out, rs_sumsq, int(rs_parts), float(rs_eps),
+                 None if streamk is None else streamk.data_ptr(), 0 if streamk is None else streamk.numel() * streamk.element_size())
     if PROFILE is None:
         _check(_lib.load().mm_gemm_fwd(C.byref(a), _stream()), "mm_gemm_fwd")
         return
@@ -138,10 +139,26 @@ def linear(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None
         parts, eps = rms_from
         assert parts.dtype == torch.float32 and parts.is_contiguous() and parts.shape[0] == M and row_scale is None
         kw.update(rs_sumsq=parts.data_ptr(), rs_parts=parts.shape[1], rs_eps=eps)
+    if STREAMK is not None and STREAMK.device == x.device:
+        kw.update(streamk=STREAMK)
     gemm_raw(M=M, N=N, K=K, A=x.data_ptr(), lda=x.stride(0), B=w.data_ptr(), ldb=w.stride(0), Cout=out.data_ptr(),
              ldc=out.stride(0), c_fp32=out.dtype == torch.float32, c_fp16=out.dtype == _F16, a_fp16=x.dtype == _F16,
              b_fp16=w.dtype == _F16, epi=epi, act=act, alpha=alpha, bias=_ptr(bias), row_scale=_ptr(row_scale), **kw)
     return out
+
+
+# Stream-K workspace handed to every `linear()` launch while set (see mm_gemm_args.sk_workspace).  The OWNER sets it
+# around a section whose GEMMs run one after another on a single stream (the LLaMA stack) and clears it afterwards: two
+# GEMMs sharing one workspace must never run concurrently.
+STREAMK: Optional[torch.Tensor] = None
+
+
+def streamk_workspace(device) -> torch.Tensor:
+    """A zero-initialised stream-K workspace (flags + one fp32 accumulator slot per SM) on `device`."""
+    _lib.load()
+    with torch.cuda.device(device):
+        n = int(_lib.load().mm_gemm_streamk_workspace_bytes())
+    return torch.zeros((n + 15) // 16 * 4, device=device, dtype=torch.int32)
 
 
 def linear_thin(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, *, act: int = ACT_NONE,
@@ -194,6 +211,63 @@ def linear_thin_splitk(x: torch.Tensor, w: torch.Tensor, *, residual: Optional[t
     _check(_lib.load().mm_thin_reduce(part.data_ptr(), S, N, M, Mp, _ptr(row_scale), _ptr(residual),
                                       0 if residual is None else residual.stride(0), out.data_ptr(), out.stride(0),
                                       _stream()), "mm_thin_reduce")
+    return out
+
+
+THIN_RES, THIN_SWIGLU, THIN_QKV = 0, 1, 2
+
+
+def linear_thin_fused(x: torch.Tensor, w: torch.Tensor, mode: int, *, row_scale: Optional[torch.Tensor] = None,
+                      rms_from=None, residual: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None,
+                      sumsq_out: Optional[torch.Tensor] = None, rope=None, cache: Optional[torch.Tensor] = None, t0: int = 0,
+                      t0_dev: Optional[torch.Tensor] = None, splits: Optional[int] = None) -> torch.Tensor:
+    """Decode-step GEMM x (M <= 64, K) @ w (N, K)^T with K split over `splits` CTAs per weight tile (fp32 partials) and ONE
+    fused tail kernel (mm_thin_fused):
+      THIN_RES     out = rs * xW^T + residual (in place allowed); sumsq_out (M, N/32) fp32 receives the next RMSNorm's statistic
+      THIN_SWIGLU  out (M, N/2) = silu(gate) * up of the [32 gate | 32 up]-interleaved fused weight
+      THIN_QKV     N = 3E: RoPE on q / k (rope = (cos, sin, pos_dev | None)), q -> out (M, 3E) columns [0, E), k / v -> `cache`
+                   (B, Tmax, 2, E) at slot t0 / *t0_dev
+    rs: `row_scale` (M,) fp32, or rms_from = (partials (M, parts) fp32, eps): rsqrt(mean(x^2) + eps) from a THIN_RES pass."""
+    _cuda(x, ACT(), "x"); _cuda(w, ACT(), "w")
+    M, K = x.shape
+    N = w.shape[0]
+    assert x.stride(1) == 1 and w.stride(1) == 1 and w.shape[1] == K and M <= 64
+    S = THIN_SPLITS if splits is None else int(splits)
+    if S < 1 or K % (S * 64) != 0:
+        S = 1
+    Kc = K // S
+    Mp = (M + 3) // 4 * 4
+    dev = x.device
+    part = torch.empty((S, N, Mp), device=dev, dtype=torch.float32)
+    gemm_raw(M=N, N=M, K=Kc, batch=S, A=w.data_ptr(), lda=w.stride(0), a_bs=Kc, B=x.data_ptr(), ldb=x.stride(0), b_bs=Kc,
+             Cout=part.data_ptr(), ldc=Mp, c_bs=N * Mp, c_fp32=True)
+    n_out = N // 2 if mode == THIN_SWIGLU else N
+    if out is None:
+        out = torch.empty((M, n_out), device=dev, dtype=ACT())
+    assert out.shape == (M, n_out) and out.stride(1) == 1
+    a = _lib.ThinArgs()
+    a.part, a.splits, a.N, a.M, a.ldp, a.mode = part.data_ptr(), S, N, M, Mp, int(mode)
+    a.row_scale = _ptr(row_scale)
+    if rms_from is not None:
+        parts, eps = rms_from
+        assert row_scale is None and parts.dtype == torch.float32 and parts.is_contiguous() and parts.shape[0] == M
+        a.rs_sumsq, a.rs_parts, a.rs_K, a.rs_eps = parts.data_ptr(), parts.shape[1], K, float(eps)
+    if residual is not None:
+        _cuda(residual, ACT(), "residual")
+        assert mode == THIN_RES and residual.stride(1) == 1
+        a.residual, a.ldr = residual.data_ptr(), residual.stride(0)
+    a.out, a.ldo = out.data_ptr(), out.stride(0)
+    if sumsq_out is not None:
+        assert mode == THIN_RES and sumsq_out.dtype == torch.float32 and sumsq_out.is_contiguous() and sumsq_out.shape == (M, N // 32)
+        a.sumsq_out = sumsq_out.data_ptr()
+    if mode == THIN_QKV:
+        cos, sin, pos_dev = rope
+        _cuda(cache, ACT(), "cache")
+        E = N // 3
+        assert cache.is_contiguous() and cache.dim() == 4 and cache.shape[0] == M and cache.shape[2] == 2 and cache.shape[3] == E
+        a.rope_cos, a.rope_sin, a.pos_dev, a.E = cos.data_ptr(), sin.data_ptr(), _ptr(pos_dev), E
+        a.cache, a.Tmax, a.t0, a.t0_dev = cache.data_ptr(), cache.shape[1], int(t0), _ptr(t0_dev)
+    _check(_lib.load().mm_thin_fused(C.byref(a), _stream()), "mm_thin_fused")
     return out
 
 

@@ -381,6 +381,59 @@ def test_gemm_multicast_pairs(M, N, K, kind):
     assert rel_err(out, x.float() @ w.float().t()) < 4e-3
 
 
+@pytest.mark.parametrize("M,N,K,kind", [
+    (2112, 4096, 4096, "res_stats"),   # o_proj at 4 samples/GPU: 272 tiles -> 1 wave + 124 (every CTA: finisher + contributor)
+    (2112, 4096, 11008, "res_stats"),  # down_proj, K = 172 k-blocks
+    (2112, 12288, 4096, "rope"),       # QKV + RoPE: 816 tiles -> 5 waves + 76
+    (1200, 4096 * 2, 2048, "swiglu"),  # 10 x 32 = 320 tiles -> 2 waves + 24: shares of ~10 k-blocks, 6+ contributors per tile
+    (19072, 256, 4096, "plain"),       # 149 tiles -> 1 wave + 1: ONE tile split over 64 CTAs (63 contributors)
+    (640, 7680, 512, "plain"),         # 5 x 30 = 150 tiles, num_k = 8: shares shorter than one k-block for most CTAs
+])
+def test_gemm_streamk_tail(M, N, K, kind):
+    """Stream-K tail (mm_gemm_args.sk_workspace): the partial last wave's k-blocks are split evenly over all CTAs, partial
+    accumulators handed over through the workspace.  Against the fp32 reference at the usual bar, against the plain
+    data-parallel launch (same math, different fp32 summation order: a handful of 1-ulp flips), bit-identical across
+    repeated launches (fixed summation order; the flags re-arm themselves)."""
+    ops = _ops()
+    x, w = rnd(M, K, seed=190), rnd(N, K, scale=K ** -0.5, seed=191)
+    ws = ops.streamk_workspace(x.device)
+
+    def run():
+        if kind == "res_stats":
+            res = rnd(M, N, seed=192)
+            ss = torch.empty((M, N // 32), device=DEV, dtype=torch.float32)
+            out = ops.linear(x, w, residual=res, sumsq_out=ss)
+            return out, ss
+        if kind == "rope":
+            return ops.linear(x, w, epi=ops.EPI_ROPE, rope=(cos_g, sin_g, 528, N * 2 // 3)), None
+        if kind == "swiglu":
+            return ops.linear(x, w, epi=ops.EPI_SWIGLU), None
+        return ops.linear(x, w), None
+
+    cos_g, sin_g = torch.rand(528, 64, device=DEV), torch.rand(528, 64, device=DEV)
+    base, base_ss = run()
+    ops.STREAMK = ws
+    try:
+        outs = [run() for _ in range(3)]
+    finally:
+        ops.STREAMK = None
+    torch.cuda.synchronize()
+    assert int(ws[:2048].abs().sum()) == 0  # every flag re-armed
+    got, got_ss = outs[0]
+    for o, o_ss in outs[1:]:
+        assert torch.equal(o, got)
+        assert o_ss is None or torch.equal(o_ss, got_ss)
+    assert rel_err(got, base) < 1e-3
+    frac = float((got != base).float().mean())
+    assert frac < 0.02, frac
+    if kind == "plain":
+        assert rel_err(got, x.float() @ w.float().t()) < 4e-3
+    if kind == "res_stats":
+        ref = x.float() @ w.float().t() + rnd(M, N, seed=192).float()
+        assert rel_err(got, ref) < 4e-3
+        assert rel_err(got_ss.sum(1), got.float().pow(2).sum(1)) < 1e-5
+
+
 @pytest.mark.parametrize("M", [1, 8, 32, 50])
 def test_linear_thin_swapped_operands(M):
     """Decode-step GEMMs: operands swapped (weights on the 128-row side), transposed epilogue."""
@@ -411,6 +464,50 @@ def test_linear_thin_splitk(M, K, N):
     h = res.clone()
     ops.linear_thin_splitk(x, w, residual=h, out=h, row_scale=rs)  # in-place residual stream update
     assert rel_err(h, ref) < 4e-3
+
+
+@pytest.mark.parametrize("M", [1, 8, 13])
+def test_linear_thin_fused_decode_tails(M):
+    """mm_thin_fused: the three fused tails of the decode step's split-K thin GEMMs against fp32 references — residual +
+    next-RMSNorm statistic, SwiGLU on the interleaved product with the row scale taken from such statistics, and
+    QKV + RoPE with k / v landing in the KV cache slot."""
+    ops = _ops()
+    E, I, Tmax, t0, eps = 512, 1280, 24, 5, 1e-6
+    x = rnd(M, E, seed=300)
+    # RES: o_proj-like, in place on the residual stream, statistics out
+    wo, res = rnd(E, E, scale=E ** -0.5, seed=301), rnd(M, E, seed=302)
+    ss = torch.empty((M, E // 32), device=DEV, dtype=torch.float32)
+    stream = res.clone()
+    ops.linear_thin_fused(x, wo, ops.THIN_RES, residual=stream, out=stream, sumsq_out=ss)
+    ref = x.float() @ wo.float().t() + res.float()
+    assert rel_err(stream, ref) < 4e-3
+    assert rel_err(ss.sum(1), stream.float().pow(2).sum(1)) < 1e-5
+    # SWIGLU with the row scale derived from those statistics (RMSNorm of `stream`)
+    wgu = rnd(2 * I, E, scale=E ** -0.5, seed=303)
+    g = ops.linear_thin_fused(stream, wgu, ops.THIN_SWIGLU, rms_from=(ss, eps))
+    rstd = torch.rsqrt(stream.float().pow(2).mean(1, keepdim=True) + eps)
+    y = ((stream.float() * rstd) @ wgu.float().t()).view(M, I // 32, 2, 32)
+    ref_g = (torch.nn.functional.silu(y[:, :, 0]) * y[:, :, 1]).reshape(M, I)
+    assert rel_err(g, ref_g) < 5e-3
+    # QKV: RoPE at device-side position, q -> out[:, :E], k / v -> cache slot
+    wqkv = rnd(3 * E, E, scale=E ** -0.5, seed=304)
+    rs = torch.rand(M, device=DEV) + 0.5
+    cos, sin = torch.rand(Tmax, 64, device=DEV), torch.rand(Tmax, 64, device=DEV)
+    cache = torch.zeros((M, Tmax, 2, E), device=DEV, dtype=torch.bfloat16)
+    pos = torch.tensor([t0], device=DEV, dtype=torch.int32)
+    out = ops.linear_thin_fused(x, wqkv, ops.THIN_QKV, row_scale=rs, rope=(cos, sin, pos), cache=cache, t0_dev=pos)
+    y = ((x.float() * rs[:, None]) @ wqkv.float().t()).view(M, 3, E // 128, 128)
+    c = torch.cat([cos[t0], cos[t0]])[None, None, :]
+    s_ = torch.cat([sin[t0], sin[t0]])[None, None, :]
+    rot = lambda t: t * c + torch.cat([-t[..., 64:], t[..., :64]], -1) * s_  # noqa: E731
+    assert rel_err(out[:, :E], rot(y[:, 0]).reshape(M, E)) < 4e-3
+    assert rel_err(cache[:, t0, 0], rot(y[:, 1]).reshape(M, E)) < 4e-3
+    assert rel_err(cache[:, t0, 1], y[:, 2].reshape(M, E)) < 4e-3
+    assert float(cache[:, :t0].abs().sum()) == 0 and float(cache[:, t0 + 1:].abs().sum()) == 0
+    # host-side slot / table offset instead of the device scalars (eager decode path)
+    cache2 = torch.zeros_like(cache)
+    out2 = ops.linear_thin_fused(x, wqkv, ops.THIN_QKV, row_scale=rs, rope=(cos[t0:], sin[t0:], None), cache=cache2, t0=t0)
+    assert torch.equal(out2[:, :E], out[:, :E]) and torch.equal(cache2, cache)
 
 
 def test_rms_statistics_carried_by_gemm_epilogues():
