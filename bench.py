@@ -346,7 +346,7 @@ def run_train(args, cfgs, hyper, rank, local_rank, world):
                        "submission": "cuda_graph_replay of the whole step" if use_graph else "host_launches",
                        "grad_sync": ("flat bf16 buffer, one NCCL all-reduce per decoder layer on a side stream, overlapped with backward ("
                                      + ("mm_nccl_allreduce" if own_nccl else "torch.distributed") + ")") if world > 1 else "none (1 rank)",
-                       "differentiable_set": "llm.* + the alignment modules of every modality (incl. the table as the alignment attention's keys/values); video_long_self_attention; encoders frozen; MHA dropout omitted"},
+                       "differentiable_set": "llm.* + the alignment modules of every modality (incl. the table as the alignment attention's keys/values); video_long_self_attention; encoders frozen; MHA attention dropout p=0.1 live (Philox mask regenerated in backward)"},
             "approx_tflops": tf / (ms / 1e3), "gpu_launches": launches, "loss_first_last": [losses[0], losses[-1]],
             "mem_gb": torch.cuda.max_memory_allocated() / 2 ** 30}), flush=True)
     if world > 1:

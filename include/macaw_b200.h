@@ -122,12 +122,16 @@ typedef struct mm_gemm_args {
    * (e.g. 272 tiles on 148 SMs), the tail's k-blocks are divided evenly over ALL CTAs; partial fp32 accumulators pass
    * through this workspace: 8192 bytes of flags (zero before the first use, self-resetting afterwards) followed by one
    * 128 x 256 fp32 slot per SM — mm_gemm_streamk_workspace_bytes().  One workspace must not be used by GEMMs running
-   * CONCURRENTLY on different streams.  Ignored for multicast-pair launches, c_trans and tiles narrower than 64. */
+   * CONCURRENTLY on different streams.  Ignored for multicast-pair launches and for launches without one full wave of
+   * tiles (the tail pieces run first and hide their hand-over behind the full tiles). */
   void* sk_workspace;
   int64_t sk_workspace_bytes;
 } mm_gemm_args;
 
 int32_t mm_gemm_fwd(const mm_gemm_args* args, void* stream);
+/* Stream-K policy of the process: 0 never, 1 when the saved MMA time exceeds the hand-over cost (default; environment
+ * MACAW_B200_GEMM_STREAMK), 2 whenever the schedule allows (tests).  mode < 0 only queries.  Returns the previous mode. */
+int32_t mm_gemm_streamk_mode(int32_t mode);
 /* bytes of mm_gemm_args.sk_workspace on the current device */
 int64_t mm_gemm_streamk_workspace_bytes(void);
 

@@ -118,24 +118,35 @@ __device__ __forceinline__ bool gemm_work(const GemmKParams& p, int worker, int 
   const int n_full = first > worker ? (first - worker + n_workers - 1) / n_workers : 0;
   w.c0 = 0;
   w.nc = 0;
-  if (it < n_full) {
-    w.tile = worker + it * n_workers;
+  // The tail pieces come FIRST (contributor, then finisher), the CTA's full tiles after them: the hand-over (partial
+  // accumulators through L2, flag latency, the finisher's extra loads) then overlaps the main loops of the full tiles
+  // instead of sitting exposed at the end of the kernel.
+  int n_sk = 0;
+  unsigned nk = 1, U = 0, u0 = 0, u1 = 0, ta = 0, end_a = 0;
+  bool has_b = false;
+  if (p.sk_tiles > 0) {
+    // 32-bit arithmetic (the host checks sk_tiles * num_k * (n_workers + 1) < 2^31): no 64-bit divisions on the tile path
+    nk = p.num_k;
+    U = static_cast<unsigned>(p.sk_tiles) * nk;
+    u0 = static_cast<unsigned>(worker) * U / n_workers;
+    u1 = static_cast<unsigned>(worker + 1) * U / n_workers;
+    if (u0 < u1) {
+      ta = u0 / nk;
+      end_a = u1 < (ta + 1) * nk ? u1 : (ta + 1) * nk;
+      has_b = u1 > end_a;  // the share runs on into tile ta + 1 (then piece A ends tile ta)
+      n_sk = has_b ? 2 : 1;
+    }
+  }
+  if (it >= n_sk) {
+    const int f = it - n_sk;
+    if (f >= n_full) return false;
+    w.tile = worker + f * n_workers;
     w.kb0 = 0;
     w.kb1 = p.num_k;
     w.role = 0;
     return true;
   }
-  if (p.sk_tiles == 0) return false;
-  const int j = it - n_full;
-  const long long nk = p.num_k;
-  const long long U = static_cast<long long>(p.sk_tiles) * nk;
-  const long long u0 = worker * U / n_workers, u1 = (worker + 1) * U / n_workers;
-  if (u0 >= u1) return false;
-  const long long ta = u0 / nk;
-  const long long end_a = u1 < (ta + 1) * nk ? u1 : (ta + 1) * nk;
-  const bool has_b = u1 > end_a;  // the share runs on into tile ta + 1 (then piece A ends tile ta)
-  if (has_b ? j > 1 : j > 0) return false;
-  if (has_b && j == 0) {  // contributor piece first
+  if (has_b && it == 0) {  // contributor piece first
     w.tile = first + static_cast<int>(ta) + 1;
     w.kb0 = 0;
     w.kb1 = static_cast<int>(u1 - end_a);
@@ -148,7 +159,7 @@ __device__ __forceinline__ bool gemm_work(const GemmKParams& p, int worker, int 
   w.role = (w.kb1 == p.num_k) ? 2 : 1;
   if (w.role == 2) {  // contributors: the CTAs below this one whose shares reach into tile ta
     int c0 = worker;
-    while (c0 > 0 && static_cast<long long>(c0) * U / n_workers > ta * nk) --c0;
+    while (c0 > 0 && static_cast<unsigned>(c0) * U / n_workers > ta * nk) --c0;
     w.c0 = c0;
     w.nc = worker - c0;
   }
@@ -436,8 +447,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN;
       if (wk.role == 1) {
         // ---- stream-K contributor: hand the raw fp32 partial accumulator of this K-range to the tile's finisher.
-        // Slot layout [32-col chunk][row 0..127][32 floats]: each thread writes 128 contiguous bytes per chunk; warp
-        // (q, half) writes exactly the part the finisher's warp (q, half) reads, so the hand-over is per warp.
+        // Slot layout [32-col chunk][4-col group 0..7][row 0..127][4 floats]: every warp store / load instruction moves
+        // 512 contiguous bytes; warp (q, half) writes exactly the part the finisher's warp (q, half) reads, so the
+        // hand-over is per warp.
         mbar_wait(&tfull_bar[acc], acc_phase);
         tc_fence_after();
         constexpr int CPH_S = BN >= 64 ? BN / 64 : 1;
@@ -447,10 +459,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           uint32_t r[32];
           tmem_ld32(taddr + c * 32, r);
           tmem_ld_wait();
-          float4* dst = reinterpret_cast<float4*>(slot + (static_cast<long long>(c) * kBlockM + q * 32 + lane) * 32);
+          float4* dst = reinterpret_cast<float4*>(slot) + static_cast<long long>(c) * 8 * kBlockM + q * 32 + lane;
 #pragma unroll
           for (int i = 0; i < 8; ++i)
-            dst[i] = make_float4(__uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1]), __uint_as_float(r[4 * i + 2]),
+            dst[i * kBlockM] = make_float4(__uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1]), __uint_as_float(r[4 * i + 2]),
                                  __uint_as_float(r[4 * i + 3]));
         }
         __threadfence();
@@ -468,18 +480,23 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       // stream-K finisher: r[] += the contributors' partials of accumulator columns col_off .. col_off + 31 (fixed
       // order: deterministic); a no-op for ordinary tiles (warp-uniform branch)
       // (a CTA whose share of the tail is empty — more CTAs than tail k-blocks — has no piece and is skipped)
-      const long long sk_units = static_cast<long long>(p.sk_tiles) * p.num_k;
-      auto sk_has = [&](int sidx) { return sidx * sk_units / n_workers < (sidx + 1) * sk_units / n_workers; };
+      const unsigned sk_units = static_cast<unsigned>(p.sk_tiles) * p.num_k;
+      auto sk_has = [&](int sidx) {
+        return static_cast<unsigned>(sidx) * sk_units / n_workers < static_cast<unsigned>(sidx + 1) * sk_units / n_workers;
+      };
       auto sk_add = [&](uint32_t (&r)[32], int col_off) {
         if (wk.nc == 0) return;
         const int c = col_off >> 5;
         for (int sidx = wk.c0; sidx < wk.c0 + wk.nc; ++sidx) {
           if (!sk_has(sidx)) continue;
-          const float4* src = reinterpret_cast<const float4*>(
-              p.sk_ws + static_cast<long long>(sidx) * (kBlockM * BN) + (static_cast<long long>(c) * kBlockM + q * 32 + lane) * 32);
+          const float4* src = reinterpret_cast<const float4*>(p.sk_ws + static_cast<long long>(sidx) * (kBlockM * BN)) +
+                              static_cast<long long>(c) * 8 * kBlockM + q * 32 + lane;
+          float4 fv[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) fv[i] = __ldcg(src + i * kBlockM);
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
-            const float4 f = __ldcg(src + i);
+            const float4 f = fv[i];
             r[4 * i] = __float_as_uint(__uint_as_float(r[4 * i]) + f.x);
             r[4 * i + 1] = __float_as_uint(__uint_as_float(r[4 * i + 1]) + f.y);
             r[4 * i + 2] = __float_as_uint(__uint_as_float(r[4 * i + 2]) + f.z);
@@ -531,6 +548,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             uint32_t r[32];
             tmem_ld32(taddr + c * 32, r);
             tmem_ld_wait();
+            sk_add(r, c * 32);
             const int col0 = t.n_blk * BN + c * 32;
             if (col0 >= p.N || !row_ok) continue;
             float v[32];
@@ -761,6 +779,12 @@ int make_map(CUtensorMap* m, const void* ptr, uint64_t inner, uint64_t rows, uin
   return 0;
 }
 
+// process-wide stream-K policy; initial value from MACAW_B200_GEMM_STREAMK (default 1)
+static int& streamk_mode() {
+  static int mode = []() { const char* e = getenv("MACAW_B200_GEMM_STREAMK"); const int v = e ? atoi(e) : 1; return v < 0 || v > 2 ? 1 : v; }();
+  return mode;
+}
+
 template <int BN, int EPI, bool B_MN, bool MC, bool A_MN = false>
 static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmKParams& p, cudaStream_t st) {
   static bool attr_set[kMaxDevices] = {};
@@ -774,7 +798,7 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmK
     const int pairs = total < num_sms() / 2 ? total : num_sms() / 2;
     e = launch_kernel(kern, dim3(2 * pairs), dim3(320), smem, st, 2, ta, tb, p);
   } else {
-    const int grid = total < num_sms() ? total : num_sms();
+    const int grid = (total < num_sms() && p.sk_tiles == 0) ? total : num_sms();  // stream-K shares the tail over ALL SMs
     e = launch_kernel(kern, dim3(grid), dim3(320), smem, st, 1, ta, tb, p);
   }
   if (e != cudaSuccess) {
@@ -900,11 +924,20 @@ extern "C" int32_t mm_gemm_fwd(const mm_gemm_args* a, void* stream) {
   }
   // ---- stream-K tail: only when the last wave is clearly partial (<= 85 % full) and K is long enough to split
   p.sk_tiles = 0; p.sk_first = 0; p.sk_ws = nullptr; p.sk_flags = nullptr;
-  static const int sk_env = []() { const char* e = getenv("MACAW_B200_GEMM_STREAMK"); return e ? atoi(e) : 1; }();
-  if (sk_env != 0 && a->sk_workspace != nullptr && !use_mc && !a->c_trans && BN >= 64 && p.num_k >= 8 && tiles256 > sms) {
+  const int sk_env = streamk_mode();  // 0 off, 1 when it pays (default), 2 whenever the schedule allows (tests)
+  // (needs at least one full wave: the tail pieces run FIRST and their hand-over hides behind the full tiles' main loops;
+  //  with fewer tiles than SMs — the thin GEMMs of a decode step — it would be exposed: measured 27 vs 22 us per GEMM
+  //  against a fixed split-K of 4 + reduce)
+  if (sk_env != 0 && a->sk_workspace != nullptr && !use_mc && p.num_k >= 8 && tiles256 > sms &&
+      static_cast<long long>(sms) * p.num_k * (sms + 1) < (1LL << 31)) {
     const int rem = static_cast<int>(tiles256 % sms);
     const long long need = 8192 + static_cast<long long>(sms) * kBlockM * BN * 4;
-    if (rem > 0 && rem * 100 <= 85 * sms && a->sk_workspace_bytes >= need &&
+    // Worth it only when the saved MMA time clearly exceeds the hand-over cost (partials through L2 compete with the
+    // operand traffic: ~9 us measured at 128 x 256 tiles).  Saved time = (1 - rem / SMs) of one tile = (SMs - rem) / SMs *
+    // num_k * 0.44 us at BN = 256; measured on B200, M = 2112: QKV (76 tiles left, K = 4096) 163.0 -> 159.6 us, down_proj
+    // (124 left, K = 11008) 150.2 -> 146.6 us, o_proj (124 left, K = 4096) 56.9 -> 60.5 us — hence the threshold.
+    const bool pays = sk_env == 2 || static_cast<long long>(sms - rem) * p.num_k * BN >= 3400LL * 256;
+    if (rem > 0 && pays && a->sk_workspace_bytes >= need &&
         (reinterpret_cast<uintptr_t>(a->sk_workspace) & 15) == 0) {
       p.sk_tiles = rem;
       p.sk_first = static_cast<int>(tiles256 - rem);
@@ -962,6 +995,12 @@ extern "C" int32_t mm_gemm_fwd(const mm_gemm_args* a, void* stream) {
   MM_LAUNCH(32, MM_EPI_STD, false);
 #undef MM_LAUNCH
 #undef MM_LAUNCH_MC
+}
+
+extern "C" int32_t mm_gemm_streamk_mode(int32_t mode) {
+  const int prev = streamk_mode();
+  if (mode >= 0 && mode <= 2) streamk_mode() = mode;
+  return prev;
 }
 
 extern "C" int64_t mm_gemm_streamk_workspace_bytes(void) {

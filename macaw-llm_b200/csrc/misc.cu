@@ -540,39 +540,99 @@ __global__ void __launch_bounds__(64) thin_fused_kernel(const ThinFusedParams p)
     n1 = (unit >> 1) * 128 + (unit & 1) * 32 + lane;
     n2 = n1 + 64;
   }
+  // The kernel moves ~100 KB: it is pure LATENCY.  A warp issues in order, so every load whose address is known up front
+  // is issued before the first dependent instruction (fully unrolled, predicated), and the one dependent pair (RoPE table
+  // row <- device-side position) comes last: two L2 round trips in total instead of one per loop iteration.
+  int pos = 0, t0 = p.t0;
+  if (MODE == MM_THIN_QKV) {  // one new token per sample: every row shares the position and the cache slot
+    if (p.pos_dev != nullptr) pos = *p.pos_dev;
+    if (p.t0_dev != nullptr) t0 = *p.t0_dev;
+  }
+  float rope_c = 1.f, rope_s = 0.f;
   for (int m0 = 0; m0 < p.M; m0 += 8) {
-    float a1[8], a2[8];
+    float a1[8], a2[8], rsv[8], resv[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) a1[j] = a2[j] = 0.f;
-    for (int s = 0; s < p.S; ++s) {
-      const float* p1 = p.part + (static_cast<long long>(s) * p.N + n1) * p.ldp + m0;
+    for (int j = 0; j < 8; ++j) {
+      a1[j] = a2[j] = resv[j] = 0.f;
+      rsv[j] = 1.0f;
+    }
+    float q1[4][8], q2[4][8];  // partial products of up to 4 K slices (further slices: the loop below)
+#pragma unroll
+    for (int s4 = 0; s4 < 4; ++s4) {
+      const float* p1 = p.part + (static_cast<long long>(s4) * p.N + n1) * p.ldp + m0;
+      const float* p2 = p.part + (static_cast<long long>(s4) * p.N + n2) * p.ldp + m0;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const bool ok = s4 < p.S && m0 + j < p.M;
+        q1[s4][j] = ok ? p1[j] : 0.f;
+        q2[s4][j] = (MODE != MM_THIN_RES && ok) ? p2[j] : 0.f;
+      }
+    }
+    float sq[4][8];
+    const bool from_ss = p.row_scale == nullptr && p.rs_sumsq != nullptr;
+    if (p.row_scale != nullptr) {
 #pragma unroll
       for (int j = 0; j < 8; ++j)
-        if (m0 + j < p.M) a1[j] += p1[j];
-      if (MODE != MM_THIN_RES) {
-        const float* p2 = p.part + (static_cast<long long>(s) * p.N + n2) * p.ldp + m0;
+        if (m0 + j < p.M) rsv[j] = p.row_scale[m0 + j];
+    } else if (from_ss) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int k = lane + 32 * i;
+          sq[i][j] = (k < p.rs_parts && m0 + j < p.M) ? p.rs_sumsq[static_cast<long long>(m0 + j) * p.rs_parts + k] : 0.f;
+        }
+    }
+    if (MODE == MM_THIN_RES && p.residual != nullptr) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if (m0 + j < p.M) resv[j] = ldv<F16>(p.residual[static_cast<long long>(m0 + j) * p.ldr + n1]);
+    }
+    if (MODE == MM_THIN_QKV && m0 == 0) {  // depends on `pos`: issued after everything else is in flight
+      const int jj = (unit & 1) * 32 + lane;
+      rope_c = p.rope_cos[static_cast<long long>(pos) * 64 + jj];
+      rope_s = p.rope_sin[static_cast<long long>(pos) * 64 + jj];
+    }
+#pragma unroll
+    for (int s4 = 0; s4 < 4; ++s4)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        a1[j] += q1[s4][j];
+        a2[j] += q2[s4][j];
+      }
+    for (int s = 4; s < p.S; ++s) {
+      const float* p1 = p.part + (static_cast<long long>(s) * p.N + n1) * p.ldp + m0;
+      const float* p2 = p.part + (static_cast<long long>(s) * p.N + n2) * p.ldp + m0;
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if (m0 + j < p.M) {
+          a1[j] += p1[j];
+          if (MODE != MM_THIN_RES) a2[j] += p2[j];
+        }
+    }
+    if (from_ss) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) rsv[j] = (sq[0][j] + sq[1][j]) + (sq[2][j] + sq[3][j]);
+      for (int k = lane + 128; k < p.rs_parts; k += 32) {
 #pragma unroll
         for (int j = 0; j < 8; ++j)
-          if (m0 + j < p.M) a2[j] += p2[j];
+          if (m0 + j < p.M) rsv[j] += p.rs_sumsq[static_cast<long long>(m0 + j) * p.rs_parts + k];
       }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) rsv[j] += __shfl_xor_sync(0xffffffffu, rsv[j], o);
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) rsv[j] = rsqrtf(rsv[j] / static_cast<float>(p.rs_K) + p.rs_eps);
     }
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const int m = m0 + j;
       if (m >= p.M) break;  // warp-uniform
-      float rs = 1.0f;
-      if (p.row_scale != nullptr) {
-        rs = p.row_scale[m];
-      } else if (p.rs_sumsq != nullptr) {
-        float t = 0.f;
-        for (int k = lane; k < p.rs_parts; k += 32) t += p.rs_sumsq[static_cast<long long>(m) * p.rs_parts + k];
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
-        rs = rsqrtf(t / static_cast<float>(p.rs_K) + p.rs_eps);
-      }
+      const float rs = rsv[j];
       if (MODE == MM_THIN_RES) {
-        float v = a1[j] * rs;
-        if (p.residual != nullptr) v += ldv<F16>(p.residual[static_cast<long long>(m) * p.ldr + n1]);
+        const float v = a1[j] * rs + resv[j];
         const bf16 st = stv<F16>(v);
         p.out[static_cast<long long>(m) * p.ldo + n1] = st;
         if (p.sumsq_out != nullptr) {
@@ -588,10 +648,7 @@ __global__ void __launch_bounds__(64) thin_fused_kernel(const ThinFusedParams p)
       } else {
         float x1 = a1[j] * rs, x2 = a2[j] * rs;
         if (n1 < 2 * p.E) {  // q and k rotate; v passes through
-          const int pos = p.pos_dev != nullptr ? *p.pos_dev : 0;
-          const int jj = (unit & 1) * 32 + lane;
-          const float c = p.rope_cos[static_cast<long long>(pos) * 64 + jj], sn = p.rope_sin[static_cast<long long>(pos) * 64 + jj];
-          const float r1 = x1 * c - x2 * sn, r2 = x2 * c + x1 * sn;
+          const float r1 = x1 * rope_c - x2 * rope_s, r2 = x2 * rope_c + x1 * rope_s;
           x1 = r1;
           x2 = r2;
         }
@@ -599,7 +656,6 @@ __global__ void __launch_bounds__(64) thin_fused_kernel(const ThinFusedParams p)
           p.out[static_cast<long long>(m) * p.ldo + n1] = stv<F16>(x1);
           p.out[static_cast<long long>(m) * p.ldo + n2] = stv<F16>(x2);
         } else {
-          const int t0 = p.t0_dev != nullptr ? *p.t0_dev : p.t0;
           const int which = n1 < 2 * p.E ? 0 : 1;
           bf16* dst = p.cache + ((static_cast<long long>(m) * p.Tmax + t0) * 2 + which) * p.E + (n1 - (which + 1) * p.E);
           dst[0] = stv<F16>(x1);

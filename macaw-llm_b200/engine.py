@@ -665,6 +665,13 @@ class Engine:
         return x
 
     def _lm_head(self, x: torch.Tensor, rows: Optional[torch.Tensor] = None) -> torch.Tensor:
+        ops.STREAMK = self._streamk_ws(x.device)
+        try:
+            return self._lm_head_impl(x, rows)
+        finally:
+            ops.STREAMK = None
+
+    def _lm_head_impl(self, x: torch.Tensor, rows: Optional[torch.Tensor] = None) -> torch.Tensor:
         """final RMSNorm (as the row scale of the GEMM) + lm_head on the rows of x (reference modeling.py:508, 597)."""
         llm = self.m.llm
         gn = llm.model.norm.weight

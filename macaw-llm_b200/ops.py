@@ -179,6 +179,8 @@ def linear_thin(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] =
         assert residual.stride(1) == 1
         kw.update(residual=residual.data_ptr(), ldr=residual.stride(0))
     # swapped problem: M' = N (weight rows), N' = M (activation rows)
+    if STREAMK is not None and STREAMK.device == x.device:
+        kw.update(streamk=STREAMK)
     gemm_raw(M=N, N=M, K=K, A=w.data_ptr(), lda=w.stride(0), B=x.data_ptr(), ldb=x.stride(0), Cout=out.data_ptr(),
              ldc=out.stride(0), c_fp32=out.dtype == torch.float32, act=act, bias=_ptr(bias), row_scale=_ptr(row_scale),
              c_trans=True, **kw)
@@ -232,6 +234,7 @@ def linear_thin_fused(x: torch.Tensor, w: torch.Tensor, mode: int, *, row_scale:
     M, K = x.shape
     N = w.shape[0]
     assert x.stride(1) == 1 and w.stride(1) == 1 and w.shape[1] == K and M <= 64
+    sk = None  # stream-K needs a full wave of tiles to hide its hand-over behind: a decode GEMM has 32..172 tiles
     S = THIN_SPLITS if splits is None else int(splits)
     if S < 1 or K % (S * 64) != 0:
         S = 1
@@ -239,8 +242,9 @@ def linear_thin_fused(x: torch.Tensor, w: torch.Tensor, mode: int, *, row_scale:
     Mp = (M + 3) // 4 * 4
     dev = x.device
     part = torch.empty((S, N, Mp), device=dev, dtype=torch.float32)
+    # fixed split-K factor; the tail kernel adds the partial sums up
     gemm_raw(M=N, N=M, K=Kc, batch=S, A=w.data_ptr(), lda=w.stride(0), a_bs=Kc, B=x.data_ptr(), ldb=x.stride(0), b_bs=Kc,
-             Cout=part.data_ptr(), ldc=Mp, c_bs=N * Mp, c_fp32=True)
+             Cout=part.data_ptr(), ldc=Mp, c_bs=N * Mp, c_fp32=True, streamk=sk)
     n_out = N // 2 if mode == THIN_SWIGLU else N
     if out is None:
         out = torch.empty((M, n_out), device=dev, dtype=ACT())

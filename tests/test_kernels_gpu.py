@@ -385,7 +385,8 @@ def test_gemm_multicast_pairs(M, N, K, kind):
     (2112, 4096, 4096, "res_stats"),   # o_proj at 4 samples/GPU: 272 tiles -> 1 wave + 124 (every CTA: finisher + contributor)
     (2112, 4096, 11008, "res_stats"),  # down_proj, K = 172 k-blocks
     (2112, 12288, 4096, "rope"),       # QKV + RoPE: 816 tiles -> 5 waves + 76
-    (1200, 4096 * 2, 2048, "swiglu"),  # 10 x 32 = 320 tiles -> 2 waves + 24: shares of ~10 k-blocks, 6+ contributors per tile
+    (1200, 4096 * 2, 1024, "swiglu"),  # 10 x 32 = 320 tiles -> 2 waves + 24: shares of ~3 k-blocks, 6+ contributors per tile
+                                       # (K = 1024 keeps the launch off the multicast-pair path, which has no stream-K)
     (19072, 256, 4096, "plain"),       # 149 tiles -> 1 wave + 1: ONE tile split over 64 CTAs (63 contributors)
     (640, 7680, 512, "plain"),         # 5 x 30 = 150 tiles, num_k = 8: shares shorter than one k-block for most CTAs
 ])
@@ -411,12 +412,16 @@ def test_gemm_streamk_tail(M, N, K, kind):
         return ops.linear(x, w), None
 
     cos_g, sin_g = torch.rand(528, 64, device=DEV), torch.rand(528, 64, device=DEV)
+    from macaw_llm_b200 import _lib
+
     base, base_ss = run()
     ops.STREAMK = ws
+    prev = _lib.load().mm_gemm_streamk_mode(2)  # force: the default policy skips shapes where it does not pay (o_proj)
     try:
         outs = [run() for _ in range(3)]
     finally:
         ops.STREAMK = None
+        _lib.load().mm_gemm_streamk_mode(prev)
     torch.cuda.synchronize()
     assert int(ws[:2048].abs().sum()) == 0  # every flag re-armed
     got, got_ss = outs[0]
@@ -426,6 +431,7 @@ def test_gemm_streamk_tail(M, N, K, kind):
     assert rel_err(got, base) < 1e-3
     frac = float((got != base).float().mean())
     assert frac < 0.02, frac
+    assert float(ws[2048:].view(torch.float32).abs().sum()) > 0  # partial accumulators did pass through the workspace
     if kind == "plain":
         assert rel_err(got, x.float() @ w.float().t()) < 4e-3
     if kind == "res_stats":
@@ -435,7 +441,7 @@ def test_gemm_streamk_tail(M, N, K, kind):
 
 
 @pytest.mark.parametrize("M", [1, 8, 32, 50])
-def test_linear_thin_swapped_operands(M):
+def test_linear_thin_swapped_operands(M, thin_streamk):
     """Decode-step GEMMs: operands swapped (weights on the 128-row side), transposed epilogue."""
     ops = _ops()
     K, N = 1024, 1536
@@ -466,9 +472,22 @@ def test_linear_thin_splitk(M, K, N):
     assert rel_err(h, ref) < 4e-3
 
 
+@pytest.fixture(params=[False, True], ids=["splitk4", "streamk"])
+def thin_streamk(request):
+    """Thin (decode) GEMMs either with the fixed split-K factor or with the stream-K workspace (fewer tiles than SMs:
+    the whole GEMM is divided evenly along K over all SMs)."""
+    ops = _ops()
+    ops.STREAMK = ops.streamk_workspace(torch.device(DEV, 0)) if request.param else None
+    yield request.param
+    ws, ops.STREAMK = ops.STREAMK, None
+    if ws is not None:
+        torch.cuda.synchronize()
+        assert int(ws[:2048].abs().sum()) == 0  # every hand-over flag re-armed
+
+
 @pytest.mark.parametrize("M", [1, 8, 13])
-def test_linear_thin_fused_decode_tails(M):
-    """mm_thin_fused: the three fused tails of the decode step's split-K thin GEMMs against fp32 references — residual +
+def test_linear_thin_fused_decode_tails(M, thin_streamk):
+    """mm_thin_fused: the three fused tails of the decode step's thin GEMMs against fp32 references — residual +
     next-RMSNorm statistic, SwiGLU on the interleaved product with the row scale taken from such statistics, and
     QKV + RoPE with k / v landing in the KV cache slot."""
     ops = _ops()

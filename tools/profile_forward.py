@@ -23,6 +23,7 @@ def main():
     ap.add_argument("--steps", type=int, default=1)
     ap.add_argument("--layers", type=int, default=0, help="truncate LLaMA depth (profiling convenience only)")
     ap.add_argument("--video-frames", type=int, default=0, help="add a video of F frames per sample and drop the image (BASELINE config 5: F=16)")
+    ap.add_argument("--kernels", action="store_true", help="print a per-kernel time table from the CUPTI trace (torch.profiler)")
     a = ap.parse_args()
     from macaw_llm_b200.modeling import MM_LLMs, MM_LLMs_Config
 
@@ -41,6 +42,23 @@ def main():
     for _ in range(a.warm):
         model(dev_in)
     torch.cuda.synchronize()
+    if a.kernels:
+        import collections
+
+        with torch.profiler.profile(activities=[torch.profiler.ProfilerActivity.CUDA]) as prof:
+            for _ in range(a.steps):
+                model(dev_in)
+            torch.cuda.synchronize()
+        acc = collections.defaultdict(lambda: [0, 0.0])
+        for ev in prof.events():
+            if ev.device_type == torch.autograd.DeviceType.CUDA:
+                acc[ev.name][0] += 1
+                acc[ev.name][1] += ev.device_time
+        tot = sum(v[1] for v in acc.values())
+        print(f"[profile_forward --kernels] B={a.batch}: kernel time {tot / a.steps / 1e3:.2f} ms/step")
+        for name, (cnt, us) in sorted(acc.items(), key=lambda kv: -kv[1][1])[:16]:
+            print(f"{name[:72]:72s} {cnt / a.steps:8.1f} {us / cnt:9.1f} us {us / a.steps / 1e3:8.3f} ms {us / tot:6.1%}")
+        return
     torch.cuda.cudart().cudaProfilerStart()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()

@@ -20,12 +20,15 @@ def main():
     ap.add_argument("--batch", type=int, default=32)
     ap.add_argument("--iters", type=int, default=1)
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp16"])
+    ap.add_argument("--streamk", type=int, default=0, help="1: hand the GEMMs a stream-K workspace (mm_gemm_args.sk_workspace)")
     a = ap.parse_args()
     from macaw_llm_b200 import ops
 
     dt = torch.float16 if a.dtype == "fp16" else torch.bfloat16
     ops.set_act_format(dt)
     dev = "cuda"
+    if a.streamk:
+        ops.STREAMK = ops.streamk_workspace(torch.device("cuda", 0))
     g = torch.Generator(device=dev).manual_seed(0)
 
     def r(*s, scale=1.0):
@@ -74,7 +77,7 @@ def main():
         ms = e0.elapsed_time(e1) / a.iters
         res.append(f"{name}: {ms * 1e3:.1f} us, {fl / ms / 1e9:.0f} TFLOP/s")
     torch.cuda.cudart().cudaProfilerStop()
-    print(f"[profile_gemms {a.family} B={a.batch} {a.dtype}] " + "; ".join(res))
+    print(f"[profile_gemms {a.family} B={a.batch} {a.dtype}{' streamk' if a.streamk else ''}] " + "; ".join(res))
 
 
 if __name__ == "__main__":
