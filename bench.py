@@ -318,6 +318,21 @@ def run_train(args, cfgs, hyper, rank, local_rank, world):
         for _ in range(2):
             losses.append(float(step()))
     barrier()
+    if args.kernel_table and rank == 0:  # attribution only (CUPTI trace of one step); printed to stderr, never a bench value
+        import collections
+
+        with torch.profiler.profile(activities=[torch.profiler.ProfilerActivity.CUDA]) as prof:
+            step()
+            torch.cuda.synchronize()
+        acc = collections.defaultdict(lambda: [0, 0.0])
+        for ev in prof.events():
+            if ev.device_type == torch.autograd.DeviceType.CUDA:
+                acc[ev.name][0] += 1
+                acc[ev.name][1] += ev.device_time
+        tot = sum(v[1] for v in acc.values())
+        print(f"[train kernel table] kernel time {tot / 1e3:.2f} ms per step", file=sys.stderr)
+        for name, (cnt, us) in sorted(acc.items(), key=lambda kv: -kv[1][1])[:28]:
+            print(f"{name[:80]:80s} {cnt:6d} {us / cnt:9.1f} us {us / 1e3:8.3f} ms {us / tot:6.1%}", file=sys.stderr)
     ops.launch_count_reset()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -412,6 +427,7 @@ def main():
     ap.add_argument("--no-graphs", action="store_true", help="launch every kernel from the host instead of replaying a CUDA graph")
     ap.add_argument("--mode", default="prefill", choices=["prefill", "train", "decode"],
                     help="prefill = the benchmark of record; train / decode = secondary lines (SURVEY.md §8f ranks 1, 2)")
+    ap.add_argument("--kernel-table", action="store_true", help="--mode train: per-kernel time table of one step on stderr")
     ap.add_argument("--micro-batch", type=int, default=4, help="--mode train: samples per GPU per step (train.sh: 4)")
     ap.add_argument("--config", default="cfg4", choices=["cfg4", "cfg5"],
                     help="cfg4 = the benchmark of record (image+audio+text, global batch 32); cfg5 = secondary line: video "

@@ -316,9 +316,12 @@ int32_t mm_ce_loss(const void* logits, const int64_t* labels, int32_t B, int32_t
  * DeepSpeed).  All contractions of the backward pass are mm_gemm_fwd calls (dX: MN-major B; dW: MN-major A and B).
  *
  * mm_rmsnorm_bwd: y = x * rstd * g (LlamaRMSNorm modeling.py:311-319).  dx = rstd*(g*dy) - rstd^3/cols * x * sum(g*dy*x)
- *   (+ dres when given: the residual branch's gradient), dg[c] += sum_r dy*x*rstd (fp32, accumulated with atomics). */
+ *   (+ dres when given: the residual branch's gradient), dg[c] += sum_r dy*x*rstd in fp32: through dg_partials
+ *   ([mm_rmsnorm_bwd_parts(rows)][cols] fp32 workspace: per-CTA column sums reduced in a fixed order — deterministic, and
+ *   no grid-size-way atomic contention on `cols` addresses) or, when dg_partials is null, with atomics. */
+int32_t mm_rmsnorm_bwd_parts(int32_t rows);
 int32_t mm_rmsnorm_bwd(const void* dy, const void* x, const float* rstd, const void* g, const void* dres, void* dx,
-                       float* dg, int32_t rows, int32_t cols, void* stream);
+                       float* dg, float* dg_partials, int32_t rows, int32_t cols, void* stream);
 /* LlamaMLP modeling.py:139-140 on separate gate / up activations: h = silu(gate) * up over n contiguous elements. */
 int32_t mm_swiglu_fwd(const void* gate, const void* up, void* h, int64_t n, void* stream);
 int32_t mm_swiglu_bwd(const void* dh, const void* gate, const void* up, void* dgate, void* dup, int64_t n, void* stream);

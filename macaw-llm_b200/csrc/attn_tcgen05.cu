@@ -40,6 +40,7 @@ struct FaParams {
 };
 
 constexpr int kFaMQ = 128;  // queries per CTA
+constexpr int kFaMaskWords = 64;  // key-validity words kept in shared memory (keys < 2048; longer rows load per tile)
 constexpr float kFaTau = 8.0f;  // lazy-rescale threshold (log2 domain)
 
 __device__ __forceinline__ float max3(float a, float b, float c) {  // one FMNMX3 on sm_100
@@ -57,7 +58,8 @@ __device__ __forceinline__ float ex2_approx(float x) {
 template <int HD, int KT, int NPB>
 __host__ __device__ constexpr size_t fa_smem_bytes() {
   // Q + 2 K stages + 2 V stages + NPB P buffers + barriers (the dynamic smem window itself is 1024-byte aligned)
-  return (size_t)(HD / 64) * 16384 + 4 * (size_t)(HD / 64) * KT * 128 + (size_t)NPB * 128 * KT * 2 + 256;  // 21 barriers + TMEM slot
+  // ... + 21 barriers + TMEM slot (256 B) + key-validity bits of up to kFaMaskWords * 32 keys (256 B)
+  return (size_t)(HD / 64) * 16384 + 4 * (size_t)(HD / 64) * KT * 128 + (size_t)NPB * 128 * KT * 2 + 256 + 256;
 }
 
 template <int HD, int KT, int NPB, bool F16>
@@ -96,6 +98,7 @@ fa_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
   uint64_t* bar_qfree = bars + 18;   // 1  all S MMAs of the current query tile complete (Q may be replaced)
   uint64_t* bar_ofree = bars + 19;   // 1  softmax warps have read O (next query tile may overwrite it)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
+  uint32_t* s_kbits = reinterpret_cast<uint32_t*>(bars + 32);  // [kFaMaskWords]: bit i of word c = key 32 c + i is attendable
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int h = blockIdx.y, b = blockIdx.z;
@@ -243,6 +246,25 @@ fa_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
     const int r = q * 32 + lane;  // row within the tile == TMEM lane
     const uint32_t lane_base = static_cast<uint32_t>(q * 32) << 16;
     const int* kmask = p.key_mask ? p.key_mask + static_cast<long long>(b) * p.Tk : nullptr;
+    // Key-validity bits (Tk bound & key-padding mask) of the whole key range, built ONCE per CTA: loading the mask words
+    // per key tile put two dependent global loads (~700 cycles of long-scoreboard stall, 13 % of all samples in
+    // profiles/r2_ncu_attention_cfg4.txt) at the head of every tile's softmax.
+    const bool bits_in_smem = Tk <= kFaMaskWords * 32;
+    if (bits_in_smem) {
+      const int n_words = (Tk + 31) >> 5;
+      uint32_t mine[kFaMaskWords / 4];
+#pragma unroll
+      for (int k = 0; k < kFaMaskWords / 4; ++k) {  // all loads in flight, then the ballots
+        const int key = (q + 4 * k) * 32 + lane;
+        mine[k] = (q + 4 * k < n_words && key < Tk && (kmask == nullptr || kmask[key] != 0)) ? 1u : 0u;
+      }
+#pragma unroll
+      for (int k = 0; k < kFaMaskWords / 4; ++k) {
+        const uint32_t bits = __ballot_sync(0xffffffffu, mine[k] != 0u);
+        if (lane == 0 && q + 4 * k < n_words) s_kbits[q + 4 * k] = bits;
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");  // the four softmax warps only
+    }
     const int sw = r & 7;
     bf16* og = p.out + static_cast<long long>(b) * p.o_bs + static_cast<long long>(h) * p.o_hs;
     int G0 = 0, qa = 0;
@@ -264,10 +286,15 @@ fa_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
         uint32_t okb[NCH];
 #pragma unroll
         for (int c = 0; c < NCH; ++c) {
-          const int key = key0 + c * 32 + lane;
-          bool ok = key < Tk;
-          if (ok && kmask != nullptr) ok = kmask[key] != 0;
-          uint32_t bits = __ballot_sync(0xffffffffu, ok);
+          uint32_t bits;
+          if (bits_in_smem) {
+            bits = (key0 + c * 32 < Tk) ? s_kbits[(key0 >> 5) + c] : 0u;
+          } else {
+            const int key = key0 + c * 32 + lane;
+            bool ok = key < Tk;
+            if (ok && kmask != nullptr) ok = kmask[key] != 0;
+            bits = __ballot_sync(0xffffffffu, ok);
+          }
           if (p.causal) {
             const int lim = qrow + shift - (key0 + c * 32);  // keys with index <= lim inside this chunk are visible
             bits &= lim >= 31 ? 0xffffffffu : (lim < 0 ? 0u : ((2u << lim) - 1u));

@@ -57,16 +57,20 @@ __device__ __forceinline__ float block_max(float v, float* sh) {
 // One CTA walks `rows_per_cta` rows; each thread owns a fixed set of 8-column chunks, so the dg partial sums stay in
 // registers across the CTA's rows and cost one fp32 atomicAdd per column per CTA.
 constexpr int kNormMaxChunks = 4;  // cols <= 256 threads * 8 * 4 = 8192
+// NCH = 8-column chunks per thread (cols <= 256 * 8 * NCH): a template parameter so that the register budget follows the row
+// width (the fixed 4-chunk version needed 162 registers -> ONE CTA per SM at cols = 4096: 55 us per launch).
+template <int NCH>
 __global__ void __launch_bounds__(256) rmsnorm_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x,
                                                           const float* __restrict__ rstd, const bf16* __restrict__ g,
                                                           const bf16* __restrict__ dres, bf16* __restrict__ dx,
-                                                          float* __restrict__ dg, int rows, int cols, int rows_per_cta) {
+                                                          float* __restrict__ dg, float* __restrict__ dg_part, int rows,
+                                                          int cols, int rows_per_cta) {
   __shared__ float sh[32];
   const int nch = cols >> 3;
-  float gacc[kNormMaxChunks][8];
-  float gv[kNormMaxChunks][8];
+  float gacc[NCH][8];
+  float gv[NCH][8];
 #pragma unroll
-  for (int k = 0; k < kNormMaxChunks; ++k) {
+  for (int k = 0; k < NCH; ++k) {
     const int c = threadIdx.x + k * blockDim.x;
 #pragma unroll
     for (int i = 0; i < 8; ++i) gacc[k][i] = 0.f;
@@ -75,10 +79,17 @@ __global__ void __launch_bounds__(256) rmsnorm_bwd_kernel(const bf16* __restrict
   const int r0 = blockIdx.x * rows_per_cta, r1 = min(rows, r0 + rows_per_cta);
   for (int r = r0; r < r1; ++r) {
     const float rs = rstd[r];
-    float xv[kNormMaxChunks][8], tv[kNormMaxChunks][8];
+    float xv[NCH][8], tv[NCH][8];
+    uint4 dru[NCH];  // the residual-branch gradient is fetched with the other operands, not after the reduction
     float dot = 0.f;
 #pragma unroll
-    for (int k = 0; k < kNormMaxChunks; ++k) {
+    for (int k = 0; k < NCH; ++k) {
+      const int c = threadIdx.x + k * blockDim.x;
+      dru[k] = make_uint4(0u, 0u, 0u, 0u);
+      if (c < nch && dres != nullptr) dru[k] = *reinterpret_cast<const uint4*>(dres + static_cast<long long>(r) * cols + c * 8);
+    }
+#pragma unroll
+    for (int k = 0; k < NCH; ++k) {
       const int c = threadIdx.x + k * blockDim.x;
       if (c < nch) {
         float dv[8];
@@ -95,31 +106,64 @@ __global__ void __launch_bounds__(256) rmsnorm_bwd_kernel(const bf16* __restrict
     dot = block_sum(dot, sh);
     const float coef = rs * rs * rs * dot / static_cast<float>(cols);
 #pragma unroll
-    for (int k = 0; k < kNormMaxChunks; ++k) {
+    for (int k = 0; k < NCH; ++k) {
       const int c = threadIdx.x + k * blockDim.x;
       if (c < nch) {
         float o[8];
-        if (dres != nullptr)
-          unpack8f(*reinterpret_cast<const uint4*>(dres + static_cast<long long>(r) * cols + c * 8), o);
-        else {
-#pragma unroll
-          for (int i = 0; i < 8; ++i) o[i] = 0.f;
-        }
+        unpack8f(dru[k], o);  // zeros when there is no residual-branch gradient
 #pragma unroll
         for (int i = 0; i < 8; ++i) o[i] += rs * tv[k][i] - coef * xv[k][i];
         *reinterpret_cast<uint4*>(dx + static_cast<long long>(r) * cols + c * 8) = pack8f(o);
       }
     }
   }
-  if (dg != nullptr) {
+  if (dg_part != nullptr) {
+    // deterministic two-stage reduction: this CTA's partial column sums, summed over CTAs by dg_reduce_kernel (the
+    // atomics below put grid-size-way contention on every one of the `cols` addresses)
+    float* dst = dg_part + static_cast<long long>(blockIdx.x) * cols;
 #pragma unroll
-    for (int k = 0; k < kNormMaxChunks; ++k) {
+    for (int k = 0; k < NCH; ++k) {
+      const int c = threadIdx.x + k * blockDim.x;
+      if (c < nch) {
+        reinterpret_cast<float4*>(dst + c * 8)[0] = make_float4(gacc[k][0], gacc[k][1], gacc[k][2], gacc[k][3]);
+        reinterpret_cast<float4*>(dst + c * 8)[1] = make_float4(gacc[k][4], gacc[k][5], gacc[k][6], gacc[k][7]);
+      }
+    }
+  } else if (dg != nullptr) {
+#pragma unroll
+    for (int k = 0; k < NCH; ++k) {
       const int c = threadIdx.x + k * blockDim.x;
       if (c < nch) {
 #pragma unroll
         for (int i = 0; i < 8; ++i) atomicAdd(&dg[c * 8 + i], gacc[k][i]);
       }
     }
+  }
+}
+
+// dg[c] += sum_b part[b][c] in a fixed order.  CTA = 32 columns x 8 slices of the partials (slice s takes b = s, s + 8, ...:
+// 128-byte coalesced loads, 8x the loads in flight of a thread-per-column loop), slices combined through shared memory.
+__global__ void __launch_bounds__(256) dg_reduce_kernel(const float* __restrict__ part, int n_parts, int cols,
+                                                        float* __restrict__ dg) {
+  __shared__ float sh[8][32];
+  const int lane = threadIdx.x & 31, sl = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + lane;
+  float a0 = 0.f, a1 = 0.f;
+  if (c < cols) {
+    int b = sl;
+    for (; b + 8 < n_parts; b += 16) {
+      a0 += part[static_cast<long long>(b) * cols + c];
+      a1 += part[static_cast<long long>(b + 8) * cols + c];
+    }
+    if (b < n_parts) a0 += part[static_cast<long long>(b) * cols + c];
+  }
+  sh[sl][lane] = a0 + a1;
+  __syncthreads();
+  if (sl == 0 && c < cols) {
+    float t = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) t += sh[k][lane];
+    dg[c] += t;
   }
 }
 
@@ -215,6 +259,85 @@ __global__ void __launch_bounds__(256) attn_softmax_bwd_kernel(const float* __re
       const float pj = ok ? __expf(s[j] * scale - mx) * inv : 0.f;
       p[j] = __float2bfloat16(pj * m[u]);
       ds[j] = __float2bfloat16(scale * pj * (m[u] * dp[j] - D));
+    }
+  }
+}
+
+// Same computation, ONE WARP per row with the row held in registers (Tk <= 32 * NV): both inputs are read once with every
+// load in flight, the three reductions are shuffles, no __syncthreads.  Lane l owns columns l, l + 32, ... (coalesced).
+// History (profiles/r2_ncu_softmax_bwd.txt): the block-per-row kernel above takes 377 us per LLaMA layer at T = 528; the
+// first warp-per-row version (NV = 24, 126 registers -> 16 warps / SM) took 357 us at 14 % of the DRAM rate with
+// long-scoreboard stalls: too few loads in flight.  Hence NV is matched to Tk (17 at T = 528), the visibility mask is one
+// bit word instead of an array, and the register budget is capped so that 32 warps are resident.
+template <int NV>
+__global__ void __launch_bounds__(256, (NV <= 20 ? 4 : 2))
+attn_softmax_bwd_warp_kernel(const float* __restrict__ S, const float* __restrict__ dP, bf16* __restrict__ P,
+                             bf16* __restrict__ dS, long long rows, int H, int Tq, int Tk, long long ld, float scale,
+                             int causal, const int* __restrict__ key_mask, float p_drop,
+                             const unsigned long long* __restrict__ seed_dev, uint32_t sid) {
+  const int lane = threadIdx.x & 31;
+  const long long row = blockIdx.x * static_cast<long long>(blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int i = static_cast<int>(row % Tq);
+  const int b = static_cast<int>(row / (static_cast<long long>(Tq) * H));
+  const float* s = S + row * ld;
+  const float* dp = dP + row * ld;
+  const int lim = causal ? min(Tk - 1, i + (Tk - Tq)) : Tk - 1;
+  const DropCfg dc = drop_cfg(p_drop, seed_dev, sid);
+  float sv[NV], dv[NV];
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    const int j = lane + 32 * k;
+    sv[k] = j < Tk ? s[j] : 0.f;
+  }
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    const int j = lane + 32 * k;
+    dv[k] = j < Tk ? dp[j] : 0.f;
+  }
+  uint32_t okb = 0u;  // bit k: column lane + 32 k is visible
+  if (key_mask != nullptr) {
+    const int* km = key_mask + static_cast<long long>(b) * Tk;
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      const int j = lane + 32 * k;
+      if (j <= lim && km[j] != 0) okb |= 1u << k;
+    }
+  } else {
+#pragma unroll
+    for (int k = 0; k < NV; ++k)
+      if (lane + 32 * k <= lim) okb |= 1u << k;
+  }
+  float mx = -INFINITY;
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    sv[k] *= scale;
+    if (okb & (1u << k)) mx = fmaxf(mx, sv[k]);
+  }
+  mx = warp_max(mx);
+  float sum = 0.f, dsum = 0.f;
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    const float e = (okb & (1u << k)) ? __expf(sv[k] - mx) : 0.f;
+    if (dc.on) dv[k] *= drop_mult1(dc, static_cast<uint32_t>(row), static_cast<uint32_t>(lane + 32 * k));
+    sv[k] = e;
+    sum += e;
+    dsum += e * dv[k];
+  }
+  sum = warp_sum(sum);
+  dsum = warp_sum(dsum);
+  const float inv = sum > 0.f ? 1.f / sum : 0.f;
+  const float D = dsum * inv;
+  bf16* p = P + row * ld;
+  bf16* ds = dS + row * ld;
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    const int j = lane + 32 * k;
+    if (j < Tk) {
+      const float pj = sv[k] * inv;
+      const float mj = dc.on ? drop_mult1(dc, static_cast<uint32_t>(row), static_cast<uint32_t>(j)) : 1.0f;
+      p[j] = __float2bfloat16(pj * mj);
+      ds[j] = __float2bfloat16(scale * pj * (dv[k] - D));
     }
   }
 }
@@ -345,6 +468,46 @@ __global__ void colsum_kernel(const bf16* __restrict__ x, long long ldx, int row
 // ------------------------------------------------------------------------------------------------ AdamW
 // Decoupled weight decay (Loshchilov & Hutter), fp32 master weights + moments, bf16 working copy:
 //   m = b1 m + (1-b1) g;  v = b2 v + (1-b2) g^2;  w -= lr (m/bc1 / (sqrt(v/bc2) + eps) + wd w);  p = bf16(w)
+// 8 elements per thread and iteration: one 128-bit gradient load, two 128-bit loads / stores per fp32 state tensor, one
+// 128-bit parameter store (28 bytes of HBM traffic per parameter; the scalar kernel below reached 4.5 TB/s of it).
+__global__ void __launch_bounds__(256) adamw_vec8_kernel(bf16* __restrict__ p, const bf16* __restrict__ g, float* __restrict__ w,
+                                                         float* __restrict__ m, float* __restrict__ v, long long n8, float lr,
+                                                         float b1, float b2, float eps, float wd, float inv_bc1, float inv_bc2,
+                                                         float gscale, const int* __restrict__ step_dev) {
+  if (step_dev != nullptr) {
+    const float t = static_cast<float>(*step_dev);
+    inv_bc1 = 1.f / (1.f - powf(b1, t));
+    inv_bc2 = 1.f / (1.f - powf(b2, t));
+  }
+  const float c1 = 1.f - b1, c2 = 1.f - b2;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n8;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const uint4 gu = __ldg(reinterpret_cast<const uint4*>(g) + i);
+    float4 w0 = reinterpret_cast<const float4*>(w)[2 * i], w1 = reinterpret_cast<const float4*>(w)[2 * i + 1];
+    float4 m0 = reinterpret_cast<const float4*>(m)[2 * i], m1 = reinterpret_cast<const float4*>(m)[2 * i + 1];
+    float4 v0 = reinterpret_cast<const float4*>(v)[2 * i], v1 = reinterpret_cast<const float4*>(v)[2 * i + 1];
+    float gf[8];
+    unpack8f(gu, gf);
+    float wf[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+    float mf[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
+    float vf[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float gi = gf[j] * gscale;
+      mf[j] = b1 * mf[j] + c1 * gi;
+      vf[j] = b2 * vf[j] + c2 * gi * gi;
+      wf[j] -= lr * (mf[j] * inv_bc1 / (sqrtf(vf[j] * inv_bc2) + eps) + wd * wf[j]);
+    }
+    reinterpret_cast<float4*>(m)[2 * i] = make_float4(mf[0], mf[1], mf[2], mf[3]);
+    reinterpret_cast<float4*>(m)[2 * i + 1] = make_float4(mf[4], mf[5], mf[6], mf[7]);
+    reinterpret_cast<float4*>(v)[2 * i] = make_float4(vf[0], vf[1], vf[2], vf[3]);
+    reinterpret_cast<float4*>(v)[2 * i + 1] = make_float4(vf[4], vf[5], vf[6], vf[7]);
+    reinterpret_cast<float4*>(w)[2 * i] = make_float4(wf[0], wf[1], wf[2], wf[3]);
+    reinterpret_cast<float4*>(w)[2 * i + 1] = make_float4(wf[4], wf[5], wf[6], wf[7]);
+    reinterpret_cast<uint4*>(p)[i] = pack8f(wf);
+  }
+}
+
 __global__ void adamw_kernel(bf16* __restrict__ p, const bf16* __restrict__ g, float* __restrict__ w, float* __restrict__ m,
                              float* __restrict__ v, long long n, float lr, float b1, float b2, float eps, float wd,
                              float inv_bc1, float inv_bc2, float gscale, const int* __restrict__ step_dev) {
@@ -531,16 +694,29 @@ static inline int grid_for(long long total, int block, int cap_mult = 16) {
 using namespace mm;
 #define AL16(p) ((reinterpret_cast<uintptr_t>(p) & 15) == 0)
 
+extern "C" int32_t mm_rmsnorm_bwd_parts(int32_t rows) {
+  int rpc = (rows + 4 * num_sms() - 1) / (4 * num_sms());
+  if (rpc < 1) rpc = 1;
+  return (rows + rpc - 1) / rpc;
+}
+
 extern "C" int32_t mm_rmsnorm_bwd(const void* dy, const void* x, const float* rstd, const void* g, const void* dres,
-                                  void* dx, float* dg, int32_t rows, int32_t cols, void* stream) {
+                                  void* dx, float* dg, float* dg_partials, int32_t rows, int32_t cols, void* stream) {
   MM_REQUIRE(dy && x && rstd && g && dx && rows > 0 && cols > 0 && cols % 8 == 0 && cols <= 256 * 8 * kNormMaxChunks,
              "mm_rmsnorm_bwd: bad arguments (cols %% 8 == 0, cols <= %d)", 256 * 8 * kNormMaxChunks);
   MM_REQUIRE(AL16(dy) && AL16(x) && AL16(g) && AL16(dx) && (dres == nullptr || AL16(dres)), "mm_rmsnorm_bwd: alignment");
   int rpc = (rows + 4 * num_sms() - 1) / (4 * num_sms());
   if (rpc < 1) rpc = 1;
   const int grid = (rows + rpc - 1) / rpc;
-  rmsnorm_bwd_kernel<<<grid, 256, 0, ST(stream)>>>((const bf16*)dy, (const bf16*)x, rstd, (const bf16*)g, (const bf16*)dres,
-                                                   (bf16*)dx, dg, rows, cols, rpc);
+  MM_REQUIRE(dg_partials == nullptr || (dg != nullptr && AL16(dg_partials)), "mm_rmsnorm_bwd: dg_partials needs dg, 16-byte aligned");
+#define MM_RB(NCH_) \
+  rmsnorm_bwd_kernel<NCH_><<<grid, 256, 0, ST(stream)>>>((const bf16*)dy, (const bf16*)x, rstd, (const bf16*)g,           \
+                                                         (const bf16*)dres, (bf16*)dx, dg, dg_partials, rows, cols, rpc)
+  if (cols <= 256 * 8) MM_RB(1);
+  else if (cols <= 256 * 8 * 2) MM_RB(2);
+  else MM_RB(4);
+#undef MM_RB
+  if (dg_partials != nullptr) dg_reduce_kernel<<<(cols + 31) / 32, 256, 0, ST(stream)>>>(dg_partials, grid, cols, dg);
   return check_launch("mm_rmsnorm_bwd");
 }
 
@@ -566,9 +742,25 @@ extern "C" int32_t mm_attn_softmax_bwd(const float* S, const float* dP, void* P,
   MM_REQUIRE(p_drop >= 0.f && p_drop < 1.f && (p_drop == 0.f || seed_dev != nullptr), "mm_attn_softmax_bwd: dropout arguments");
   const long long rows = static_cast<long long>(B) * H * Tq;
   MM_REQUIRE(rows < (1LL << 31), "mm_attn_softmax_bwd: too many rows");
-  attn_softmax_bwd_kernel<<<static_cast<unsigned>(rows), 256, 0, ST(stream)>>>(S, dP, (bf16*)P, (bf16*)dS, H, Tq, Tk, ld,
-                                                                               scale, causal, key_mask, p_drop,
-                                                                               (const unsigned long long*)seed_dev, sid);
+  const unsigned wgrid = static_cast<unsigned>((rows + 7) / 8);
+#define MM_SB(NV_) \
+  attn_softmax_bwd_warp_kernel<NV_><<<wgrid, 256, 0, ST(stream)>>>(S, dP, (bf16*)P, (bf16*)dS, rows, H, Tq, Tk, ld, scale, \
+                                                                   causal, key_mask, p_drop,                               \
+                                                                   (const unsigned long long*)seed_dev, sid)
+  const int need = (Tk + 31) / 32;  // columns per lane
+  if (need <= 4) MM_SB(4);
+  else if (need <= 8) MM_SB(8);
+  else if (need <= 12) MM_SB(12);
+  else if (need <= 16) MM_SB(16);
+  else if (need <= 17) MM_SB(17);  // T = 528: the training bench's sequence length
+  else if (need <= 20) MM_SB(20);
+  else if (need <= 24) MM_SB(24);
+  else if (need <= 32) MM_SB(32);
+  else
+    attn_softmax_bwd_kernel<<<static_cast<unsigned>(rows), 256, 0, ST(stream)>>>(S, dP, (bf16*)P, (bf16*)dS, H, Tq, Tk, ld,
+                                                                                 scale, causal, key_mask, p_drop,
+                                                                                 (const unsigned long long*)seed_dev, sid);
+#undef MM_SB
   return check_launch("mm_attn_softmax_bwd");
 }
 
@@ -636,8 +828,17 @@ extern "C" int32_t mm_adamw(void* p, const void* g, float* master, float* m, flo
   if (step <= 0) step = 1;
   const float inv_bc1 = 1.f / (1.f - powf(beta1, static_cast<float>(step)));
   const float inv_bc2 = 1.f / (1.f - powf(beta2, static_cast<float>(step)));
-  adamw_kernel<<<grid_for(n, 256), 256, 0, ST(stream)>>>((bf16*)p, (const bf16*)g, master, m, v, n, lr, beta1, beta2, eps,
-                                                        weight_decay, inv_bc1, inv_bc2, grad_scale, step_dev);
+  const long long n8 = (AL16(p) && AL16(g) && AL16(master) && AL16(m) && AL16(v)) ? n / 8 : 0;
+  if (n8 > 0)
+    adamw_vec8_kernel<<<grid_for(n8, 256, 32), 256, 0, ST(stream)>>>((bf16*)p, (const bf16*)g, master, m, v, n8, lr, beta1,
+                                                                     beta2, eps, weight_decay, inv_bc1, inv_bc2, grad_scale,
+                                                                     step_dev);
+  if (n - 8 * n8 > 0) {  // unaligned tensors / the last n % 8 elements
+    const long long o = 8 * n8;
+    adamw_kernel<<<grid_for(n - o, 256), 256, 0, ST(stream)>>>((bf16*)p + o, (const bf16*)g + o, master + o, m + o, v + o, n - o,
+                                                               lr, beta1, beta2, eps, weight_decay, inv_bc1, inv_bc2, grad_scale,
+                                                               step_dev);
+  }
   return check_launch("mm_adamw");
 }
 

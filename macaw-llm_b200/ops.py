@@ -578,8 +578,13 @@ def rmsnorm_bwd(dy: torch.Tensor, x: torch.Tensor, rstd: torch.Tensor, g: torch.
     assert dy.is_contiguous() and x.is_contiguous() and (dres is None or dres.is_contiguous())
     rows, cols = x.shape
     dx = torch.empty_like(x)
-    _check(_lib.load().mm_rmsnorm_bwd(dy.data_ptr(), x.data_ptr(), rstd.data_ptr(), g.data_ptr(), _ptr(dres), dx.data_ptr(),
-                                      _ptr(dg), rows, cols, _stream()), "mm_rmsnorm_bwd")
+    lib = _lib.load()
+    parts = None
+    if dg is not None:  # per-CTA partial column sums, reduced in a fixed order (no atomics)
+        with torch.cuda.device(x.device):
+            parts = torch.empty((int(lib.mm_rmsnorm_bwd_parts(rows)), cols), device=x.device, dtype=torch.float32)
+    _check(lib.mm_rmsnorm_bwd(dy.data_ptr(), x.data_ptr(), rstd.data_ptr(), g.data_ptr(), _ptr(dres), dx.data_ptr(),
+                              _ptr(dg), _ptr(parts), rows, cols, _stream()), "mm_rmsnorm_bwd")
     return dx
 
 
