@@ -912,14 +912,8 @@ extern "C" int32_t mm_gemm_fwd(const mm_gemm_args* a, void* stream) {
   static const int mc_env = []() { const char* e = getenv("MACAW_B200_GEMM_MC"); return e ? atoi(e) : 1; }();
   const long long tiles256 = (long long)a->batch * batch2 * p.m_tiles * p.n_tiles;
   // (measured A/B on one box, cfg4: LLaMA GEMMs 1282 -> 1325 TFLOP/s; short-K CLIP GEMMs do not gain, hence K >= 2048)
-  // An odd number of M tiles leaves the last pair with an idle half (its CTA only feeds the multicast).  That is free as
-  // long as the pair schedule needs no more waves than the single-CTA schedule would (M = 2112, 17 M tiles — the per-GPU
-  // batch of the 8-GPU run: QKV 432 pair-tiles on 74 pairs = 6 waves vs 816 tiles on 148 CTAs = 6 waves; gate-up 11 vs 10).
-  const long long pair_tiles = (long long)a->batch * batch2 * ((p.m_tiles + 1) / 2) * p.n_tiles;
-  const long long pair_waves = (pair_tiles + sms / 2 - 1) / (sms / 2), single_waves = (tiles256 + sms - 1) / sms;
-  const bool odd_ok = (((p.m_tiles + 1) / 2) * 2 - p.m_tiles) * 32 <= p.m_tiles || (mc_env == 2 && pair_waves <= single_waves);
-  const bool use_mc = mc_env != 0 && !a->a_mn_major && BN == 256 && p.m_tiles >= 2 && p.num_k >= 32 &&
-                      (tiles256 >= 2LL * sms || (mc_env == 2 && tiles256 > sms)) && odd_ok;
+  const bool use_mc = mc_env != 0 && !a->a_mn_major && BN == 256 && p.m_tiles >= 2 && p.num_k >= 32 && tiles256 >= 2LL * sms &&
+                      (((p.m_tiles + 1) / 2) * 2 - p.m_tiles) * 32 <= p.m_tiles;
   // rasterisation: keep one group's A rows (~32 MiB) resident in the 126 MB L2 while its B tiles stream
   // (measured on cfg4: 16 pairs at K=4096 is the optimum; 4 / 8 / 32 cost +5 % / +1 % / +9 % step time)
   {
