@@ -296,8 +296,9 @@ def run_train(args, cfgs, hyper, rank, local_rank, world):
     launches_per_step = ops.launch_count()
     # ---- the whole step (forward, backward, optimizer: ~5000 launches issued from Python) replayed from ONE CUDA graph.
     #      Every step-dependent scalar lives on the device (AdamW step counter, upstream loss gradient), buffers are static.
-    #      With a data-parallel group the eager launches are kept (the NCCL buckets are issued from the host).
-    use_graph = (world == 1) and not args.no_graphs
+    # (data-parallel group: the per-layer bucket all-reduces are captured too — NCCL calls on a side stream forked from the
+    #  capturing stream — when they go through the library's own communicator; --ddp-graph 0 keeps the host launches)
+    use_graph = (world == 1 or (own_nccl and args.ddp_graph)) and not args.no_graphs
     if use_graph:
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream())
@@ -427,6 +428,7 @@ def main():
     ap.add_argument("--no-graphs", action="store_true", help="launch every kernel from the host instead of replaying a CUDA graph")
     ap.add_argument("--mode", default="prefill", choices=["prefill", "train", "decode"],
                     help="prefill = the benchmark of record; train / decode = secondary lines (SURVEY.md §8f ranks 1, 2)")
+    ap.add_argument("--ddp-graph", type=int, default=1, help="--mode train, N > 1: capture the step incl. the NCCL buckets in a CUDA graph")
     ap.add_argument("--kernel-table", action="store_true", help="--mode train: per-kernel time table of one step on stderr")
     ap.add_argument("--micro-batch", type=int, default=4, help="--mode train: samples per GPU per step (train.sh: 4)")
     ap.add_argument("--config", default="cfg4", choices=["cfg4", "cfg5"],

@@ -48,6 +48,15 @@ __device__ __forceinline__ float max3(float a, float b, float c) {  // one FMNMX
   asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
   return d;
 }
+__device__ __forceinline__ uint64_t pack_b32x2(uint32_t lo, uint32_t hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(lo), "r"(hi));
+  return r;
+}
+__device__ __forceinline__ uint64_t pack_f32x2(float lo, float hi) { return pack_b32x2(__float_as_uint(lo), __float_as_uint(hi)); }
+__device__ __forceinline__ void unpack_f32x2(uint64_t v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
 __device__ __forceinline__ float ex2_approx(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -352,25 +361,52 @@ fa_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
         }
         uint8_t* prow = sP + pb * PB + r * 128;
         float psum = 0.f;
+        if (full_tile) {
+          // packed fp32x2 arithmetic (FFMA2 / FADD2, sm_100): the softmax warps are issue-bound, and the scale-and-shift
+          // and the row-sum accumulation are the two fp32 ops per element besides the ex2 — half the instructions each
+          const uint64_t sc2 = pack_f32x2(p.scale_log2, p.scale_log2), nm2 = pack_f32x2(-m_ref, -m_ref);
+          uint64_t ps2 = pack_f32x2(0.f, 0.f);
 #pragma unroll
-        for (int c = 0; c < NCH; ++c) {
-          uint32_t pk[16];
+          for (int c = 0; c < NCH; ++c) {
+            uint32_t pk[16];
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            float e0 = ex2_approx(fmaf(__uint_as_float(v[c][2 * i]), p.scale_log2, -m_ref));
-            float e1 = ex2_approx(fmaf(__uint_as_float(v[c][2 * i + 1]), p.scale_log2, -m_ref));
-            if (!full_tile) {
+            for (int i = 0; i < 16; ++i) {
+              uint64_t t2;
+              asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(t2) : "l"(pack_b32x2(v[c][2 * i], v[c][2 * i + 1])), "l"(sc2), "l"(nm2));
+              float t0, t1;
+              unpack_f32x2(t2, t0, t1);
+              const float e0 = ex2_approx(t0), e1 = ex2_approx(t1);
+              asm("add.rn.f32x2 %0, %1, %2;" : "=l"(ps2) : "l"(ps2), "l"(pack_f32x2(e0, e1)));
+              pk[i] = pack2<F16>(e0, e1);
+            }
+            uint8_t* blk = prow + (c >> 1) * 16384;
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+              *reinterpret_cast<uint4*>(blk + ((((c & 1) * 4 + i) ^ sw) << 4)) =
+                  make_uint4(pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
+          }
+          float s0, s1;
+          unpack_f32x2(ps2, s0, s1);
+          psum = s0 + s1;
+        } else {
+#pragma unroll
+          for (int c = 0; c < NCH; ++c) {
+            uint32_t pk[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              float e0 = ex2_approx(fmaf(__uint_as_float(v[c][2 * i]), p.scale_log2, -m_ref));
+              float e1 = ex2_approx(fmaf(__uint_as_float(v[c][2 * i + 1]), p.scale_log2, -m_ref));
               e0 = (okb[c] & (1u << (2 * i))) ? e0 : 0.f;
               e1 = (okb[c] & (1u << (2 * i + 1))) ? e1 : 0.f;
+              psum += e0 + e1;
+              pk[i] = pack2<F16>(e0, e1);
             }
-            psum += e0 + e1;
-            pk[i] = pack2<F16>(e0, e1);
-          }
-          uint8_t* blk = prow + (c >> 1) * 16384;
+            uint8_t* blk = prow + (c >> 1) * 16384;
 #pragma unroll
-          for (int i = 0; i < 4; ++i)
-            *reinterpret_cast<uint4*>(blk + ((((c & 1) * 4 + i) ^ sw) << 4)) =
-                make_uint4(pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
+            for (int i = 0; i < 4; ++i)
+              *reinterpret_cast<uint4*>(blk + ((((c & 1) * 4 + i) ^ sw) << 4)) =
+                  make_uint4(pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
+          }
         }
         l = l * alpha + psum;
         // ---- lazy rescale of the TMEM accumulator (rare): needs PV_{j-1} complete, must finish before PV_j starts

@@ -285,12 +285,18 @@ __device__ __forceinline__ void store_row32(const GemmKParams& p, void* crow, in
 // k-block.  A smem slot is free only when BOTH CTAs' MMAs have retired (they both receive the peer's multicast).
 // A_MN = true: A is given as [K][M] with M contiguous (the transpose of a row-major [tokens][features] activation): the
 // weight-gradient GEMM dW = dY^T X reads dY and X exactly as the forward pass wrote them, no transpose copies.
-template <int BN, int EPI, bool B_MN, bool MC, bool A_MN = false>
+// CG2 = true (with MC): the pair runs as ONE cta_group::2 MMA unit — 256 x BN tile, each CTA stages its own 128 rows of A
+// and HALF of the B tile (no multicast: the tensor core reads both halves across the pair), so a CTA's shared memory
+// delivers 32 KiB per k-block instead of 48 and the ring is 6 stages deep.  Only the leader (rank 0) issues MMAs; both
+// producers credit their loads to the leader's full barrier; commits are multicast to both CTAs' barriers; the epilogue
+// warps of both CTAs release the accumulator on the leader's barrier.
+template <int BN, int EPI, bool B_MN, bool MC, bool A_MN = false, bool CG2 = false>
 __global__ void __launch_bounds__(320, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const GemmKParams p) {
-  constexpr int STAGES = gemm_stages(BN);
-  constexpr uint32_t B_BYTES = BN * kBlockK * 2;
+  static_assert(!CG2 || (MC && !B_MN && !A_MN && BN == 256), "cta_group::2 variant: multicast-pair schedule, K-major, BN 256");
+  constexpr int STAGES = CG2 ? 6 : gemm_stages(BN);
+  constexpr uint32_t B_BYTES = (CG2 ? BN / 2 : BN) * kBlockK * 2;
   constexpr uint32_t TMEM_COLS = gemm_tmem_cols(BN);
 
   extern __shared__ uint8_t smem_raw[];
@@ -318,18 +324,23 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   if (warp == 1) {
     if (elect_one()) {
       for (int s = 0; s < STAGES; ++s) {
-        mbar_init(&full_bar[s], 1);
-        mbar_init(&empty_bar[s], MC ? 2 : 1);
+        mbar_init(&full_bar[s], CG2 ? 2 : 1);                // CG2: one arrive.expect_tx per producer, on the LEADER's barrier
+        mbar_init(&empty_bar[s], CG2 ? 1 : (MC ? 2 : 1));    // CG2: one multicast commit from the leader
       }
       for (int s = 0; s < 2; ++s) {
         mbar_init(&tfull_bar[s], 1);
-        mbar_init(&tempty_bar[s], 8);
+        mbar_init(&tempty_bar[s], CG2 ? 16 : 8);             // CG2: the epilogue warps of BOTH CTAs, on the leader's barrier
       }
       fence_mbar_init();
     }
     __syncwarp();
-    tmem_alloc(tmem_slot, TMEM_COLS);
-    tmem_relinquish();
+    if constexpr (CG2) {
+      tmem_alloc2(tmem_slot, TMEM_COLS);
+      tmem_relinquish2();
+    } else {
+      tmem_alloc(tmem_slot, TMEM_COLS);
+      tmem_relinquish();
+    }
   }
   tc_fence_before();
   if constexpr (MC) cluster_sync_all(); else __syncthreads();
@@ -352,6 +363,17 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const int bh = p.b2_shared ? 0 : t.b_hi;
         for (int kb = wk.kb0; kb < wk.kb1; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
+          if constexpr (CG2) {
+            const uint32_t lfull = mapa_u32(smem_u32(&full_bar[stage]), 0);  // the leader's barrier
+            mbar_arrive_expect_tx_cluster(lfull, kABytes + B_BYTES);
+            tma_load_4d_cg2(&tmA, lfull, sA + stage * kABytes, kb * kBlockK, t.m_blk * kBlockM, t.b_lo, t.b_hi);
+            tma_load_4d_cg2(&tmB, lfull, sB + stage * B_BYTES, kb * kBlockK, t.n_blk * BN + cta_rank * (BN / 2), bb, bh);
+            if (++stage == STAGES) {
+              stage = 0;
+              phase ^= 1;
+            }
+            continue;
+          }
           mbar_arrive_expect_tx(&full_bar[stage], kABytes + B_BYTES);
           if constexpr (A_MN) {
 #pragma unroll
@@ -390,8 +412,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer
-    if (elect_one()) {
+    // ------------------------------------------------------------------ MMA issuer (CG2: the pair's leader only)
+    if ((!CG2 || cta_rank == 0) && elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -414,16 +436,20 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           for (int kk = 0; kk < kBlockK / 16; ++kk) {
             const uint64_t a_k = a_desc + static_cast<uint64_t>(A_MN ? kk * 128 : kk * 2);  // +2048 B | +32 B along K
             const uint64_t b_k = b_desc + static_cast<uint64_t>(B_MN ? kk * 128 : kk * 2);  // +2048 B | +32 B
-            umma_bf16(d_tmem, a_k, b_k, p.idesc, (kb != wk.kb0 || kk != 0) ? 1u : 0u);
+            if constexpr (CG2) umma_bf16_cg2(d_tmem, a_k, b_k, p.idesc, (kb != wk.kb0 || kk != 0) ? 1u : 0u);
+            else umma_bf16(d_tmem, a_k, b_k, p.idesc, (kb != wk.kb0 || kk != 0) ? 1u : 0u);
           }
           // frees the smem slot once these MMAs retire (in both CTAs of a multicast pair)
-          if constexpr (MC) umma_commit_mc(&empty_bar[stage], 3); else umma_commit(&empty_bar[stage]);
+          if constexpr (CG2) umma_commit_cg2_mc(&empty_bar[stage], 3);
+          else if constexpr (MC) umma_commit_mc(&empty_bar[stage], 3);
+          else umma_commit(&empty_bar[stage]);
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1;
           }
         }
-        umma_commit(&tfull_bar[acc]);  // accumulator complete
+        if constexpr (CG2) umma_commit_cg2_mc(&tfull_bar[acc], 3);  // both CTAs' epilogues read their own 128 rows
+        else umma_commit(&tfull_bar[acc]);                           // accumulator complete
         if (++acc == 2) {
           acc = 0;
           acc_phase ^= 1;
@@ -718,7 +744,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       // release this accumulator buffer back to the MMA warp
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      if (lane == 0) {
+        if constexpr (CG2) mbar_arrive_cluster(mapa_u32(smem_u32(&tempty_bar[acc]), 0));  // the leader's barrier
+        else mbar_arrive(&tempty_bar[acc]);
+      }
       if (++acc == 2) {
         acc = 0;
         acc_phase ^= 1;
@@ -730,7 +759,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   if constexpr (MC) cluster_sync_all(); else __syncthreads();  // a pair exits together: the peer may still signal us
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, TMEM_COLS);
+    if constexpr (CG2) tmem_dealloc2(tmem_base, TMEM_COLS); else tmem_dealloc(tmem_base, TMEM_COLS);
   }
 }
 
@@ -779,17 +808,23 @@ int make_map(CUtensorMap* m, const void* ptr, uint64_t inner, uint64_t rows, uin
   return 0;
 }
 
+// pair launches as ONE cta_group::2 MMA unit (0 = multicast pairs of cta_group::1 MMAs); initial value from MACAW_B200_GEMM_CG2
+static int& cg2_mode() {
+  static int mode = []() { const char* e = getenv("MACAW_B200_GEMM_CG2"); return e ? (atoi(e) != 0 ? 1 : 0) : 0; }();
+  return mode;
+}
+
 // process-wide stream-K policy; initial value from MACAW_B200_GEMM_STREAMK (default 1)
 static int& streamk_mode() {
   static int mode = []() { const char* e = getenv("MACAW_B200_GEMM_STREAMK"); const int v = e ? atoi(e) : 1; return v < 0 || v > 2 ? 1 : v; }();
   return mode;
 }
 
-template <int BN, int EPI, bool B_MN, bool MC, bool A_MN = false>
+template <int BN, int EPI, bool B_MN, bool MC, bool A_MN = false, bool CG2 = false>
 static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmKParams& p, cudaStream_t st) {
   static bool attr_set[kMaxDevices] = {};
   constexpr size_t smem = gemm_smem_bytes(BN);
-  auto kern = gemm_bf16_kernel<BN, EPI, B_MN, MC, A_MN>;
+  auto kern = gemm_bf16_kernel<BN, EPI, B_MN, MC, A_MN, CG2>;
   if (int rc = ensure_smem_attr(kern, smem, attr_set, "mm_gemm_fwd")) return rc;
   const int m_units = MC ? (p.m_tiles + 1) / 2 : p.m_tiles;
   const int total = p.batch * p.batch2 * m_units * p.n_tiles;
@@ -965,6 +1000,12 @@ extern "C" int32_t mm_gemm_fwd(const mm_gemm_args* a, void* stream) {
 
 #define MM_LAUNCH(BN_, EPI_, MN_) return launch_gemm<BN_, EPI_, MN_, false>(ta, tb, p, st)
 #define MM_LAUNCH_MC(EPI_, MN_) return launch_gemm<256, EPI_, MN_, true>(ta, tb, p, st)
+  if (use_mc && cg2_mode() != 0 && !a->b_mn_major) {
+    p.idesc = make_idesc_f16(2 * kBlockM, BN, false, false, a->a_fp16 != 0, a->b_fp16 != 0);
+    if (a->epi == MM_EPI_ROPE) return launch_gemm<256, MM_EPI_ROPE, false, true, false, true>(ta, tb, p, st);
+    if (a->epi == MM_EPI_SWIGLU) return launch_gemm<256, MM_EPI_SWIGLU, false, true, false, true>(ta, tb, p, st);
+    return launch_gemm<256, MM_EPI_STD, false, true, false, true>(ta, tb, p, st);
+  }
   if (use_mc) {
     if (a->epi == MM_EPI_ROPE) MM_LAUNCH_MC(MM_EPI_ROPE, false);
     if (a->epi == MM_EPI_SWIGLU) MM_LAUNCH_MC(MM_EPI_SWIGLU, false);
@@ -995,6 +1036,12 @@ extern "C" int32_t mm_gemm_fwd(const mm_gemm_args* a, void* stream) {
   MM_LAUNCH(32, MM_EPI_STD, false);
 #undef MM_LAUNCH
 #undef MM_LAUNCH_MC
+}
+
+extern "C" int32_t mm_gemm_cg2_mode(int32_t mode) {
+  const int prev = cg2_mode();
+  if (mode == 0 || mode == 1) cg2_mode() = mode;
+  return prev;
 }
 
 extern "C" int32_t mm_gemm_streamk_mode(int32_t mode) {

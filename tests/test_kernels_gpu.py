@@ -338,8 +338,21 @@ def test_rms_rstd_and_fused_norm_linear():
         (16896, 4096, 4096, "std"),    # cfg4 o_proj
     ],
 )
-def test_gemm_multicast_pairs(M, N, K, kind):
-    """Shapes large enough to take the 2-CTA TMA-multicast path (BN = 256, >= 2 waves)."""
+@pytest.mark.parametrize("cg2", [0, 1], ids=["mc_pairs", "cta_group2"])
+def test_gemm_multicast_pairs(M, N, K, kind, cg2):
+    """Shapes large enough to take the 2-CTA path (BN = 256, >= 2 waves): as two cta_group::1 MMAs sharing a multicast B
+    tile, and as ONE cta_group::2 MMA unit (mm_gemm_cg2_mode)."""
+    from macaw_llm_b200 import _lib
+
+    prev = _lib.load().mm_gemm_cg2_mode(cg2)
+    try:
+        _multicast_pairs_case(M, N, K, kind)
+        torch.cuda.synchronize()
+    finally:
+        _lib.load().mm_gemm_cg2_mode(prev)
+
+
+def _multicast_pairs_case(M, N, K, kind):
     ops = _ops()
     x = rnd(M, K, seed=80)
     if kind == "mn":

@@ -20,6 +20,7 @@ def main():
     ap.add_argument("--batch", type=int, default=32)
     ap.add_argument("--iters", type=int, default=1)
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp16"])
+    ap.add_argument("--cg2", type=int, default=0, help="1: pair launches as one cta_group::2 MMA unit (mm_gemm_cg2_mode)")
     ap.add_argument("--streamk", type=int, default=0, help="1: hand the GEMMs a stream-K workspace (mm_gemm_args.sk_workspace)")
     a = ap.parse_args()
     from macaw_llm_b200 import ops
@@ -27,6 +28,9 @@ def main():
     dt = torch.float16 if a.dtype == "fp16" else torch.bfloat16
     ops.set_act_format(dt)
     dev = "cuda"
+    if a.cg2:
+        from macaw_llm_b200 import _lib
+        _lib.load().mm_gemm_cg2_mode(1)
     if a.streamk:
         ops.STREAMK = ops.streamk_workspace(torch.device("cuda", 0))
     g = torch.Generator(device=dev).manual_seed(0)
@@ -77,7 +81,7 @@ def main():
         ms = e0.elapsed_time(e1) / a.iters
         res.append(f"{name}: {ms * 1e3:.1f} us, {fl / ms / 1e9:.0f} TFLOP/s")
     torch.cuda.cudart().cudaProfilerStop()
-    print(f"[profile_gemms {a.family} B={a.batch} {a.dtype}{' streamk' if a.streamk else ''}] " + "; ".join(res))
+    print(f"[profile_gemms {a.family} B={a.batch} {a.dtype}{' streamk' if a.streamk else ''}{' cg2' if a.cg2 else ''}] " + "; ".join(res))
 
 
 if __name__ == "__main__":
