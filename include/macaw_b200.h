@@ -132,8 +132,9 @@ int32_t mm_gemm_fwd(const mm_gemm_args* args, void* stream);
 /* Stream-K policy of the process: 0 never, 1 when the saved MMA time exceeds the hand-over cost (default; environment
  * MACAW_B200_GEMM_STREAMK), 2 whenever the schedule allows (tests).  mode < 0 only queries.  Returns the previous mode. */
 int32_t mm_gemm_streamk_mode(int32_t mode);
-/* Pair launches (wide tiles, several waves — the LLaMA GEMMs at batch 32) as ONE cta_group::2 MMA unit (mode 1) instead of
- * two cta_group::1 MMAs sharing a multicast B tile (mode 0).  Environment MACAW_B200_GEMM_CG2.  mode < 0 only queries. */
+/* Pair launches (wide tiles, several waves — the LLaMA GEMMs at batch 32) as ONE cta_group::2 MMA unit (mode 1, default)
+ * instead of two cta_group::1 MMAs sharing a multicast B tile (mode 0).  Environment MACAW_B200_GEMM_CG2.  mode < 0 only
+ * queries.  Returns the previous mode. */
 int32_t mm_gemm_cg2_mode(int32_t mode);
 /* bytes of mm_gemm_args.sk_workspace on the current device */
 int64_t mm_gemm_streamk_workspace_bytes(void);

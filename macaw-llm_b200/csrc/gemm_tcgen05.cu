@@ -324,7 +324,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   if (warp == 1) {
     if (elect_one()) {
       for (int s = 0; s < STAGES; ++s) {
-        mbar_init(&full_bar[s], CG2 ? 2 : 1);                // CG2: one arrive.expect_tx per producer, on the LEADER's barrier
+        mbar_init(&full_bar[s], 1);                          // CG2: only the LEADER's barrier is used (see the producer)
         mbar_init(&empty_bar[s], CG2 ? 1 : (MC ? 2 : 1));    // CG2: one multicast commit from the leader
       }
       for (int s = 0; s < 2; ++s) {
@@ -364,8 +364,12 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         for (int kb = wk.kb0; kb < wk.kb1; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           if constexpr (CG2) {
-            const uint32_t lfull = mapa_u32(smem_u32(&full_bar[stage]), 0);  // the leader's barrier
-            mbar_arrive_expect_tx_cluster(lfull, kABytes + B_BYTES);
+            // Both CTAs' loads credit the LEADER's barrier; the leader alone announces the bytes of the pair (a remote
+            // arrive.expect_tx per k-block from the peer is a cluster-scope release in the producer's critical loop:
+            // measured 767 instead of 1483 TFLOP/s).  The peer's bytes may land before the announcement: the phase cannot
+            // complete until the leader's arrival is in.
+            const uint32_t lfull = mapa_u32(smem_u32(&full_bar[stage]), 0);
+            if (cta_rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * (kABytes + B_BYTES));
             tma_load_4d_cg2(&tmA, lfull, sA + stage * kABytes, kb * kBlockK, t.m_blk * kBlockM, t.b_lo, t.b_hi);
             tma_load_4d_cg2(&tmB, lfull, sB + stage * B_BYTES, kb * kBlockK, t.n_blk * BN + cta_rank * (BN / 2), bb, bh);
             if (++stage == STAGES) {
@@ -808,9 +812,16 @@ int make_map(CUtensorMap* m, const void* ptr, uint64_t inner, uint64_t rows, uin
   return 0;
 }
 
-// pair launches as ONE cta_group::2 MMA unit (0 = multicast pairs of cta_group::1 MMAs); initial value from MACAW_B200_GEMM_CG2
+// pair launches as ONE cta_group::2 MMA unit (default; 0 = multicast pairs of cta_group::1 MMAs); MACAW_B200_GEMM_CG2.
+// Measured on B200, cfg4 LLaMA GEMMs at M = 16896: QKV 1153 -> 1086 us, o_proj 414 -> 383, gate-up 1950 -> 1877, down 1180 ->
+// 1041 (1.46 - 1.64 PFLOP/s); in-step under the power cap: 212.8 -> 206.2 ms (fp16), 202.6 -> 196.8 ms (bf16).
 static int& cg2_mode() {
-  static int mode = []() { const char* e = getenv("MACAW_B200_GEMM_CG2"); return e ? (atoi(e) != 0 ? 1 : 0) : 0; }();
+  static int mode = []() { const char* e = getenv("MACAW_B200_GEMM_CG2"); return e ? (atoi(e) != 0 ? 1 : 0) : 1; }();
+  return mode;
+}
+
+static int& odd_cg2_mode() {  // experiment switch for the rule above (MACAW_B200_GEMM_CG2_ODD, default off until measured)
+  static int mode = []() { const char* e = getenv("MACAW_B200_GEMM_CG2_ODD"); return e ? atoi(e) : 0; }();
   return mode;
 }
 
@@ -947,8 +958,16 @@ extern "C" int32_t mm_gemm_fwd(const mm_gemm_args* a, void* stream) {
   static const int mc_env = []() { const char* e = getenv("MACAW_B200_GEMM_MC"); return e ? atoi(e) : 1; }();
   const long long tiles256 = (long long)a->batch * batch2 * p.m_tiles * p.n_tiles;
   // (measured A/B on one box, cfg4: LLaMA GEMMs 1282 -> 1325 TFLOP/s; short-K CLIP GEMMs do not gain, hence K >= 2048)
-  const bool use_mc = mc_env != 0 && !a->a_mn_major && BN == 256 && p.m_tiles >= 2 && p.num_k >= 32 && tiles256 >= 2LL * sms &&
-                      (((p.m_tiles + 1) / 2) * 2 - p.m_tiles) * 32 <= p.m_tiles;
+  // Pairs with an odd number of M tiles leave the last pair with an idle half.  Two cases are worth it: (a) the idle rows are
+  // <= 3 % of the tile rows; (b) the pair runs as a cta_group::2 unit (worth 6 - 12 % on these shapes) and the pair schedule
+  // needs no more waves than the single-CTA schedule would — M = 2112 (17 M tiles, the per-GPU batch of the 8-GPU run):
+  // QKV 432 pair-tiles on 74 pairs = 6 waves vs 816 tiles on 148 CTAs = 6 waves; gate-up 11 vs 10 waves stays single.
+  const int pairs_m = (p.m_tiles + 1) / 2;
+  const long long pair_tiles = (long long)a->batch * batch2 * pairs_m * p.n_tiles;
+  const long long pair_waves = (pair_tiles + sms / 2 - 1) / (sms / 2), single_waves = (tiles256 + sms - 1) / sms;
+  const bool odd_small = (pairs_m * 2 - p.m_tiles) * 32 <= p.m_tiles && tiles256 >= 2LL * sms;
+  const bool odd_cg2 = cg2_mode() != 0 && odd_cg2_mode() != 0 && !a->b_mn_major && tiles256 > sms && pair_waves <= single_waves;
+  const bool use_mc = mc_env != 0 && !a->a_mn_major && BN == 256 && p.m_tiles >= 2 && p.num_k >= 32 && (odd_small || odd_cg2);
   // rasterisation: keep one group's A rows (~32 MiB) resident in the 126 MB L2 while its B tiles stream
   // (measured on cfg4: 16 pairs at K=4096 is the optimum; 4 / 8 / 32 cost +5 % / +1 % / +9 % step time)
   {
