@@ -15,6 +15,10 @@
 // epilogue of tile i overlap the main loop of tile i+1.  One CTA per SM, static round-robin tile schedule with
 // grouped rasterisation for L2 reuse.
 //
+// Wide, multi-wave problems (the LLaMA GEMMs) run as CTA PAIRS: a 2-CTA cluster is ONE tcgen05.mma.cta_group::2 unit on a
+// 256 x 256 tile (template parameter CG2; see the comment at the kernel) — or, for MN-major B, two cta_group::1 MMAs that
+// share a TMA-multicast B tile (MC).  A partial last wave can be split along K over all CTAs (stream-K tail, gemm_work()).
+//
 // Thin problems (decode steps) are launched with the operands swapped and `c_trans` set: the weight matrix takes the
 // 128-row A side, the few activation rows the narrow B side, and the standard epilogue stores transposed.
 //
@@ -820,8 +824,10 @@ static int& cg2_mode() {
   return mode;
 }
 
-static int& odd_cg2_mode() {  // experiment switch for the rule above (MACAW_B200_GEMM_CG2_ODD, default off until measured)
-  static int mode = []() { const char* e = getenv("MACAW_B200_GEMM_CG2_ODD"); return e ? atoi(e) : 0; }();
+// switch for rule (b) above (MACAW_B200_GEMM_CG2_ODD, default on).  Measured at M = 2112 (tools/profile_gemms.py --batch 4):
+// QKV 165.0 -> 154.8 us, down_proj 152.7 -> 144.5, o_proj 56.9 -> 56.7; bench.py --global-batch 4: 30.7 / 31.2 -> 29.6 ms.
+static int& odd_cg2_mode() {
+  static int mode = []() { const char* e = getenv("MACAW_B200_GEMM_CG2_ODD"); return e ? atoi(e) : 1; }();
   return mode;
 }
 

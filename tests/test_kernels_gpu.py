@@ -336,6 +336,8 @@ def test_rms_rstd_and_fused_norm_linear():
         (4096, 5504, 1024, "swiglu"),
         (3072, 4096, 3001, "mn"),      # P x table shape, MN-major B, ragged K
         (16896, 4096, 4096, "std"),    # cfg4 o_proj
+        (2176, 12288, 4096, "rope"),   # 17 M tiles (odd): pairs only as cta_group::2 units (same wave count as single CTAs)
+        (2112, 4096, 11008, "bias_res"),
     ],
 )
 @pytest.mark.parametrize("cg2", [0, 1], ids=["mc_pairs", "cta_group2"])
@@ -427,14 +429,18 @@ def test_gemm_streamk_tail(M, N, K, kind):
     cos_g, sin_g = torch.rand(528, 64, device=DEV), torch.rand(528, 64, device=DEV)
     from macaw_llm_b200 import _lib
 
-    base, base_ss = run()
-    ops.STREAMK = ws
-    prev = _lib.load().mm_gemm_streamk_mode(2)  # force: the default policy skips shapes where it does not pay (o_proj)
+    prev_cg2 = _lib.load().mm_gemm_cg2_mode(0)  # M = 2112 would otherwise run as cta_group::2 pairs (no stream-K there)
     try:
-        outs = [run() for _ in range(3)]
+        base, base_ss = run()
+        ops.STREAMK = ws
+        prev = _lib.load().mm_gemm_streamk_mode(2)  # force: the default policy skips shapes where it does not pay (o_proj)
+        try:
+            outs = [run() for _ in range(3)]
+        finally:
+            ops.STREAMK = None
+            _lib.load().mm_gemm_streamk_mode(prev)
     finally:
-        ops.STREAMK = None
-        _lib.load().mm_gemm_streamk_mode(prev)
+        _lib.load().mm_gemm_cg2_mode(prev_cg2)
     torch.cuda.synchronize()
     assert int(ws[:2048].abs().sum()) == 0  # every flag re-armed
     got, got_ss = outs[0]
