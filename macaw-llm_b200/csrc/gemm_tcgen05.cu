@@ -298,7 +298,7 @@ template <int BN, int EPI, bool B_MN, bool MC, bool A_MN = false, bool CG2 = fal
 __global__ void __launch_bounds__(320, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const GemmKParams p) {
-  static_assert(!CG2 || (MC && !B_MN && !A_MN && BN == 256), "cta_group::2 variant: multicast-pair schedule, K-major, BN 256");
+  static_assert(!CG2 || (MC && !A_MN && BN == 256), "cta_group::2 variant: pair schedule, K-major A, BN 256");
   constexpr int STAGES = CG2 ? 6 : gemm_stages(BN);
   constexpr uint32_t B_BYTES = (CG2 ? BN / 2 : BN) * kBlockK * 2;
   constexpr uint32_t TMEM_COLS = gemm_tmem_cols(BN);
@@ -375,7 +375,14 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             const uint32_t lfull = mapa_u32(smem_u32(&full_bar[stage]), 0);
             if (cta_rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * (kABytes + B_BYTES));
             tma_load_4d_cg2(&tmA, lfull, sA + stage * kABytes, kb * kBlockK, t.m_blk * kBlockM, t.b_lo, t.b_hi);
-            tma_load_4d_cg2(&tmB, lfull, sB + stage * B_BYTES, kb * kBlockK, t.n_blk * BN + cta_rank * (BN / 2), bb, bh);
+            if constexpr (!B_MN) {
+              tma_load_4d_cg2(&tmB, lfull, sB + stage * B_BYTES, kb * kBlockK, t.n_blk * BN + cta_rank * (BN / 2), bb, bh);
+            } else {  // MN-major B: this CTA's half of the N extent = BN / 128 boxes of 64 columns x 64 k
+#pragma unroll
+              for (int jj = 0; jj < BN / 128; ++jj)
+                tma_load_4d_cg2(&tmB, lfull, sB + stage * B_BYTES + jj * 8192,
+                                t.n_blk * BN + (cta_rank * (BN / 128) + jj) * 64, kb * kBlockK, bb, bh);
+            }
             if (++stage == STAGES) {
               stage = 0;
               phase ^= 1;
@@ -972,8 +979,9 @@ extern "C" int32_t mm_gemm_fwd(const mm_gemm_args* a, void* stream) {
   const long long pair_tiles = (long long)a->batch * batch2 * pairs_m * p.n_tiles;
   const long long pair_waves = (pair_tiles + sms / 2 - 1) / (sms / 2), single_waves = (tiles256 + sms - 1) / sms;
   const bool odd_small = (pairs_m * 2 - p.m_tiles) * 32 <= p.m_tiles && tiles256 >= 2LL * sms;
-  const bool odd_cg2 = cg2_mode() != 0 && odd_cg2_mode() != 0 && !a->b_mn_major && tiles256 > sms && pair_waves <= single_waves;
-  const bool use_mc = mc_env != 0 && !a->a_mn_major && BN == 256 && p.m_tiles >= 2 && p.num_k >= 32 && (odd_small || odd_cg2);
+  const bool odd_cg2 = cg2_mode() != 0 && odd_cg2_mode() != 0 && tiles256 > sms && pair_waves <= single_waves;
+  static const int min_k = []() { const char* e = getenv("MACAW_B200_GEMM_PAIR_MIN_KBLOCKS"); return e ? atoi(e) : 32; }();
+  const bool use_mc = mc_env != 0 && !a->a_mn_major && BN == 256 && p.m_tiles >= 2 && p.num_k >= min_k && (odd_small || odd_cg2);
   // rasterisation: keep one group's A rows (~32 MiB) resident in the 126 MB L2 while its B tiles stream
   // (measured on cfg4: 16 pairs at K=4096 is the optimum; 4 / 8 / 32 cost +5 % / +1 % / +9 % step time)
   {
@@ -1025,8 +1033,9 @@ extern "C" int32_t mm_gemm_fwd(const mm_gemm_args* a, void* stream) {
 
 #define MM_LAUNCH(BN_, EPI_, MN_) return launch_gemm<BN_, EPI_, MN_, false>(ta, tb, p, st)
 #define MM_LAUNCH_MC(EPI_, MN_) return launch_gemm<256, EPI_, MN_, true>(ta, tb, p, st)
-  if (use_mc && cg2_mode() != 0 && !a->b_mn_major) {
-    p.idesc = make_idesc_f16(2 * kBlockM, BN, false, false, a->a_fp16 != 0, a->b_fp16 != 0);
+  if (use_mc && cg2_mode() != 0) {
+    p.idesc = make_idesc_f16(2 * kBlockM, BN, false, a->b_mn_major != 0, a->a_fp16 != 0, a->b_fp16 != 0);
+    if (a->b_mn_major) return launch_gemm<256, MM_EPI_STD, true, true, false, true>(ta, tb, p, st);
     if (a->epi == MM_EPI_ROPE) return launch_gemm<256, MM_EPI_ROPE, false, true, false, true>(ta, tb, p, st);
     if (a->epi == MM_EPI_SWIGLU) return launch_gemm<256, MM_EPI_SWIGLU, false, true, false, true>(ta, tb, p, st);
     return launch_gemm<256, MM_EPI_STD, false, true, false, true>(ta, tb, p, st);
