@@ -81,3 +81,40 @@ def test_integration_md_stub_matches_abi():
     doc = ns["GemmArgs"]
     assert [f[0] for f in doc._fields_] == [f[0] for f in _lib.GemmArgs._fields_]
     assert ctypes.sizeof(doc) == ctypes.sizeof(_lib.GemmArgs)
+
+
+def test_product_kernels_are_blackwell_native_sass():
+    """Static check of the shipped cubin (cuobjdump, no GPU): the GEMM, flash-attention and fused alignment kernels carry
+    tcgen05.mma (UTCHMMA) + TMA (UTMALDG) + TMEM loads (LDTM); the pair GEMMs carry the cta_group::2 form; mma.sync (HMMA)
+    appears only in the second attention implementation the tests use as a cross-check; nothing spills to local memory."""
+    import shutil
+    import sys
+
+    if shutil.which("cuobjdump") is None:
+        pytest.skip("cuobjdump not on PATH")
+    from macaw_llm_b200 import _lib
+
+    _lib.load()
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "sass_inventory.py")], capture_output=True, text=True,
+                         timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = out.stdout.splitlines()
+    hdr = next(l for l in lines if l.startswith("kernel "))
+    cols = hdr.split()[1:]
+    rows = {}
+    for l in lines:
+        if l.startswith(("#", "kernel ", "TOTAL")):
+            continue
+        m = re.match(r"(.+?)\s+((?:\d+\s+){%d}\d+)\s*$" % (len(cols) - 1), l)
+        assert m, l
+        rows[m.group(1).strip()] = dict(zip(cols, map(int, m.group(2).split())))
+    for fam in ("gemm_bf16_kernel<", "fa_tcgen05_kernel<", "align_fused_kernel"):
+        fam_rows = {k: v for k, v in rows.items() if k.startswith(fam)}
+        assert fam_rows, fam
+        for k, v in fam_rows.items():
+            assert v["UTCHMMA"] + v["UTCHMMA.2CTA"] > 0 and v["UTMALDG"] > 0 and v["LDTM"] > 0 and v["HMMA"] == 0, (k, v)
+    # cta_group::2 pair instantiations exist (last template argument true) and use the 2-CTA MMA only
+    pairs = {k: v for k, v in rows.items() if k.startswith("gemm_bf16_kernel<") and k.rstrip(">").endswith(", true")}
+    assert pairs and all(v["UTCHMMA.2CTA"] > 0 and v["UTCHMMA"] == 0 for v in pairs.values()), pairs
+    assert {k for k, v in rows.items() if v["HMMA"]} <= {k for k in rows if k.startswith("flash_attn_kernel<")}
+    assert all(v["LOCAL"] == 0 for v in rows.values()), {k: v["LOCAL"] for k, v in rows.items() if v["LOCAL"]}
