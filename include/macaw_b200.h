@@ -129,6 +129,25 @@ typedef struct mm_gemm_args {
 } mm_gemm_args;
 
 int32_t mm_gemm_fwd(const mm_gemm_args* args, void* stream);
+/* The schedule mm_gemm_fwd would use for `args` on the current device (148 SMs when no device is visible), without
+ * touching memory or launching: the host-side decisions — tile width from the cost model, CTA pairs / cta_group::2,
+ * rasterisation group, stream-K tail — are a pure function of the shapes, strides, alignments and flags.  Operand
+ * pointers are only checked for null / alignment, never dereferenced.  Host logic made testable without a GPU
+ * (tests/test_gemm_plan.py) and printable per BASELINE shape (tools/gemm_plan.py -> profiles/r2_gemm_schedules.txt). */
+typedef struct mm_gemm_schedule {
+  int32_t block_n;             /* tile = 128 x block_n x 64 (pairs: 256 x 256 x 64 per CTA pair) */
+  int32_t pairs;               /* 0 = single CTAs, 1 = multicast pairs of cta_group::1 MMAs, 2 = cta_group::2 pairs */
+  int32_t m_tiles, n_tiles, k_blocks;
+  int64_t units;               /* work units over all batches: tiles, or pair tiles (2 M tiles x 1 N tile) */
+  int32_t workers;             /* units in flight: SMs, or SM pairs */
+  int32_t grid;                /* CTAs launched (persistent: <= SM count) */
+  int32_t waves;               /* ceil(units / workers) */
+  int32_t group_m;             /* rasterisation: M units per L2 group */
+  int32_t streamk_tiles;       /* tiles of the partial last wave shared over all CTAs (0 = plain tiles) */
+  int32_t smem_bytes;          /* dynamic shared memory per CTA */
+  int32_t vectorised_epilogue; /* 1 = 128-bit epilogue accesses (all alignments hold) */
+} mm_gemm_schedule;
+int32_t mm_gemm_plan(const mm_gemm_args* args, mm_gemm_schedule* plan);
 /* Stream-K policy of the process: 0 never, 1 when the saved MMA time exceeds the hand-over cost (default; environment
  * MACAW_B200_GEMM_STREAMK), 2 whenever the schedule allows (tests).  mode < 0 only queries.  Returns the previous mode. */
 int32_t mm_gemm_streamk_mode(int32_t mode);

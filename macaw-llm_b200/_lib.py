@@ -34,6 +34,14 @@ class GemmArgs(C.Structure):
     ]
 
 
+class GemmPlan(C.Structure):
+    """Mirror of `mm_gemm_schedule` (include/macaw_b200.h), filled by mm_gemm_plan()."""
+
+    _fields_ = [("block_n", c_i32), ("pairs", c_i32), ("m_tiles", c_i32), ("n_tiles", c_i32), ("k_blocks", c_i32),
+                ("units", c_i64), ("workers", c_i32), ("grid", c_i32), ("waves", c_i32), ("group_m", c_i32),
+                ("streamk_tiles", c_i32), ("smem_bytes", c_i32), ("vectorised_epilogue", c_i32)]
+
+
 class ThinArgs(C.Structure):
     """mirror of mm_thin_args"""
     _fields_ = [("part", c_vp), ("splits", c_i32), ("N", c_i32), ("M", c_i32), ("ldp", c_i32), ("mode", c_i32),
@@ -90,6 +98,7 @@ SIGNATURES = {
     "mm_set_act_format": (None, [c_i32]),
     "mm_get_act_format": (c_i32, []),
     "mm_gemm_fwd": (c_i32, [C.POINTER(GemmArgs), c_vp]),
+    "mm_gemm_plan": (c_i32, [C.POINTER(GemmArgs), C.POINTER(GemmPlan)]),
     "mm_splitk_reduce": (c_i32, [c_vp, c_i32, c_i32, c_i32, c_vp, c_vp, c_i64, c_i32, c_vp]),
     "mm_attn_fwd": (c_i32, [C.POINTER(AttnArgs), c_vp]),
     "mm_rmsnorm_fwd": (c_i32, [c_vp, c_vp, c_vp, c_i32, c_i32, c_f32, c_vp]),

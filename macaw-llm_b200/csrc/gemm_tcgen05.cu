@@ -871,7 +871,10 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmK
 
 using namespace mm;
 
-extern "C" int32_t mm_gemm_fwd(const mm_gemm_args* a, void* stream) {
+// The whole host side of a GEMM call: argument checks, tile width, pair / cta_group::2 / stream-K decisions, rasterisation
+// group, tensor maps, launch.  With `plan` set it stops after the decisions (nothing is dereferenced, encoded or launched):
+// mm_gemm_plan() exposes the schedule to the CPU test tier and to tools/gemm_plan.py.
+static int32_t gemm_dispatch(const mm_gemm_args* a, void* stream, mm_gemm_schedule* plan) {
   MM_REQUIRE(a != nullptr, "mm_gemm_fwd: null args");
   MM_REQUIRE(a->M > 0 && a->N > 0 && a->K > 0 && a->batch > 0 && a->batch2 >= 0,
              "mm_gemm_fwd: bad shape M=%d N=%d K=%d batch=%d batch2=%d", a->M, a->N, a->K, a->batch, a->batch2);
@@ -1013,10 +1016,31 @@ extern "C" int32_t mm_gemm_fwd(const mm_gemm_args* a, void* stream) {
       p.sk_ws = reinterpret_cast<float*>(reinterpret_cast<char*>(a->sk_workspace) + 8192);
     }
   }
+  MM_REQUIRE(!a->a_mn_major || (a->b_mn_major && a->epi == MM_EPI_STD && !a->c_trans),
+             "mm_gemm_fwd: MN-major A needs MN-major B and the standard epilogue");
+  MM_REQUIRE(!a->b_mn_major || a->epi == MM_EPI_STD, "mm_gemm_fwd: MN-major B only with the standard epilogue");
+  if (plan != nullptr) {
+    const int m_units = use_mc ? (p.m_tiles + 1) / 2 : p.m_tiles;
+    const long long units = (long long)a->batch * batch2 * m_units * p.n_tiles;
+    const int workers = use_mc ? sms / 2 : sms;  // CTAs, or CTA pairs
+    plan->block_n = BN;
+    plan->pairs = use_mc ? (cg2_mode() != 0 ? 2 : 1) : 0;
+    plan->m_tiles = p.m_tiles;
+    plan->n_tiles = p.n_tiles;
+    plan->k_blocks = p.num_k;
+    plan->units = units;
+    plan->workers = workers;
+    plan->grid = use_mc ? 2 * static_cast<int>(units < workers ? units : workers)
+                        : static_cast<int>((units < sms && p.sk_tiles == 0) ? units : sms);
+    plan->waves = static_cast<int>((units + workers - 1) / workers);
+    plan->group_m = p.group_m;
+    plan->streamk_tiles = p.sk_tiles;
+    plan->smem_bytes = static_cast<int32_t>(gemm_smem_bytes(BN));
+    plan->vectorised_epilogue = p.vec_ok;
+    return 0;
+  }
   CUtensorMap ta, tb;
   if (a->a_mn_major) {
-    MM_REQUIRE(a->b_mn_major && a->epi == MM_EPI_STD && !a->c_trans,
-               "mm_gemm_fwd: MN-major A needs MN-major B and the standard epilogue");
     if (make_map(&ta, a->A, a->M, a->K, a->batch, batch2, a->lda, a->a_bs, a->a_bs2, 64)) return 1;
   } else if (make_map(&ta, a->A, a->K, a->M, a->batch, batch2, a->lda, a->a_bs, a->a_bs2, kBlockM)) {
     return 1;
@@ -1026,7 +1050,6 @@ extern "C" int32_t mm_gemm_fwd(const mm_gemm_args* a, void* stream) {
   if (!a->b_mn_major) {
     if (make_map(&tb, a->B, a->K, a->N, b_batch, b_batch2, a->ldb, a->b_bs, a->b_bs2, use_mc ? BN / 2 : BN)) return 1;
   } else {
-    MM_REQUIRE(a->epi == MM_EPI_STD, "mm_gemm_fwd: MN-major B only with the standard epilogue");
     if (make_map(&tb, a->B, a->N, a->K, b_batch, b_batch2, a->ldb, a->b_bs, a->b_bs2, 64)) return 1;
   }
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
@@ -1070,6 +1093,13 @@ extern "C" int32_t mm_gemm_fwd(const mm_gemm_args* a, void* stream) {
   MM_LAUNCH(32, MM_EPI_STD, false);
 #undef MM_LAUNCH
 #undef MM_LAUNCH_MC
+}
+
+extern "C" int32_t mm_gemm_fwd(const mm_gemm_args* a, void* stream) { return gemm_dispatch(a, stream, nullptr); }
+
+extern "C" int32_t mm_gemm_plan(const mm_gemm_args* a, mm_gemm_schedule* plan) {
+  MM_REQUIRE(plan != nullptr, "mm_gemm_plan: null plan");
+  return gemm_dispatch(a, nullptr, plan);
 }
 
 extern "C" int32_t mm_gemm_cg2_mode(int32_t mode) {

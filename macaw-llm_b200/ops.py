@@ -105,6 +105,33 @@ def gemm_raw(*, M, N, K, A, lda, B, ldb, Cout, ldc, batch=1, a_bs=0, b_bs=0, c_b
     PROFILE.append((TAG, 2.0 * M * N * K * batch * max(1, batch2), e0, e1))
 
 
+def gemm_plan(*, M: int, N: int, K: int, batch: int = 1, batch2: int = 1, epi: int = EPI_STD, b_mn_major: bool = False,
+              a_mn_major: bool = False, c_fp32: bool = False, c_trans: bool = False, fp16: bool = False,
+              streamk: bool = False) -> dict:
+    """The schedule mm_gemm_fwd would pick for a dense, 16-byte-aligned GEMM of this shape (mm_gemm_plan: the host-side
+    dispatch run without touching memory or launching — works without a GPU, where the library assumes 148 SMs).
+    `streamk=True` hands the dispatcher a stream-K workspace, as the LLaMA stack does."""
+    lib = _lib.load()
+    fake = 1 << 20  # operand addresses are only checked for null / alignment
+    lda = M if a_mn_major else K
+    ldb = N if b_mn_major else K
+    n_out = N // 2 if epi == EPI_SWIGLU else N
+    ldc = M if c_trans else n_out
+    ws = int(lib.mm_gemm_streamk_workspace_bytes()) if streamk else 0
+    rope = dict(rope_cos=fake, rope_sin=fake, rope_T=max(1, M), rope_cols=(N // 128) * 128) if epi == EPI_ROPE else {}
+    kw = dict(M=M, N=N, K=K, batch=batch, batch2=batch2, A=fake, lda=lda, a_bs=M * K, a_bs2=M * K * batch, B=fake, ldb=ldb,
+              b_bs=N * K, b_bs2=N * K * batch, b_mn_major=int(b_mn_major), C=fake, ldc=ldc, c_bs=M * n_out,
+              c_bs2=M * n_out * batch, c_fp32=int(c_fp32), epi=epi, act=ACT_NONE, alpha=1.0, c_trans=int(c_trans),
+              a_fp16=int(fp16), b_fp16=int(fp16), c_fp16=int(fp16 and not c_fp32), a_mn_major=int(a_mn_major),
+              sk_workspace=fake if streamk else None, sk_workspace_bytes=ws, **rope)
+    a = GemmArgs(**kw)
+    plan = _lib.GemmPlan()
+    _check(lib.mm_gemm_plan(C.byref(a), C.byref(plan)), "mm_gemm_plan")
+    d = {name: int(getattr(plan, name)) for name, _ in _lib.GemmPlan._fields_}
+    d["fill"] = d["units"] / float(d["waves"] * d["workers"])  # share of the scheduled tile slots that carry work
+    return d
+
+
 def linear(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, *, act: int = ACT_NONE,
            residual: Optional[torch.Tensor] = None, res_row_mod: int = 0, out: Optional[torch.Tensor] = None,
            out_fp32: bool = False, alpha: float = 1.0, row_scale: Optional[torch.Tensor] = None, epi: int = EPI_STD,
