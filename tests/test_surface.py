@@ -157,3 +157,44 @@ def test_allreduced_gradient_equals_single_process_gradient_world2_gloo():
         want = 0.5 * (g0[k] + g1[k])
         assert H.rel_err(got, want) < 1e-2, k                       # bf16 storage of the gradient buffer
         assert torch.equal(got, torch.from_numpy(res[1][k]))        # both ranks hold the same averaged gradient
+
+
+def test_grad_buffer_layout_and_reference_freezing():
+    """Host logic of the training step (reference run_clm_llms.py:390-393, llm_trainer.py:184-188): the trainable set is
+    everything whose name lacks 'encoder' that the step differentiates; the flat gradient buffer lists it in BACKWARD order
+    (lm_head, final norm, layers L-1 .. 0, then table + alignment modules) in contiguous, 16-byte aligned buckets."""
+    from macaw_llm_b200.training import GradBuffer, freeze_like_reference, trainable_parameters
+
+    model, spec, hp, _ = H.build_tiny_model("cpu", torch.bfloat16)
+    freeze_like_reference(model)
+    frozen = {n for n, p in model.named_parameters() if not p.requires_grad}
+    assert frozen and all("encoder" in n for n in frozen)
+    assert all(p.requires_grad for n, p in model.named_parameters() if "encoder" not in n)
+    train = dict(trainable_parameters(model))
+    assert not (set(train) & frozen)
+    gb = GradBuffer(model)
+    assert {id(p) for p in gb.params} == {id(p) for p in train.values()}, "buffer covers exactly the differentiated set"
+    L = len(model.llm.model.layers)
+    assert len(gb.buckets) == L + 2
+    # buckets tile the flat buffer in order, every view is 16-byte aligned and views do not overlap
+    assert gb.buckets[0][0] == 0 and gb.buckets[-1][1] == gb.flat.numel()
+    assert all(gb.buckets[i][1] == gb.buckets[i + 1][0] for i in range(len(gb.buckets) - 1))
+    spans = sorted((v.data_ptr(), v.numel() * 2) for v in gb.views.values())
+    assert all(a % 16 == 0 for a, _ in spans)
+    assert all(spans[i][0] + spans[i][1] <= spans[i + 1][0] for i in range(len(spans) - 1))
+    assert sum(n for _, n in spans) == gb.flat.numel() * 2
+    # backward order: lm_head first, layer L-1 before layer 0, the embedding table in the last bucket
+    off = {id(p): (gb.views[id(p)].data_ptr() - gb.flat.data_ptr()) // 2 for p in gb.params}
+    llm = model.llm
+    assert off[id(llm.lm_head.weight)] == 0
+    assert off[id(llm.model.layers[L - 1].mlp.down_proj.weight)] < off[id(llm.model.layers[0].mlp.down_proj.weight)]
+    s, e = gb.buckets[-1]
+    assert s <= off[id(llm.model.embed_tokens.weight)] < e and s <= off[id(model.image_align_attention.in_proj_weight)] < e
+    # attach(): p.grad views the buffer; a second attach reports "accumulate", zero() detaches
+    fresh = gb.attach(skip=gb.align_params["video"])
+    assert all(fresh.values()) and model.video_align_attention.in_proj_weight.grad is None
+    assert llm.lm_head.weight.grad.data_ptr() == gb.flat.data_ptr()
+    again = gb.attach(skip=gb.align_params["video"])
+    assert not again[id(llm.lm_head.weight)] and again[id(model.video_align_attention.in_proj_weight)]
+    gb.zero()
+    assert llm.lm_head.weight.grad is None
