@@ -9,7 +9,8 @@ accumulation inside a matmul, 16-bit storage between ops — what the reference'
 norm-wise difference is the floor any fp16 implementation of this model sits on; the B200 path's measured error
 (prefix 6-7e-4, logits 5.1e-3, top-1 agreement 0.98-0.996) is read against it.
 
-Usage: python tools/fp16_yardstick.py [--configs cfg2,cfg4] [--layers 32] [--dtype fp16|bf16] > profiles/r2_fp16_yardstick.txt
+Lives under tests/ because it drives the oracle (test infrastructure: only tests/, smoke() and bench.py's CPU arm may).
+Usage: python tests/golden/fp16_yardstick.py [--configs cfg2,cfg4] [--layers 32] [--dtype fp16|bf16] > profiles/r2_fp16_yardstick.txt
 """
 import argparse
 import os
@@ -18,7 +19,7 @@ import time
 
 import torch
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 
 
